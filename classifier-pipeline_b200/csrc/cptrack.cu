@@ -1,0 +1,474 @@
+// cptrack.cu -- C ABI (include/cptrack.h) over the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "cptrack_kernels.cuh"
+
+namespace cpt {
+__global__ void extract_clips_kernel(const KernelArgs a);
+}
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) return fail(CPT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct HostWeightTable {
+    std::vector<double> w;
+    uint32_t *d_ceil = nullptr;
+    double *d_w = nullptr;
+    int max_count = 0;
+};
+
+}  // namespace
+
+struct cpt_ctx {
+    int device = 0;
+    cpt::Geometry g{};
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    int num_sms = 0;
+    HostWeightTable tables[4];
+    float *scratch = nullptr;
+    size_t scratch_ctas = 0;
+    int *work_counter = nullptr;
+    // staging buffers of cpt_extract_batch_host
+    void *stage_frames[2] = {nullptr, nullptr};
+    size_t stage_frames_bytes = 0;
+    cpt_region *stage_regions[2] = {nullptr, nullptr};
+    cpt_frame_info *stage_info[2] = {nullptr, nullptr};
+    float *stage_filtered[2] = {nullptr, nullptr};
+    uint8_t *stage_labels[2] = {nullptr, nullptr};
+    size_t stage_out_frames = 0;
+    bool stage_has_filtered = false, stage_has_labels = false;
+    cpt_clip *d_clips = nullptr;
+    size_t d_clips_cap = 0;
+    cudaEvent_t ev_h2d[2], ev_compute[2], ev_d2h[2];
+    bool events = false;
+};
+
+extern "C" {
+
+const char *cpt_last_error(void) { return g_error; }
+
+int cpt_version(void) { return 100; }
+
+int cpt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int max_regions) {
+    if (width <= 0 || height <= 0 || width % 8 != 0 || width > cpt::kMaxW || height > cpt::kMaxH ||
+        width * height > cpt::kMaxPx || (width * height) % 16 != 0) {
+        fail(CPT_ERR_INVALID, "unsupported geometry %dx%d (need width%%8==0, width<=160, height<=120)", width, height);
+        return nullptr;
+    }
+    if (edge_pixels < 0 || 2 * edge_pixels >= std::min(width, height)) {
+        fail(CPT_ERR_INVALID, "bad edge_pixels %d", edge_pixels);
+        return nullptr;
+    }
+    if (max_regions < 1 || max_regions > CPT_MAX_COMPONENTS) {
+        fail(CPT_ERR_INVALID, "max_regions must be in [1,%d]", CPT_MAX_COMPONENTS);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(CPT_ERR_CUDA, "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    cpt_ctx *c = new cpt_ctx();
+    c->device = device;
+    cpt::Geometry &g = c->g;
+    g.W = width; g.H = height; g.edge = edge_pixels;
+    g.npx = width * height; g.groups = g.npx / 8; g.gpr = width / 8;
+    g.row_words = (width + 31) / 32; g.words = height * g.row_words;
+    g.crop_w = width - 2 * edge_pixels; g.crop_h = height - 2 * edge_pixels; g.ncrop = g.crop_w * g.crop_h;
+    g.block_w = (width + 1) / 2; g.max_regions = max_regions;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        fail(CPT_ERR_CUDA, "cudaGetDeviceProperties failed");
+        delete c;
+        return nullptr;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(CPT_ERR_CUDA, "cudaStreamCreate failed");
+        delete c;
+        return nullptr;
+    }
+    c->stream = c->own_stream;
+    if (cudaFuncSetAttribute(cpt::extract_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(cpt::Smem)) != cudaSuccess) {
+        fail(CPT_ERR_CUDA, "cannot opt in to %zu bytes of shared memory: %s", sizeof(cpt::Smem),
+             cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    if (cudaMalloc(&c->work_counter, sizeof(int)) != cudaSuccess) {
+        fail(CPT_ERR_NOMEM, "cudaMalloc failed");
+        delete c;
+        return nullptr;
+    }
+    g_error[0] = 0;
+    return c;
+}
+
+static void free_stage(cpt_ctx *c) {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->stage_frames[i]); c->stage_frames[i] = nullptr;
+        cudaFree(c->stage_regions[i]); c->stage_regions[i] = nullptr;
+        cudaFree(c->stage_info[i]); c->stage_info[i] = nullptr;
+        cudaFree(c->stage_filtered[i]); c->stage_filtered[i] = nullptr;
+        cudaFree(c->stage_labels[i]); c->stage_labels[i] = nullptr;
+    }
+    c->stage_frames_bytes = 0;
+    c->stage_out_frames = 0;
+}
+
+void cpt_ctx_destroy(cpt_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &t : c->tables) {
+        cudaFree(t.d_ceil);
+        cudaFree(t.d_w);
+    }
+    cudaFree(c->scratch);
+    cudaFree(c->work_counter);
+    cudaFree(c->d_clips);
+    free_stage(c);
+    if (c->events)
+        for (int i = 0; i < 2; ++i) {
+            cudaEventDestroy(c->ev_h2d[i]);
+            cudaEventDestroy(c->ev_compute[i]);
+            cudaEventDestroy(c->ev_d2h[i]);
+        }
+    cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->d2h_stream);
+    delete c;
+}
+
+int cpt_ctx_set_stream(cpt_ctx *c, void *cuda_stream) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return CPT_OK;
+}
+
+int cpt_ctx_synchronize(cpt_ctx *c) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPT_OK;
+}
+
+int cpt_set_weight_table(cpt_ctx *c, int slot, double weight_add, int max_frames) {
+    if (!c || slot < 0 || slot >= 4) return fail(CPT_ERR_INVALID, "weight table slot must be 0..3");
+    if (max_frames < 1 || max_frames > 65535) return fail(CPT_ERR_INVALID, "max_frames must be in [1,65535]");
+    if (!(weight_add >= 0.0)) return fail(CPT_ERR_INVALID, "weight_add must be >= 0");
+    CUDA_TRY(cudaSetDevice(c->device));
+    HostWeightTable &t = c->tables[slot];
+    int n = max_frames + 1;
+    t.w.assign(n, 0.0);
+    std::vector<uint32_t> ceil_w(n);
+    // background_weight accumulates by repeated += weight_add in fp64 (motiondetector.py:222-226)
+    volatile double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+        t.w[k] = acc;
+        double cw = std::ceil(acc);
+        ceil_w[k] = cw > 2.0e9 ? 2000000000u : (uint32_t)cw;  // > any int32 pixel difference
+        acc = acc + weight_add;
+    }
+    cudaFree(t.d_ceil);
+    cudaFree(t.d_w);
+    t.d_ceil = nullptr; t.d_w = nullptr;
+    CUDA_TRY(cudaMalloc(&t.d_ceil, sizeof(uint32_t) * n));
+    CUDA_TRY(cudaMalloc(&t.d_w, sizeof(double) * n));
+    CUDA_TRY(cudaMemcpy(t.d_ceil, ceil_w.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.d_w, t.w.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    t.max_count = max_frames;
+    return CPT_OK;
+}
+
+double cpt_weight_value(const cpt_ctx *c, int slot, int count) {
+    if (!c || slot < 0 || slot >= 4) return NAN;
+    const HostWeightTable &t = c->tables[slot];
+    if (count < 0 || count >= (int)t.w.size()) return NAN;
+    return t.w[count];
+}
+
+int cpt_device_alloc(cpt_ctx *c, void **d_ptr, uint64_t bytes) {
+    if (!c || !d_ptr) return fail(CPT_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(d_ptr, bytes);
+    if (e != cudaSuccess) return fail(CPT_ERR_NOMEM, "cudaMalloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return CPT_OK;
+}
+
+int cpt_device_free(cpt_ctx *c, void *d_ptr) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaFree(d_ptr));
+    return CPT_OK;
+}
+
+int cpt_host_alloc_pinned(void **h_ptr, uint64_t bytes) {
+    if (!h_ptr) return fail(CPT_ERR_INVALID, "null argument");
+    cudaError_t e = cudaHostAlloc(h_ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(CPT_ERR_NOMEM, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return CPT_OK;
+}
+
+int cpt_host_free_pinned(void *h_ptr) {
+    CUDA_TRY(cudaFreeHost(h_ptr));
+    return CPT_OK;
+}
+
+int cpt_copy_to_device(cpt_ctx *c, void *d_dst, const void *h_src, uint64_t bytes) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return CPT_OK;
+}
+
+int cpt_copy_to_host(cpt_ctx *c, void *h_dst, const void *d_src, uint64_t bytes) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return CPT_OK;
+}
+
+uint64_t cpt_state_bytes(const cpt_ctx *c) { return c ? cpt::state_bytes(c->g.npx) : 0; }
+
+static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_clips, int n_clips,
+                          const cpt_outputs *out, void *d_state, cudaStream_t stream) {
+    if (n_clips == 0) return CPT_OK;
+    int grid = std::min(n_clips, c->num_sms);
+    if (!out->d_filtered && c->scratch_ctas < (size_t)grid) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(c->scratch);
+        c->scratch = nullptr;
+        size_t ctas = (size_t)std::max(grid, c->num_sms);
+        CUDA_TRY(cudaMalloc(&c->scratch, ctas * 2 * c->g.npx * sizeof(float)));
+        c->scratch_ctas = ctas;
+    }
+    cpt::KernelArgs a{};
+    a.g = c->g;
+    a.frames = d_frames;
+    a.clips = d_clips;
+    a.n_clips = n_clips;
+    a.regions = out->d_regions;
+    a.info = out->d_info;
+    a.filtered = out->d_filtered;
+    a.labels = out->d_labels;
+    a.scratch = out->d_filtered ? nullptr : c->scratch;
+    a.state = (uint8_t *)d_state;
+    for (int i = 0; i < 4; ++i) {
+        a.tables[i].ceil_w = c->tables[i].d_ceil;
+        a.tables[i].w = c->tables[i].d_w;
+        a.tables[i].max_count = c->tables[i].max_count;
+    }
+    a.work_counter = c->work_counter;
+    CUDA_TRY(cudaMemsetAsync(c->work_counter, 0, sizeof(int), stream));
+    cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return CPT_OK;
+}
+
+int cpt_extract_batch(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_clips, int n_clips,
+                      const cpt_outputs *out, void *d_state) {
+    if (!c || !out) return fail(CPT_ERR_INVALID, "null argument");
+    if (n_clips < 0) return fail(CPT_ERR_INVALID, "n_clips < 0");
+    if (n_clips == 0) return CPT_OK;
+    if (!d_frames || !d_clips) return fail(CPT_ERR_INVALID, "null frames / clips");
+    if (!out->d_info || !out->d_regions) return fail(CPT_ERR_INVALID, "d_info and d_regions are required");
+    if (!c->tables[0].d_ceil && !c->tables[1].d_ceil && !c->tables[2].d_ceil && !c->tables[3].d_ceil)
+        return fail(CPT_ERR_INVALID, "no weight table set (cpt_set_weight_table)");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return launch_extract(c, d_frames, d_clips, n_clips, out, d_state, c->stream);
+}
+
+static int ensure_stage(cpt_ctx *c, size_t frames_bytes, size_t out_frames, bool filtered, bool labels) {
+    if (!c->events) {
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+        }
+        c->events = true;
+    }
+    bool need = frames_bytes > c->stage_frames_bytes || out_frames > c->stage_out_frames ||
+                (filtered && !c->stage_has_filtered) || (labels && !c->stage_has_labels);
+    if (!need) return CPT_OK;
+    CUDA_TRY(cudaDeviceSynchronize());
+    free_stage(c);
+    filtered = filtered || c->stage_has_filtered;
+    labels = labels || c->stage_has_labels;
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc(&c->stage_frames[i], frames_bytes));
+        CUDA_TRY(cudaMalloc(&c->stage_regions[i], out_frames * c->g.max_regions * sizeof(cpt_region)));
+        CUDA_TRY(cudaMalloc(&c->stage_info[i], out_frames * sizeof(cpt_frame_info)));
+        if (filtered) CUDA_TRY(cudaMalloc(&c->stage_filtered[i], out_frames * c->g.npx * sizeof(float)));
+        if (labels) CUDA_TRY(cudaMalloc(&c->stage_labels[i], out_frames * c->g.npx));
+    }
+    c->stage_frames_bytes = frames_bytes;
+    c->stage_out_frames = out_frames;
+    c->stage_has_filtered = filtered;
+    c->stage_has_labels = labels;
+    return CPT_OK;
+}
+
+int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip *h_clips, int n_clips,
+                           int64_t total_frames, cpt_region *h_regions, cpt_frame_info *h_info,
+                           float *h_filtered, uint8_t *h_labels, int chunk_clips) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    if (n_clips < 0 || total_frames < 0) return fail(CPT_ERR_INVALID, "negative sizes");
+    if (n_clips == 0) return CPT_OK;
+    if (!h_frames || !h_clips || !h_regions || !h_info) return fail(CPT_ERR_INVALID, "null host buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (chunk_clips <= 0) chunk_clips = c->num_sms;
+    const size_t npx = c->g.npx;
+    const int n_chunks = (n_clips + chunk_clips - 1) / chunk_clips;
+    // per chunk: the span of input frames and of output frames its clips touch
+    struct Span { int64_t in_lo, in_hi, out_lo, out_hi; };
+    std::vector<Span> spans(n_chunks);
+    std::vector<cpt_clip> rebased(h_clips, h_clips + n_clips);
+    size_t max_in = 0, max_out = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        int c0 = ch * chunk_clips, c1 = std::min(n_clips, c0 + chunk_clips);
+        Span sp{INT64_MAX, 0, INT64_MAX, 0};
+        for (int i = c0; i < c1; ++i) {
+            const cpt_clip &k = h_clips[i];
+            if (k.flags & CPT_CLIP_RESUME) return fail(CPT_ERR_INVALID, "CPT_CLIP_RESUME is not supported by the host-staged call");
+            if (k.n_frames < 0 || k.frame_offset < 0 || k.init_offset < 0 || k.out_offset < 0 || k.ring_frames != 0)
+                return fail(CPT_ERR_INVALID, "clip %d: bad offsets", i);
+            if (k.out_offset + k.n_frames > total_frames) return fail(CPT_ERR_INVALID, "clip %d: outputs exceed total_frames", i);
+            sp.in_lo = std::min(sp.in_lo, std::min(k.frame_offset, k.init_offset));
+            sp.in_hi = std::max(sp.in_hi, std::max(k.frame_offset + k.n_frames, k.init_offset + 1));
+            sp.out_lo = std::min(sp.out_lo, k.out_offset);
+            sp.out_hi = std::max(sp.out_hi, k.out_offset + k.n_frames);
+        }
+        for (int i = c0; i < c1; ++i) {
+            rebased[i].frame_offset -= sp.in_lo;
+            rebased[i].init_offset -= sp.in_lo;
+            rebased[i].out_offset -= sp.out_lo;
+        }
+        spans[ch] = sp;
+        max_in = std::max(max_in, (size_t)(sp.in_hi - sp.in_lo));
+        max_out = std::max(max_out, (size_t)std::max<int64_t>(sp.out_hi - sp.out_lo, 1));
+    }
+    int rc = ensure_stage(c, max_in * npx * sizeof(uint16_t), max_out, h_filtered != nullptr, h_labels != nullptr);
+    if (rc) return rc;
+    if (c->d_clips_cap < (size_t)n_clips) {
+        cudaFree(c->d_clips);
+        c->d_clips = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_clips, sizeof(cpt_clip) * n_clips));
+        c->d_clips_cap = n_clips;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_clips, rebased.data(), sizeof(cpt_clip) * n_clips, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int b = ch & 1;
+        const int c0 = ch * chunk_clips, c1 = std::min(n_clips, c0 + chunk_clips);
+        const Span &sp = spans[ch];
+        // frames buffer b is free once the kernel of chunk ch-2 has run
+        if (ch >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(c->stage_frames[b], h_frames + (size_t)sp.in_lo * npx,
+                                 (size_t)(sp.in_hi - sp.in_lo) * npx * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+        if (ch >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
+        cpt_outputs out{c->stage_regions[b], c->stage_info[b], h_filtered ? c->stage_filtered[b] : nullptr,
+                        h_labels ? c->stage_labels[b] : nullptr};
+        rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_compute[b], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->ev_compute[b], 0));
+        const size_t nf = (size_t)(sp.out_hi - sp.out_lo);
+        CUDA_TRY(cudaMemcpyAsync(h_regions + (size_t)sp.out_lo * c->g.max_regions, c->stage_regions[b],
+                                 nf * c->g.max_regions * sizeof(cpt_region), cudaMemcpyDeviceToHost, c->d2h_stream));
+        CUDA_TRY(cudaMemcpyAsync(h_info + sp.out_lo, c->stage_info[b], nf * sizeof(cpt_frame_info), cudaMemcpyDeviceToHost, c->d2h_stream));
+        if (h_filtered)
+            CUDA_TRY(cudaMemcpyAsync(h_filtered + (size_t)sp.out_lo * npx, c->stage_filtered[b], nf * npx * sizeof(float),
+                                     cudaMemcpyDeviceToHost, c->d2h_stream));
+        if (h_labels)
+            CUDA_TRY(cudaMemcpyAsync(h_labels + (size_t)sp.out_lo * npx, c->stage_labels[b], nf * npx, cudaMemcpyDeviceToHost, c->d2h_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_d2h[b], c->d2h_stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPT_OK;
+}
+
+int cpt_state_read(cpt_ctx *c, const void *d_state, int clip_index, int32_t *h_background, uint16_t *h_weight_count,
+                   double *h_average, uint32_t *h_sliding_sum, int32_t *h_frames_seen) {
+    if (!c || !d_state || clip_index < 0) return fail(CPT_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const cpt::Geometry &g = c->g;
+    size_t sb = cpt::state_bytes(g.npx);
+    std::vector<uint8_t> buf(sb);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(buf.data(), (const uint8_t *)d_state + sb * clip_index, sb, cudaMemcpyDeviceToHost));
+    const cpt::StateHeader *h = (const cpt::StateHeader *)buf.data();
+    const uint16_t *B = (const uint16_t *)(buf.data() + sizeof(cpt::StateHeader));
+    const uint16_t *K = B + g.npx;
+    const uint32_t *S = (const uint32_t *)(K + g.npx);
+    if (h_background)
+        for (int i = 0; i < g.npx; ++i) h_background[i] = B[i];
+    if (h_weight_count)
+        for (int y = 0; y < g.crop_h; ++y)
+            for (int x = 0; x < g.crop_w; ++x) h_weight_count[y * g.crop_w + x] = K[(y + g.edge) * g.W + x + g.edge];
+    if (h_average) *h_average = h->average;
+    if (h_sliding_sum) memcpy(h_sliding_sum, S, sizeof(uint32_t) * g.npx);
+    if (h_frames_seen) *h_frames_seen = h->frames_seen;
+    return CPT_OK;
+}
+
+int cpt_state_write(cpt_ctx *c, void *d_state, int clip_index, const int32_t *h_background,
+                    const uint16_t *h_weight_count, double average) {
+    if (!c || !d_state || clip_index < 0 || !h_background) return fail(CPT_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const cpt::Geometry &g = c->g;
+    size_t sb = cpt::state_bytes(g.npx);
+    std::vector<uint8_t> buf(sb, 0);
+    cpt::StateHeader *h = (cpt::StateHeader *)buf.data();
+    uint16_t *B = (uint16_t *)(buf.data() + sizeof(cpt::StateHeader));
+    uint16_t *K = B + g.npx;
+    for (int i = 0; i < g.npx; ++i) {
+        if (h_background[i] < 0 || h_background[i] > 65535) return fail(CPT_ERR_INVALID, "background value out of uint16 range");
+        B[i] = (uint16_t)h_background[i];
+    }
+    if (h_weight_count)
+        for (int y = 0; y < g.crop_h; ++y)
+            for (int x = 0; x < g.crop_w; ++x) K[(y + g.edge) * g.W + x + g.edge] = h_weight_count[y * g.crop_w + x];
+    h->average = average;
+    h->initialised = 1;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy((uint8_t *)d_state + sb * clip_index, buf.data(), sb, cudaMemcpyHostToDevice));
+    return CPT_OK;
+}
+
+}  // extern "C"

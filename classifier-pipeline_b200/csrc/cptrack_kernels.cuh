@@ -1,0 +1,171 @@
+// cptrack_kernels.cuh -- sm_100a kernels for thermal-clip track extraction.
+//
+// One persistent CTA per clip.  The whole per-clip recurrence state of the reference
+// (WeightedBackground: background + per-pixel weight counter, the 45-frame sliding sum that
+// replaces np.mean(get_last_x(45)), piclassifier/motiondetector.py:178-248 and
+// track/cliptrackextractor.py:168-176) stays resident in shared memory for the life of the clip;
+// frames stream through once from HBM (uint16, 16-byte vector loads), and each frame emits
+//   filtered fp32 (K1), the uint8 label image (K5) and a compact region list (K5/K6).
+// Per-frame stages:
+//   sweep 1   F = P - B, sum P, min/max F, sliding sum update                       (K1, K7, K8)
+//   scalars   avg_change, normalisation range, mapped threshold                     (K2)
+//   sweep 2   U = uint8(255*(G-min)/(max-min))                                      (K2)
+//   stencil   5x5 binomial blur in packed 16-bit lanes, threshold -> bit rows       (K4)
+//   close     C[y] = M[y-1] | (M[y] & M[y-2]) on 32-bit row words                   (K4)
+//   label     run-based union-find on the bit rows, OpenCV label order              (K5)
+//   regions   bbox / area / centroid sums per component, delta-frame variance       (K5, K6)
+//   sweep 3   weighted background update + edge replication                         (K7)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cptrack.h"
+
+namespace cpt {
+
+constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxPx = 19200;
+constexpr int kMaxW = 160;
+constexpr int kMaxH = 120;
+constexpr int kRowWords = kMaxW / 32;           // 5
+constexpr int kMaxWords = kMaxH * kRowWords;    // 600
+constexpr int kRunsPerRow = kMaxW / 2;          // 80
+constexpr int kMaxRuns = kMaxH * kRunsPerRow;   // 9600
+constexpr int kCompSlots = 256;                 // slot 255 = overflow sink
+constexpr int kMeanFrames = CPT_MEAN_FRAMES;
+constexpr uint16_t kSlotFlag = 0x8000u;
+
+struct Geometry {
+    int W, H, edge;
+    int npx;        // W*H
+    int groups;     // npx / 8
+    int gpr;        // groups per row = W/8
+    int row_words;  // ceil(W/32)
+    int words;      // H*row_words
+    int crop_w, crop_h, ncrop;
+    int block_w;    // ceil(W/2): key = (y/2)*block_w + x/2
+    int max_regions;
+};
+
+// Per-clip persistent record in global memory (cpt_state_bytes()).
+struct StateHeader {
+    double average;
+    int32_t frames_seen;
+    int32_t initialised;
+    int32_t prev_fmin, prev_fmax;
+    int32_t have_prev;
+    int32_t pad[9];
+};
+static_assert(sizeof(StateHeader) == 64, "state header is one 64-byte line");
+
+__host__ __device__ inline size_t state_bytes(int npx) {
+    return sizeof(StateHeader) + (size_t)npx * (2 + 2 + 4 + 4);
+}
+
+struct WeightTable {
+    const uint32_t *ceil_w;  // c_k = ceil(w_k)
+    const double *w;         // w_k (fp64, accumulated by repeated addition on the host)
+    int max_count;
+};
+
+struct KernelArgs {
+    Geometry g;
+    const uint16_t *frames;
+    const cpt_clip *clips;
+    int n_clips;
+    cpt_region *regions;
+    cpt_frame_info *info;
+    float *filtered;
+    uint8_t *labels;
+    float *scratch;       // [gridDim.x][2][npx] fp32 when filtered == nullptr
+    uint8_t *state;       // n_clips * state_bytes or nullptr
+    int *work_counter;    // zeroed before launch
+    WeightTable tables[4];
+};
+
+struct __align__(16) Smem {
+    uint32_t S[kMaxPx];        // sliding sum of the last <=45 frames
+    uint16_t B[kMaxPx];        // background (integer valued)
+    uint16_t K[kMaxPx];        // weight counter k (background_weight = w_k)
+    uint8_t U[kMaxPx];         // normalised uint8 image; reused as the label image
+    uint16_t parent[kMaxRuns]; // union-find over runs
+    uint32_t M[kMaxWords];     // thresholded mask, bit rows (byte g = 8 pixels of group g)
+    uint32_t C[kMaxWords];     // closed mask
+    uint32_t ST[kMaxWords];    // run-start bits of C
+    uint8_t base[kMaxWords + 8]; // run starts in earlier words of the same row
+    int32_t c_key[kCompSlots], c_area[kCompSlots], c_sx[kCompSlots], c_sy[kCompSlots];
+    int32_t c_l[kCompSlots], c_t[kCompSlots], c_r[kCompSlots], c_b[kCompSlots];
+    uint8_t c_rank[kCompSlots];
+    uint32_t red_u[kWarps * 6];
+    int32_t bcast_i[16];
+    double bcast_d[4];
+    uint32_t hist[256];
+    int32_t ncomp;
+};
+
+__device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+__device__ __forceinline__ void unpack8(const uint4 &v, int (&o)[8]) {
+    o[0] = v.x & 0xffff; o[1] = v.x >> 16; o[2] = v.y & 0xffff; o[3] = v.y >> 16;
+    o[4] = v.z & 0xffff; o[5] = v.z >> 16; o[6] = v.w & 0xffff; o[7] = v.w >> 16;
+}
+
+__device__ __forceinline__ uint4 pack8(const int (&o)[8]) {
+    uint4 v;
+    v.x = (uint32_t)o[0] | ((uint32_t)o[1] << 16); v.y = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
+    v.z = (uint32_t)o[4] | ((uint32_t)o[5] << 16); v.w = (uint32_t)o[6] | ((uint32_t)o[7] << 16);
+    return v;
+}
+
+// K2: uint8(255*(v)/(range)) exactly as numpy fp32: fl(fl(255*v)/range), truncated.
+__device__ __forceinline__ uint32_t norm_u8(int v, float range_f) {
+    float num = __fmul_rn(255.0f, (float)v);
+    return (uint32_t)__fdiv_rn(num, range_f);
+}
+
+// normalize(F, new_max=255) of get_delta_frame (track/cliptracker.py:249-261): fp64 arithmetic
+// because min/max are float64 scalars there; result cast to fp32.
+__device__ __forceinline__ float norm255_f64(float f, double mn, double mx) {
+    if (mx == mn) return (mx == 0.0) ? 0.0f : (float)((double)f / mx);
+    return (float)(255.0 * ((double)f - mn) / (mx - mn));
+}
+
+// ---- run bookkeeping on the closed mask ------------------------------------------------------
+__device__ __forceinline__ int run_id(const Smem &s, const Geometry &g, int x, int y) {
+    int w = y * g.row_words + (x >> 5), b = x & 31;
+    uint32_t below = s.ST[w] & (0xffffffffu >> (31 - b));
+    return y * kRunsPerRow + (int)s.base[w] + __popc(below) - 1;
+}
+
+__device__ __forceinline__ int uf_find(volatile uint16_t *parent, int a) {
+    // follows parents until a root (parent == self) or a flagged slot entry
+    while (true) {
+        int p = parent[a];
+        if (p == a || (p & kSlotFlag)) return a;
+        a = p;
+    }
+}
+
+__device__ __forceinline__ void uf_union(uint16_t *parent, int a, int b) {
+    volatile uint16_t *vp = parent;
+    while (true) {
+        a = uf_find(vp, a);
+        b = uf_find(vp, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }  // a > b: hang the larger root under the smaller
+        unsigned short old = atomicCAS(reinterpret_cast<unsigned short *>(parent + a), (unsigned short)a,
+                                       (unsigned short)b);
+        if (old == (unsigned short)a) return;
+    }
+}
+
+__device__ __forceinline__ int uf_slot(volatile uint16_t *parent, int a) {
+    while (true) {
+        int p = parent[a];
+        if (p & kSlotFlag) return p & 0xff;
+        a = p;
+    }
+}
+
+}  // namespace cpt

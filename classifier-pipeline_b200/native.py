@@ -1,0 +1,246 @@
+"""ctypes binding of ``libcptrack.so`` (C ABI in ``include/cptrack.h``).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this module
+raises.  Device buffers are plain ``torch`` CUDA tensors (PyTorch is only the allocator /
+stream plumbing) whose ``data_ptr()`` crosses the C boundary.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcptrack.so")
+
+CLIP_UPDATE_BACKGROUND = 1
+CLIP_RESUME = 2
+CLIP_DENOISE = 4
+CLIP_FRAME_STATS = 8
+MAX_COMPONENTS = 255
+MEAN_FRAMES = 45
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class CptRegion(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_int32), ("y", ctypes.c_int32), ("width", ctypes.c_int32), ("height", ctypes.c_int32),
+        ("area", ctypes.c_int32), ("sum_x", ctypes.c_int32), ("sum_y", ctypes.c_int32), ("key", ctypes.c_int32),
+        ("pixel_variance", ctypes.c_double),
+    ]
+
+
+class CptFrameInfo(ctypes.Structure):
+    _fields_ = [
+        ("background_average", ctypes.c_double), ("threshold", ctypes.c_float),
+        ("norm_min", ctypes.c_int32), ("norm_max", ctypes.c_int32), ("avg_change", ctypes.c_int32),
+        ("filtered_min", ctypes.c_int32), ("filtered_max", ctypes.c_int32), ("n_components", ctypes.c_int32),
+        ("thermal_min", ctypes.c_int32), ("thermal_max", ctypes.c_int32), ("thermal_sum", ctypes.c_uint32),
+        ("abs_filtered_sum", ctypes.c_uint32), ("thermal_median", ctypes.c_float), ("reserved", ctypes.c_int32 * 2),
+    ]
+
+
+class CptClip(ctypes.Structure):
+    _fields_ = [
+        ("frame_offset", ctypes.c_int64), ("init_offset", ctypes.c_int64), ("out_offset", ctypes.c_int64),
+        ("n_frames", ctypes.c_int32), ("first_frame", ctypes.c_int32), ("ring_frames", ctypes.c_int32),
+        ("background_thresh", ctypes.c_int32), ("weight_table", ctypes.c_int32), ("flags", ctypes.c_uint32),
+    ]
+
+
+class CptOutputs(ctypes.Structure):
+    _fields_ = [
+        ("d_regions", ctypes.c_void_p), ("d_info", ctypes.c_void_p), ("d_filtered", ctypes.c_void_p),
+        ("d_labels", ctypes.c_void_p),
+    ]
+
+
+REGION_DTYPE = np.dtype(
+    [("x", "<i4"), ("y", "<i4"), ("width", "<i4"), ("height", "<i4"), ("area", "<i4"), ("sum_x", "<i4"),
+     ("sum_y", "<i4"), ("key", "<i4"), ("pixel_variance", "<f8")]
+)
+INFO_DTYPE = np.dtype(
+    [("background_average", "<f8"), ("threshold", "<f4"), ("norm_min", "<i4"), ("norm_max", "<i4"),
+     ("avg_change", "<i4"), ("filtered_min", "<i4"), ("filtered_max", "<i4"), ("n_components", "<i4"),
+     ("thermal_min", "<i4"), ("thermal_max", "<i4"), ("thermal_sum", "<u4"), ("abs_filtered_sum", "<u4"),
+     ("thermal_median", "<f4"), ("reserved", "<i4", (2,))]
+)
+CLIP_DTYPE = np.dtype(
+    [("frame_offset", "<i8"), ("init_offset", "<i8"), ("out_offset", "<i8"), ("n_frames", "<i4"),
+     ("first_frame", "<i4"), ("ring_frames", "<i4"), ("background_thresh", "<i4"), ("weight_table", "<i4"),
+     ("flags", "<u4")]
+)
+assert REGION_DTYPE.itemsize == ctypes.sizeof(CptRegion) == 40
+assert INFO_DTYPE.itemsize == ctypes.sizeof(CptFrameInfo) == 64
+assert CLIP_DTYPE.itemsize == ctypes.sizeof(CptClip) == 48
+
+# every symbol include/cptrack.h declares: (name, restype, argtypes)
+_vp, _i, _i64, _u64, _d, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_float
+SYMBOLS = {
+    "cpt_last_error": (ctypes.c_char_p, []),
+    "cpt_device_count": (_i, []),
+    "cpt_version": (_i, []),
+    "cpt_ctx_create": (_vp, [_i, _i, _i, _i, _i]),
+    "cpt_ctx_destroy": (None, [_vp]),
+    "cpt_ctx_set_stream": (_i, [_vp, _vp]),
+    "cpt_ctx_synchronize": (_i, [_vp]),
+    "cpt_set_weight_table": (_i, [_vp, _i, _d, _i]),
+    "cpt_device_alloc": (_i, [_vp, ctypes.POINTER(_vp), _u64]),
+    "cpt_device_free": (_i, [_vp, _vp]),
+    "cpt_host_alloc_pinned": (_i, [ctypes.POINTER(_vp), _u64]),
+    "cpt_host_free_pinned": (_i, [_vp]),
+    "cpt_copy_to_device": (_i, [_vp, _vp, _vp, _u64]),
+    "cpt_copy_to_host": (_i, [_vp, _vp, _vp, _u64]),
+    "cpt_state_bytes": (_u64, [_vp]),
+    "cpt_extract_batch": (_i, [_vp, _vp, _vp, _i, ctypes.POINTER(CptOutputs), _vp]),
+    "cpt_extract_batch_host": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _i]),
+    "cpt_state_read": (_i, [_vp, _vp, _i, _vp, _vp, ctypes.POINTER(_d), _vp, ctypes.POINTER(ctypes.c_int32)]),
+    "cpt_state_write": (_i, [_vp, _vp, _i, _vp, _vp, _d]),
+    "cpt_weight_value": (_d, [_vp, _i, _i]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libcptrack.so; raise loudly when it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "libcptrack.so not found at {}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.".format(LIB_PATH)
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError("libcptrack error {}: {}".format(rc, load().cpt_last_error().decode()))
+
+
+def _ptr(t):
+    """Device or host pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Context:
+    """One cpt_ctx: fixed geometry, one device, one stream."""
+
+    def __init__(self, device=0, width=160, height=120, edge_pixels=1, max_regions=16):
+        lib = load()
+        if lib.cpt_device_count() <= 0:
+            raise NativeError("no CUDA device visible: the extraction path runs on the GPU only")
+        self.lib = lib
+        self.device = device
+        self.width, self.height, self.edge = width, height, edge_pixels
+        self.max_regions = max_regions
+        self._h = lib.cpt_ctx_create(device, width, height, edge_pixels, max_regions)
+        if not self._h:
+            raise NativeError("cpt_ctx_create failed: " + lib.cpt_last_error().decode())
+        self.state_bytes = lib.cpt_state_bytes(self._h)
+        self._tables = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.cpt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        import torch
+
+        check(self.lib.cpt_ctx_set_stream(self._h, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def synchronize(self):
+        check(self.lib.cpt_ctx_synchronize(self._h))
+
+    def weight_table(self, weight_add, max_frames=65535):
+        """Slot holding the table for ``weight_add`` (uploads it on first use)."""
+        key = float(weight_add)
+        if key in self._tables and self._tables[key][1] >= max_frames:
+            return self._tables[key][0]
+        slot = self._tables[key][0] if key in self._tables else len(self._tables)
+        if slot >= 4:
+            raise NativeError("at most 4 distinct weight_add values per context")
+        check(self.lib.cpt_set_weight_table(self._h, slot, key, int(max_frames)))
+        self._tables[key] = (slot, max_frames)
+        return slot
+
+    def weight_value(self, slot, count):
+        return self.lib.cpt_weight_value(self._h, slot, int(count))
+
+    def extract_batch(self, d_frames, d_clips, n_clips, d_regions, d_info, d_filtered=None, d_labels=None, d_state=None):
+        out = CptOutputs(_ptr(d_regions), _ptr(d_info), _ptr(d_filtered), _ptr(d_labels))
+        check(self.lib.cpt_extract_batch(self._h, _ptr(d_frames), _ptr(d_clips), int(n_clips), ctypes.byref(out), _ptr(d_state)))
+
+    def extract_batch_host(self, h_frames, h_clips, total_frames, h_regions, h_info, h_filtered=None, h_labels=None, chunk_clips=0):
+        check(
+            self.lib.cpt_extract_batch_host(
+                self._h, _ptr(h_frames), _ptr(h_clips), len(h_clips), int(total_frames), _ptr(h_regions), _ptr(h_info),
+                _ptr(h_filtered), _ptr(h_labels), int(chunk_clips),
+            )
+        )
+
+    def state_read(self, d_state, clip_index=0, sliding_sum=False):
+        bg = np.empty((self.height, self.width), np.int32)
+        cnt = np.empty((self.height - 2 * self.edge, self.width - 2 * self.edge), np.uint16)
+        avg = ctypes.c_double()
+        seen = ctypes.c_int32()
+        ssum = np.empty((self.height, self.width), np.uint32) if sliding_sum else None
+        check(self.lib.cpt_state_read(self._h, _ptr(d_state), clip_index, _ptr(bg), _ptr(cnt), ctypes.byref(avg), _ptr(ssum), ctypes.byref(seen)))
+        return dict(background=bg, weight_count=cnt, average=avg.value, frames_seen=seen.value, sliding_sum=ssum)
+
+    def state_write(self, d_state, clip_index, background, weight_count, average):
+        bg = np.ascontiguousarray(background, dtype=np.int32)
+        cnt = None if weight_count is None else np.ascontiguousarray(weight_count, dtype=np.uint16)
+        check(self.lib.cpt_state_write(self._h, _ptr(d_state), clip_index, _ptr(bg), _ptr(cnt), float(average)))
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over cudaHostAlloc memory (freed when the array is collected)."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    check(lib.cpt_host_alloc_pinned(ctypes.byref(p), max(n, 1)))
+    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.cpt_host_free_pinned(self.ptr)
+            except Exception:
+                pass
+
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    owner = _Owner(p.value)
+    _PINNED_OWNERS[id(arr)] = owner
+    import weakref
+
+    weakref.finalize(arr, _PINNED_OWNERS.pop, id(arr), None)
+    return arr
+
+
+_PINNED_OWNERS = {}

@@ -1,0 +1,155 @@
+/*
+ * cptrack.h -- C ABI of libcptrack.so: B200 (sm_100a) kernels for classifier-pipeline's
+ * track-extraction and classifier-input preprocessing path.
+ *
+ * The reference has no FFI layer of its own (it is pure Python over numpy/OpenCV wheels); the
+ * entry points below are what its Python classes bind instead of those wheels.  Each one cites
+ * the reference interface (path:line under the reference's src/) whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes stubs a maintainer adds on the reference side.
+ *
+ * Conventions: every function returns 0 on success or a negative CPT_ERR_* code and records a
+ * message readable with cpt_last_error() (thread local).  A cpt_ctx is bound to one CUDA
+ * device and one stream and is not thread safe; use one ctx per host thread / per GPU.
+ * Pointers named d_* are device pointers (cudaMalloc / torch tensor .data_ptr()), h_* are host
+ * pointers; the caller owns every buffer it passes in.  No torch types cross this boundary.
+ */
+#ifndef CPTRACK_H
+#define CPTRACK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPT_OK 0
+#define CPT_ERR_INVALID (-1)     /* bad argument (geometry, NULL, sizes) */
+#define CPT_ERR_CUDA (-2)        /* CUDA runtime error, see cpt_last_error() */
+#define CPT_ERR_UNSUPPORTED (-3) /* option not available in this build */
+#define CPT_ERR_NOMEM (-4)
+
+#define CPT_MEAN_FRAMES 45       /* track/cliptrackextractor.py:173 get_last_x(x=45) */
+#define CPT_MAX_COMPONENTS 255   /* labels are written as uint8; more components => overflow flag */
+
+/* clip flags */
+#define CPT_CLIP_UPDATE_BACKGROUND 1u /* ClipTrackExtractor(update_background=True), cliptrackextractor.py:168-176 */
+#define CPT_CLIP_RESUME 2u            /* continue from the state saved in d_state instead of initialising */
+#define CPT_CLIP_DENOISE 4u           /* TrackingConfig.denoise: cv2.fastNlMeansDenoising, cliptracker.py:116-117 */
+#define CPT_CLIP_FRAME_STATS 8u       /* ClipStats.add_frame, clip.py:474-487 (min/max/median/mean, sum|filtered|) */
+
+typedef struct cpt_ctx cpt_ctx;
+
+/* One connected component of the closed mask == one row of
+ * cv2.connectedComponentsWithStats (ml_tools/imageprocessing.py:248) plus the per-region
+ * variance ClipTracker._get_regions_of_interest computes (track/cliptracker.py:316-318).
+ * Regions are emitted in OpenCV label order (label = index + 1).
+ * centroid = (sum_x / area, sum_y / area) in double on the host. */
+typedef struct {
+    int32_t x, y, width, height; /* cv2 stats: left, top, width, height */
+    int32_t area;                /* cv2 stats area == Region.mass */
+    int32_t sum_x, sum_y;        /* centroid numerators */
+    int32_t key;                 /* first 2x2 block in raster order (label ordering key) */
+    double pixel_variance;       /* np.var of the filtered delta frame over the box; 0 on frame 0 */
+} cpt_region;
+
+/* Per-frame scalars of ClipTracker._get_filtered_frame (track/cliptracker.py:93-122). */
+typedef struct {
+    double background_average; /* WeightedBackground.average the frame was filtered against */
+    float threshold;      /* mapped_thresh handed to detect_objects (fp32) */
+    int32_t norm_min;     /* min / max of G = max(thermal - background - avg_change, 0) */
+    int32_t norm_max;
+    int32_t avg_change;   /* int(round(mean(thermal) - background average)) */
+    int32_t filtered_min; /* min / max of filtered = thermal - background (K1) */
+    int32_t filtered_max;
+    int32_t n_components; /* true component count (may exceed max_regions / CPT_MAX_COMPONENTS) */
+    int32_t thermal_min;  /* ClipStats (only with CPT_CLIP_FRAME_STATS) */
+    int32_t thermal_max;
+    uint32_t thermal_sum;     /* mean = thermal_sum / (W*H) */
+    uint32_t abs_filtered_sum; /* sum |filtered| */
+    float thermal_median;
+    int32_t reserved[2];
+} cpt_frame_info;
+
+/* One clip (or one stream step) of a batch. Frame indices are in units of W*H uint16 frames
+ * from the start of d_frames.  ring_frames == 0: the clip is stored linearly; otherwise frame t
+ * lives at frame_offset + ((first_frame + t) % ring_frames) (streaming ring buffers). */
+typedef struct {
+    int64_t frame_offset;      /* first tracked frame */
+    int64_t init_offset;       /* frame WeightedBackground is initialised from (cliptrackextractor.py:129-139);
+                                  ignored with CPT_CLIP_RESUME */
+    int64_t out_offset;        /* index of this clip's first frame in every per-frame output */
+    int32_t n_frames;
+    int32_t first_frame;       /* absolute number of the first frame of this call (streaming), else 0 */
+    int32_t ring_frames;
+    int32_t background_thresh; /* clip.background_thresh (config/trackingmotionconfig.py:24-59) */
+    int32_t weight_table;      /* slot set with cpt_set_weight_table */
+    uint32_t flags;
+} cpt_clip;
+
+/* Outputs of an extraction launch; any pointer except d_info may be NULL. */
+typedef struct {
+    cpt_region *d_regions;   /* [total_frames][max_regions] */
+    cpt_frame_info *d_info;  /* [total_frames] */
+    float *d_filtered;       /* [total_frames][H][W]  K1: float32(thermal) - background */
+    uint8_t *d_labels;       /* [total_frames][H][W]  K5 label image (0 = background) */
+} cpt_outputs;
+
+/* Persistent per-clip state (WeightedBackground + sliding sum), one record per clip:
+ * layout returned by cpt_state_bytes(); opaque to the caller except through cpt_state_*. */
+
+const char *cpt_last_error(void);
+int cpt_device_count(void);
+int cpt_version(void);
+
+/* Context: geometry is fixed per ctx.  width % 8 == 0, width <= 160, width*height <= 19200
+ * (Lepton 3/3.5 is 160x120).  edge_pixels as TrackingConfig.edge_pixels (1 for thermal). */
+cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int max_regions);
+void cpt_ctx_destroy(cpt_ctx *ctx);
+int cpt_ctx_set_stream(cpt_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = ctx-owned stream */
+int cpt_ctx_synchronize(cpt_ctx *ctx);
+
+/* WeightedBackground.weight_add (motiondetector.py:182): the fp64 table w_k = fl(w_{k-1} + weight_add)
+ * is built on the host and uploaded; max_frames bounds k (<= 65535). */
+int cpt_set_weight_table(cpt_ctx *ctx, int slot, double weight_add, int max_frames);
+
+/* Device memory helpers so that non-torch hosts can drive the library. */
+int cpt_device_alloc(cpt_ctx *ctx, void **d_ptr, uint64_t bytes);
+int cpt_device_free(cpt_ctx *ctx, void *d_ptr);
+int cpt_host_alloc_pinned(void **h_ptr, uint64_t bytes);
+int cpt_host_free_pinned(void *h_ptr);
+int cpt_copy_to_device(cpt_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);   /* async on ctx stream */
+int cpt_copy_to_host(cpt_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);     /* async on ctx stream */
+
+/* Bytes of one per-clip state record for this ctx's geometry. */
+uint64_t cpt_state_bytes(const cpt_ctx *ctx);
+
+/* ClipTrackExtractor.parse_clip / process_frame for a batch of clips
+ * (track/cliptrackextractor.py:141-247; K1,K2,K4,K5,K6,K7,K8 of SURVEY.md section 8a).
+ * One persistent CTA per clip.  d_clips is a DEVICE array of n_clips cpt_clip records,
+ * d_state (optional unless a clip has CPT_CLIP_RESUME, then required) receives each clip's
+ * final state: n_clips * cpt_state_bytes(). */
+int cpt_extract_batch(cpt_ctx *ctx, const uint16_t *d_frames, const cpt_clip *d_clips, int n_clips,
+                      const cpt_outputs *outputs, void *d_state);
+
+/* Same call with HOST buffers: stages frames to the device in chunks of clips on two streams
+ * (copy / compute overlapped) and copies regions + info (and filtered / labels when
+ * requested) back.  h_frames should be pinned (cpt_host_alloc_pinned) for full PCIe speed. */
+int cpt_extract_batch_host(cpt_ctx *ctx, const uint16_t *h_frames, const cpt_clip *h_clips, int n_clips,
+                           int64_t total_frames, cpt_region *h_regions, cpt_frame_info *h_info,
+                           float *h_filtered, uint8_t *h_labels, int chunk_clips);
+
+/* State access for WeightedBackground.background / .background_weight / .average
+ * (motiondetector.py:178-248).  h_background int32 [H][W]; h_weight_count uint16 [(H-2e)][(W-2e)]
+ * (background_weight = table[count]); h_average double. Any output may be NULL. */
+int cpt_state_read(cpt_ctx *ctx, const void *d_state, int clip_index, int32_t *h_background,
+                   uint16_t *h_weight_count, double *h_average, uint32_t *h_sliding_sum,
+                   int32_t *h_frames_seen);
+int cpt_state_write(cpt_ctx *ctx, void *d_state, int clip_index, const int32_t *h_background,
+                    const uint16_t *h_weight_count, double average);
+/* the fp64 weight for a count (host copy of the uploaded table) */
+double cpt_weight_value(const cpt_ctx *ctx, int slot, int count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPTRACK_H */
