@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- thermal frames/s tracked (160x120) on N B200s, with roofline and CPU baseline.
+
+One *step* = one pass of the extraction hot path (ClipTrackExtractor.parse_clip arithmetic:
+K1,K2,K4,K5,K6,K7 of SURVEY.md section 8) over one batch of synthetic Lepton clips resident in
+HBM: BASELINE.json configs[1], 1024 clips x 900 frames x 160x120 uint16 per GPU, emitting
+filtered fp32 + uint8 label image + region lists for every frame.  Clips are independent, so
+N GPUs each take their own 1024 clips (weak scaling, no collective on the data path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips C] [--frames T]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # CPU port of the reference path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 160, 120
+NPX = W * H
+# algorithmic bytes per frame = read uint16 frame + write fp32 filtered +
+# write uint8 label image (region lists and per-clip state ignored).
+BYTES_PER_FRAME = NPX * 2 + NPX * 4 + NPX * 1
+METRIC = "thermal frames/sec tracked+preprocessed (160x120)"
+UNIT = "frames/s"
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max((int(s[1]) for s in self.samples if s[1].isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_baseline(n_threads, clips_per_thread, frames, pix=None):
+    """The C port of the reference path (oracle/) on the host cores, regions-only outputs."""
+    from classifier_pipeline_b200.synthetic import clip_model, make_clip
+    from oracle import oracle as orc
+
+    n_clips = n_threads * clips_per_thread
+    if pix is None:
+        pix = np.stack([make_clip(i, frames=frames)[0] for i in range(n_clips)])
+    n_clips, frames = pix.shape[0], pix.shape[1]
+    params = [orc.make_params(background_thresh=clip_model(i)[2], weight_add=clip_model(i)[3], max_comp=16) for i in range(n_clips)]
+    orc.extract_batch(pix[:1, : min(frames, 20)], params[:1], 1)  # warm the library
+    t0 = time.perf_counter()
+    orc.extract_batch(pix, params, n_threads)
+    dt = time.perf_counter() - t0
+    return n_clips * frames / dt, dt, n_clips
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    frames = 200
+    per_thread = 1
+    values = []
+    sample = ""
+    for step in range(args.warmup + args.steps):
+        v, dt, n_clips = cpu_baseline(threads, per_thread, frames)
+        sample = "{} clips x {} frames of the bench workload ({} synthetic clips family), {:.1f} s".format(n_clips, frames, "seeded", dt)
+        if step >= args.warmup:
+            values.append((v, dt))
+    value = float(np.mean([v for v, _ in values]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean([dt for _, dt in values]) * 1e3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32 (fp32+fp64 scalars)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 1024 clips x 900 frames 160x120 uint16 extraction; CPU arm runs a bounded sample of it"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips", type=int, default=1024, help="clips per GPU")
+    ap.add_argument("--frames", type=int, default=900)
+    ap.add_argument("--e2e-clips", type=int, default=0, help="clips per e2e step (0 = auto from host RAM)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from classifier_pipeline_b200 import native
+    from classifier_pipeline_b200.batch import BatchExtractor, linear_clips
+    from classifier_pipeline_b200.synthetic import MODELS, make_clips_torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    C, T = args.clips, args.frames
+    ex = BatchExtractor(device=local_rank, max_regions=16)
+    slots = [ex.ctx.weight_table(m[3], max_frames=max(T, 1024)) for m in MODELS]
+    first = rank * C  # each rank owns its own clips (clip-wise sharding)
+    d_frames, models = make_clips_torch(C, T, torch.device("cuda", local_rank), first_index=first)
+    bts = np.array([MODELS[m][2] for m in models])
+    wts = np.array([slots[m] for m in models])
+    clips = linear_clips([T] * C, bts, wts)
+    total = C * T
+    out = {}
+    torch.cuda.synchronize()
+
+    def step():
+        ex.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, out=out)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_events = []
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            kernel_events.append((e0, e1))
+        stop.record()
+        barrier()
+    ms_total = start.elapsed_time(stop)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    if dist is not None:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_per_step = ms_total / args.steps
+    value = world * total / (ms_per_step * 1e-3)
+    info = ex.info_numpy(out["info"])
+    regions_total = int(np.minimum(info["n_components"], 16).sum())
+
+    # ---- e2e: host frames in, host region lists out, through the C-ABI host call
+    e2e = None
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 16 << 30
+    e2e_clips = args.e2e_clips or int(max(8, min(C, (avail // 4) // (T * NPX * 2), 256)))
+    h_frames = native.pinned_empty((e2e_clips * T, H, W), np.uint16)
+    h_frames[:] = d_frames.view(torch.int16)[:e2e_clips].reshape(-1, H, W).cpu().numpy().view(np.uint16)
+    e_clips = linear_clips([T] * e2e_clips, bts[:e2e_clips], wts[:e2e_clips])
+    del d_frames
+    out.clear()
+    torch.cuda.empty_cache()
+    hout = {}
+    for _ in range(2):
+        ex.extract_host(h_frames, e_clips, chunk_clips=32, out=hout)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        ex.extract_host(h_frames, e_clips, chunk_clips=32, out=hout)
+    barrier()
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        tt = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_dt = float(tt.item())
+    e2e = {
+        "value": world * e2e_clips * T / e2e_dt, "unit": UNIT,
+        "h2d_bytes_per_step": int(e2e_clips * T * NPX * 2),
+        "d2h_bytes_per_step": int(e2e_clips * T * (16 * native.REGION_DTYPE.itemsize + native.INFO_DTYPE.itemsize)),
+        "clips_per_step": e2e_clips, "api": "cpt_extract_batch_host (pinned host frames -> host region lists)",
+    }
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_FRAME * total / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16/int32 (fp32+fp64 scalars)", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[1]: {} clips x {} frames 160x120 uint16 per GPU, full extraction (filtered fp32 + labels u8 + regions)".format(C, T),
+            "clips_per_gpu": C, "frames_per_clip": T, "l2": "inputs ({:.1f} GB) far larger than L2".format(total * NPX * 2 / 1e9),
+            "denoise": False, "regions_found": regions_total,
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "extract_clips_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "peak_source": peak_src,
+        },
+        "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary(),
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        cores = min(os.cpu_count() or 1, 64)
+        n_cpu = min(cores, e2e_clips)
+        sample = np.ascontiguousarray(h_frames.reshape(e2e_clips, T, H, W)[:n_cpu, : min(T, 300)])
+        v, dt, n_clips = cpu_baseline(cores, 1, 300, pix=sample)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "first {} clips x {} frames of this run's batch, {:.1f} s".format(n_clips, sample.shape[1], dt)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,8 +34,7 @@ int fail(int code, const char *fmt, ...) {
 
 struct HostWeightTable {
     std::vector<double> w;
-    uint32_t *d_ceil = nullptr;
-    double *d_w = nullptr;
+    uint32_t *d_thr = nullptr;
     int max_count = 0;
 };
 
@@ -105,6 +104,8 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     g.row_words = (width + 31) / 32; g.words = height * g.row_words;
     g.crop_w = width - 2 * edge_pixels; g.crop_h = height - 2 * edge_pixels; g.ncrop = g.crop_w * g.crop_h;
     g.block_w = (width + 1) / 2; g.max_regions = max_regions;
+    g.gpr_magic = ((1u << 17) + g.gpr - 1) / g.gpr;
+    g.rw_magic = ((1u << 13) + g.row_words - 1) / g.row_words;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         fail(CPT_ERR_CUDA, "cudaGetDeviceProperties failed");
@@ -153,8 +154,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &t : c->tables) {
-        cudaFree(t.d_ceil);
-        cudaFree(t.d_w);
+        cudaFree(t.d_thr);
     }
     cudaFree(c->scratch);
     cudaFree(c->work_counter);
@@ -174,7 +174,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
 
 int cpt_ctx_set_stream(cpt_ctx *c, void *cuda_stream) {
     if (!c) return fail(CPT_ERR_INVALID, "null ctx");
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    c->stream = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream (what torch calls stream 0)
     return CPT_OK;
 }
 
@@ -182,6 +182,39 @@ int cpt_ctx_synchronize(cpt_ctx *c) {
     if (!c) return fail(CPT_ERR_INVALID, "null ctx");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPT_OK;
+}
+
+int cpt_build_weight_table(double weight_add, int n, uint32_t *thr_out, double *w_out) {
+    if (n < 1 || !thr_out || !(weight_add >= 0.0)) return fail(CPT_ERR_INVALID, "bad weight table request");
+    // background_weight accumulates by repeated += weight_add in fp64 (motiondetector.py:222-226);
+    // entry layout and derivation: cptrack_kernels.cuh (WeightTable).
+    volatile double acc = 0.0;
+    for (int k = 0; k < n; ++k) {
+        double w = acc;
+        if (w_out) w_out[k] = w;
+        double cw = std::ceil(w);
+        double gap = cw - w;  // exact: cw and w agree in exponent range or gap is tiny
+        uint32_t c = cw >= 65536.0 ? 65536u : (uint32_t)cw;
+        uint32_t thr, ecode = 0;
+        if (c >= 65536u) {
+            thr = 65536u;
+        } else if (gap == 0.0) {
+            thr = c + 1u;
+        } else {
+            int ex;
+            double m = std::frexp(gap, &ex);          // gap = m * 2^ex, m in [0.5, 1)
+            int ceil_log2 = (m == 0.5) ? ex - 1 : ex;  // ceil(log2 gap)
+            int E = ceil_log2 + 53;
+            if (E >= 17) thr = c;
+            else {
+                thr = c + 1u;
+                ecode = (uint32_t)std::max(E, 0) + 1u;
+            }
+        }
+        thr_out[k] = std::min(thr, 65536u) | (ecode << 17);
+        acc = acc + weight_add;
+    }
     return CPT_OK;
 }
 
@@ -193,22 +226,12 @@ int cpt_set_weight_table(cpt_ctx *c, int slot, double weight_add, int max_frames
     HostWeightTable &t = c->tables[slot];
     int n = max_frames + 1;
     t.w.assign(n, 0.0);
-    std::vector<uint32_t> ceil_w(n);
-    // background_weight accumulates by repeated += weight_add in fp64 (motiondetector.py:222-226)
-    volatile double acc = 0.0;
-    for (int k = 0; k < n; ++k) {
-        t.w[k] = acc;
-        double cw = std::ceil(acc);
-        ceil_w[k] = cw > 2.0e9 ? 2000000000u : (uint32_t)cw;  // > any int32 pixel difference
-        acc = acc + weight_add;
-    }
-    cudaFree(t.d_ceil);
-    cudaFree(t.d_w);
-    t.d_ceil = nullptr; t.d_w = nullptr;
-    CUDA_TRY(cudaMalloc(&t.d_ceil, sizeof(uint32_t) * n));
-    CUDA_TRY(cudaMalloc(&t.d_w, sizeof(double) * n));
-    CUDA_TRY(cudaMemcpy(t.d_ceil, ceil_w.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(t.d_w, t.w.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> thr(n);
+    cpt_build_weight_table(weight_add, n, thr.data(), t.w.data());
+    cudaFree(t.d_thr);
+    t.d_thr = nullptr;
+    CUDA_TRY(cudaMalloc(&t.d_thr, sizeof(uint32_t) * n));
+    CUDA_TRY(cudaMemcpy(t.d_thr, thr.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
     t.max_count = max_frames;
     return CPT_OK;
 }
@@ -287,8 +310,7 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     a.scratch = out->d_filtered ? nullptr : c->scratch;
     a.state = (uint8_t *)d_state;
     for (int i = 0; i < 4; ++i) {
-        a.tables[i].ceil_w = c->tables[i].d_ceil;
-        a.tables[i].w = c->tables[i].d_w;
+        a.tables[i].thr = c->tables[i].d_thr;
         a.tables[i].max_count = c->tables[i].max_count;
     }
     a.work_counter = c->work_counter;
@@ -305,7 +327,7 @@ int cpt_extract_batch(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_cl
     if (n_clips == 0) return CPT_OK;
     if (!d_frames || !d_clips) return fail(CPT_ERR_INVALID, "null frames / clips");
     if (!out->d_info || !out->d_regions) return fail(CPT_ERR_INVALID, "d_info and d_regions are required");
-    if (!c->tables[0].d_ceil && !c->tables[1].d_ceil && !c->tables[2].d_ceil && !c->tables[3].d_ceil)
+    if (!c->tables[0].d_thr && !c->tables[1].d_thr && !c->tables[2].d_thr && !c->tables[3].d_thr)
         return fail(CPT_ERR_INVALID, "no weight table set (cpt_set_weight_table)");
     CUDA_TRY(cudaSetDevice(c->device));
     return launch_extract(c, d_frames, d_clips, n_clips, out, d_state, c->stream);

@@ -46,6 +46,8 @@ struct Geometry {
     int crop_w, crop_h, ncrop;
     int block_w;    // ceil(W/2): key = (y/2)*block_w + x/2
     int max_regions;
+    uint32_t gpr_magic;  // grp / gpr == (grp * gpr_magic) >> 17   (grp < 4096, gpr < 32)
+    uint32_t rw_magic;   // w / row_words == (w * rw_magic) >> 13  (w < 1024, row_words < 8)
 };
 
 // Per-clip persistent record in global memory (cpt_state_bytes()).
@@ -63,11 +65,20 @@ __host__ __device__ inline size_t state_bytes(int npx) {
     return sizeof(StateHeader) + (size_t)npx * (2 + 2 + 4 + 4);
 }
 
+// keep-test table for WeightedBackground (motiondetector.py:214-218):
+//   keep  <=>  fp64(B) < fl64(fp64(A) - w_k)   for integers 0 <= B, A < 2^16, w_k accumulated in fp64.
+// With c = ceil(w_k), g = c - w_k, d = A - B:  d > c keeps, d < c does not, and for d == c the exact
+// right-hand side is B + g, which rounds above B iff g > ulp(B)/2, i.e. iff B < 2^E with
+// E = ceil(log2 g) + 53 (any g > 0 when B == 0).  Entry layout (cpt_build_weight_table):
+//   bits 0..16  thr   = c if E >= 17 (always rounds up), else c + 1        (clamped to 65536 = never)
+//   bits 17..21 ecode = 0 if g == 0 or E >= 17, else max(E, 0) + 1;  bound = (1 << ecode) >> 1
+//   keep = (d >= thr) || (d == thr - 1 && B < bound)
 struct WeightTable {
-    const uint32_t *ceil_w;  // c_k = ceil(w_k)
-    const double *w;         // w_k (fp64, accumulated by repeated addition on the host)
+    const uint32_t *thr;
     int max_count;
 };
+constexpr int kSmemWeights = 1024;
+constexpr uint32_t kThrMask = 0x1ffffu;
 
 struct KernelArgs {
     Geometry g;
@@ -101,6 +112,10 @@ struct __align__(16) Smem {
     int32_t bcast_i[16];
     double bcast_d[4];
     uint32_t hist[256];
+    double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
+    uint32_t wthr[kSmemWeights];                   // first entries of the clip's keep-test table
+    uint32_t need_u[kMaxH];   // per row: groups whose U is an input of a blur window that can exceed the threshold
+    uint32_t need_b[kMaxH];   // per row: groups whose blurred output can exceed the threshold
     int32_t ncomp;
 };
 
@@ -122,6 +137,13 @@ __device__ __forceinline__ uint4 pack8(const int (&o)[8]) {
 __device__ __forceinline__ uint32_t norm_u8(int v, float range_f) {
     float num = __fmul_rn(255.0f, (float)v);
     return (uint32_t)__fdiv_rn(num, range_f);
+}
+// Same value in integers when 255*range < 2^24 (every product exact in fp32): the fp32
+// quotient of two integers n < 2^24, r < 2^17 can only round up to an integer q when
+// q - n/r <= ulp/2 <= 2^-17 < 1/r, i.e. never unless exact, so trunc(fl(n/r)) == n / r.
+// n / r by multiplication: m = ceil(2^(24+l) / r), l = ceil(log2 r)  (Granlund-Montgomery).
+__device__ __forceinline__ uint32_t norm_u8_int(int v, uint32_t m, int shift) {
+    return (uint32_t)(((unsigned long long)(uint32_t)(255 * v) * m) >> shift);
 }
 
 // normalize(F, new_max=255) of get_delta_frame (track/cliptracker.py:249-261): fp64 arithmetic

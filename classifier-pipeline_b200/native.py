@@ -87,6 +87,7 @@ SYMBOLS = {
     "cpt_ctx_set_stream": (_i, [_vp, _vp]),
     "cpt_ctx_synchronize": (_i, [_vp]),
     "cpt_set_weight_table": (_i, [_vp, _i, _d, _i]),
+    "cpt_build_weight_table": (_i, [_d, _i, _vp, _vp]),
     "cpt_device_alloc": (_i, [_vp, ctypes.POINTER(_vp), _u64]),
     "cpt_device_free": (_i, [_vp, _vp]),
     "cpt_host_alloc_pinned": (_i, [ctypes.POINTER(_vp), _u64]),

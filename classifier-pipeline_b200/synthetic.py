@@ -112,6 +112,7 @@ def make_clips_torch(n_clips, frames, device, first_index=0, width=WIDTH, height
             if b == 1:
                 alive = alive & two
             img = img + torch.where(alive, amp, 0.0) * torch.exp(-(dx * dx + dy * dy) / (2.0 * sigma * sigma))
-        out[c0:c1] = torch.clamp(torch.round(img), 0, 65535).to(torch.int32).to(torch.uint16)
+        v = torch.clamp(torch.round(img), 0, 65535).to(torch.int32)
+        out[c0:c1].view(torch.int16).copy_(torch.where(v >= 32768, v - 65536, v).to(torch.int16))
     models = [(first_index + i) % 2 for i in range(n_clips)]
     return out, models

@@ -105,12 +105,15 @@ int cpt_version(void);
  * (Lepton 3/3.5 is 160x120).  edge_pixels as TrackingConfig.edge_pixels (1 for thermal). */
 cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int max_regions);
 void cpt_ctx_destroy(cpt_ctx *ctx);
-int cpt_ctx_set_stream(cpt_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = ctx-owned stream */
+int cpt_ctx_set_stream(cpt_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = the legacy default stream. A new ctx launches on its own non-blocking stream */
 int cpt_ctx_synchronize(cpt_ctx *ctx);
 
 /* WeightedBackground.weight_add (motiondetector.py:182): the fp64 table w_k = fl(w_{k-1} + weight_add)
  * is built on the host and uploaded; max_frames bounds k (<= 65535). */
 int cpt_set_weight_table(cpt_ctx *ctx, int slot, double weight_add, int max_frames);
+/* Host-only builder of that table (no device needed; exposed for testing): thr_out[k] encodes the integer
+ * form of the fp64 keep test `background < frame - w_k` (see csrc/cptrack_kernels.cuh), w_out[k] = w_k. */
+int cpt_build_weight_table(double weight_add, int n, uint32_t *thr_out, double *w_out);
 
 /* Device memory helpers so that non-torch hosts can drive the library. */
 int cpt_device_alloc(cpt_ctx *ctx, void **d_ptr, uint64_t bytes);
