@@ -25,6 +25,12 @@ namespace cpt {
 
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
+// warp-specialised pipeline: pixel warps stream frames (sweeps, blur, background update) while the
+// component warps label the previous frame's mask
+constexpr int kPThreads = 800;                  // 25 warps: 2400 groups of 8 pixels = 3 per thread at 160x120
+constexpr int kPWarps = kPThreads / 32;
+constexpr int kCThreads = kThreads - kPThreads; // 7 warps
+constexpr int kCWarps = kCThreads / 32;
 constexpr int kMaxPx = 19200;
 constexpr int kMaxW = 160;
 constexpr int kMaxH = 120;
@@ -89,7 +95,7 @@ struct KernelArgs {
     cpt_frame_info *info;
     float *filtered;
     uint8_t *labels;
-    float *scratch;       // [gridDim.x][2][npx] fp32 when filtered == nullptr
+    float *scratch;       // [gridDim.x][4][npx] fp32 when filtered == nullptr
     uint8_t *state;       // n_clips * state_bytes or nullptr
     int *work_counter;    // zeroed before launch
     WeightTable tables[4];
@@ -101,7 +107,7 @@ struct __align__(16) Smem {
     uint16_t K[kMaxPx];        // weight counter k (background_weight = w_k)
     uint8_t U[kMaxPx];         // normalised uint8 image; reused as the label image
     uint16_t parent[kMaxRuns]; // union-find over runs
-    uint32_t M[kMaxWords];     // thresholded mask, bit rows (byte g = 8 pixels of group g)
+    uint32_t M[2][kMaxWords];  // thresholded mask, bit rows (byte g = 8 pixels of group g), double buffered
     uint32_t C[kMaxWords];     // closed mask
     uint32_t ST[kMaxWords];    // run-start bits of C
     uint8_t base[kMaxWords + 8]; // run starts in earlier words of the same row
@@ -110,6 +116,7 @@ struct __align__(16) Smem {
     uint8_t c_rank[kCompSlots];
     uint32_t red_u[kWarps * 6];
     int32_t bcast_i[16];
+    int32_t msg[2][4];         // pixel warps -> component warps, per mask buffer: filtered min, max
     double bcast_d[4];
     uint32_t hist[256];
     double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
