@@ -36,6 +36,7 @@ struct HostWeightTable {
     std::vector<double> w;
     uint32_t *d_thr = nullptr;
     int max_count = 0;
+    int has_bounds = 0;
 };
 
 }  // namespace
@@ -51,6 +52,7 @@ struct cpt_ctx {
     float *scratch = nullptr;
     size_t scratch_ctas = 0;
     int *work_counter = nullptr;
+    long long *debug = nullptr;
     // staging buffers of cpt_extract_batch_host
     void *stage_frames[2] = {nullptr, nullptr};
     size_t stage_frames_bytes = 0;
@@ -158,6 +160,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     }
     cudaFree(c->scratch);
     cudaFree(c->work_counter);
+    cudaFree(c->debug);
     cudaFree(c->d_clips);
     free_stage(c);
     if (c->events)
@@ -195,10 +198,10 @@ int cpt_build_weight_table(double weight_add, int n, uint32_t *thr_out, double *
         if (w_out) w_out[k] = w;
         double cw = std::ceil(w);
         double gap = cw - w;  // exact: cw and w agree in exponent range or gap is tiny
-        uint32_t c = cw >= 65536.0 ? 65536u : (uint32_t)cw;
-        uint32_t thr, ecode = 0;
-        if (c >= 65536u) {
-            thr = 65536u;
+        uint32_t c = cw >= 65535.0 ? 65535u : (uint32_t)cw;
+        uint32_t thr, bound = 0;
+        if (c >= 65535u) {
+            thr = 65535u;  // never keeps (d <= 65535 only when frame == 65535 and background == 0)
         } else if (gap == 0.0) {
             thr = c + 1u;
         } else {
@@ -206,13 +209,13 @@ int cpt_build_weight_table(double weight_add, int n, uint32_t *thr_out, double *
             double m = std::frexp(gap, &ex);          // gap = m * 2^ex, m in [0.5, 1)
             int ceil_log2 = (m == 0.5) ? ex - 1 : ex;  // ceil(log2 gap)
             int E = ceil_log2 + 53;
-            if (E >= 17) thr = c;
+            if (E >= 16) thr = c;
             else {
                 thr = c + 1u;
-                ecode = (uint32_t)std::max(E, 0) + 1u;
+                bound = 1u << std::max(E, 0);
             }
         }
-        thr_out[k] = std::min(thr, 65536u) | (ecode << 17);
+        thr_out[k] = std::min(thr, 65535u) | (bound << 16);
         acc = acc + weight_add;
     }
     return CPT_OK;
@@ -220,7 +223,7 @@ int cpt_build_weight_table(double weight_add, int n, uint32_t *thr_out, double *
 
 int cpt_set_weight_table(cpt_ctx *c, int slot, double weight_add, int max_frames) {
     if (!c || slot < 0 || slot >= 4) return fail(CPT_ERR_INVALID, "weight table slot must be 0..3");
-    if (max_frames < 1 || max_frames > 65535) return fail(CPT_ERR_INVALID, "max_frames must be in [1,65535]");
+    if (max_frames < 1 || max_frames > 65534) return fail(CPT_ERR_INVALID, "max_frames must be in [1,65534]");
     if (!(weight_add >= 0.0)) return fail(CPT_ERR_INVALID, "weight_add must be >= 0");
     CUDA_TRY(cudaSetDevice(c->device));
     HostWeightTable &t = c->tables[slot];
@@ -228,11 +231,14 @@ int cpt_set_weight_table(cpt_ctx *c, int slot, double weight_add, int max_frames
     t.w.assign(n, 0.0);
     std::vector<uint32_t> thr(n);
     cpt_build_weight_table(weight_add, n, thr.data(), t.w.data());
+    thr[n - 1] = 0xffffu;  // a count can never pass the end of the table: the last entry never keeps
     cudaFree(t.d_thr);
     t.d_thr = nullptr;
     CUDA_TRY(cudaMalloc(&t.d_thr, sizeof(uint32_t) * n));
     CUDA_TRY(cudaMemcpy(t.d_thr, thr.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
     t.max_count = max_frames;
+    t.has_bounds = 0;
+    for (int k = 0; k < n; ++k) t.has_bounds |= (thr[k] >> 16) != 0;
     return CPT_OK;
 }
 
@@ -284,6 +290,29 @@ int cpt_copy_to_host(cpt_ctx *c, void *h_dst, const void *d_src, uint64_t bytes)
     return CPT_OK;
 }
 
+/* Debug builds only (-DCPT_PHASE_TIMING): allocate / read the per-CTA phase cycle counters. */
+int cpt_debug_phase_cycles(cpt_ctx *c, long long *h_out32, int reset) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    size_t bytes = sizeof(long long) * 32 * (size_t)c->num_sms;
+    if (!c->debug) {
+        CUDA_TRY(cudaMalloc(&c->debug, bytes));
+        CUDA_TRY(cudaMemset(c->debug, 0, bytes));
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (h_out32) {
+        std::vector<long long> all(32 * (size_t)c->num_sms);
+        CUDA_TRY(cudaMemcpy(all.data(), c->debug, bytes, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 32; ++i) {
+            long long sum = 0;
+            for (int b = 0; b < c->num_sms; ++b) sum += all[(size_t)b * 32 + i];
+            h_out32[i] = sum;
+        }
+    }
+    if (reset) CUDA_TRY(cudaMemset(c->debug, 0, bytes));
+    return CPT_OK;
+}
+
 uint64_t cpt_state_bytes(const cpt_ctx *c) { return c ? cpt::state_bytes(c->g.npx) : 0; }
 
 static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_clips, int n_clips,
@@ -312,8 +341,10 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     for (int i = 0; i < 4; ++i) {
         a.tables[i].thr = c->tables[i].d_thr;
         a.tables[i].max_count = c->tables[i].max_count;
+        a.tables[i].has_bounds = c->tables[i].has_bounds;
     }
     a.work_counter = c->work_counter;
+    a.debug = c->debug;
     CUDA_TRY(cudaMemsetAsync(c->work_counter, 0, sizeof(int), stream));
     cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
     CUDA_TRY(cudaGetLastError());

@@ -76,15 +76,15 @@ __host__ __device__ inline size_t state_bytes(int npx) {
 // With c = ceil(w_k), g = c - w_k, d = A - B:  d > c keeps, d < c does not, and for d == c the exact
 // right-hand side is B + g, which rounds above B iff g > ulp(B)/2, i.e. iff B < 2^E with
 // E = ceil(log2 g) + 53 (any g > 0 when B == 0).  Entry layout (cpt_build_weight_table):
-//   bits 0..16  thr   = c if E >= 17 (always rounds up), else c + 1        (clamped to 65536 = never)
-//   bits 17..21 ecode = 0 if g == 0 or E >= 17, else max(E, 0) + 1;  bound = (1 << ecode) >> 1
-//   keep = (d >= thr) || (d == thr - 1 && B < bound)
+//   bits 0..15  thr   = c if E >= 16 (always rounds up), else c + 1   (clamped to 65535)
+//   bits 16..31 bound = 0 if g == 0 or E >= 16, else 2^max(E, 0)
+//   keep = (d >= thr) || (d == thr - 1 && B < bound)   ==   d >= thr - (B < bound)
 struct WeightTable {
     const uint32_t *thr;
     int max_count;
+    int has_bounds;  // some entry has a non-zero bound
 };
 constexpr int kSmemWeights = 1024;
-constexpr uint32_t kThrMask = 0x1ffffu;
 
 struct KernelArgs {
     Geometry g;
@@ -98,6 +98,7 @@ struct KernelArgs {
     float *scratch;       // [gridDim.x][4][npx] fp32 when filtered == nullptr
     uint8_t *state;       // n_clips * state_bytes or nullptr
     int *work_counter;    // zeroed before launch
+    long long *debug;     // [gridDim.x][32] phase cycle counters (CPT_PHASE_TIMING builds), else nullptr
     WeightTable tables[4];
 };
 
@@ -122,11 +123,21 @@ struct __align__(16) Smem {
     double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
     uint32_t wthr[kSmemWeights];                   // first entries of the clip's keep-test table
     uint32_t need_u[kMaxH];   // per row: groups whose U is an input of a blur window that can exceed the threshold
-    uint32_t need_b[kMaxH];   // per row: groups whose blurred output can exceed the threshold
+    uint32_t need_b[kMaxH];
+    uint32_t hotbits[kMaxPx / 8 / 32 + 3];  // one bit per 8-pixel group: some pixel can exceed the threshold   // per row: groups whose blurred output can exceed the threshold
     int32_t ncomp;
 };
 
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+// dp2a on packed uint16 pairs (IDP runs beside IMAD/FFMA, not on the half-rate integer ALU pipe):
+//   c + a.lo * b.byte0 + a.hi * b.byte1, a unsigned 16-bit halves, b signed bytes.
+__device__ __forceinline__ int dp2a_us(uint32_t a, int b, int c) {
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+constexpr int kLoP = 0x0001, kLoN = 0x00ff, kHiP = 0x0100, kHiN = 0xff00, kBoth = 0x0101;
 
 __device__ __forceinline__ void unpack8(const uint4 &v, int (&o)[8]) {
     o[0] = v.x & 0xffff; o[1] = v.x >> 16; o[2] = v.y & 0xffff; o[3] = v.y >> 16;

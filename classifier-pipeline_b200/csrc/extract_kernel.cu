@@ -11,6 +11,34 @@ namespace cpt {
 
 namespace {
 
+// Optional phase timing (build with -DCPT_PHASE_TIMING): thread 0 of each role accumulates clock64()
+// deltas per phase into a.debug[blockIdx.x][32].
+#ifdef CPT_PHASE_TIMING
+#define CPT_TICK_START(cond) long long tick_last_ = clock64(); (void)tick_last_
+#define CPT_TICK(cond, i)                                                                     \
+    do {                                                                                      \
+        if ((cond) && a.debug) {                                                              \
+            long long now_ = clock64();                                                       \
+            atomicAdd((unsigned long long *)&a.debug[blockIdx.x * 32 + (i)], (unsigned long long)(now_ - tick_last_)); \
+            tick_last_ = now_;                                                                \
+        }                                                                                     \
+    } while (0)
+#define CPT_TICK_START2(cond) long long tick2_last_ = clock64(); (void)tick2_last_
+#define CPT_TICK2(cond, i)                                                                    \
+    do {                                                                                      \
+        if ((cond) && a.debug) {                                                              \
+            long long now_ = clock64();                                                       \
+            atomicAdd((unsigned long long *)&a.debug[blockIdx.x * 32 + (i)], (unsigned long long)(now_ - tick2_last_)); \
+            tick2_last_ = now_;                                                               \
+        }                                                                                     \
+    } while (0)
+#else
+#define CPT_TICK_START2(cond) do { } while (0)
+#define CPT_TICK2(cond, i) do { } while (0)
+#define CPT_TICK_START(cond) do { } while (0)
+#define CPT_TICK(cond, i) do { } while (0)
+#endif
+
 enum : int { BAR_P = 1, BAR_C = 2, BAR_FULL = 3 /* +buffer */, BAR_EMPTY = 5 /* +buffer */ };
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -34,6 +62,12 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 __device__ __forceinline__ const uint16_t *frame_ptr(const KernelArgs &a, const cpt_clip &c, int t) {
     int64_t idx = c.ring_frames ? (int64_t)((c.first_frame + t) % c.ring_frames) : (int64_t)t;
     return a.frames + (size_t)(c.frame_offset + idx) * a.g.npx;
+}
+
+// The sliding sum is kept as two planes (pixels 0-3 / 4-7 of every 8-pixel group) so that a warp's
+// 16-byte accesses are bank-conflict free: pixel px lives at s_index(px).
+__device__ __forceinline__ int s_index(int px, int npx) {
+    return ((px >> 2) & 1) * (npx >> 1) + (px >> 3) * 4 + (px & 3);
 }
 
 __device__ __forceinline__ float *filtered_ptr(const KernelArgs &a, const cpt_clip &c, float *scratch, int t) {
@@ -90,6 +124,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
     constexpr int kIter = (kMaxWords + kCThreads - 1) / kCThreads;  // 3
     RunCursor rc[kIter];
     bool any = false;
+    CPT_TICK_START2(ctid == 0);
     // ---- close: C[y] = M[y-1] | (M[y] & M[y-2]) (C[0] = M[0]); slot tables reset
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
@@ -116,6 +151,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
     }
     if (ctid == 0) s.ncomp = 0;
     if (!bar_or(BAR_C, kCThreads, any)) return;  // no foreground: info.n_components stays 0
+    CPT_TICK2(ctid == 0, 20);  // close + reset + barrier
 
     // ---- run starts and ids
 #pragma unroll
@@ -145,6 +181,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
         }
     }
     bar_sync(BAR_C, kCThreads);
+    CPT_TICK2(ctid == 0, 21);  // run starts + barrier
     // ---- unions with the row above (8-connectivity)
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
@@ -182,6 +219,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
         }
     }
     bar_sync(BAR_C, kCThreads);
+    CPT_TICK2(ctid == 0, 22);  // unions + barrier
     // ---- roots -> component slots
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
@@ -198,6 +236,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
         }
     }
     bar_sync(BAR_C, kCThreads);
+    CPT_TICK2(ctid == 0, 23);  // roots + barrier
     const int ncomp = s.ncomp;
     // ---- per-run statistics into the slot tables
 #pragma unroll
@@ -237,6 +276,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
         }
     }
     bar_sync(BAR_C, kCThreads);
+    CPT_TICK2(ctid == 0, 24);  // run statistics + barrier
     // ---- OpenCV label order: rank by the key of the component's first 2x2 block
     const int nslots = min(ncomp, CPT_MAX_COMPONENTS);
     const int nout = min(nslots, g.max_regions);
@@ -246,6 +286,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
         s.c_rank[i] = (uint8_t)rank;
     }
     bar_sync(BAR_C, kCThreads);
+    CPT_TICK2(ctid == 0, 25);  // rank + barrier
     // ---- label image: the pixel warps already stored zeros for this frame; write the runs
     if (a.labels) {
         uint8_t *lab_frame = a.labels + o * g.npx;
@@ -267,6 +308,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             }
         }
     }
+    CPT_TICK2(ctid == 0, 26);  // label writes
     // ---- delta-frame variance over each component's bounding box (K6)
     if (have_prev) {
         const bool exact = 255ll * max(cur_fmax - cur_fmin, prev_fmax - prev_fmin) < (1ll << 24) &&
@@ -295,6 +337,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
         }
     }
     bar_sync(BAR_C, kCThreads);
+    CPT_TICK2(ctid == 0, 27);  // variance + barrier
     for (int i = ctid; i < nslots; i += kCThreads) {
         const int rank = s.c_rank[i];
         if (rank < nout) {
@@ -324,8 +367,10 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         have_prev = st_hdr->have_prev != 0;
     }
     for (int t = 0; t < clip.n_frames; ++t) {
+        CPT_TICK_START(ctid == 0);
         const int buf = t & 1;
         bar_sync(BAR_FULL + buf, kThreads);  // mask of frame t is in s.M[buf]
+        CPT_TICK(ctid == 0, 11);  // waiting for a mask
         const int cur_fmin = s.msg[buf][0], cur_fmax = s.msg[buf][1];
         const float *fcur = filtered_ptr(a, clip, scratch, t);
         const float *fprev = (t == 0) ? st_F : filtered_ptr(a, clip, scratch, t - 1);
@@ -335,8 +380,8 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         prev_fmax = cur_fmax;
         have_prev = true;
         // all component threads are done with s.M[buf] (and s.C etc.) -> the pixel warps may refill it
+        CPT_TICK(ctid == 0, 12);  // components of the frame
         if (t + 2 < clip.n_frames) bar_arrive(BAR_EMPTY + buf, kThreads);
-        else bar_sync(BAR_C, kCThreads);
     }
 }
 
@@ -417,13 +462,13 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
 
     // ---------------------------------------------------------------- init / resume
     for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
-    for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 65536u;
+    for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
     if (ptid < kMaxH) { s.need_u[ptid] = 0; s.need_b[ptid] = 0; }
     if (clip.flags & CPT_CLIP_RESUME) {
         for (int i = ptid; i < npx; i += kPThreads) {
             s.B[i] = st_B[i];
             s.K[i] = st_K[i];
-            s.S[i] = st_S[i];
+            s.S[s_index(i, npx)] = st_S[i];
         }
         average = st_hdr->average;
         prev_fmin = st_hdr->prev_fmin;
@@ -456,6 +501,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     }
 
     for (int t = 0; t < clip.n_frames; ++t) {
+        CPT_TICK_START(ptid == 0);
         const int t_abs = clip.first_frame + t;
         const int buf = t & 1;
         const size_t o = (size_t)(clip.out_offset + t);
@@ -476,48 +522,79 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         for (int j = 0; j < kIter; ++j) {
             int grp = ptid + j * kPThreads;
             gmaxf[j] = INT32_MIN;
+            const unsigned active = __ballot_sync(0xffffffffu, grp < g.groups);  // groups is even: lane pairs stay together
             if (grp < g.groups) {
                 pv[j] = ldg16(P + grp * 8);
                 uint4 qv = make_uint4(0, 0, 0, 0);
-                if (Pold) qv = ldg16(Pold + grp * 8);
+#if defined(CPT_EXP) && CPT_EXP == 3
+                if (Pold && grp == 0x7fffffff)  // experiment: no P_old loads
+#else
+                if (Pold)
+#endif
+                    qv = ldg16(Pold + grp * 8);
                 if ((grp & 7) == 0) {  // one 128-byte line per 8 groups: pull the next frame into L2
                     if (Pnext) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pnext + grp * 8));
                     if (Pold_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pold_next + grp * 8));
                 }
-                int p[8], b[8], q[8];
-                unpack8(pv[j], p);
-                unpack8(qv, q);
-                unpack8(*reinterpret_cast<const uint4 *>(s.B + grp * 8), b);
+                const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
+                const uint32_t pw[4] = {pv[j].x, pv[j].y, pv[j].z, pv[j].w};
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+                uint4 *sp0 = reinterpret_cast<uint4 *>(s.S + grp * 4), *sp1 = reinterpret_cast<uint4 *>(s.S + npx / 2 + grp * 4);
+                uint4 s0 = *sp0, s1 = *sp1;
+                int sv[8] = {(int)s0.x, (int)s0.y, (int)s0.z, (int)s0.w, (int)s1.x, (int)s1.y, (int)s1.z, (int)s1.w};
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    int d = p[i] - b[i];
-                    psum += p[i];
-                    fmin = min(fmin, d);
-                    gmaxf[j] = max(gmaxf[j], d);
-                    f[i] = (float)d;
-                }
-                fmax = max(fmax, gmaxf[j]);
-                if (want_stats) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        pmin = min(pmin, p[i]);
-                        pmax = max(pmax, p[i]);
-                        fabs_sum += abs(p[i] - b[i]);
+                for (int w = 0; w < 4; ++w) {
+                    // packed uint16 pairs straight into dp2a: F = P - B, S += P - P_old, sum P
+                    const int d0 = dp2a_us(pw[w], kLoP, dp2a_us(bw[w], kLoN, 0));
+                    const int d1 = dp2a_us(pw[w], kHiP, dp2a_us(bw[w], kHiN, 0));
+                    sv[2 * w] = dp2a_us(pw[w], kLoP, dp2a_us(qw[w], kLoN, sv[2 * w]));
+                    sv[2 * w + 1] = dp2a_us(pw[w], kHiP, dp2a_us(qw[w], kHiN, sv[2 * w + 1]));
+                    psum = (uint32_t)dp2a_us(pw[w], kBoth, (int)psum);
+                    fmin = min(fmin, min(d0, d1));
+                    gmaxf[j] = max(gmaxf[j], max(d0, d1));
+                    f[2 * w] = (float)d0;
+                    f[2 * w + 1] = (float)d1;
+                    if (want_stats) {
+                        const int p0 = (int)(pw[w] & 0xffffu), p1 = (int)(pw[w] >> 16);
+                        pmin = min(pmin, min(p0, p1));
+                        pmax = max(pmax, max(p0, p1));
+                        fabs_sum += abs(d0) + abs(d1);
                     }
                 }
-                float4 *dst = reinterpret_cast<float4 *>(fcur + grp * 8);
-                dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-                dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                fmax = max(fmax, gmaxf[j]);
+                if (j == 0) CPT_TICK(ptid == 0, 13);  // sweep 1: first group computed (load latency)
+                {
+                    // lane pairs trade halves so that each 16-byte store instruction fills whole 32-byte sectors:
+                    // even lane: own[0:4] -> own group, then partner[0:4] -> partner group; odd lane: the upper halves
+                    const bool odd = lane & 1;
+                    float r[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r[i] = __shfl_xor_sync(active, odd ? f[i] : f[4 + i], 1);
+                    float *own = fcur + grp * 8, *partner = fcur + (grp ^ 1) * 8;
+#if defined(CPT_EXP) && CPT_EXP == 1
+                    if (f[0] == 123456.f)  // experiment: no filtered stores
+#endif
+                    if (!odd) {
+                        *reinterpret_cast<float4 *>(own) = make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4 *>(partner) = make_float4(r[0], r[1], r[2], r[3]);
+                    } else {
+                        *reinterpret_cast<float4 *>(partner + 4) = make_float4(r[0], r[1], r[2], r[3]);
+                        *reinterpret_cast<float4 *>(own + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                    }
+                }
                 if (lab_frame) *reinterpret_cast<uint2 *>(lab_frame + grp * 8) = make_uint2(0, 0);
-                uint4 *sp = reinterpret_cast<uint4 *>(s.S + grp * 8);
-                uint4 s0 = sp[0], s1 = sp[1];
-                s0.x += p[0] - q[0]; s0.y += p[1] - q[1]; s0.z += p[2] - q[2]; s0.w += p[3] - q[3];
-                s1.x += p[4] - q[4]; s1.y += p[5] - q[5]; s1.z += p[6] - q[6]; s1.w += p[7] - q[7];
-                sp[0] = s0;
-                sp[1] = s1;
+#if defined(CPT_EXP) && CPT_EXP == 2
+                if (sv[0] == 0x7fffffff)  // experiment: no sliding-sum stores
+#endif
+                {
+                *sp0 = make_uint4((uint32_t)sv[0], (uint32_t)sv[1], (uint32_t)sv[2], (uint32_t)sv[3]);
+                *sp1 = make_uint4((uint32_t)sv[4], (uint32_t)sv[5], (uint32_t)sv[6], (uint32_t)sv[7]);
+                }
             }
         }
+        CPT_TICK(ptid == 0, 14);  // sweep 1: all groups computed, stores issued
         psum = __reduce_add_sync(0xffffffffu, psum);
         fmin = __reduce_min_sync(0xffffffffu, fmin);
         fmax = __reduce_max_sync(0xffffffffu, fmax);
@@ -535,6 +612,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             s.red_u[warp * 6 + 5] = fabs_sum;
         }
         bar_sync(BAR_P, kPThreads);
+        CPT_TICK(ptid == 0, 2);   // sweep 1 + barrier
         // ------------------------------------------------------------ scalars (K2), pixel warp 0
         if (warp == 0) {
             const bool in = lane < kPWarps;
@@ -600,6 +678,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             }
         }
         bar_sync(BAR_P, kPThreads);
+        CPT_TICK(ptid == 0, 3);   // scalars + barrier
         const int ac = s.bcast_i[0], gmn = s.bcast_i[1], gmx = s.bcast_i[2];
         const int cur_fmin = s.bcast_i[3], cur_fmax = s.bcast_i[4];
         const float thr = __int_as_float(s.bcast_i[5]);
@@ -618,19 +697,32 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         if (!all_hot) {
 #pragma unroll
             for (int j = 0; j < kIter; ++j) {
-                int grp = ptid + j * kPThreads;
-                if (grp < g.groups && gmaxf[j] >= fth) {
-                    int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr;
-                    uint32_t mu = (0x1fu << gx) >> 2, mb = (0x7u << gx) >> 1;
-                    for (int yy = max(y - 4, 0); yy <= min(y + 4, g.H - 1); ++yy) atomicOr(&s.need_u[yy], mu);
-                    for (int yy = max(y - 2, 0); yy <= min(y + 2, g.H - 1); ++yy) atomicOr(&s.need_b[yy], mb);
+                const int grp = ptid + j * kPThreads;
+                const unsigned m = __ballot_sync(0xffffffffu, grp < g.groups && gmaxf[j] >= fth);
+                if (lane == 0) s.hotbits[grp >> 5] = m;  // kPThreads is a multiple of 32: bit (grp & 31) of word grp >> 5
+            }
+            bar_sync(BAR_P, kPThreads);
+            if (ptid < g.H) {
+                // row ptid: OR the hot bits of the rows around it, then widen by the neighbouring groups
+                const uint32_t rowmask = (1u << g.gpr) - 1u;
+                uint32_t near2 = 0, near4 = 0;
+                for (int dy = -4; dy <= 4; ++dy) {
+                    const int yy = ptid + dy;
+                    if (yy < 0 || yy >= g.H) continue;
+                    const int base = yy * g.gpr;
+                    const uint32_t bits = __funnelshift_r(s.hotbits[base >> 5], s.hotbits[(base >> 5) + 1], base & 31) & rowmask;
+                    near4 |= bits;
+                    if (dy >= -2 && dy <= 2) near2 |= bits;
                 }
+                s.need_u[ptid] = near4 | (near4 << 1) | (near4 << 2) | (near4 >> 1) | (near4 >> 2);
+                s.need_b[ptid] = near2 | (near2 << 1) | (near2 >> 1);
             }
         } else if (ptid < g.H) {
             s.need_u[ptid] = 0xffffffffu;
             s.need_b[ptid] = 0xffffffffu;
         }
         bar_sync(BAR_P, kPThreads);
+        CPT_TICK(ptid == 0, 4);   // sweep 2a + barrier
         // ------------------------------------------------------------ sweep 2b: U (K2)
         if (!no_fg) {
             const float range_f = (float)gmx - (float)gmn;
@@ -641,19 +733,22 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 if (grp < g.groups) {
                     int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr;
                     if (!((s.need_u[y] >> gx) & 1u)) continue;
-                    int p[8], b[8];
-                    unpack8(pv[j], p);
-                    unpack8(*reinterpret_cast<const uint4 *>(s.B + grp * 8), b);
+                    const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
+                    const uint32_t pw[4] = {pv[j].x, pv[j].y, pv[j].z, pv[j].w};
+                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
                     uint32_t u[8];
-                    if (degenerate) {
+                    const int off = -ac;  // G - min = max(F - ac, 0) - gmn
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) u[i] = degen_val;
-                    } else if (umagic) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) u[i] = norm_u8_int(max(p[i] - b[i] - ac, 0) - gmn, umagic, ushift);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) u[i] = norm_u8(max(p[i] - b[i] - ac, 0) - gmn, range_f);
+                    for (int w = 0; w < 4; ++w) {
+                        const int g0 = max(dp2a_us(pw[w], kLoP, dp2a_us(bw[w], kLoN, off)), 0) - gmn;
+                        const int g1 = max(dp2a_us(pw[w], kHiP, dp2a_us(bw[w], kHiN, off)), 0) - gmn;
+                        if (degenerate) {
+                            u[2 * w] = degen_val; u[2 * w + 1] = degen_val;
+                        } else if (umagic) {
+                            u[2 * w] = norm_u8_int(g0, umagic, ushift); u[2 * w + 1] = norm_u8_int(g1, umagic, ushift);
+                        } else {
+                            u[2 * w] = norm_u8(g0, range_f); u[2 * w + 1] = norm_u8(g1, range_f);
+                        }
                     }
                     uint2 w;
                     w.x = u[0] | (u[1] << 8) | (u[2] << 16) | (u[3] << 24);
@@ -663,19 +758,23 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             }
         }
         bar_sync(BAR_P, kPThreads);
+        CPT_TICK(ptid == 0, 5);   // sweep 2b + barrier
 
         // ------------------------------------------------------------ blur + threshold (K4) -> s.M[buf]
         if (t >= 2) bar_sync(BAR_EMPTY + buf, kThreads);  // component warps are done with frame t-2's mask
+        CPT_TICK(ptid == 0, 6);   // wait for the mask buffer
         blur_threshold(s, g, ptid, buf, ith);
         if (ptid == 0) { s.msg[buf][0] = cur_fmin; s.msg[buf][1] = cur_fmax; }
         bar_arrive(BAR_FULL + buf, kThreads);
+        CPT_TICK(ptid == 0, 7);   // blur
 
         // ------------------------------------------------------------ sweep 3: background (K7)
         int any_changed = 0;
         if (clip.flags & CPT_CLIP_UPDATE_BACKGROUND) {
             const uint32_t cnt = (uint32_t)min(t_abs + 1, kMeanFrames);
-            // A = floor(S / cnt) == umulhi(2S, 2^31/cnt + 1): exact for S < 2^22, cnt <= 45
-            const uint32_t magic = (0x80000000u / cnt) + 1u;
+            // A = floor(S / cnt) == umulhi(S, 2^32/cnt + 1) for cnt >= 2: exact for S < 2^22, cnt <= 45
+            const bool first_frame = (cnt == 1u);
+            const uint32_t magic = first_frame ? 0u : (uint32_t)(0x100000000ull / cnt) + 1u;
             const bool table_in_smem = (t_abs + 1 < kSmemWeights);  // k never exceeds the frames seen
             uint32_t bsum = 0;
             int changed = 0;
@@ -687,30 +786,64 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                     if (yy >= g.edge && yy < g.H - g.edge) {
                         const int lo = max(g.edge - x0, 0), hi = min(W - g.edge - x0, 8);
                         const uint32_t inc = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-                        int b[8], k[8];
-                        unpack8(*reinterpret_cast<const uint4 *>(s.B + grp * 8), b);
-                        unpack8(*reinterpret_cast<const uint4 *>(s.K + grp * 8), k);
-                        const uint4 *sp = reinterpret_cast<const uint4 *>(s.S + grp * 8);
-                        uint4 s0 = sp[0], s1 = sp[1];
-                        uint32_t sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
+                        const uint4 kv = *reinterpret_cast<const uint4 *>(s.K + grp * 8);
+                        const uint4 s0 = *reinterpret_cast<const uint4 *>(s.S + grp * 4);
+                        const uint4 s1 = *reinterpret_cast<const uint4 *>(s.S + npx / 2 + grp * 4);
+                        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                        const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
+                        const uint32_t sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        uint32_t nbw[4], nkw[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int A = (int)__umulhi(sv[i] << 1, magic);
-                            const int d = A - b[i];
-                            const int kk = k[i];
-                            const uint32_t e = table_in_smem ? s.wthr[kk] : __ldg(wt.thr + kk);
-                            const int thr_d = (int)(e & kThrMask);
-                            const int bound = (int)((1u << (e >> 17)) >> 1);
-                            const bool keep = (d >= thr_d) || (d == thr_d - 1 && b[i] < bound);
-                            const bool on = (inc >> i) & 1u;
-                            const int nb = (on && !keep) ? A : b[i];
-                            changed |= nb ^ b[i];
-                            k[i] = on ? (keep ? min(kk + 1, wt.max_count) : 0) : kk;
-                            b[i] = nb;
-                            bsum += on ? (uint32_t)nb : 0u;
+                        for (int w = 0; w < 4; ++w) {
+                            const int b0 = (int)(bw[w] & 0xffffu), b1 = (int)(bw[w] >> 16);
+                            const int k0 = (int)(kw[w] & 0xffffu), k1 = (int)(kw[w] >> 16);
+                            const int A0 = first_frame ? (int)sv[2 * w] : (int)__umulhi(sv[2 * w], magic);
+                            const int A1 = first_frame ? (int)sv[2 * w + 1] : (int)__umulhi(sv[2 * w + 1], magic);
+#if defined(CPT_EXP) && CPT_EXP == 4
+                            const uint32_t e0 = 1u + (k0 >> 4), e1 = 1u + (k1 >> 4);  // experiment: no table gather
+#else
+                            const uint32_t e0 = table_in_smem ? s.wthr[k0] : __ldg(wt.thr + k0);
+                            const uint32_t e1 = table_in_smem ? s.wthr[k1] : __ldg(wt.thr + k1);
+#endif
+                            int t0 = (int)(e0 & 0xffffu), t1 = (int)(e1 & 0xffffu);
+                            if (wt.has_bounds) {
+                                t0 -= (b0 < (int)(e0 >> 16)) ? 1 : 0;
+                                t1 -= (b1 < (int)(e1 >> 16)) ? 1 : 0;
+                            }
+                            // keep <=> A - B >= thr  <=>  thr + (B - A) - 1 < 0
+                            const int dd0 = b0 - A0, dd1 = b1 - A1;
+                            const uint32_t keep0 = (uint32_t)(t0 + dd0 - 1) >> 31, keep1 = (uint32_t)(t1 + dd1 - 1) >> 31;
+                            const uint32_t n0 = (uint32_t)(A0 + (int)keep0 * dd0), n1 = (uint32_t)(A1 + (int)keep1 * dd1);
+                            nbw[w] = n1 * 65536u + n0;
+                            const uint32_t kmask = keep0 * 0xffffu + keep1 * 0xffff0000u;
+                            nkw[w] = (kw[w] + 0x00010001u) & kmask;
                         }
-                        *reinterpret_cast<uint4 *>(s.B + grp * 8) = pack8(b);
-                        *reinterpret_cast<uint4 *>(s.K + grp * 8) = pack8(k);
+                        if (inc != 0xffu) {
+                            // crop border columns inside this group keep their old state (they are rewritten by the
+                            // edge replication) and do not count
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (!((inc >> i) & 1u)) {
+                                    const uint32_t m = 0xffffu << (16 * (i & 1));
+                                    nbw[i >> 1] = (nbw[i >> 1] & ~m) | (bw[i >> 1] & m);
+                                    nkw[i >> 1] = (nkw[i >> 1] & ~m) | (kw[i >> 1] & m);
+                                    bsum -= (bw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            changed |= (int)(nbw[w] ^ bw[w]);
+                            bsum = (uint32_t)dp2a_us(nbw[w], kBoth, (int)bsum);
+                        }
+#if defined(CPT_EXP) && CPT_EXP == 5
+                        if (nbw[0] == 0x12345678u)  // experiment: no B / K stores
+#endif
+                        {
+                        *reinterpret_cast<uint4 *>(s.B + grp * 8) = make_uint4(nbw[0], nbw[1], nbw[2], nbw[3]);
+                        *reinterpret_cast<uint4 *>(s.K + grp * 8) = make_uint4(nkw[0], nkw[1], nkw[2], nkw[3]);
+                        }
                     }
                 }
             }
@@ -720,8 +853,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         } else {
             bar_sync(BAR_P, kPThreads);
         }
-        // every pixel thread is past the blur: the need maps can be cleared for the next frame
-        if (ptid < kMaxH) { s.need_u[ptid] = 0; s.need_b[ptid] = 0; }
+        CPT_TICK(ptid == 0, 8);   // sweep 3 + barrier
         if (any_changed) {
             if (warp == 0) {
                 uint32_t v = __reduce_add_sync(0xffffffffu, (lane < kPWarps) ? s.red_u[lane * 6] : 0u);
@@ -734,6 +866,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         have_prev = 1;
         ++frames_seen;
         bar_sync(BAR_P, kPThreads);
+        CPT_TICK(ptid == 0, 9);   // edges + end barrier
     }
 
     // ---------------------------------------------------------------- save state
@@ -741,7 +874,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         for (int i = ptid; i < npx; i += kPThreads) {
             st_B[i] = s.B[i];
             st_K[i] = s.K[i];
-            st_S[i] = s.S[i];
+            st_S[i] = s.S[s_index(i, npx)];
         }
         if (clip.n_frames > 0) {
             const float *flast = filtered_ptr(a, clip, scratch, clip.n_frames - 1);

@@ -88,6 +88,7 @@ SYMBOLS = {
     "cpt_ctx_synchronize": (_i, [_vp]),
     "cpt_set_weight_table": (_i, [_vp, _i, _d, _i]),
     "cpt_build_weight_table": (_i, [_d, _i, _vp, _vp]),
+    "cpt_debug_phase_cycles": (_i, [_vp, _vp, _i]),
     "cpt_device_alloc": (_i, [_vp, ctypes.POINTER(_vp), _u64]),
     "cpt_device_free": (_i, [_vp, _vp]),
     "cpt_host_alloc_pinned": (_i, [ctypes.POINTER(_vp), _u64]),
@@ -174,7 +175,7 @@ class Context:
     def synchronize(self):
         check(self.lib.cpt_ctx_synchronize(self._h))
 
-    def weight_table(self, weight_add, max_frames=65535):
+    def weight_table(self, weight_add, max_frames=65534):
         """Slot holding the table for ``weight_add`` (uploads it on first use)."""
         key = float(weight_add)
         if key in self._tables and self._tables[key][1] >= max_frames:

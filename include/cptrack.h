@@ -123,6 +123,10 @@ int cpt_host_free_pinned(void *h_ptr);
 int cpt_copy_to_device(cpt_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);   /* async on ctx stream */
 int cpt_copy_to_host(cpt_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);     /* async on ctx stream */
 
+/* Diagnostics: per-phase clock64() totals summed over CTAs (all zero unless the library was built with
+ * -DCPT_PHASE_TIMING); the first call allocates the counters. h_out32 (32 counters) may be NULL. */
+int cpt_debug_phase_cycles(cpt_ctx *ctx, long long *h_out32, int reset);
+
 /* Bytes of one per-clip state record for this ctx's geometry. */
 uint64_t cpt_state_bytes(const cpt_ctx *ctx);
 

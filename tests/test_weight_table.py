@@ -34,9 +34,8 @@ def test_table_equals_fp64_comparison(weight_add):
     n = 3000
     thr, w = build(weight_add, n)
     assert np.array_equal(w, literal_weights(weight_add, n))
-    t = (thr & 0x1FFFF).astype(np.int64)
-    ecode = (thr >> 17).astype(np.int64)
-    bound = (np.int64(1) << ecode) >> 1
+    t = (thr & 0xFFFF).astype(np.int64)
+    bound = (thr >> 16).astype(np.int64)
     rng = np.random.default_rng(0)
     # all k, backgrounds across every binade (incl. 0 and powers of two +-1), d around the threshold
     bs = np.unique(np.concatenate([[0, 1, 2, 3], 2 ** np.arange(1, 16), 2 ** np.arange(1, 16) - 1, 2 ** np.arange(1, 16) + 1,
@@ -48,7 +47,9 @@ def test_table_equals_fp64_comparison(weight_add):
             ok = (a >= 0) & (a <= 65535)
             literal = np.float64(b) < (a.astype(np.float64) - w)
             table = (d >= t) | ((d == t - 1) & (b < bound))
+            ok &= t < 65535  # clamped entries (w_k beyond any pixel difference) are excluded by the host check
             assert np.array_equal(literal[ok], table[ok]), (weight_add, int(b), dd)
+            assert np.array_equal(table, d >= t - (b < bound))
 
 
 def test_known_rounding_trap():
@@ -56,5 +57,5 @@ def test_known_rounding_trap():
     although 1 > w, because fl(frame - w) rounds to background."""
     thr, w = build(0.1, 32)
     assert w[10] == 0.9999999999999999
-    t, bound = int(thr[10] & 0x1FFFF), (1 << int(thr[10] >> 17)) >> 1
+    t, bound = int(thr[10] & 0xFFFF), int(thr[10] >> 16)
     assert t == 2 and bound == 1  # d == 1 keeps only when background == 0

@@ -1,0 +1,50 @@
+"""Build a -DCPT_PHASE_TIMING copy of the library and print where the cycles of a frame go (GPU box)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "classifier-pipeline_b200")
+
+
+def main(clips=148, frames=300, exp=0):
+    import torch
+    from classifier_pipeline_b200 import native
+
+    dbg = os.path.join(PKG, "libcptrack_timing.so")
+    srcs = [os.path.join(PKG, "csrc", f) for f in sorted(os.listdir(os.path.join(PKG, "csrc"))) if f.endswith(".cu")]
+    subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-DCPT_PHASE_TIMING", "-DCPT_EXP={}".format(exp),
+                    "-Xcompiler", "-fPIC", "-shared", "-o", dbg] + srcs, check=True)
+    native.LIB_PATH = dbg
+    from classifier_pipeline_b200.batch import BatchExtractor, linear_clips
+    from classifier_pipeline_b200.synthetic import MODELS, make_clips_torch
+
+    ex = BatchExtractor(device=0, max_regions=16)
+    slots = [ex.ctx.weight_table(m[3], max_frames=2048) for m in MODELS]
+    d_frames, models = make_clips_torch(clips, frames, torch.device("cuda", 0))
+    cl = linear_clips([frames] * clips, np.array([MODELS[m][2] for m in models]), np.array([slots[m] for m in models]))
+    out = {}
+    ex.extract_device(d_frames, cl, out=out)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * 32)()
+    native.check(ex.ctx.lib.cpt_debug_phase_cycles(ex.ctx._h, buf, 1))
+    ex.extract_device(d_frames, cl, out=out)
+    torch.cuda.synchronize()
+    native.check(ex.ctx.lib.cpt_debug_phase_cycles(ex.ctx._h, buf, 0))
+    names = {13: "P s1 first group", 14: "P s1 rest of groups", 2: "P s1 reduce+bar", 3: "P scalars+bar", 4: "P sweep2a+bar", 5: "P sweep2b+bar", 6: "P wait mask buffer", 7: "P blur",
+             8: "P sweep3+bar", 9: "P edges+bar", 11: "C wait mask", 12: "C components",
+             20: "C  close+reset+bar", 21: "C  run starts+bar", 22: "C  unions+bar", 23: "C  roots+bar", 24: "C  run stats+bar",
+             25: "C  rank+bar", 26: "C  label writes", 27: "C  variance+bar"}
+    total = clips * frames
+    psum = sum(buf[i] for i in list(range(2, 10)) + [13, 14])
+    for i, n in names.items():
+        print("{:22s} {:9.0f} cycles/frame".format(n, buf[i] / total))
+    print("P total {:.0f} cycles/frame, C total {:.0f}".format(psum / total, (buf[11] + buf[12]) / total))
+
+
+if __name__ == "__main__":
+    main(*[int(x) for x in sys.argv[1:]])
