@@ -12,6 +12,8 @@
 
 namespace cpt {
 __global__ void extract_clips_kernel(const KernelArgs a);
+__global__ void background_step_kernel(Geometry g, uint8_t *state, const int32_t *frames, const int *record_index, WeightTable wt);
+__global__ void frame_median_kernel(const uint16_t *frames, int npx, float *out);
 }
 
 namespace {
@@ -473,6 +475,30 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
     }
     CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPT_OK;
+}
+
+int cpt_background_process(cpt_ctx *c, void *d_state, const int32_t *d_record_index, int n_records,
+                           const int32_t *d_frames, int weight_slot) {
+    if (!c || !d_state || !d_frames) return fail(CPT_ERR_INVALID, "null argument");
+    if (n_records < 0) return fail(CPT_ERR_INVALID, "n_records < 0");
+    if (weight_slot < 0 || weight_slot >= 4 || !c->tables[weight_slot].d_thr)
+        return fail(CPT_ERR_INVALID, "weight table slot %d is not set (cpt_set_weight_table)", weight_slot);
+    if (n_records == 0) return CPT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cpt::WeightTable wt{c->tables[weight_slot].d_thr, c->tables[weight_slot].max_count, c->tables[weight_slot].has_bounds};
+    cpt::background_step_kernel<<<n_records, 1024, 0, c->stream>>>(c->g, (uint8_t *)d_state, d_frames, d_record_index, wt);
+    CUDA_TRY(cudaGetLastError());
+    return CPT_OK;
+}
+
+int cpt_frame_medians(cpt_ctx *c, const uint16_t *d_frames, int64_t n_frames, float *d_medians) {
+    if (!c || !d_frames || !d_medians) return fail(CPT_ERR_INVALID, "null argument");
+    if (n_frames < 0 || n_frames > 0x7fffffff) return fail(CPT_ERR_INVALID, "bad n_frames");
+    if (n_frames == 0) return CPT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cpt::frame_median_kernel<<<(unsigned)n_frames, 256, (size_t)c->g.npx * sizeof(uint16_t), c->stream>>>(d_frames, c->g.npx, d_medians);
+    CUDA_TRY(cudaGetLastError());
     return CPT_OK;
 }
 

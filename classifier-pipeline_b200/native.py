@@ -18,6 +18,7 @@ CLIP_DENOISE = 4
 CLIP_FRAME_STATS = 8
 MAX_COMPONENTS = 255
 MEAN_FRAMES = 45
+HAS_NLM = False  # cv2.fastNlMeansDenoising kernel not built yet
 
 
 class NativeError(RuntimeError):
@@ -98,6 +99,8 @@ SYMBOLS = {
     "cpt_state_bytes": (_u64, [_vp]),
     "cpt_extract_batch": (_i, [_vp, _vp, _vp, _i, ctypes.POINTER(CptOutputs), _vp]),
     "cpt_extract_batch_host": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _i]),
+    "cpt_background_process": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "cpt_frame_medians": (_i, [_vp, _vp, _i64, _vp]),
     "cpt_state_read": (_i, [_vp, _vp, _i, _vp, _vp, ctypes.POINTER(_d), _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cpt_state_write": (_i, [_vp, _vp, _i, _vp, _vp, _d]),
     "cpt_weight_value": (_d, [_vp, _i, _i]),
@@ -201,6 +204,12 @@ class Context:
                 _ptr(h_filtered), _ptr(h_labels), int(chunk_clips),
             )
         )
+
+    def background_process(self, d_state, d_frames_i32, weight_slot, n_records=1, d_record_index=None):
+        check(self.lib.cpt_background_process(self._h, _ptr(d_state), _ptr(d_record_index), int(n_records), _ptr(d_frames_i32), int(weight_slot)))
+
+    def frame_medians(self, d_frames, n_frames, d_medians):
+        check(self.lib.cpt_frame_medians(self._h, _ptr(d_frames), int(n_frames), _ptr(d_medians)))
 
     def state_read(self, d_state, clip_index=0, sliding_sum=False):
         bg = np.empty((self.height, self.width), np.int32)

@@ -1,0 +1,311 @@
+"""``ClipTrackExtractor``: thermal-clip track extraction on the B200 (track/cliptrackextractor.py:35-247).
+
+Same constructor, attributes and methods as the reference class.  The per-pixel work of one frame
+(background subtraction, normalisation, blur / threshold / close, connected components, delta-frame
+variance, the weighted background update and the frame statistics) runs in the persistent
+extraction kernel behind ``libcptrack.so``; this class decodes the clip, launches the kernel once
+per clip (``parse_clip``) or once per frame (``process_frame`` / ``start_tracking``, streaming), and
+feeds the region lists it gets back to the host-side matcher inherited from ``ClipTracker``.
+
+``parse_clips`` is the batched entry point the reference does not have: many clips in one launch
+(one persistent CTA per clip), which is how a B200 is kept busy.
+"""
+import logging
+import time
+from datetime import datetime
+
+import numpy as np
+
+from .. import engine as _engine
+from .. import native
+from ..batch import linear_clips
+from ..cptv import CptvReader
+from ..piclassifier.cptvmotiondetector import is_affected_by_ffc
+from ..piclassifier.motiondetector import WeightedBackground
+from .clip import Clip
+from .cliptracker import ClipTracker
+
+RING_FRAMES = 64  # streaming ring: the kernel reads frame t-45 for the sliding mean
+
+
+class ClipTrackExtractor(ClipTracker):
+    PREVIEW = "preview"
+    VERSION = 11
+    TYPE = "thermal"
+    # how clips are opened; tests and in-memory pipelines may substitute any object with
+    # get_header() / next_frame() (the interface of cptv_rs_python_bindings.CptvReader)
+    reader_factory = staticmethod(lambda path: CptvReader(str(path)))
+
+    @property
+    def tracker_version(self):
+        return self.version
+
+    @property
+    def type(self):
+        return ClipTrackExtractor.TYPE
+
+    def __init__(self, config, use_opt_flow, cache_to_disk=False, keep_frames=True, calc_stats=True,
+                 high_quality_optical_flow=False, verbose=False, do_tracking=True, update_background=True,
+                 calculate_filtered=False, calculate_thumbnail_info=False, from_pi=False, max_frames=None, device=None):
+        super().__init__(config, cache_to_disk, keep_frames=keep_frames, calc_stats=calc_stats, verbose=verbose,
+                         do_tracking=do_tracking, calculate_thumbnail_info=calculate_thumbnail_info, max_frames=max_frames)
+        self.version = f"PI-{ClipTrackExtractor.VERSION}" if from_pi else ClipTrackExtractor.VERSION
+        if use_opt_flow:
+            raise NotImplementedError("optical flow is not part of the B200 extraction path")
+        if getattr(self.config, "denoise", False) and not native.HAS_NLM:
+            raise native.NativeError(
+                "TrackingConfig.denoise=True needs the non-local-means kernel, which this build of libcptrack.so "
+                "does not have; set config.tracking['thermal'].denoise = False (the Pi configuration)")
+        self.use_opt_flow = use_opt_flow
+        self.high_quality_optical_flow = high_quality_optical_flow
+        self.background_alg = None
+        self.update_background = update_background
+        self.calculate_filtered = calculate_filtered
+        self.weighting_percent = 1
+        self.device = device
+        self._stream = None  # streaming session (process_frame)
+
+    @property
+    def tracking_time(self):
+        return self._tracking_time
+
+    # ------------------------------------------------------------------ clip set-up
+    def init_clip(self, clip):
+        """Header, crop rectangle, thresholds; the first frame initialises both backgrounds
+        (cliptrackextractor.py:98-139)."""
+        clip.set_frame_buffer(self.high_quality_optical_flow, self.cache_to_disk, self.use_opt_flow, self.keep_frames,
+                              self.max_frames)
+        clip.type = self.type
+        reader = self.reader_factory(clip.source_file)
+        header = reader.get_header()
+        clip.set_res(header.x_resolution, header.y_resolution)
+        if clip.from_metadata:
+            for track in clip.tracks:
+                track.crop_regions()
+        clip.set_model(header.model if header.model else None)
+        start = datetime.fromtimestamp(header.timestamp / 1000000).astimezone(Clip.local_tz)
+        clip.set_video_stats(start)
+        frame = reader.next_frame()
+        clip.update_background(frame.pix)
+        clip._background_calculated()
+        self.background_alg = self._new_background(clip)
+        self.background_alg.process_frame(frame.pix)
+        self._stream = None
+        return reader
+
+    def _weight_add(self, clip):
+        return (1 if clip.camera_model == "lepton3.5" else 0.1) / self.weighting_percent
+
+    def _new_background(self, clip):
+        return WeightedBackground(clip.crop_rectangle.x, clip.crop_rectangle, clip.res_x, clip.res_y, self._weight_add(clip),
+                                  device=self.device)
+
+    # ------------------------------------------------------------------ whole clips
+    def parse_clip(self, clip, process_background=False):
+        """Loads a cptv file and extracts its tracks.  Returns True."""
+        self._tracking_time = None
+        start = time.time()
+        self.parse_clips([clip], process_background=process_background)
+        self._tracking_time = time.time() - start
+        return True
+
+    def parse_clips(self, clips, process_background=False):
+        """Batched ``parse_clip``: decode every clip, ONE kernel launch for all of them, then the
+        host-side matcher per clip.  Track ids restart at 1 for every clip, as they do when the
+        reference processes the clips one after another."""
+        from .track import Track
+
+        jobs = []
+        for clip in clips:
+            reader = self.init_clip(clip)
+            if clip.background is None:
+                logging.error("Clip has no background have you called init_clip first")
+                raise Exception("Clip has no background have you called init_clip first")
+            # the reference re-opens the file (cliptrackextractor.py:160): the first frame is tracked too
+            reader = self.reader_factory(clip.source_file)
+            reader.get_header()
+            frames = []
+            while True:
+                frame = reader.next_frame()
+                if frame is None:
+                    break
+                if not process_background and frame.background_frame:
+                    continue
+                frames.append(frame)
+            jobs.append((clip, self.background_alg, frames))
+        results = self._run_batch(jobs)
+        for (clip, background_alg, frames), res in zip(jobs, results):
+            self.background_alg = background_alg
+            Track._track_id = 1
+            for t, frame in enumerate(frames):
+                self._consume_frame(clip, frame, res, t)
+            if not clip.from_metadata and self.do_tracking:
+                self.apply_track_filtering(clip)
+            if self.calc_stats:
+                clip.stats.completed()
+        return True
+
+    def _flags(self):
+        flags = 0
+        if self.update_background:
+            flags |= native.CLIP_UPDATE_BACKGROUND
+        if self.calc_stats:
+            flags |= native.CLIP_FRAME_STATS
+        if getattr(self.config, "denoise", False):
+            flags |= native.CLIP_DENOISE
+        return flags
+
+    def _run_batch(self, jobs):
+        """One launch over every clip of ``jobs``; per clip a dict of host arrays for its frames."""
+        import torch
+
+        if not jobs:
+            return []
+        geoms = {(c.res_x, c.res_y, c.config.edge_pixels) for c, _, _ in jobs}
+        if len(geoms) != 1:
+            raise ValueError("clips of one batch must share resolution and edge_pixels")
+        res_x, res_y, edge = geoms.pop()
+        eng = _engine.get_engine(self.device, res_x, res_y, edge)
+        ctx = eng.ctx
+        counts = [len(frames) for _, _, frames in jobs]
+        total = sum(counts)
+        keep_images = self.keep_frames or self.calculate_filtered
+        # frame layout: [init frame of clip 0][tracked frames of clip 0][init frame of clip 1]...
+        h_frames = np.empty((total + len(jobs), res_y, res_x), np.uint16)
+        clips = linear_clips(counts, 0, 0, flags=self._flags())
+        pos = 0
+        for i, (clip, background_alg, frames) in enumerate(jobs):
+            h_frames[pos] = clip.background if clip.background.dtype == np.uint16 else np.uint16(clip.background)
+            clips["init_offset"][i] = pos
+            clips["frame_offset"][i] = pos + 1
+            for t, frame in enumerate(frames):
+                h_frames[pos + 1 + t] = frame.pix
+            pos += 1 + counts[i]
+            clips["background_thresh"][i] = clip.background_thresh
+            clips["weight_table"][i] = ctx.weight_table(background_alg.weight_add, max_frames=max(max(counts), 1024))
+        d_frames = torch.from_numpy(h_frames.view(np.int16)).to(eng.device).view(torch.uint16)
+        out = eng.extract_device(d_frames, clips, keep_filtered=keep_images, keep_labels=keep_images, keep_state=True, out={})
+        medians = None
+        if self.calc_stats and total:
+            d_med = torch.empty((total + len(jobs),), dtype=torch.float32, device=eng.device)
+            ctx.frame_medians(d_frames, total + len(jobs), d_med)
+            medians = d_med.cpu().numpy()
+        regions = eng.regions_numpy(out["regions"])
+        info = eng.info_numpy(out["info"])
+        if total and int(info["n_components"][:total].max()) > eng.max_regions:
+            raise native.NativeError("a frame has more than {} components; raise engine.API_MAX_REGIONS".format(eng.max_regions))
+        filtered = out["filtered"].cpu().numpy() if keep_images else None
+        labels = out["labels"].cpu().numpy() if keep_images else None
+        results = []
+        for i, (clip, background_alg, frames) in enumerate(jobs):
+            o0, n = int(clips["out_offset"][i]), counts[i]
+            f0 = int(clips["frame_offset"][i])
+            # the clip's final WeightedBackground state is the kernel's state record
+            background_alg.d_state.copy_(out["state"][i : i + 1])
+            background_alg.invalidate()
+            results.append(dict(
+                regions=regions[o0 : o0 + n], info=info[o0 : o0 + n],
+                filtered=None if filtered is None else filtered[o0 : o0 + n],
+                labels=None if labels is None else labels[o0 : o0 + n],
+                medians=None if medians is None else medians[f0 : f0 + n],
+            ))
+        return results
+
+    def _consume_frame(self, clip, frame, res, t):
+        """Host half of ``process_frame`` for frame ``t`` of a kernel result."""
+        ffc_affected = is_affected_by_ffc(frame)
+        clip.ffc_affected = ffc_affected
+        info = res["info"][t]
+        tracking = self.do_tracking or self.calculate_thumbnail_info
+        filtered = res["filtered"][t] if res["filtered"] is not None else None
+        mask = res["labels"][t] if (res["labels"] is not None and tracking) else None
+        stats = None
+        if self.calc_stats:
+            npx = frame.pix.size
+            stats = (res["medians"][t], int(info["thermal_max"]), int(info["thermal_min"]), int(info["thermal_sum"]) / npx,
+                     float(info["abs_filtered_sum"]))
+        clip.add_frame(frame.pix.copy(), filtered, mask, ffc_affected, frame_stats=stats)
+        if not self.do_tracking:
+            return []
+        new_tracks = []
+        if not clip.from_metadata:
+            regions = []
+            if ffc_affected:
+                clip.active_tracks = set()
+            else:
+                n = int(info["n_components"])
+                r = res["regions"][t][:n]
+                area = r["area"].astype(np.float64)
+                components = np.stack([r["x"], r["y"], r["width"], r["height"], r["area"]], axis=1)
+                centroids = np.stack([r["sum_x"] / area, r["sum_y"] / area], axis=1)
+                variances = r["pixel_variance"] if clip.current_frame > 0 or res.get("have_prev") else None
+                regions = self._get_regions_of_interest(clip, components, centroids, variances)
+                new_tracks = self._apply_region_matchings(clip, regions)
+            clip.region_history.append(regions)
+        return new_tracks
+
+    # ------------------------------------------------------------------ streaming
+    def start_tracking(self, clip, frames, track_frames=True, background_alg=None, **args):
+        """Feed the preview frames of a new recording (cliptrackextractor.py:182-196)."""
+        do_tracking = self.do_tracking
+        self.background_alg = background_alg
+        self._stream = None
+        self.do_tracking = self.do_tracking and track_frames
+        new_tracks = []
+        for frame in frames:
+            new_tracks.extend(self.process_frame(clip, frame))
+        self.do_tracking = do_tracking
+        return new_tracks
+
+    def _open_stream(self, clip):
+        import torch
+
+        if self.background_alg is None or not self.background_alg.initialised:
+            raise Exception("Clip has no background have you called init_clip first")
+        eng = _engine.get_engine(self.device, clip.res_x, clip.res_y, clip.config.edge_pixels)
+        if self.background_alg.engine is not eng:
+            raise native.NativeError("background_alg lives on another device / geometry than the clip")
+        self._stream = dict(
+            eng=eng, t=0, out={}, background_alg=self.background_alg,
+            ring=torch.zeros((RING_FRAMES, clip.res_y, clip.res_x), dtype=torch.uint16, device=eng.device),
+            median=torch.empty((1,), dtype=torch.float32, device=eng.device),
+        )
+        return self._stream
+
+    def process_frame(self, clip, frame):
+        """Track one more frame of a clip (streaming; one kernel launch)."""
+        import torch
+
+        st = self._stream
+        if st is None or st["background_alg"] is not self.background_alg:
+            st = self._open_stream(clip)
+        eng, t = st["eng"], st["t"]
+        slot = t % RING_FRAMES
+        pix = np.ascontiguousarray(frame.pix, dtype=np.uint16)
+        st["ring"][slot].view(torch.int16).copy_(torch.from_numpy(pix.view(np.int16)))
+        # the kernel resumes from (and saves to) the background's own state record
+        flags = (self._flags() | native.CLIP_RESUME)
+        c = linear_clips([1], clip.background_thresh, self.background_alg.weight_slot, flags=flags)
+        c["frame_offset"] = 0
+        c["init_offset"] = 0
+        c["first_frame"] = t
+        c["ring_frames"] = RING_FRAMES
+        c["out_offset"] = 0
+        keep_images = self.keep_frames or self.calculate_filtered
+        out = eng.extract_device(st["ring"], c, keep_filtered=keep_images, keep_labels=keep_images,
+                                 d_state=self.background_alg.d_state, out=st["out"])
+        medians = None
+        if self.calc_stats:
+            eng.ctx.frame_medians(st["ring"][slot], 1, st["median"])
+            medians = st["median"].cpu().numpy()
+        self.background_alg.invalidate()
+        res = dict(
+            regions=eng.regions_numpy(out["regions"])[:1], info=eng.info_numpy(out["info"])[:1],
+            filtered=out["filtered"][:1].cpu().numpy() if keep_images else None,
+            labels=out["labels"][:1].cpu().numpy() if keep_images else None,
+            medians=medians, have_prev=t > 0,
+        )
+        if int(res["info"]["n_components"][0]) > eng.max_regions:
+            raise native.NativeError("a frame has more than {} components; raise engine.API_MAX_REGIONS".format(eng.max_regions))
+        st["t"] = t + 1
+        return self._consume_frame(clip, frame, res, 0)

@@ -145,6 +145,17 @@ int cpt_extract_batch_host(cpt_ctx *ctx, const uint16_t *h_frames, const cpt_cli
                            int64_t total_frames, cpt_region *h_regions, cpt_frame_info *h_info,
                            float *h_filtered, uint8_t *h_labels, int chunk_clips);
 
+/* WeightedBackground.process_frame(frame) (piclassifier/motiondetector.py:197-244) on n_records state
+ * records: record d_record_index[i] (or i when NULL) is updated with int32 frame i of d_frames
+ * ([n_records][H][W], already truncated like np.int32(frame)).  A record whose `initialised` flag is 0
+ * (fresh, zero-filled memory) takes the first-call path: background = frame, average = mean (unrounded). */
+int cpt_background_process(cpt_ctx *ctx, void *d_state, const int32_t *d_record_index, int n_records,
+                           const int32_t *d_frames, int weight_slot);
+
+/* np.median of each uint16 frame (ClipStats.add_frame, track/clip.py:474-487; the per-frame median of
+ * Interpreter.preprocess_segments, ml_tools/interpreter.py:389).  d_medians float32 [n_frames]. */
+int cpt_frame_medians(cpt_ctx *ctx, const uint16_t *d_frames, int64_t n_frames, float *d_medians);
+
 /* State access for WeightedBackground.background / .background_weight / .average
  * (motiondetector.py:178-248).  h_background int32 [H][W]; h_weight_count uint16 [(H-2e)][(W-2e)]
  * (background_weight = table[count]); h_average double. Any output may be NULL. */
