@@ -39,7 +39,7 @@ namespace {
 #define CPT_TICK(cond, i) do { } while (0)
 #endif
 
-enum : int { BAR_P = 1, BAR_C = 2, BAR_FULL = 3 /* +buffer */, BAR_EMPTY = 5 /* +buffer */ };
+enum : int { BAR_P = 1, BAR_C = 2, BAR_FULL = 3 /* +buffer */, BAR_EMPTY = 5 /* +buffer */, BAR_DONE = 7 };
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -383,6 +383,8 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         CPT_TICK(ctid == 0, 12);  // components of the frame
         if (t + 2 < clip.n_frames) bar_arrive(BAR_EMPTY + buf, kThreads);
     }
+    // the saved state (previous filtered frame, header) may be overwritten now
+    bar_arrive(BAR_DONE, kThreads);
 }
 
 // ================================================================================================
@@ -870,6 +872,8 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     }
 
     // ---------------------------------------------------------------- save state
+    // (the component warps read the resumed state's filtered frame and header until their last frame is done)
+    bar_sync(BAR_DONE, kThreads);
     if (st_raw) {
         for (int i = ptid; i < npx; i += kPThreads) {
             st_B[i] = s.B[i];

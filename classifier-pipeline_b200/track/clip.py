@@ -230,9 +230,11 @@ class ClipStats:
         self.frame_stats_median.append(f_median)
         self.frame_stats_mean.append(f_mean)
         if abs_filtered_sum is not None:
-            self.filtered_sum += abs_filtered_sum
+            self.filtered_sum += np.float64(abs_filtered_sum)
 
     def completed(self):
-        if self.filtered_sum is not None:
-            self.filtered_deviation = np.mean(np.uint16(self.filtered_sum))
-        self.mean_temp = np.mean(np.uint16(self.frame_stats_mean))
+        # parity: the reference casts the float64 totals to uint16 (clip.py:489-492); out-of-range values wrap
+        with np.errstate(invalid="ignore", over="ignore"):
+            if self.filtered_sum is not None:
+                self.filtered_deviation = np.mean(np.asarray(self.filtered_sum, dtype=np.float64).astype(np.int64).astype(np.uint16))
+            self.mean_temp = np.mean(np.asarray(self.frame_stats_mean, dtype=np.float64).astype(np.int64).astype(np.uint16))
