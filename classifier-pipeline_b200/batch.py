@@ -110,3 +110,121 @@ class BatchExtractor:
         self.ctx.extract_batch_host(h_frames, clips, total, regions, info, filtered, labels, chunk_clips)
         out["total_frames"] = total
         return out
+
+
+def pad_segment_samples(n_frames, tiles, seed=None):
+    """Indices into a segment's frame list for its ``tiles`` cells: ``preprocess_movement`` repeats
+    randomly chosen frames (seeded generator) when the segment is short, then sorts
+    (ml_tools/preprocess.py:160-168)."""
+    samples = list(np.arange(n_frames))
+    if n_frames < tiles:
+        rng = np.random.default_rng(seed)
+        samples.extend(rng.choice(samples, tiles - n_frames))
+        samples.sort()
+    return np.asarray(samples[:tiles], dtype=np.int64)
+
+
+class BatchPreprocessor:
+    """``Interpreter.preprocess_segments`` (ml_tools/interpreter.py:365-474) for many tracks in three
+    launches (csrc/preprocess_kernels.cu): track-wide filtered limits, per-frame medians + the
+    clip-at-zero test, then one CTA per (segment, tile) that crops, resizes, normalises and writes the
+    tile into the segment image.  Frames stay in HBM (the extraction's thermal input and filtered output)."""
+
+    def __init__(self, extractor, frame_size=32, frames_per_row=5, tiles=None, preprocess_fn=0):
+        self.ex = extractor
+        self.torch = extractor.torch
+        self.device = extractor.device
+        self.frame_size = frame_size
+        self.frames_per_row = frames_per_row
+        self.tiles = tiles if tiles is not None else frames_per_row * 5  # preprocess.py:161: frames_per_row * 5
+        self.preprocess_fn = preprocess_fn
+
+    def build_tables(self, tracks, seed=None):
+        """tracks: list of (regions, segments); regions int array (n, >=6) rows [frame, x, y, w, h, blank] with
+        ``frame`` an index into the device frame buffers, segments a list of frame arrays (same index space).
+        Returns (limit_regions SAMPLE_DTYPE, samples SAMPLE_DTYPE, segment_samples int32 (n_seg, tiles), seg_track)."""
+        W, H = self.ex.width, self.ex.height
+        lim_parts, samp_parts, seg_rows, seg_track = [], [], [], []
+        n_samples = 0
+        for ti, (regions, segments) in enumerate(tracks):
+            regions = np.asarray(regions)
+            if regions.ndim != 2 or regions.shape[1] < 6:
+                raise ValueError("regions must be (n, >=6) rows [frame, x, y, w, h, blank]")
+            ok = (regions[:, 5] == 0) & (regions[:, 3] > 0) & (regions[:, 4] > 0) & (regions[:, 0] >= 0)
+            r = regions[ok]
+            if len(r) and ((r[:, 1] < 0).any() or (r[:, 2] < 0).any() or (r[:, 1] + r[:, 3] > W).any() or (r[:, 2] + r[:, 4] > H).any()):
+                raise ValueError("track {}: a region lies outside the {}x{} frame".format(ti, W, H))
+            lim = np.zeros(len(r), native.SAMPLE_DTYPE)
+            lim["frame"], lim["x"], lim["y"], lim["width"], lim["height"], lim["track"] = r[:, 0], r[:, 1], r[:, 2], r[:, 3], r[:, 4], ti
+            lim_parts.append(lim)
+            if not segments:
+                continue
+            seg_frames = [np.asarray(s, dtype=np.int64).reshape(-1) for s in segments]
+            uniq, inverse = np.unique(np.concatenate(seg_frames), return_inverse=True)
+            # the region of each unique frame (first row with that frame number, as unique_regions keeps the first)
+            order = np.argsort(regions[:, 0], kind="stable")
+            pos = np.searchsorted(regions[order, 0], uniq)
+            if (pos >= len(order)).any() or (regions[order[np.minimum(pos, len(order) - 1)], 0] != uniq).any():
+                raise ValueError("track {}: a segment names a frame the track has no region for".format(ti))
+            rows = regions[order[pos]]
+            if (rows[:, 3] <= 0).any() or (rows[:, 4] <= 0).any():
+                raise ValueError("track {}: a segment frame has an empty region".format(ti))
+            if (rows[:, 1] < 0).any() or (rows[:, 2] < 0).any() or (rows[:, 1] + rows[:, 3] > W).any() or (rows[:, 2] + rows[:, 4] > H).any():
+                raise ValueError("track {}: a region lies outside the {}x{} frame".format(ti, W, H))
+            smp = np.zeros(len(uniq), native.SAMPLE_DTYPE)
+            smp["frame"], smp["x"], smp["y"], smp["width"], smp["height"], smp["track"] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], ti
+            samp_parts.append(smp)
+            at = 0
+            for s in seg_frames:
+                idx = inverse[at : at + len(s)] + n_samples
+                at += len(s)
+                if len(s) == 0:
+                    continue
+                seg_rows.append(idx[pad_segment_samples(len(s), self.tiles, seed)])
+                seg_track.append(ti)
+            n_samples += len(uniq)
+        cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
+        seg = np.asarray(seg_rows, dtype=np.int32).reshape(-1, self.tiles)
+        return cat(lim_parts, native.SAMPLE_DTYPE), cat(samp_parts, native.SAMPLE_DTYPE), seg, np.asarray(seg_track, np.int32)
+
+    def run_tables(self, d_thermal, d_filtered, limit_regions, samples, segment_samples, n_tracks, crop_rectangle, out=None):
+        """Launch on prepared tables (host numpy or CUDA uint8/int32 tensors).  Returns the CUDA float32
+        tensor (n_segments, rows*size, per_row*size, 2) plus the device tables."""
+        torch = self.torch
+        ctx = self.ex.ctx
+        ctx.use_torch_stream()
+
+        def dev(a):
+            if isinstance(a, np.ndarray):
+                return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(self.device)
+            return a
+
+        n_lim = len(limit_regions) if isinstance(limit_regions, np.ndarray) else limit_regions.numel() // native.SAMPLE_DTYPE.itemsize
+        n_smp = len(samples) if isinstance(samples, np.ndarray) else samples.numel() // native.SAMPLE_DTYPE.itemsize
+        n_seg = segment_samples.shape[0]
+        d_lim, d_smp = dev(limit_regions), dev(samples)
+        d_seg = torch.from_numpy(np.ascontiguousarray(segment_samples, dtype=np.int32)).to(self.device) if isinstance(segment_samples, np.ndarray) else segment_samples
+        d_tracks = torch.empty((max(n_tracks, 1), native.TRACK_NORM_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        rows = (self.tiles + self.frames_per_row - 1) // self.frames_per_row
+        shape = (n_seg, rows * self.frame_size, self.frames_per_row * self.frame_size, 2)
+        d_out = None if out is None else out.get("segments")
+        if d_out is None or tuple(d_out.shape) != shape:
+            d_out = torch.empty(shape, dtype=torch.float32, device=self.device)
+            if out is not None:
+                out["segments"] = d_out
+        ctx.preprocess_limits(d_filtered, d_lim, n_lim, d_tracks, n_tracks)
+        ctx.preprocess_medians(d_thermal, d_smp, n_smp, d_tracks)
+        ctx.preprocess_segments(d_thermal, d_filtered, d_smp, d_tracks, d_seg, n_seg, self.tiles, self.frames_per_row,
+                                self.frame_size, crop_rectangle, self.preprocess_fn, d_out)
+        return dict(segments=d_out, tracks=d_tracks, samples=d_smp)
+
+    def run(self, d_thermal, d_filtered, tracks, crop_rectangle, seed=None, out=None):
+        lim, smp, seg, seg_track = self.build_tables(tracks, seed=seed)
+        res = self.run_tables(d_thermal, d_filtered, lim, smp, seg, len(tracks), crop_rectangle, out=out)
+        res["segment_track"] = seg_track
+        return res
+
+    @staticmethod
+    def tracks_numpy(t):
+        a = t.cpu().numpy()
+        return a.reshape(-1).view(native.TRACK_NORM_DTYPE)

@@ -1,0 +1,65 @@
+// cptrack_internal.cuh -- what the translation units behind the C ABI share: the context record,
+// error reporting and the CUDA_TRY macro.  Not part of the public interface (include/cptrack.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "cptrack_kernels.cuh"
+
+namespace cpt {
+
+char *error_buffer();  // thread local, 512 bytes (cptrack.cu)
+
+inline int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct HostWeightTable {
+    std::vector<double> w;
+    uint32_t *d_thr = nullptr;
+    int max_count = 0;
+    int has_bounds = 0;
+};
+
+}  // namespace cpt
+
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) return cpt::fail(CPT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct cpt_ctx {
+    int device = 0;
+    cpt::Geometry g{};
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    int num_sms = 0;
+    cpt::HostWeightTable tables[4];
+    float *scratch = nullptr;
+    size_t scratch_ctas = 0;
+    int *work_counter = nullptr;
+    long long *debug = nullptr;
+    // staging buffers of cpt_extract_batch_host
+    void *stage_frames[2] = {nullptr, nullptr};
+    size_t stage_frames_bytes = 0;
+    cpt_region *stage_regions[2] = {nullptr, nullptr};
+    cpt_frame_info *stage_info[2] = {nullptr, nullptr};
+    float *stage_filtered[2] = {nullptr, nullptr};
+    uint8_t *stage_labels[2] = {nullptr, nullptr};
+    size_t stage_out_frames = 0;
+    bool stage_has_filtered = false, stage_has_labels = false;
+    cpt_clip *d_clips = nullptr;
+    size_t d_clips_cap = 0;
+    cudaEvent_t ev_h2d[2], ev_compute[2], ev_d2h[2];
+    bool events = false;
+};
+

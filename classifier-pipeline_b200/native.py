@@ -51,6 +51,20 @@ class CptClip(ctypes.Structure):
     ]
 
 
+class CptSample(ctypes.Structure):
+    _fields_ = [
+        ("frame", ctypes.c_int64), ("x", ctypes.c_int32), ("y", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("height", ctypes.c_int32), ("track", ctypes.c_int32), ("median", ctypes.c_float),
+    ]
+
+
+class CptTrackNorm(ctypes.Structure):
+    _fields_ = [
+        ("filtered_min", ctypes.c_float), ("filtered_max", ctypes.c_float), ("clip_at_zero", ctypes.c_int32),
+        ("has_limits", ctypes.c_int32),
+    ]
+
+
 class CptOutputs(ctypes.Structure):
     _fields_ = [
         ("d_regions", ctypes.c_void_p), ("d_info", ctypes.c_void_p), ("d_filtered", ctypes.c_void_p),
@@ -73,6 +87,12 @@ CLIP_DTYPE = np.dtype(
      ("first_frame", "<i4"), ("ring_frames", "<i4"), ("background_thresh", "<i4"), ("weight_table", "<i4"),
      ("flags", "<u4")]
 )
+SAMPLE_DTYPE = np.dtype(
+    [("frame", "<i8"), ("x", "<i4"), ("y", "<i4"), ("width", "<i4"), ("height", "<i4"), ("track", "<i4"), ("median", "<f4")]
+)
+TRACK_NORM_DTYPE = np.dtype([("filtered_min", "<f4"), ("filtered_max", "<f4"), ("clip_at_zero", "<i4"), ("has_limits", "<i4")])
+assert SAMPLE_DTYPE.itemsize == ctypes.sizeof(CptSample) == 32
+assert TRACK_NORM_DTYPE.itemsize == ctypes.sizeof(CptTrackNorm) == 16
 assert REGION_DTYPE.itemsize == ctypes.sizeof(CptRegion) == 40
 assert INFO_DTYPE.itemsize == ctypes.sizeof(CptFrameInfo) == 64
 assert CLIP_DTYPE.itemsize == ctypes.sizeof(CptClip) == 48
@@ -101,6 +121,12 @@ SYMBOLS = {
     "cpt_extract_batch_host": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _i]),
     "cpt_background_process": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
     "cpt_frame_medians": (_i, [_vp, _vp, _i64, _vp]),
+    "cpt_preprocess_limits": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "cpt_preprocess_medians": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "cpt_preprocess_segments": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "cpt_minmax_f32": (_i, [_vp, _vp, _i64, _vp]),
+    "cpt_normalize_f32": (_i, [_vp, _vp, _i64, _d, _d, _d, _i, _vp]),
+    "cpt_resize_pad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "cpt_state_read": (_i, [_vp, _vp, _i, _vp, _vp, ctypes.POINTER(_d), _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cpt_state_write": (_i, [_vp, _vp, _i, _vp, _vp, _d]),
     "cpt_weight_value": (_d, [_vp, _i, _i]),
@@ -210,6 +236,29 @@ class Context:
 
     def frame_medians(self, d_frames, n_frames, d_medians):
         check(self.lib.cpt_frame_medians(self._h, _ptr(d_frames), int(n_frames), _ptr(d_medians)))
+
+    def preprocess_limits(self, d_filtered, d_regions, n_regions, d_tracks, n_tracks):
+        check(self.lib.cpt_preprocess_limits(self._h, _ptr(d_filtered), _ptr(d_regions), int(n_regions), _ptr(d_tracks), int(n_tracks)))
+
+    def preprocess_medians(self, d_thermal, d_samples, n_samples, d_tracks):
+        check(self.lib.cpt_preprocess_medians(self._h, _ptr(d_thermal), _ptr(d_samples), int(n_samples), _ptr(d_tracks)))
+
+    def preprocess_segments(self, d_thermal, d_filtered, d_samples, d_tracks, d_segment_samples, n_segments, tiles, per_row,
+                            frame_size, crop_rectangle, preprocess_fn, d_out):
+        crop = None if crop_rectangle is None else (ctypes.c_int32 * 4)(*[int(v) for v in crop_rectangle])
+        check(self.lib.cpt_preprocess_segments(
+            self._h, _ptr(d_thermal), _ptr(d_filtered), _ptr(d_samples), _ptr(d_tracks), _ptr(d_segment_samples), int(n_segments),
+            int(tiles), int(per_row), int(frame_size), crop, int(preprocess_fn), _ptr(d_out)))
+
+    def minmax_f32(self, d_in, n, d_out2):
+        check(self.lib.cpt_minmax_f32(self._h, _ptr(d_in), int(n), _ptr(d_out2)))
+
+    def normalize_f32(self, d_in, n, mn, mx, new_max, use_f64, d_out):
+        check(self.lib.cpt_normalize_f32(self._h, _ptr(d_in), int(n), float(mn), float(mx), float(new_max), int(use_f64), _ptr(d_out)))
+
+    def resize_pad_f32(self, d_src, sw, sh, fw, fh, ox, oy, dw, dh, pad, interpolation, d_out):
+        check(self.lib.cpt_resize_pad_f32(self._h, _ptr(d_src), int(sw), int(sh), int(fw), int(fh), int(ox), int(oy), int(dw),
+                                          int(dh), float(pad), int(interpolation), _ptr(d_out)))
 
     def state_read(self, d_state, clip_index=0, sliding_sum=False):
         bg = np.empty((self.height, self.width), np.int32)

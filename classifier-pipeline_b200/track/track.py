@@ -501,10 +501,14 @@ class Track:
                 out.append(SegmentHeader(self.clip_id, self._id, start_frame=start_frame, frames=len(frames), weight=1,
                                          mass=np.sum(masses[rel]), label=None, regions=regions[rel], frame_indices=frames))
             return out
-        return get_segments(self.clip_id, self._id, start_frame, segment_frame_spacing=segment_frame_spacing,
-                            segment_width=segment_width, regions=regions, ffc_frames=ffc_frames, repeats=repeats,
-                            min_frames=min_frames, max_segments=max_segments, dont_filter=dont_filter,
-                            min_segments=min_segments, seed=seed)
+        from ..ml_tools.segments import SegmentType
+
+        segments, _ = get_segments(self.clip_id, self._id, start_frame, segment_frame_spacing=segment_frame_spacing,
+                                   segment_width=segment_width, regions=regions, ffc_frames=ffc_frames, repeats=repeats,
+                                   min_frames=min_frames,
+                                   segment_types=[SegmentType.ALL_RANDOM] if segment_types is None else segment_types,
+                                   max_segments=max_segments, dont_filter=dont_filter, min_segments=min_segments, seed=seed)
+        return segments
 
     # ------------------------------------------------------------------ (de)serialisation
     def start_and_end_in_secs(self):

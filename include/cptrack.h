@@ -156,6 +156,56 @@ int cpt_background_process(cpt_ctx *ctx, void *d_state, const int32_t *d_record_
  * Interpreter.preprocess_segments, ml_tools/interpreter.py:389).  d_medians float32 [n_frames]. */
 int cpt_frame_medians(cpt_ctx *ctx, const uint16_t *d_frames, int64_t n_frames, float *d_medians);
 
+/* ---- classifier-input preprocessing: Interpreter.preprocess_segments (ml_tools/interpreter.py:365-474) ----
+ * One cpt_sample per unique (track, frame) region, one cpt_track_norm per track.  Frames are addressed by
+ * their index in the uint16 thermal buffer and the float32 filtered buffer of an extraction
+ * (cpt_outputs.d_filtered), both [n_frames][H][W]. */
+typedef struct {
+    int64_t frame;               /* frame index into d_thermal / d_filtered */
+    int32_t x, y, width, height; /* Region bounds (track/region.py), inside the frame, width/height >= 1 */
+    int32_t track;               /* row of the cpt_track_norm table */
+    float median;                /* np.median(frame.thermal) (interpreter.py:389), written by cpt_preprocess_medians */
+} cpt_sample;
+
+typedef struct {
+    float filtered_min, filtered_max; /* Interpreter.get_limits with diff_norm (interpreter.py:315-363) */
+    int32_t clip_at_zero;             /* clip_thermals_at_zero (interpreter.py:391-399) */
+    int32_t has_limits;               /* 0: the track had no usable region, normalise by the tile's own minimum */
+} cpt_track_norm;
+
+/* get_limits: resets all n_tracks rows (min unset, max 0, clip_at_zero 1), then folds the min / max of
+ * region.subimage(frame.filtered) of every entry of d_regions (all non-blank regions of each track). */
+int cpt_preprocess_limits(cpt_ctx *ctx, const float *d_filtered, const cpt_sample *d_regions, int n_regions,
+                          cpt_track_norm *d_tracks, int n_tracks);
+/* Pass 1 of preprocess_segments over the unique track-frames: fills sample.median and clears the track's
+ * clip_at_zero when np.median(region.subimage(thermal) - median) <= 0. */
+int cpt_preprocess_medians(cpt_ctx *ctx, const uint16_t *d_thermal, cpt_sample *d_samples, int n_samples,
+                           cpt_track_norm *d_tracks);
+/* Pass 2 + preprocess_movement (ml_tools/preprocess.py:56-113,151-202; imageprocessing.py:11-104): every
+ * segment is tiles_per_segment sample indices (d_segment_samples [n_segments][tiles_per_segment], already padded
+ * and sorted as preprocess_movement does); tile i lands in row i / frames_per_row, column i % frames_per_row of
+ * d_out [n_segments][rows*frame_size][frames_per_row*frame_size][2] float32 (channels thermal, filtered).
+ * crop_rectangle = {x, y, width, height} of Clip.crop_rectangle (keep_edge anchoring) or NULL;
+ * preprocess_fn 0 = none, 1 = x / 127.5 - 1 (interpreter.py:563-566). */
+int cpt_preprocess_segments(cpt_ctx *ctx, const uint16_t *d_thermal, const float *d_filtered, const cpt_sample *d_samples,
+                            const cpt_track_norm *d_tracks, const int32_t *d_segment_samples, int n_segments,
+                            int tiles_per_segment, int frames_per_row, int frame_size, const int32_t *crop_rectangle,
+                            int preprocess_fn, float *d_out);
+
+/* ---- ml_tools/imageprocessing.py helpers on single images (device buffers) ----
+ * normalize() (imageprocessing.py:151-169): cpt_minmax_f32 writes {min, max} of d_in to d_out2; cpt_normalize_f32
+ * computes new_max * (float32(data) - min) / (max - min) (max == min: zeros if max == 0, else data / max) in fp32
+ * (d_out float32) or, with use_f64, in fp64 on the fp32-rounded data (d_out float64) -- numpy picks one or the
+ * other from the operand types; the host mirror makes that choice. */
+int cpt_minmax_f32(cpt_ctx *ctx, const float *d_in, int64_t n, float *d_out2);
+int cpt_normalize_f32(cpt_ctx *ctx, const float *d_in, int64_t n, double min, double max, double new_max, int use_f64,
+                      void *d_out);
+/* resize_and_pad() / resize_cv() (imageprocessing.py:11-82): cv2.resize of the src_w x src_h float32 image to
+ * resized_w x resized_h (interpolation 1 = INTER_LINEAR, 0 = INTER_NEAREST), pasted at (offset_x, offset_y) into an
+ * out_w x out_h image filled with pad. */
+int cpt_resize_pad_f32(cpt_ctx *ctx, const float *d_src, int src_w, int src_h, int resized_w, int resized_h, int offset_x,
+                       int offset_y, int out_w, int out_h, float pad, int interpolation, float *d_out);
+
 /* State access for WeightedBackground.background / .background_weight / .average
  * (motiondetector.py:178-248).  h_background int32 [H][W]; h_weight_count uint16 [(H-2e)][(W-2e)]
  * (background_weight = table[count]); h_average double. Any output may be NULL. */
