@@ -65,6 +65,14 @@ class CptTrackNorm(ctypes.Structure):
     ]
 
 
+class CptMotionResult(ctypes.Structure):
+    _fields_ = [("average", ctypes.c_double), ("diff", ctypes.c_int32), ("error", ctypes.c_int32),
+                ("mean_frames", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+MOTION_MEAN, MOTION_MEAN_RESTART, MOTION_BACKGROUND, MOTION_DETECT, MOTION_WARMER_ONLY, MOTION_ONE_DIFF = 1, 2, 4, 8, 16, 32
+
+
 class CptOutputs(ctypes.Structure):
     _fields_ = [
         ("d_regions", ctypes.c_void_p), ("d_info", ctypes.c_void_p), ("d_filtered", ctypes.c_void_p),
@@ -127,6 +135,11 @@ SYMBOLS = {
     "cpt_minmax_f32": (_i, [_vp, _vp, _i64, _vp]),
     "cpt_normalize_f32": (_i, [_vp, _vp, _i64, _d, _d, _d, _i, _vp]),
     "cpt_resize_pad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "cpt_motion_open": (_vp, [_vp, _i, _i, _i, _i]),
+    "cpt_motion_close": (None, [_vp]),
+    "cpt_motion_store": (_i, [_vp, _vp, _i]),
+    "cpt_motion_mean_init": (_i, [_vp, _vp, _i]),
+    "cpt_motion_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_uint32, _i, _d, ctypes.POINTER(CptMotionResult)]),
     "cpt_state_read": (_i, [_vp, _vp, _i, _vp, _vp, ctypes.POINTER(_d), _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cpt_state_write": (_i, [_vp, _vp, _i, _vp, _vp, _d]),
     "cpt_weight_value": (_d, [_vp, _i, _i]),

@@ -137,10 +137,12 @@ class WeightedBackground:
         self._init_average = init_average
 
     # ------------------------------------------------------------------ device state
-    def invalidate(self):
-        """Call after a kernel has written ``d_state`` (the extractor does)."""
+    def invalidate(self, average=None):
+        """Call after a kernel has written ``d_state`` (the extractor and the motion detector do);
+        ``average`` is the new average when the kernel already returned it (saves a state read)."""
         self._cache = None
         self._initialised = True
+        self._known_average = average
 
     def _read(self):
         if self._cache is None:
@@ -175,7 +177,8 @@ class WeightedBackground:
             if self._init_average is None:
                 raise AttributeError("average")
             return self._init_average
-        avg = float(self._read()["average"])
+        known = getattr(self, "_known_average", None)
+        avg = float(known) if known is not None else float(self._read()["average"])
         # np.average(frame) after the first call, int(round(.)) once the background has changed
         # (motiondetector.py:210,232): integral values are handed back as Python ints
         return int(avg) if avg.is_integer() else avg
@@ -198,6 +201,7 @@ class WeightedBackground:
         self.ctx.background_process(self.d_state, self._d_frame, self.weight_slot)
         self._cache = None
         self._initialised = True
+        self._known_average = None
 
     def set_background_edges(self):
         """Edges are replicated on the device whenever the background changes; nothing to do."""

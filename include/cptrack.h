@@ -206,6 +206,38 @@ int cpt_normalize_f32(cpt_ctx *ctx, const float *d_in, int64_t n, double min, do
 int cpt_resize_pad_f32(cpt_ctx *ctx, const float *d_src, int src_w, int src_h, int resized_w, int resized_h, int offset_x,
                        int offset_y, int out_w, int out_h, float pad, int interpolation, float *d_out);
 
+/* ---- CPTVMotionDetector (piclassifier/cptvmotiondetector.py:14-205), streaming, one launch per frame ----
+ * The detector owns a ring of the last ring_frames frames (SlidingWindow of preview_secs * fps + 1 frames), the
+ * uint32 running sum (RunningMean over mean_frames = 45) and, for one_diff_only == False, a ring of diff_frames
+ * clamped delta frames.  Ring bookkeeping (which slot is newest / oldest / oldest non-FFC) stays on the host. */
+typedef struct cpt_motion cpt_motion;
+#define CPT_MOTION_MEAN 1u          /* RunningMean.add(new, oldest) (motiondetector.py:166-172) */
+#define CPT_MOTION_MEAN_RESTART 2u  /* start the running sum from this frame alone */
+#define CPT_MOTION_BACKGROUND 4u    /* WeightedBackground.process_frame(running_mean.mean()) (cptvmotiondetector.py:152-153) */
+#define CPT_MOTION_DETECT 8u        /* detect() (cptvmotiondetector.py:74-120) */
+#define CPT_MOTION_WARMER_ONLY 16u  /* config.warmer_only */
+#define CPT_MOTION_ONE_DIFF 32u     /* config.one_diff_only */
+typedef struct {
+    double average;      /* WeightedBackground.average after this frame == temp_thresh */
+    int32_t diff;        /* pixels over the delta threshold (compare with count_thresh on the host) */
+    int32_t error;       /* 1: running mean left the uint16 range */
+    int32_t mean_frames; /* RunningMean.running_mean_frames */
+    int32_t reserved;
+} cpt_motion_result;
+cpt_motion *cpt_motion_open(cpt_ctx *ctx, int ring_frames, int mean_frames, int diff_frames, int weight_slot);
+void cpt_motion_close(cpt_motion *m);
+/* SlidingWindow.update_current_frame / add without processing: host frame -> ring slot. */
+int cpt_motion_store(cpt_motion *m, const uint16_t *h_pix, int slot);
+/* RunningMean(frames, window) from the listed ring slots (first processed frame after frames were only stored). */
+int cpt_motion_mean_init(cpt_motion *m, const int32_t *h_slots, int n);
+/* One process_frame: copies h_pix into ring slot slot_new, runs the fused step on the ctx stream, waits and
+ * returns the result.  d_background_state is the WeightedBackground state record (cpt_state_bytes) the detector
+ * shares with the streaming extractor; slot_oldest = SlidingWindow.oldest (-1: none); slot_nonffc / diff_slot_old =
+ * the oldest non-FFC entries of the two rings (diff_slot_old -1: fewer than 3 frames processed). */
+int cpt_motion_step(cpt_motion *m, const uint16_t *h_pix, void *d_background_state, int slot_new, int slot_oldest,
+                    int slot_nonffc, int diff_slot_new, int diff_slot_old, uint32_t flags, int delta_thresh,
+                    double init_average, cpt_motion_result *h_result);
+
 /* State access for WeightedBackground.background / .background_weight / .average
  * (motiondetector.py:178-248).  h_background int32 [H][W]; h_weight_count uint16 [(H-2e)][(W-2e)]
  * (background_weight = table[count]); h_average double. Any output may be NULL. */
