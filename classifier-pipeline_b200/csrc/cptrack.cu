@@ -121,6 +121,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     cudaFree(c->work_counter);
     cudaFree(c->debug);
     cudaFree(c->d_clips);
+    cudaFree(c->detect_scratch);
     free_stage(c);
     if (c->events)
         for (int i = 0; i < 2; ++i) {

@@ -61,5 +61,8 @@ struct cpt_ctx {
     size_t d_clips_cap = 0;
     cudaEvent_t ev_h2d[2], ev_compute[2], ev_d2h[2];
     bool events = false;
+    // scratch of cpt_detect_objects_u8 (grown on demand)
+    void *detect_scratch = nullptr;
+    size_t detect_scratch_bytes = 0;
 };
 

@@ -135,6 +135,7 @@ SYMBOLS = {
     "cpt_minmax_f32": (_i, [_vp, _vp, _i64, _vp]),
     "cpt_normalize_f32": (_i, [_vp, _vp, _i64, _d, _d, _d, _i, _vp]),
     "cpt_resize_pad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "cpt_detect_objects_u8": (_i, [_vp, _vp, _i, _i, _d, _i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cpt_motion_open": (_vp, [_vp, _i, _i, _i, _i]),
     "cpt_motion_close": (None, [_vp]),
     "cpt_motion_store": (_i, [_vp, _vp, _i]),
@@ -272,6 +273,13 @@ class Context:
     def resize_pad_f32(self, d_src, sw, sh, fw, fh, ox, oy, dw, dh, pad, interpolation, d_out):
         check(self.lib.cpt_resize_pad_f32(self._h, _ptr(d_src), int(sw), int(sh), int(fw), int(fh), int(ox), int(oy), int(dw),
                                           int(dh), float(pad), int(interpolation), _ptr(d_out)))
+
+    def detect_objects_u8(self, d_image, width, height, threshold, blur_ksize, close, max_components, d_labels, d_stats, d_centroids):
+        n = ctypes.c_int32()
+        check(self.lib.cpt_detect_objects_u8(self._h, _ptr(d_image), int(width), int(height), float(threshold), int(blur_ksize),
+                                             int(close), int(max_components), _ptr(d_labels), _ptr(d_stats), _ptr(d_centroids),
+                                             ctypes.byref(n)))
+        return n.value
 
     def state_read(self, d_state, clip_index=0, sliding_sum=False):
         bg = np.empty((self.height, self.width), np.int32)

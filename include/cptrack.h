@@ -206,6 +206,16 @@ int cpt_normalize_f32(cpt_ctx *ctx, const float *d_in, int64_t n, double min, do
 int cpt_resize_pad_f32(cpt_ctx *ctx, const float *d_src, int src_w, int src_h, int resized_w, int resized_h, int offset_x,
                        int offset_y, int out_w, int out_h, float pad, int interpolation, float *d_out);
 
+/* detect_objects() (imageprocessing.py:240-248) on one uint8 image of any size: GaussianBlur (blur_ksize 5, or 0
+ * for none) -> threshold (src > floor(threshold)) -> morphologyEx CLOSE with a tuple kernel (close != 0; OpenCV turns
+ * the tuple into a 2x1 element) -> connectedComponentsWithStats (8-connectivity, OpenCV label numbering).
+ * d_labels int32 [H][W]; d_stats int32 [max_components + 1][5] = left, top, width, height, area; d_centroids double
+ * [max_components + 1][2]; row 0 is the background.  *h_count = number of labels including the background.
+ * Synchronises the ctx stream. */
+int cpt_detect_objects_u8(cpt_ctx *ctx, const uint8_t *d_image, int width, int height, double threshold, int blur_ksize,
+                          int close, int max_components, int32_t *d_labels, int32_t *d_stats, double *d_centroids,
+                          int32_t *h_count);
+
 /* ---- CPTVMotionDetector (piclassifier/cptvmotiondetector.py:14-205), streaming, one launch per frame ----
  * The detector owns a ring of the last ring_frames frames (SlidingWindow of preview_secs * fps + 1 frames), the
  * uint32 running sum (RunningMean over mean_frames = 45) and, for one_diff_only == False, a ring of diff_frames

@@ -109,3 +109,39 @@ def _approx(v, rel):
     import pytest
 
     return pytest.approx(v, rel=rel, abs=1e-4)
+
+
+def track_clip_from_golden(name):
+    """Host tracker (H1-H3) over the C oracle's component lists for a golden clip; returns the Clip.
+    No GPU involved: the device calls of the extractor are stubbed (used by the CPU sharding test)."""
+    from classifier_pipeline_b200.config import Config
+    from classifier_pipeline_b200.track import cliptrackextractor as cte
+    from classifier_pipeline_b200.track.clip import Clip
+    from classifier_pipeline_b200.track.track import Track
+    from oracle import oracle as orc
+    from tests import helpers
+
+    class NoBackground:
+        weight_add = 0.1
+        initialised = True
+
+        def process_frame(self, frame):
+            pass
+
+    d, meta = helpers.load_golden(name)
+    init, tracked = helpers.clip_input(name)
+    o = orc.extract_clip(tracked, init, orc.make_params(background_thresh=meta["background_thresh"], weight_add=meta["weight_add"], max_comp=64))
+    config = Config.get_defaults()
+    config.tracking["thermal"].denoise = False
+    ext = cte.ClipTrackExtractor(config.tracking, False, cache_to_disk=False, calc_stats=False)
+    ext._new_background = lambda clip: NoBackground()
+    ext.reader_factory = lambda path: MemReader(tracked, meta["camera_model"])
+    clip = Clip(config.tracking["thermal"], name)
+    ext.init_clip(clip)
+    res = oracle_result(o, len(tracked))
+    Track._track_id = 1
+    reader = ext.reader_factory(name)
+    for t, frame in enumerate(iter(reader.next_frame, None)):
+        ext._consume_frame(clip, frame, res, t)
+    ext.apply_track_filtering(clip)
+    return clip
