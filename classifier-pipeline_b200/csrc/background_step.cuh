@@ -48,6 +48,7 @@ __device__ __forceinline__ void background_step(const Geometry &g, uint8_t *st_r
     if (lane == 0) red_sum[warp] = sum;
     if (changed) *red_changed = 1;
     __syncthreads();
+    if (tid == 0 && !first) hdr->frames_seen += 1;  // number of updates applied (bounds the weight counters)
     const bool any_changed = first || *red_changed;
     if (any_changed) {
         // edges: clamp the coordinate into the crop rectangle (rows, then columns: motiondetector.py:239-244)

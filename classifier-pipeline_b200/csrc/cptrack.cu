@@ -45,8 +45,8 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
         fail(CPT_ERR_INVALID, "unsupported geometry %dx%d (need width%%8==0, width<=160, height<=120)", width, height);
         return nullptr;
     }
-    if (edge_pixels < 0 || 2 * edge_pixels >= std::min(width, height)) {
-        fail(CPT_ERR_INVALID, "bad edge_pixels %d", edge_pixels);
+    if (edge_pixels < 0 || edge_pixels > 1 || height < 4) {
+        fail(CPT_ERR_INVALID, "edge_pixels must be 0 or 1 (got %d) and height >= 4", edge_pixels);
         return nullptr;
     }
     if (max_regions < 1 || max_regions > CPT_MAX_COMPONENTS) {
@@ -67,6 +67,15 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     g.block_w = (width + 1) / 2; g.max_regions = max_regions;
     g.gpr_magic = ((1u << 17) + g.gpr - 1) / g.gpr;
     g.rw_magic = ((1u << 13) + g.row_words - 1) / g.row_words;
+    g.qpr = width / 4;
+    g.n_owned = (height - 2 * edge_pixels) * g.qpr;
+    g.qpr_magic = ((1u << 18) + g.qpr - 1) / g.qpr;
+    for (uint32_t q = 0; q < (uint32_t)(g.npx / 4); ++q)
+        if (((q * g.qpr_magic) >> 18) != q / (uint32_t)g.qpr) {
+            fail(CPT_ERR_INVALID, "internal: quad division constant is not exact for width %d", width);
+            delete c;
+            return nullptr;
+        }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         fail(CPT_ERR_CUDA, "cudaGetDeviceProperties failed");
@@ -198,7 +207,13 @@ int cpt_set_weight_table(cpt_ctx *c, int slot, double weight_add, int max_frames
     CUDA_TRY(cudaMemcpy(t.d_thr, thr.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
     t.max_count = max_frames;
     t.has_bounds = 0;
-    for (int k = 0; k < n; ++k) t.has_bounds |= (thr[k] >> 16) != 0;
+    t.max_bound = 0;
+    t.linear_upto = n;
+    for (int k = 0; k < n; ++k) {
+        t.has_bounds |= (thr[k] >> 16) != 0;
+        t.max_bound = std::max(t.max_bound, (int)(thr[k] >> 16));
+        if (t.linear_upto == n && thr[k] != (uint32_t)(k + 1)) t.linear_upto = k;
+    }
     return CPT_OK;
 }
 
@@ -298,11 +313,7 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     a.labels = out->d_labels;
     a.scratch = out->d_filtered ? nullptr : c->scratch;
     a.state = (uint8_t *)d_state;
-    for (int i = 0; i < 4; ++i) {
-        a.tables[i].thr = c->tables[i].d_thr;
-        a.tables[i].max_count = c->tables[i].max_count;
-        a.tables[i].has_bounds = c->tables[i].has_bounds;
-    }
+    for (int i = 0; i < 4; ++i) a.tables[i] = c->tables[i].device();
     a.work_counter = c->work_counter;
     a.debug = c->debug;
     CUDA_TRY(cudaMemsetAsync(c->work_counter, 0, sizeof(int), stream));
@@ -444,7 +455,7 @@ int cpt_background_process(cpt_ctx *c, void *d_state, const int32_t *d_record_in
         return fail(CPT_ERR_INVALID, "weight table slot %d is not set (cpt_set_weight_table)", weight_slot);
     if (n_records == 0) return CPT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
-    cpt::WeightTable wt{c->tables[weight_slot].d_thr, c->tables[weight_slot].max_count, c->tables[weight_slot].has_bounds};
+    cpt::WeightTable wt = c->tables[weight_slot].device();
     cpt::background_step_kernel<<<n_records, 1024, 0, c->stream>>>(c->g, (uint8_t *)d_state, d_frames, d_record_index, wt);
     CUDA_TRY(cudaGetLastError());
     return CPT_OK;

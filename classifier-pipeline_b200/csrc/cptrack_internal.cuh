@@ -26,6 +26,9 @@ struct HostWeightTable {
     uint32_t *d_thr = nullptr;
     int max_count = 0;
     int has_bounds = 0;
+    int max_bound = 0;
+    int linear_upto = 0;
+    cpt::WeightTable device() const { return cpt::WeightTable{d_thr, max_count, has_bounds, max_bound, linear_upto}; }
 };
 
 }  // namespace cpt

@@ -32,6 +32,7 @@ constexpr int kPWarps = kPThreads / 32;
 constexpr int kCThreads = kThreads - kPThreads; // 7 warps
 constexpr int kCWarps = kCThreads / 32;
 constexpr int kMaxPx = 19200;
+constexpr int kQIter = (kMaxPx / 4 + kPThreads - 1) / kPThreads;  // 6 quads of 4 pixels per pixel thread
 constexpr int kMaxW = 160;
 constexpr int kMaxH = 120;
 constexpr int kRowWords = kMaxW / 32;           // 5
@@ -54,6 +55,11 @@ struct Geometry {
     int max_regions;
     uint32_t gpr_magic;  // grp / gpr == (grp * gpr_magic) >> 17   (grp < 4096, gpr < 32)
     uint32_t rw_magic;   // w / row_words == (w * rw_magic) >> 13  (w < 1024, row_words < 8)
+    // quads of 4 pixels: the unit of the fused pixel sweep.  Rows edge .. H-1-edge are "owned"; the owner of
+    // the first / last owned row also produces the border rows above / below it.
+    int qpr;             // quads per row = W/4
+    int n_owned;         // (H - 2*edge) * qpr
+    uint32_t qpr_magic;  // q / qpr == (q * qpr_magic) >> 18   (q < 4800, qpr <= 40; verified at ctx creation)
 };
 
 // Per-clip persistent record in global memory (cpt_state_bytes()).
@@ -82,7 +88,9 @@ __host__ __device__ inline size_t state_bytes(int npx) {
 struct WeightTable {
     const uint32_t *thr;
     int max_count;
-    int has_bounds;  // some entry has a non-zero bound
+    int has_bounds;   // some entry has a non-zero bound
+    int max_bound;    // largest bound of the table: backgrounds >= max_bound never need the correction
+    int linear_upto;  // entries [0, linear_upto) are exactly thr = k + 1, bound = 0 (weight_add == 1)
 };
 constexpr int kSmemWeights = 1024;
 
@@ -115,16 +123,16 @@ struct __align__(16) Smem {
     int32_t c_key[kCompSlots], c_area[kCompSlots], c_sx[kCompSlots], c_sy[kCompSlots];
     int32_t c_l[kCompSlots], c_t[kCompSlots], c_r[kCompSlots], c_b[kCompSlots];
     uint8_t c_rank[kCompSlots];
-    uint32_t red_u[kWarps * 6];
+    uint32_t red_u[kWarps * 12];
     int32_t bcast_i[16];
     int32_t msg[2][4];         // pixel warps -> component warps, per mask buffer: filtered min, max
     double bcast_d[4];
     uint32_t hist[256];
     double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
     uint32_t wthr[kSmemWeights];                   // first entries of the clip's keep-test table
-    uint32_t need_u[kMaxH];   // per row: groups whose U is an input of a blur window that can exceed the threshold
-    uint32_t need_b[kMaxH];
-    uint32_t hotbits[kMaxPx / 8 / 32 + 3];  // one bit per 8-pixel group: some pixel can exceed the threshold   // per row: groups whose blurred output can exceed the threshold
+    unsigned long long need_u[kMaxH];  // per row, one bit per quad: U is an input of a blur window that can exceed the threshold
+    unsigned long long need_b[kMaxH];  // per row, one bit per quad: the blurred output can exceed the threshold
+    uint32_t hotbits[kMaxPx / 4 / 32 + 4];  // one bit per owned quad: some pixel can exceed the threshold
     int32_t ncomp;
 };
 

@@ -64,12 +64,6 @@ __device__ __forceinline__ const uint16_t *frame_ptr(const KernelArgs &a, const 
     return a.frames + (size_t)(c.frame_offset + idx) * a.g.npx;
 }
 
-// The sliding sum is kept as two planes (pixels 0-3 / 4-7 of every 8-pixel group) so that a warp's
-// 16-byte accesses are bank-conflict free: pixel px lives at s_index(px).
-__device__ __forceinline__ int s_index(int px, int npx) {
-    return ((px >> 2) & 1) * (npx >> 1) + (px >> 3) * 4 + (px & 3);
-}
-
 __device__ __forceinline__ float *filtered_ptr(const KernelArgs &a, const cpt_clip &c, float *scratch, int t) {
     // frame t's fp32 filtered image: the caller's output, or a 4-deep per-CTA ring (the pixel warps may
     // run two frames ahead of the component warps, which read frames t and t-1)
@@ -404,7 +398,7 @@ __device__ __forceinline__ void blur_threshold(Smem &s, const Geometry &g, int p
         uint32_t bits = 0;
         if (ith < 0) {
             bits = 0xffu;
-        } else if (ith < 255 && ((s.need_b[y] >> gx) & 1u)) {
+        } else if (ith < 255 && ((s.need_b[y] >> (2 * gx)) & 3ull)) {
             // (groups outside need_b cannot exceed the threshold: every input of their window is <= ith)
             uint32_t V[6] = {0, 0, 0, 0, 0, 0};
             const bool left_edge = (x0 == 0), right_edge = (x0 + 8 == W);
@@ -441,8 +435,182 @@ __device__ __forceinline__ void blur_threshold(Smem &s, const Geometry &g, int p
                 bits |= ((sum >> 16) >= T ? 1u : 0u) << (2 * q + 1);
             }
         }
+        if (ith >= 0) {
+            // outputs of a quad that is not marked cannot fire; their windows may reach inputs that were not refreshed
+            const uint32_t q2 = (uint32_t)(s.need_b[y] >> (2 * gx)) & 3u;
+            bits &= ((q2 & 1u) ? 0x0fu : 0u) | ((q2 & 2u) ? 0xf0u : 0u);
+        }
         M8[y * g.row_words * 4 + gx] = (uint8_t)bits;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused pixel sweep.  For every owned quad (4 pixels) in one pass over the on-chip state:
+//   [update]  WeightedBackground.process_frame for the PREVIOUS frame (K7): A = floor(S / cnt),
+//             keep = B < A - w_k (table form), B' = keep ? B : A, k' = keep ? k + 1 : 0
+//   [frame]   K1 for THIS frame against B': F = P - B', S += P - P_old, sum P, min / max F (+ K8 scalars),
+//             fp32 filtered store, label image zero fill
+// so B, k and S are read and written once per frame.  Border columns live inside owned quads and copy their
+// neighbour's B'; border rows are produced by the owner of the adjacent row (edge replication of
+// motiondetector.py:239-244 folded into the sweep).
+struct SweepMode {
+    bool update;      // apply the background update of the previous frame
+    bool frame;       // filter the current frame
+    bool slow;        // exact unpacked keep test (bounds / 16-bit overflow possible)
+    bool first_mean;  // cnt == 1: A = S
+    int table;        // 0: thr = k + 1, 1: table in shared memory, 2: table in global memory
+    uint32_t magic;   // floor(S / cnt) == umulhi(S, magic)
+};
+
+struct SweepAcc {
+    uint32_t psum = 0, bsum = 0, changed = 0, fabs_sum = 0;
+    uint32_t bmin2 = 0xffffffffu, bmax2 = 0;  // packed uint16 pairs
+    int fmin = INT32_MAX, fmax = INT32_MIN, pmin = INT32_MAX, pmax = INT32_MIN;
+};
+
+__device__ __forceinline__ uint2 ldg8(const void *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+
+// K1 + sliding sum + statistics of one quad against the packed background words nb (2 x 2 pixels)
+__device__ __forceinline__ int filter_quad(const uint16_t *P, const uint16_t *Pold, int p4, uint2 nb, uint32_t *S, float *fcur,
+                                           uint8_t *lab_frame, bool want_stats, SweepAcc &acc) {
+    const uint2 pw = ldg8(P + p4);
+    uint2 ow = make_uint2(0, 0);
+    if (Pold) ow = ldg8(Pold + p4);
+    uint4 sv = *reinterpret_cast<const uint4 *>(S + p4);
+    const int f0 = dp2a_us(pw.x, kLoP, dp2a_us(nb.x, kLoN, 0)), f1 = dp2a_us(pw.x, kHiP, dp2a_us(nb.x, kHiN, 0));
+    const int f2 = dp2a_us(pw.y, kLoP, dp2a_us(nb.y, kLoN, 0)), f3 = dp2a_us(pw.y, kHiP, dp2a_us(nb.y, kHiN, 0));
+    sv.x = (uint32_t)dp2a_us(pw.x, kLoP, dp2a_us(ow.x, kLoN, (int)sv.x));
+    sv.y = (uint32_t)dp2a_us(pw.x, kHiP, dp2a_us(ow.x, kHiN, (int)sv.y));
+    sv.z = (uint32_t)dp2a_us(pw.y, kLoP, dp2a_us(ow.y, kLoN, (int)sv.z));
+    sv.w = (uint32_t)dp2a_us(pw.y, kHiP, dp2a_us(ow.y, kHiN, (int)sv.w));
+    *reinterpret_cast<uint4 *>(S + p4) = sv;
+    acc.psum = (uint32_t)dp2a_us(pw.x, kBoth, dp2a_us(pw.y, kBoth, (int)acc.psum));
+    const int lo = min(min(f0, f1), min(f2, f3)), hi = max(max(f0, f1), max(f2, f3));
+    acc.fmin = min(acc.fmin, lo);
+    acc.fmax = max(acc.fmax, hi);
+    if (want_stats) {
+        const int p0 = (int)(pw.x & 0xffffu), p1 = (int)(pw.x >> 16), p2 = (int)(pw.y & 0xffffu), p3 = (int)(pw.y >> 16);
+        acc.pmin = min(acc.pmin, min(min(p0, p1), min(p2, p3)));
+        acc.pmax = max(acc.pmax, max(max(p0, p1), max(p2, p3)));
+        acc.fabs_sum += (uint32_t)(abs(f0) + abs(f1) + abs(f2) + abs(f3));
+    }
+    *reinterpret_cast<float4 *>(fcur + p4) = make_float4((float)f0, (float)f1, (float)f2, (float)f3);
+    if (lab_frame) *reinterpret_cast<uint32_t *>(lab_frame + p4) = 0u;
+    return hi;
+}
+
+// keep mask (0xffff per kept pixel) of one packed pair
+__device__ __forceinline__ uint32_t keep_pair(uint32_t b2, uint32_t k2, uint32_t A0, uint32_t A1, const SweepMode &m,
+                                               const uint32_t *smem_table, const WeightTable &wt) {
+    uint32_t e0 = 0, e1 = 0;
+    if (m.table == 1) { e0 = smem_table[k2 & 0xffffu]; e1 = smem_table[k2 >> 16]; }
+    else if (m.table == 2) { e0 = __ldg(wt.thr + (k2 & 0xffffu)); e1 = __ldg(wt.thr + (k2 >> 16)); }
+    if (!m.slow) {
+        // packed: keep <=> A >= B + thr, no 16-bit overflow possible in this mode
+        const uint32_t thr2 = (m.table == 0) ? __vadd2(k2, 0x00010001u) : __byte_perm(e0, e1, 0x5410);
+        const uint32_t x2 = __vadd2(b2, thr2), a2 = A0 | (A1 << 16);
+        bool hi, lo;
+        (void)__vibmax_u16x2(a2, x2, &hi, &lo);  // predicates: a >= x per half
+        return (lo ? 0x0000ffffu : 0u) | (hi ? 0xffff0000u : 0u);
+    }
+    if (m.table == 0) { e0 = (k2 & 0xffffu) + 1u; e1 = (k2 >> 16) + 1u; }
+    const int b0 = (int)(b2 & 0xffffu), b1 = (int)(b2 >> 16);
+    const int t0 = (int)(e0 & 0xffffu) - ((b0 < (int)(e0 >> 16)) ? 1 : 0);
+    const int t1 = (int)(e1 & 0xffffu) - ((b1 < (int)(e1 >> 16)) ? 1 : 0);
+    return (((int)A0 - b0 >= t0) ? 0x0000ffffu : 0u) | (((int)A1 - b1 >= t1) ? 0xffff0000u : 0u);
+}
+
+__device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const WeightTable &wt, int ptid, const SweepMode m,
+                                            const uint16_t *P, const uint16_t *Pold, const uint16_t *Pnext,
+                                            const uint16_t *Pold_next, float *fcur, uint8_t *lab_frame, bool want_stats,
+                                            SweepAcc &acc, int (&gmaxq)[kQIter]) {
+    const Geometry &g = a.g;
+    const int W = g.W, H = g.H, e = g.edge;
+#pragma unroll
+    for (int it = 0; it < kQIter; ++it) {
+        const int q = it * kPThreads + ptid;
+        gmaxq[it] = INT32_MIN;
+        if (q >= g.n_owned) continue;
+        const int yo = (int)(((uint32_t)q * g.qpr_magic) >> 18), qx = q - yo * g.qpr;
+        const int y = yo + e, p4 = y * W + qx * 4;
+        if (m.frame && (qx & 15) == 0) {  // one 128-byte line per 16 quads: pull the next frame towards L2
+            if (Pnext) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pnext + p4));
+            if (Pold_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pold_next + p4));
+        }
+        const uint2 bw = *reinterpret_cast<const uint2 *>(s.B + p4);
+        uint2 nb = bw;
+        if (m.update) {
+            const uint2 kw = *reinterpret_cast<const uint2 *>(s.K + p4);
+            const uint4 sv = *reinterpret_cast<const uint4 *>(s.S + p4);
+            const uint32_t A0 = m.first_mean ? sv.x : __umulhi(sv.x, m.magic), A1 = m.first_mean ? sv.y : __umulhi(sv.y, m.magic);
+            const uint32_t A2 = m.first_mean ? sv.z : __umulhi(sv.z, m.magic), A3 = m.first_mean ? sv.w : __umulhi(sv.w, m.magic);
+            const uint32_t keep_x = keep_pair(bw.x, kw.x, A0, A1, m, s.wthr, wt), keep_y = keep_pair(bw.y, kw.y, A2, A3, m, s.wthr, wt);
+            nb.x = (bw.x & keep_x) | ((A0 | (A1 << 16)) & ~keep_x);
+            nb.y = (bw.y & keep_y) | ((A2 | (A3 << 16)) & ~keep_y);
+            uint2 nk;
+            nk.x = __vadd2(kw.x, 0x00010001u) & keep_x;
+            nk.y = __vadd2(kw.y, 0x00010001u) & keep_y;
+            // crop-border columns copy their neighbour and do not count (motiondetector.py:239-244)
+            uint32_t cmask_x = 0xffffffffu, cmask_y = 0xffffffffu;
+            int sel_x = kBoth, sel_y = kBoth;
+            if (e) {
+                if (qx == 0) { nb.x = __byte_perm(nb.x, 0, 0x3232); cmask_x = 0xffff0000u; sel_x = kHiP; }
+                if (qx == g.qpr - 1) { nb.y = __byte_perm(nb.y, 0, 0x1010); cmask_y = 0x0000ffffu; sel_y = kLoP; }
+            }
+            acc.changed |= ((nb.x ^ bw.x) & cmask_x) | ((nb.y ^ bw.y) & cmask_y);
+            acc.bsum = (uint32_t)dp2a_us(nb.x, sel_x, dp2a_us(nb.y, sel_y, (int)acc.bsum));
+            *reinterpret_cast<uint2 *>(s.B + p4) = nb;
+            *reinterpret_cast<uint2 *>(s.K + p4) = nk;
+        }
+        acc.bmin2 = __vminu2(acc.bmin2, __vminu2(nb.x, nb.y));
+        acc.bmax2 = __vmaxu2(acc.bmax2, __vmaxu2(nb.x, nb.y));
+        int hi = INT32_MIN;
+        if (m.frame) hi = filter_quad(P, Pold, p4, nb, s.S, fcur, lab_frame, want_stats, acc);
+        if (e) {
+            // border rows take the adjacent owned row's background
+            if (yo == 0) {
+                const int pb = p4 - W;
+                if (m.update) *reinterpret_cast<uint2 *>(s.B + pb) = nb;
+                if (m.frame) hi = max(hi, filter_quad(P, Pold, pb, nb, s.S, fcur, lab_frame, want_stats, acc));
+            }
+            if (y == H - 2) {
+                const int pb = p4 + W;
+                if (m.update) *reinterpret_cast<uint2 *>(s.B + pb) = nb;
+                if (m.frame) hi = max(hi, filter_quad(P, Pold, pb, nb, s.S, fcur, lab_frame, want_stats, acc));
+            }
+        }
+        gmaxq[it] = hi;
+    }
+}
+
+// per-warp partial results -> s.red_u[warp * 12 + i]
+__device__ __forceinline__ void sweep_reduce_store(Smem &s, int lane, int warp, const SweepAcc &acc, bool want_stats) {
+    const uint32_t psum = __reduce_add_sync(0xffffffffu, acc.psum), bsum = __reduce_add_sync(0xffffffffu, acc.bsum);
+    const uint32_t changed = __reduce_or_sync(0xffffffffu, acc.changed);
+    const int fmin = __reduce_min_sync(0xffffffffu, acc.fmin), fmax = __reduce_max_sync(0xffffffffu, acc.fmax);
+    const uint32_t bmin = __reduce_min_sync(0xffffffffu, min(acc.bmin2 & 0xffffu, acc.bmin2 >> 16));
+    const uint32_t bmax = __reduce_max_sync(0xffffffffu, max(acc.bmax2 & 0xffffu, acc.bmax2 >> 16));
+    int pmin = 0, pmax = 0;
+    uint32_t fabs_sum = 0;
+    if (want_stats) {
+        pmin = __reduce_min_sync(0xffffffffu, acc.pmin);
+        pmax = __reduce_max_sync(0xffffffffu, acc.pmax);
+        fabs_sum = __reduce_add_sync(0xffffffffu, acc.fabs_sum);
+    }
+    if (lane == 0) {
+        uint32_t *r = s.red_u + warp * 12;
+        r[0] = psum; r[1] = (uint32_t)fmin; r[2] = (uint32_t)fmax; r[3] = (uint32_t)pmin; r[4] = (uint32_t)pmax; r[5] = fabs_sum;
+        r[6] = bsum; r[7] = changed; r[8] = bmin; r[9] = bmax;
+    }
+}
+
+// 40-bit row field of the owned-quad hot bits starting at bit `pos`
+__device__ __forceinline__ unsigned long long hot_field(const uint32_t *bits, int pos) {
+    const int w = pos >> 5, sh = pos & 31;
+    const unsigned long long lo = ((unsigned long long)bits[w + 1] << 32) | bits[w];
+    unsigned long long v = lo >> sh;
+    if (sh) v |= (unsigned long long)bits[w + 2] << (64 - sh);
+    return v;
 }
 
 __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int ptid, float *scratch,
@@ -457,7 +625,8 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     uint32_t *st_S = reinterpret_cast<uint32_t *>(st_K + npx);
     float *st_F = reinterpret_cast<float *>(st_S + npx);
     const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
-    constexpr int kIter = (kMaxPx / 8 + kPThreads - 1) / kPThreads;  // 3
+    const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
+    constexpr int kIter = (kMaxPx / 8 + kPThreads - 1) / kPThreads;  // 3: 8-pixel groups of sweep 2b / blur
 
     double average = 0.0;  // WeightedBackground.average: only lane 0 of pixel warp 0 uses it
     int prev_fmin = 0, prev_fmax = 0, have_prev = 0, frames_seen = 0;
@@ -467,17 +636,26 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
     if (ptid < kMaxH) { s.need_u[ptid] = 0; s.need_b[ptid] = 0; }
     if (clip.flags & CPT_CLIP_RESUME) {
+        if (ptid == 0) s.bcast_i[10] = 0;
+        bar_sync(BAR_P, kPThreads);
+        int kmax = 0;
         for (int i = ptid; i < npx; i += kPThreads) {
+            const uint16_t k = st_K[i];
             s.B[i] = st_B[i];
-            s.K[i] = st_K[i];
-            s.S[s_index(i, npx)] = st_S[i];
+            s.K[i] = k;
+            s.S[i] = st_S[i];
+            kmax = max(kmax, (int)k);
         }
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) atomicMax(&s.bcast_i[10], kmax);
         average = st_hdr->average;
         prev_fmin = st_hdr->prev_fmin;
         prev_fmax = st_hdr->prev_fmax;
         have_prev = st_hdr->have_prev;
-        frames_seen = st_hdr->frames_seen;
         bar_sync(BAR_P, kPThreads);
+        // the number of updates applied so far bounds every weight counter; the record may also have been
+        // advanced by the stand-alone background kernels, so trust the counters themselves as well
+        frames_seen = max(st_hdr->frames_seen, s.bcast_i[10]);
     } else {
         // WeightedBackground first call: motiondetector.py:199-212
         const uint16_t *init = a.frames + (size_t)clip.init_offset * npx;
@@ -501,134 +679,72 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         replicate_edges(s, g, ptid);
         bar_sync(BAR_P, kPThreads);
     }
+    if (ptid == 0) s.bcast_i[9] = 1;  // the first update of a launch takes the exact path (no background extrema yet)
+    bar_sync(BAR_P, kPThreads);
 
-    for (int t = 0; t < clip.n_frames; ++t) {
+    // t == n_frames is the tail pass: only the background update of the last frame
+    for (int t = 0; t <= clip.n_frames; ++t) {
         CPT_TICK_START(ptid == 0);
+        const bool is_frame = t < clip.n_frames;
         const int t_abs = clip.first_frame + t;
         const int buf = t & 1;
         const size_t o = (size_t)(clip.out_offset + t);
-        const uint16_t *P = frame_ptr(a, clip, t);
-        const uint16_t *Pold = (t_abs >= kMeanFrames) ? frame_ptr(a, clip, t - kMeanFrames) : nullptr;
-        float *fcur = filtered_ptr(a, clip, scratch, t);
-        uint8_t *lab_frame = a.labels ? a.labels + o * npx : nullptr;
-
-        // ------------------------------------------------------------ sweep 1 (K1, K7 sum, K8)
-        uint4 pv[kIter];
-        int gmaxf[kIter];
-        uint32_t psum = 0, fabs_sum = 0;
-        int fmin = INT32_MAX, fmax = INT32_MIN, pmin = INT32_MAX, pmax = INT32_MIN;
+        SweepMode m;
+        m.update = update_bg && t > 0;
+        m.frame = is_frame;
+        if (!m.update && !m.frame) break;
+        {
+            // the update belongs to frame t-1: the mean covers min(t_abs, 45) frames
+            const uint32_t cnt = (uint32_t)min(max(t_abs, 1), kMeanFrames);
+            m.first_mean = (cnt == 1u);
+            m.magic = m.first_mean ? 0u : (uint32_t)(0x100000000ull / cnt) + 1u;  // exact for S < 2^22, cnt <= 45
+            m.slow = s.bcast_i[9] != 0;
+            const int k_cap = frames_seen;  // no weight counter can exceed the number of updates so far
+            m.table = (k_cap < wt.linear_upto) ? 0 : ((k_cap < kSmemWeights) ? 1 : 2);
+        }
+        const uint16_t *P = is_frame ? frame_ptr(a, clip, t) : nullptr;
+        const uint16_t *Pold = (is_frame && t_abs >= kMeanFrames) ? frame_ptr(a, clip, t - kMeanFrames) : nullptr;
         const bool more = (t + 1 < clip.n_frames);
         const uint16_t *Pnext = more ? frame_ptr(a, clip, t + 1) : nullptr;
         const uint16_t *Pold_next = (more && t_abs + 1 >= kMeanFrames) ? frame_ptr(a, clip, t + 1 - kMeanFrames) : nullptr;
-#pragma unroll
-        for (int j = 0; j < kIter; ++j) {
-            int grp = ptid + j * kPThreads;
-            gmaxf[j] = INT32_MIN;
-            const unsigned active = __ballot_sync(0xffffffffu, grp < g.groups);  // groups is even: lane pairs stay together
-            if (grp < g.groups) {
-                pv[j] = ldg16(P + grp * 8);
-                uint4 qv = make_uint4(0, 0, 0, 0);
-#if defined(CPT_EXP) && CPT_EXP == 3
-                if (Pold && grp == 0x7fffffff)  // experiment: no P_old loads
-#else
-                if (Pold)
-#endif
-                    qv = ldg16(Pold + grp * 8);
-                if ((grp & 7) == 0) {  // one 128-byte line per 8 groups: pull the next frame into L2
-                    if (Pnext) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pnext + grp * 8));
-                    if (Pold_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pold_next + grp * 8));
-                }
-                const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
-                const uint32_t pw[4] = {pv[j].x, pv[j].y, pv[j].z, pv[j].w};
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-                const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
-                uint4 *sp0 = reinterpret_cast<uint4 *>(s.S + grp * 4), *sp1 = reinterpret_cast<uint4 *>(s.S + npx / 2 + grp * 4);
-                uint4 s0 = *sp0, s1 = *sp1;
-                int sv[8] = {(int)s0.x, (int)s0.y, (int)s0.z, (int)s0.w, (int)s1.x, (int)s1.y, (int)s1.z, (int)s1.w};
-                float f[8];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    // packed uint16 pairs straight into dp2a: F = P - B, S += P - P_old, sum P
-                    const int d0 = dp2a_us(pw[w], kLoP, dp2a_us(bw[w], kLoN, 0));
-                    const int d1 = dp2a_us(pw[w], kHiP, dp2a_us(bw[w], kHiN, 0));
-                    sv[2 * w] = dp2a_us(pw[w], kLoP, dp2a_us(qw[w], kLoN, sv[2 * w]));
-                    sv[2 * w + 1] = dp2a_us(pw[w], kHiP, dp2a_us(qw[w], kHiN, sv[2 * w + 1]));
-                    psum = (uint32_t)dp2a_us(pw[w], kBoth, (int)psum);
-                    fmin = min(fmin, min(d0, d1));
-                    gmaxf[j] = max(gmaxf[j], max(d0, d1));
-                    f[2 * w] = (float)d0;
-                    f[2 * w + 1] = (float)d1;
-                    if (want_stats) {
-                        const int p0 = (int)(pw[w] & 0xffffu), p1 = (int)(pw[w] >> 16);
-                        pmin = min(pmin, min(p0, p1));
-                        pmax = max(pmax, max(p0, p1));
-                        fabs_sum += abs(d0) + abs(d1);
-                    }
-                }
-                fmax = max(fmax, gmaxf[j]);
-                if (j == 0) CPT_TICK(ptid == 0, 13);  // sweep 1: first group computed (load latency)
-                {
-                    // lane pairs trade halves so that each 16-byte store instruction fills whole 32-byte sectors:
-                    // even lane: own[0:4] -> own group, then partner[0:4] -> partner group; odd lane: the upper halves
-                    const bool odd = lane & 1;
-                    float r[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) r[i] = __shfl_xor_sync(active, odd ? f[i] : f[4 + i], 1);
-                    float *own = fcur + grp * 8, *partner = fcur + (grp ^ 1) * 8;
-#if defined(CPT_EXP) && CPT_EXP == 1
-                    if (f[0] == 123456.f)  // experiment: no filtered stores
-#endif
-                    if (!odd) {
-                        *reinterpret_cast<float4 *>(own) = make_float4(f[0], f[1], f[2], f[3]);
-                        *reinterpret_cast<float4 *>(partner) = make_float4(r[0], r[1], r[2], r[3]);
-                    } else {
-                        *reinterpret_cast<float4 *>(partner + 4) = make_float4(r[0], r[1], r[2], r[3]);
-                        *reinterpret_cast<float4 *>(own + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                    }
-                }
-                if (lab_frame) *reinterpret_cast<uint2 *>(lab_frame + grp * 8) = make_uint2(0, 0);
-#if defined(CPT_EXP) && CPT_EXP == 2
-                if (sv[0] == 0x7fffffff)  // experiment: no sliding-sum stores
-#endif
-                {
-                *sp0 = make_uint4((uint32_t)sv[0], (uint32_t)sv[1], (uint32_t)sv[2], (uint32_t)sv[3]);
-                *sp1 = make_uint4((uint32_t)sv[4], (uint32_t)sv[5], (uint32_t)sv[6], (uint32_t)sv[7]);
-                }
-            }
-        }
-        CPT_TICK(ptid == 0, 14);  // sweep 1: all groups computed, stores issued
-        psum = __reduce_add_sync(0xffffffffu, psum);
-        fmin = __reduce_min_sync(0xffffffffu, fmin);
-        fmax = __reduce_max_sync(0xffffffffu, fmax);
-        if (want_stats) {
-            pmin = __reduce_min_sync(0xffffffffu, pmin);
-            pmax = __reduce_max_sync(0xffffffffu, pmax);
-            fabs_sum = __reduce_add_sync(0xffffffffu, fabs_sum);
-        }
-        if (lane == 0) {
-            s.red_u[warp * 6 + 0] = psum;
-            s.red_u[warp * 6 + 1] = (uint32_t)fmin;
-            s.red_u[warp * 6 + 2] = (uint32_t)fmax;
-            s.red_u[warp * 6 + 3] = (uint32_t)pmin;
-            s.red_u[warp * 6 + 4] = (uint32_t)pmax;
-            s.red_u[warp * 6 + 5] = fabs_sum;
-        }
+        float *fcur = is_frame ? filtered_ptr(a, clip, scratch, t) : nullptr;
+        uint8_t *lab_frame = (is_frame && a.labels) ? a.labels + o * npx : nullptr;
+
+        // ------------------------------------------------------------ fused sweep (K7 of frame t-1, K1/K8 of frame t)
+        SweepAcc acc;
+        int gmaxq[kQIter];
+        pixel_sweep(a, s, wt, ptid, m, P, Pold, Pnext, Pold_next, fcur, lab_frame, want_stats, acc, gmaxq);
+        CPT_TICK(ptid == 0, 14);  // sweep issued
+        sweep_reduce_store(s, lane, warp, acc, want_stats);
         bar_sync(BAR_P, kPThreads);
-        CPT_TICK(ptid == 0, 2);   // sweep 1 + barrier
-        // ------------------------------------------------------------ scalars (K2), pixel warp 0
+        CPT_TICK(ptid == 0, 2);   // sweep reduce + barrier
+        // ------------------------------------------------------------ scalars (K2, K7 average), pixel warp 0
         if (warp == 0) {
             const bool in = lane < kPWarps;
-            uint32_t v0 = __reduce_add_sync(0xffffffffu, in ? s.red_u[lane * 6 + 0] : 0u);
-            int v1 = __reduce_min_sync(0xffffffffu, in ? (int)s.red_u[lane * 6 + 1] : INT32_MAX);
-            int v2 = __reduce_max_sync(0xffffffffu, in ? (int)s.red_u[lane * 6 + 2] : INT32_MIN);
+            const uint32_t *r = s.red_u + lane * 12;
+            uint32_t v0 = __reduce_add_sync(0xffffffffu, in ? r[0] : 0u);
+            int v1 = __reduce_min_sync(0xffffffffu, in ? (int)r[1] : INT32_MAX);
+            int v2 = __reduce_max_sync(0xffffffffu, in ? (int)r[2] : INT32_MIN);
+            const uint32_t bsum = __reduce_add_sync(0xffffffffu, in ? r[6] : 0u);
+            const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? r[7] : 0u);
+            const uint32_t bmin = __reduce_min_sync(0xffffffffu, in ? r[8] : 0xffffffffu);
+            const uint32_t bmax = __reduce_max_sync(0xffffffffu, in ? r[9] : 0u);
             int v3 = 0, v4 = 0;
             uint32_t v5 = 0;
             if (want_stats) {
-                v3 = __reduce_min_sync(0xffffffffu, in ? (int)s.red_u[lane * 6 + 3] : INT32_MAX);
-                v4 = __reduce_max_sync(0xffffffffu, in ? (int)s.red_u[lane * 6 + 4] : INT32_MIN);
-                v5 = __reduce_add_sync(0xffffffffu, in ? s.red_u[lane * 6 + 5] : 0u);
+                v3 = __reduce_min_sync(0xffffffffu, in ? (int)r[3] : INT32_MAX);
+                v4 = __reduce_max_sync(0xffffffffu, in ? (int)r[4] : INT32_MIN);
+                v5 = __reduce_add_sync(0xffffffffu, in ? r[5] : 0u);
             }
             if (lane == 0) {
+                if (m.update && changed) average = rint((double)bsum / (double)g.ncrop);  // int(round(np.average(background))), motiondetector.py:232
+                // mode of the NEXT update: the packed keep test needs B + thr < 2^16 and no bound corrections
+                {
+                    const int k_next = min(frames_seen + 1, wt.max_count);
+                    const uint32_t thr_cap = (k_next < wt.linear_upto) ? (uint32_t)k_next + 1u : (__ldg(wt.thr + k_next) & 0xffffu);
+                    s.bcast_i[9] = (bmax + thr_cap > 65535u) || (wt.has_bounds && (int)bmin < wt.max_bound);
+                }
+                if (is_frame) {
                 // avg_change = int(round(np.average(thermal) - background average)), cliptracker.py:103-105
                 int ac;
                 const double avg_int = rint(average);
@@ -659,7 +775,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                         // ceil(2^shift / r): the fp64 quotient is within 2^-27 of the truth and the truth is
                         // either an integer or at least 1/r away from one, so ceil() of it is exact
                         magic = (uint32_t)ceil(ldexp(1.0, shift) / (double)r);
-                        // a group can only produce foreground if one of its pixels has U > floor(thr):
+                        // a quad can only produce foreground if one of its pixels has U > floor(thr):
                         // U = floor(255 v / r) >= ith + 1  <=>  v >= ceil((ith + 1) r / 255), v = max(F - ac, 0) - gmn,
                         // i.e. F >= fth (the bound is >= 1, so the clamp never matters)
                         int it = (int)floorf(thr);
@@ -677,10 +793,13 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 fi.abs_filtered_sum = v5; fi.thermal_median = 0.f;
                 fi.background_average = average; fi.reserved[0] = 0; fi.reserved[1] = 0;
                 a.info[o] = fi;
+                }
             }
         }
+        if (m.update) ++frames_seen;
         bar_sync(BAR_P, kPThreads);
         CPT_TICK(ptid == 0, 3);   // scalars + barrier
+        if (!is_frame) break;
         const int ac = s.bcast_i[0], gmn = s.bcast_i[1], gmx = s.bcast_i[2];
         const int cur_fmin = s.bcast_i[3], cur_fmax = s.bcast_i[4];
         const float thr = __int_as_float(s.bcast_i[5]);
@@ -689,43 +808,41 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         const int fth = s.bcast_i[8];
         const int ith = (int)floorf(thr);
 
-        // ------------------------------------------------------------ sweep 2a: hot groups
+        // ------------------------------------------------------------ hot quads
         // Blur weights sum to 256, so an output can exceed ith only if some input of its 5x5 window
-        // does.  Hot groups mark the outputs that may fire (rows +-2, neighbouring groups) and the
-        // inputs those outputs read (rows +-4, groups +-2); everything else skips K2/K4 arithmetic.
+        // does.  Hot quads mark the outputs that may fire (rows +-2, neighbouring quads) and the
+        // inputs those outputs read (rows +-4, quads +-2); everything else skips K2/K4 arithmetic.
+        // (a border row's quads count for the owned row next to them, which only widens the marks)
         const bool degenerate = (gmx == gmn);
         const bool no_fg = ith >= 255;
         const bool all_hot = (fth == INT32_MIN);
         if (!all_hot) {
 #pragma unroll
-            for (int j = 0; j < kIter; ++j) {
-                const int grp = ptid + j * kPThreads;
-                const unsigned m = __ballot_sync(0xffffffffu, grp < g.groups && gmaxf[j] >= fth);
-                if (lane == 0) s.hotbits[grp >> 5] = m;  // kPThreads is a multiple of 32: bit (grp & 31) of word grp >> 5
+            for (int it = 0; it < kQIter; ++it) {
+                const unsigned mbits = __ballot_sync(0xffffffffu, gmaxq[it] >= fth);  // unowned slots hold INT32_MIN
+                if (lane == 0) s.hotbits[it * kPWarps + warp] = mbits;  // bit (q & 31) of word q >> 5, q = it * kPThreads + ptid
             }
             bar_sync(BAR_P, kPThreads);
             if (ptid < g.H) {
-                // row ptid: OR the hot bits of the rows around it, then widen by the neighbouring groups
-                const uint32_t rowmask = (1u << g.gpr) - 1u;
-                uint32_t near2 = 0, near4 = 0;
+                const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
+                unsigned long long near2 = 0, near4 = 0;
                 for (int dy = -4; dy <= 4; ++dy) {
-                    const int yy = ptid + dy;
-                    if (yy < 0 || yy >= g.H) continue;
-                    const int base = yy * g.gpr;
-                    const uint32_t bits = __funnelshift_r(s.hotbits[base >> 5], s.hotbits[(base >> 5) + 1], base & 31) & rowmask;
+                    const int yy = ptid + dy - g.edge;  // owned-row index
+                    if (yy < 0 || yy >= g.H - 2 * g.edge) continue;
+                    const unsigned long long bits = hot_field(s.hotbits, yy * g.qpr) & rowmask;
                     near4 |= bits;
                     if (dy >= -2 && dy <= 2) near2 |= bits;
                 }
-                s.need_u[ptid] = near4 | (near4 << 1) | (near4 << 2) | (near4 >> 1) | (near4 >> 2);
-                s.need_b[ptid] = near2 | (near2 << 1) | (near2 >> 1);
+                s.need_u[ptid] = (near4 | (near4 << 1) | (near4 << 2) | (near4 >> 1) | (near4 >> 2)) & rowmask;
+                s.need_b[ptid] = (near2 | (near2 << 1) | (near2 >> 1)) & rowmask;
             }
         } else if (ptid < g.H) {
-            s.need_u[ptid] = 0xffffffffu;
-            s.need_b[ptid] = 0xffffffffu;
+            s.need_u[ptid] = ~0ull;
+            s.need_b[ptid] = ~0ull;
         }
         bar_sync(BAR_P, kPThreads);
-        CPT_TICK(ptid == 0, 4);   // sweep 2a + barrier
-        // ------------------------------------------------------------ sweep 2b: U (K2)
+        CPT_TICK(ptid == 0, 4);   // hot map + barrier
+        // ------------------------------------------------------------ sweep 2b: U (K2) for the marked groups
         if (!no_fg) {
             const float range_f = (float)gmx - (float)gmn;
             const uint32_t degen_val = (gmx == 0) ? 0u : 1u;
@@ -734,9 +851,10 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 int grp = ptid + j * kPThreads;
                 if (grp < g.groups) {
                     int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr;
-                    if (!((s.need_u[y] >> gx) & 1u)) continue;
+                    if (!((s.need_u[y] >> (2 * gx)) & 3ull)) continue;
+                    const uint4 pv = ldg16(P + grp * 8);  // just streamed: an L1 / L2 hit
                     const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
-                    const uint32_t pw[4] = {pv[j].x, pv[j].y, pv[j].z, pv[j].w};
+                    const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
                     const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
                     uint32_t u[8];
                     const int off = -ac;  // G - min = max(F - ac, 0) - gmn
@@ -769,106 +887,10 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         if (ptid == 0) { s.msg[buf][0] = cur_fmin; s.msg[buf][1] = cur_fmax; }
         bar_arrive(BAR_FULL + buf, kThreads);
         CPT_TICK(ptid == 0, 7);   // blur
-
-        // ------------------------------------------------------------ sweep 3: background (K7)
-        int any_changed = 0;
-        if (clip.flags & CPT_CLIP_UPDATE_BACKGROUND) {
-            const uint32_t cnt = (uint32_t)min(t_abs + 1, kMeanFrames);
-            // A = floor(S / cnt) == umulhi(S, 2^32/cnt + 1) for cnt >= 2: exact for S < 2^22, cnt <= 45
-            const bool first_frame = (cnt == 1u);
-            const uint32_t magic = first_frame ? 0u : (uint32_t)(0x100000000ull / cnt) + 1u;
-            const bool table_in_smem = (t_abs + 1 < kSmemWeights);  // k never exceeds the frames seen
-            uint32_t bsum = 0;
-            int changed = 0;
-#pragma unroll
-            for (int j = 0; j < kIter; ++j) {
-                int grp = ptid + j * kPThreads;
-                if (grp < g.groups) {
-                    int yy = (int)(((uint32_t)grp * g.gpr_magic) >> 17), x0 = (grp - yy * g.gpr) * 8;
-                    if (yy >= g.edge && yy < g.H - g.edge) {
-                        const int lo = max(g.edge - x0, 0), hi = min(W - g.edge - x0, 8);
-                        const uint32_t inc = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-                        const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
-                        const uint4 kv = *reinterpret_cast<const uint4 *>(s.K + grp * 8);
-                        const uint4 s0 = *reinterpret_cast<const uint4 *>(s.S + grp * 4);
-                        const uint4 s1 = *reinterpret_cast<const uint4 *>(s.S + npx / 2 + grp * 4);
-                        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-                        const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
-                        const uint32_t sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                        uint32_t nbw[4], nkw[4];
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            const int b0 = (int)(bw[w] & 0xffffu), b1 = (int)(bw[w] >> 16);
-                            const int k0 = (int)(kw[w] & 0xffffu), k1 = (int)(kw[w] >> 16);
-                            const int A0 = first_frame ? (int)sv[2 * w] : (int)__umulhi(sv[2 * w], magic);
-                            const int A1 = first_frame ? (int)sv[2 * w + 1] : (int)__umulhi(sv[2 * w + 1], magic);
-#if defined(CPT_EXP) && CPT_EXP == 4
-                            const uint32_t e0 = 1u + (k0 >> 4), e1 = 1u + (k1 >> 4);  // experiment: no table gather
-#else
-                            const uint32_t e0 = table_in_smem ? s.wthr[k0] : __ldg(wt.thr + k0);
-                            const uint32_t e1 = table_in_smem ? s.wthr[k1] : __ldg(wt.thr + k1);
-#endif
-                            int t0 = (int)(e0 & 0xffffu), t1 = (int)(e1 & 0xffffu);
-                            if (wt.has_bounds) {
-                                t0 -= (b0 < (int)(e0 >> 16)) ? 1 : 0;
-                                t1 -= (b1 < (int)(e1 >> 16)) ? 1 : 0;
-                            }
-                            // keep <=> A - B >= thr  <=>  thr + (B - A) - 1 < 0
-                            const int dd0 = b0 - A0, dd1 = b1 - A1;
-                            const uint32_t keep0 = (uint32_t)(t0 + dd0 - 1) >> 31, keep1 = (uint32_t)(t1 + dd1 - 1) >> 31;
-                            const uint32_t n0 = (uint32_t)(A0 + (int)keep0 * dd0), n1 = (uint32_t)(A1 + (int)keep1 * dd1);
-                            nbw[w] = n1 * 65536u + n0;
-                            const uint32_t kmask = keep0 * 0xffffu + keep1 * 0xffff0000u;
-                            nkw[w] = (kw[w] + 0x00010001u) & kmask;
-                        }
-                        if (inc != 0xffu) {
-                            // crop border columns inside this group keep their old state (they are rewritten by the
-                            // edge replication) and do not count
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                if (!((inc >> i) & 1u)) {
-                                    const uint32_t m = 0xffffu << (16 * (i & 1));
-                                    nbw[i >> 1] = (nbw[i >> 1] & ~m) | (bw[i >> 1] & m);
-                                    nkw[i >> 1] = (nkw[i >> 1] & ~m) | (kw[i >> 1] & m);
-                                    bsum -= (bw[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            changed |= (int)(nbw[w] ^ bw[w]);
-                            bsum = (uint32_t)dp2a_us(nbw[w], kBoth, (int)bsum);
-                        }
-#if defined(CPT_EXP) && CPT_EXP == 5
-                        if (nbw[0] == 0x12345678u)  // experiment: no B / K stores
-#endif
-                        {
-                        *reinterpret_cast<uint4 *>(s.B + grp * 8) = make_uint4(nbw[0], nbw[1], nbw[2], nbw[3]);
-                        *reinterpret_cast<uint4 *>(s.K + grp * 8) = make_uint4(nkw[0], nkw[1], nkw[2], nkw[3]);
-                        }
-                    }
-                }
-            }
-            bsum = __reduce_add_sync(0xffffffffu, bsum);
-            if (lane == 0) s.red_u[warp * 6] = bsum;
-            any_changed = bar_or(BAR_P, kPThreads, changed != 0);
-        } else {
-            bar_sync(BAR_P, kPThreads);
-        }
-        CPT_TICK(ptid == 0, 8);   // sweep 3 + barrier
-        if (any_changed) {
-            if (warp == 0) {
-                uint32_t v = __reduce_add_sync(0xffffffffu, (lane < kPWarps) ? s.red_u[lane * 6] : 0u);
-                average = rint((double)v / (double)g.ncrop);  // int(round(np.average(background))), motiondetector.py:232
-            }
-            replicate_edges(s, g, ptid);
-        }
         prev_fmin = cur_fmin;
         prev_fmax = cur_fmax;
         have_prev = 1;
-        ++frames_seen;
-        bar_sync(BAR_P, kPThreads);
-        CPT_TICK(ptid == 0, 9);   // edges + end barrier
+        // no barrier here: the next sweep touches B / K / S / red_u only, which nothing above still reads
     }
 
     // ---------------------------------------------------------------- save state
@@ -878,7 +900,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         for (int i = ptid; i < npx; i += kPThreads) {
             st_B[i] = s.B[i];
             st_K[i] = s.K[i];
-            st_S[i] = s.S[s_index(i, npx)];
+            st_S[i] = s.S[i];
         }
         if (clip.n_frames > 0) {
             const float *flast = filtered_ptr(a, clip, scratch, clip.n_frames - 1);

@@ -257,7 +257,7 @@ int cpt_motion_step(cpt_motion *m, const uint16_t *h_pix, void *d_background_sta
     a.g = c->g;
     a.ring = m->d_ring; a.sum = m->d_sum; a.diff = m->d_diff; a.mean_count = m->d_mean_count;
     a.bg_state = (uint8_t *)d_background_state;
-    a.wt = cpt::WeightTable{c->tables[m->weight_slot].d_thr, c->tables[m->weight_slot].max_count, c->tables[m->weight_slot].has_bounds};
+    a.wt = c->tables[m->weight_slot].device();
     a.result = m->d_result;
     a.slot_new = slot_new; a.slot_oldest = slot_oldest; a.slot_nonffc = slot_nonffc;
     a.diff_slot_new = diff_slot_new; a.diff_slot_old = diff_slot_old;
