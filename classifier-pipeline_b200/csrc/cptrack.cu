@@ -68,14 +68,12 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     g.gpr_magic = ((1u << 17) + g.gpr - 1) / g.gpr;
     g.rw_magic = ((1u << 13) + g.row_words - 1) / g.row_words;
     g.qpr = width / 4;
-    g.n_owned = (height - 2 * edge_pixels) * g.qpr;
-    g.qpr_magic = ((1u << 18) + g.qpr - 1) / g.qpr;
-    for (uint32_t q = 0; q < (uint32_t)(g.npx / 4); ++q)
-        if (((q * g.qpr_magic) >> 18) != q / (uint32_t)g.qpr) {
-            fail(CPT_ERR_INVALID, "internal: quad division constant is not exact for width %d", width);
-            delete c;
-            return nullptr;
-        }
+    g.rows_per_it = cpt::kPThreads / g.qpr;
+    if ((height - 2 * edge_pixels + g.rows_per_it - 1) / g.rows_per_it > cpt::kQIter) {
+        fail(CPT_ERR_INVALID, "unsupported geometry %dx%d: too many sweep iterations", width, height);
+        delete c;
+        return nullptr;
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         fail(CPT_ERR_CUDA, "cudaGetDeviceProperties failed");

@@ -58,8 +58,7 @@ struct Geometry {
     // quads of 4 pixels: the unit of the fused pixel sweep.  Rows edge .. H-1-edge are "owned"; the owner of
     // the first / last owned row also produces the border rows above / below it.
     int qpr;             // quads per row = W/4
-    int n_owned;         // (H - 2*edge) * qpr
-    uint32_t qpr_magic;  // q / qpr == (q * qpr_magic) >> 18   (q < 4800, qpr <= 40; verified at ctx creation)
+    int rows_per_it;     // owned rows the pixel threads cover per sweep iteration = kPThreads / qpr (20 at 160 pixels)
 };
 
 // Per-clip persistent record in global memory (cpt_state_bytes()).

@@ -471,12 +471,8 @@ struct SweepAcc {
 __device__ __forceinline__ uint2 ldg8(const void *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
 
 // K1 + sliding sum + statistics of one quad against the packed background words nb (2 x 2 pixels)
-__device__ __forceinline__ int filter_quad(const uint16_t *P, const uint16_t *Pold, int p4, uint2 nb, uint32_t *S, float *fcur,
+__device__ __forceinline__ int filter_quad(uint2 pw, uint2 ow, int p4, uint2 nb, uint4 sv, uint32_t *S, float *fcur,
                                            uint8_t *lab_frame, bool want_stats, SweepAcc &acc) {
-    const uint2 pw = ldg8(P + p4);
-    uint2 ow = make_uint2(0, 0);
-    if (Pold) ow = ldg8(Pold + p4);
-    uint4 sv = *reinterpret_cast<const uint4 *>(S + p4);
     const int f0 = dp2a_us(pw.x, kLoP, dp2a_us(nb.x, kLoN, 0)), f1 = dp2a_us(pw.x, kHiP, dp2a_us(nb.x, kHiN, 0));
     const int f2 = dp2a_us(pw.y, kLoP, dp2a_us(nb.y, kLoN, 0)), f3 = dp2a_us(pw.y, kHiP, dp2a_us(nb.y, kHiN, 0));
     sv.x = (uint32_t)dp2a_us(pw.x, kLoP, dp2a_us(ow.x, kLoN, (int)sv.x));
@@ -499,88 +495,192 @@ __device__ __forceinline__ int filter_quad(const uint16_t *P, const uint16_t *Po
     return hi;
 }
 
-// keep mask (0xffff per kept pixel) of one packed pair
-__device__ __forceinline__ uint32_t keep_pair(uint32_t b2, uint32_t k2, uint32_t A0, uint32_t A1, const SweepMode &m,
-                                               const uint32_t *smem_table, const WeightTable &wt) {
+// Per-thread constants of the sweep: thread ptid owns column quad qx of rows r0, r0 + rows_per_it, ... of the
+// owned rows (kPThreads = rows_per_it * qpr threads are active: 20 rows x 40 quads at 160 pixels).
+struct SweepThread {
+    int p4_0;        // pixel index of the thread's first quad
+    int stride;      // pixels between its consecutive quads (rows_per_it * W)
+    int r0;          // owned-row index of the first quad
+    int last_it;     // iteration that holds the last owned row, if this thread owns it; else -1
+    bool active;     // ptid < rows_per_it * qpr
+    bool prefetch;   // first quad of a 128-byte line
+    bool first_col, last_col;  // the quad holds a crop-border column (edge == 1)
+    uint32_t perm_x, perm_y;   // crop-border columns copy their neighbour (motiondetector.py:239-244)
+};
+
+// keep mask (0xffff per kept pixel) of one packed pair (K7: `background < frame - weight` in table form, see
+// cptrack_kernels.cuh).  kTable: 0 thr = k + 1 (no bounds), 1 table in shared memory, 2 table in global memory;
+// kPacked: 16-bit SIMD form, valid while B + thr cannot overflow 16 bits.
+template <bool kPacked, int kTable>
+__device__ __forceinline__ uint32_t keep_pair(uint32_t b2, uint32_t k2, uint32_t A0, uint32_t A1, const uint32_t *smem_table,
+                                               const WeightTable &wt) {
     uint32_t e0 = 0, e1 = 0;
-    if (m.table == 1) { e0 = smem_table[k2 & 0xffffu]; e1 = smem_table[k2 >> 16]; }
-    else if (m.table == 2) { e0 = __ldg(wt.thr + (k2 & 0xffffu)); e1 = __ldg(wt.thr + (k2 >> 16)); }
-    if (!m.slow) {
-        // packed: keep <=> A >= B + thr, no 16-bit overflow possible in this mode
-        const uint32_t thr2 = (m.table == 0) ? __vadd2(k2, 0x00010001u) : __byte_perm(e0, e1, 0x5410);
-        const uint32_t x2 = __vadd2(b2, thr2), a2 = A0 | (A1 << 16);
+    if (kTable == 1) { e0 = smem_table[k2 & 0xffffu]; e1 = smem_table[k2 >> 16]; }
+    if (kTable == 2) { e0 = __ldg(wt.thr + (k2 & 0xffffu)); e1 = __ldg(wt.thr + (k2 >> 16)); }
+    if (kPacked) {
+        // keep <=> A >= B + thr - (B < bound)
+        uint32_t thr2;
+        if (kTable == 0) {
+            thr2 = __vadd2(k2, 0x00010001u);
+        } else {
+            thr2 = __byte_perm(e0, e1, 0x5410);
+            bool ge_hi, ge_lo;
+            (void)__vibmax_u16x2(b2, __byte_perm(e0, e1, 0x7632), &ge_hi, &ge_lo);  // B >= bound per half
+            if (!ge_lo) thr2 -= 0x00000001u;  // thr >= 1 whenever bound > 0: no borrow
+            if (!ge_hi) thr2 -= 0x00010000u;
+        }
         bool hi, lo;
-        (void)__vibmax_u16x2(a2, x2, &hi, &lo);  // predicates: a >= x per half
+        (void)__vibmax_u16x2(A0 | (A1 << 16), __vadd2(b2, thr2), &hi, &lo);  // A >= B + thr per half
         return (lo ? 0x0000ffffu : 0u) | (hi ? 0xffff0000u : 0u);
     }
-    if (m.table == 0) { e0 = (k2 & 0xffffu) + 1u; e1 = (k2 >> 16) + 1u; }
+    if (kTable == 0) { e0 = (k2 & 0xffffu) + 1u; e1 = (k2 >> 16) + 1u; }
     const int b0 = (int)(b2 & 0xffffu), b1 = (int)(b2 >> 16);
     const int t0 = (int)(e0 & 0xffffu) - ((b0 < (int)(e0 >> 16)) ? 1 : 0);
     const int t1 = (int)(e1 & 0xffffu) - ((b1 < (int)(e1 >> 16)) ? 1 : 0);
     return (((int)A0 - b0 >= t0) ? 0x0000ffffu : 0u) | (((int)A1 - b1 >= t1) ? 0xffff0000u : 0u);
 }
 
-__device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const WeightTable &wt, int ptid, const SweepMode m,
-                                            const uint16_t *P, const uint16_t *Pold, const uint16_t *Pnext,
-                                            const uint16_t *Pold_next, float *fcur, uint8_t *lab_frame, bool want_stats,
-                                            SweepAcc &acc, int (&gmaxq)[kQIter]) {
-    const Geometry &g = a.g;
-    const int W = g.W, H = g.H, e = g.edge;
-#pragma unroll
-    for (int it = 0; it < kQIter; ++it) {
-        const int q = it * kPThreads + ptid;
-        gmaxq[it] = INT32_MIN;
-        if (q >= g.n_owned) continue;
-        const int yo = (int)(((uint32_t)q * g.qpr_magic) >> 18), qx = q - yo * g.qpr;
-        const int y = yo + e, p4 = y * W + qx * 4;
-        if (m.frame && (qx & 15) == 0) {  // one 128-byte line per 16 quads: pull the next frame towards L2
-            if (Pnext) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pnext + p4));
-            if (Pold_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(Pold_next + p4));
+// One owned quad: [update] then [frame].  Returns the quad's max F (INT32_MIN without a frame); nb_out = B'.
+template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats>
+__device__ __forceinline__ int sweep_quad(Smem &s, const WeightTable &wt, const SweepThread &th, const SweepMode &m, int p4,
+                                          const uint16_t *P, const uint16_t *Pold, long long next_bytes, bool old_next,
+                                          float *fcur, uint8_t *lab_frame, SweepAcc &acc, uint2 &nb_out) {
+    uint2 pw = make_uint2(0, 0), ow = make_uint2(0, 0);
+    if (kFrame) {
+        pw = ldg8(P + p4);
+        if (Pold) ow = ldg8(Pold + p4);
+        if (th.prefetch && next_bytes) {  // pull the next frame (same layout, next_bytes further on) towards L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(P + p4) + next_bytes));
+            if (old_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(Pold + p4) + next_bytes));
         }
-        const uint2 bw = *reinterpret_cast<const uint2 *>(s.B + p4);
-        uint2 nb = bw;
-        if (m.update) {
-            const uint2 kw = *reinterpret_cast<const uint2 *>(s.K + p4);
-            const uint4 sv = *reinterpret_cast<const uint4 *>(s.S + p4);
-            const uint32_t A0 = m.first_mean ? sv.x : __umulhi(sv.x, m.magic), A1 = m.first_mean ? sv.y : __umulhi(sv.y, m.magic);
-            const uint32_t A2 = m.first_mean ? sv.z : __umulhi(sv.z, m.magic), A3 = m.first_mean ? sv.w : __umulhi(sv.w, m.magic);
-            const uint32_t keep_x = keep_pair(bw.x, kw.x, A0, A1, m, s.wthr, wt), keep_y = keep_pair(bw.y, kw.y, A2, A3, m, s.wthr, wt);
-            nb.x = (bw.x & keep_x) | ((A0 | (A1 << 16)) & ~keep_x);
-            nb.y = (bw.y & keep_y) | ((A2 | (A3 << 16)) & ~keep_y);
-            uint2 nk;
-            nk.x = __vadd2(kw.x, 0x00010001u) & keep_x;
-            nk.y = __vadd2(kw.y, 0x00010001u) & keep_y;
-            // crop-border columns copy their neighbour and do not count (motiondetector.py:239-244)
-            uint32_t cmask_x = 0xffffffffu, cmask_y = 0xffffffffu;
-            int sel_x = kBoth, sel_y = kBoth;
-            if (e) {
-                if (qx == 0) { nb.x = __byte_perm(nb.x, 0, 0x3232); cmask_x = 0xffff0000u; sel_x = kHiP; }
-                if (qx == g.qpr - 1) { nb.y = __byte_perm(nb.y, 0, 0x1010); cmask_y = 0x0000ffffu; sel_y = kLoP; }
-            }
-            acc.changed |= ((nb.x ^ bw.x) & cmask_x) | ((nb.y ^ bw.y) & cmask_y);
-            acc.bsum = (uint32_t)dp2a_us(nb.x, sel_x, dp2a_us(nb.y, sel_y, (int)acc.bsum));
-            *reinterpret_cast<uint2 *>(s.B + p4) = nb;
-            *reinterpret_cast<uint2 *>(s.K + p4) = nk;
-        }
-        acc.bmin2 = __vminu2(acc.bmin2, __vminu2(nb.x, nb.y));
-        acc.bmax2 = __vmaxu2(acc.bmax2, __vmaxu2(nb.x, nb.y));
-        int hi = INT32_MIN;
-        if (m.frame) hi = filter_quad(P, Pold, p4, nb, s.S, fcur, lab_frame, want_stats, acc);
-        if (e) {
-            // border rows take the adjacent owned row's background
-            if (yo == 0) {
-                const int pb = p4 - W;
-                if (m.update) *reinterpret_cast<uint2 *>(s.B + pb) = nb;
-                if (m.frame) hi = max(hi, filter_quad(P, Pold, pb, nb, s.S, fcur, lab_frame, want_stats, acc));
-            }
-            if (y == H - 2) {
-                const int pb = p4 + W;
-                if (m.update) *reinterpret_cast<uint2 *>(s.B + pb) = nb;
-                if (m.frame) hi = max(hi, filter_quad(P, Pold, pb, nb, s.S, fcur, lab_frame, want_stats, acc));
-            }
-        }
-        gmaxq[it] = hi;
     }
+    const uint2 bw = *reinterpret_cast<const uint2 *>(s.B + p4);
+    const uint4 sv = *reinterpret_cast<const uint4 *>(s.S + p4);
+    uint2 nb = bw;
+    if (kUpdate) {
+        const uint2 kw = *reinterpret_cast<const uint2 *>(s.K + p4);
+        uint32_t A0, A1, A2, A3;
+        if (!kPacked && m.first_mean) { A0 = sv.x; A1 = sv.y; A2 = sv.z; A3 = sv.w; }
+        else { A0 = __umulhi(sv.x, m.magic); A1 = __umulhi(sv.y, m.magic); A2 = __umulhi(sv.z, m.magic); A3 = __umulhi(sv.w, m.magic); }
+        const uint32_t keep_x = keep_pair<kPacked, kTable>(bw.x, kw.x, A0, A1, s.wthr, wt);
+        const uint32_t keep_y = keep_pair<kPacked, kTable>(bw.y, kw.y, A2, A3, s.wthr, wt);
+        nb.x = __byte_perm((bw.x & keep_x) | ((A0 | (A1 << 16)) & ~keep_x), 0, th.perm_x);
+        nb.y = __byte_perm((bw.y & keep_y) | ((A2 | (A3 << 16)) & ~keep_y), 0, th.perm_y);
+        uint2 nk;
+        nk.x = __vadd2(kw.x, 0x00010001u) & keep_x;
+        nk.y = __vadd2(kw.y, 0x00010001u) & keep_y;
+        // a border column always equals its neighbour, before and after: it cannot change `changed`, and its
+        // share of the sum is taken out again below
+        acc.changed |= (nb.x ^ bw.x) | (nb.y ^ bw.y);
+        acc.bsum = (uint32_t)dp2a_us(nb.x, kBoth, dp2a_us(nb.y, kBoth, (int)acc.bsum));
+        if (th.first_col) acc.bsum -= nb.x & 0xffffu;
+        if (th.last_col) acc.bsum -= nb.y >> 16;
+        *reinterpret_cast<uint2 *>(s.B + p4) = nb;
+        *reinterpret_cast<uint2 *>(s.K + p4) = nk;
+    }
+    acc.bmin2 = __vminu2(acc.bmin2, __vminu2(nb.x, nb.y));
+    acc.bmax2 = __vmaxu2(acc.bmax2, __vmaxu2(nb.x, nb.y));
+    nb_out = nb;
+    return kFrame ? filter_quad(pw, ow, p4, nb, sv, s.S, fcur, lab_frame, kStats, acc) : INT32_MIN;
+}
+
+// A border row takes the adjacent owned row's background (edge replication); run by that row's owner thread,
+// out of line (two rows of the frame) with its partial results returned by value.
+struct BorderOut {
+    uint32_t psum, fabs_sum;
+    int fmin, fmax, pmin, pmax;
+};
+
+template <bool kUpdate, bool kFrame, bool kStats>
+__device__ __noinline__ BorderOut border_quad(uint16_t *B, uint32_t *S, int pb, uint2 nb, const uint16_t *P, const uint16_t *Pold,
+                                              float *fcur, uint8_t *lab_frame) {
+    SweepAcc acc;
+    if (kUpdate) *reinterpret_cast<uint2 *>(B + pb) = nb;
+    if (kFrame) {
+        const uint2 pw = ldg8(P + pb);
+        const uint2 ow = Pold ? ldg8(Pold + pb) : make_uint2(0, 0);
+        const uint4 sv = *reinterpret_cast<const uint4 *>(S + pb);
+        (void)filter_quad(pw, ow, pb, nb, sv, S, fcur, lab_frame, kStats, acc);
+    }
+    return BorderOut{acc.psum, acc.fabs_sum, acc.fmin, acc.fmax, acc.pmin, acc.pmax};
+}
+
+__device__ __forceinline__ void merge_border(SweepAcc &acc, const BorderOut &b) {
+    acc.psum += b.psum;
+    acc.fabs_sum += b.fabs_sum;
+    acc.fmin = min(acc.fmin, b.fmin);
+    acc.fmax = max(acc.fmax, b.fmax);
+    acc.pmin = min(acc.pmin, b.pmin);
+    acc.pmax = max(acc.pmax, b.pmax);
+}
+
+// kUnrolled: straight-line code with the per-quad maxima in registers (the steady state); otherwise a rolled
+// loop whose maxima go through local memory (first frame, tail pass, exact keep test: once per clip).
+template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled>
+__device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
+                                            const SweepMode &m, const uint16_t *P, const uint16_t *Pold, long long next_bytes,
+                                            bool old_next, float *fcur, uint8_t *lab_frame, SweepAcc &acc,
+                                            int (&gmaxq)[kQIter]) {
+    const Geometry &g = a.g;
+    const int owned_rows = g.H - 2 * g.edge;
+    uint2 nb_top = make_uint2(0, 0), nb_bottom = make_uint2(0, 0);
+    if (kUnrolled) {
+#pragma unroll
+        for (int it = 0; it < kQIter; ++it) {
+            gmaxq[it] = INT32_MIN;
+            if (!th.active || th.r0 + it * g.rows_per_it >= owned_rows) continue;
+            uint2 nb;
+            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * th.stride, P, Pold,
+                                                                              next_bytes, old_next, fcur, lab_frame, acc, nb);
+            if (it == 0) nb_top = nb;
+            if (it == th.last_it) nb_bottom = nb;
+        }
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < kQIter; ++it) {
+            gmaxq[it] = INT32_MIN;
+            if (!th.active || th.r0 + it * g.rows_per_it >= owned_rows) continue;
+            uint2 nb;
+            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * th.stride, P, Pold,
+                                                                              next_bytes, old_next, fcur, lab_frame, acc, nb);
+            if (it == 0) nb_top = nb;
+            if (it == th.last_it) nb_bottom = nb;
+        }
+    }
+    if (g.edge && th.active) {
+        if (th.r0 == 0) {
+            const BorderOut b = border_quad<kUpdate, kFrame, kStats>(s.B, s.S, th.p4_0 - g.W, nb_top, P, Pold, fcur, lab_frame);
+            merge_border(acc, b);
+            gmaxq[0] = max(gmaxq[0], b.fmax);  // the quad's only pixels: its max F
+        }
+        if (th.last_it >= 0) {
+            const BorderOut b = border_quad<kUpdate, kFrame, kStats>(s.B, s.S, th.p4_0 + th.last_it * th.stride + g.W, nb_bottom, P,
+                                                                     Pold, fcur, lab_frame);
+            merge_border(acc, b);
+#pragma unroll
+            for (int it = 0; it < kQIter; ++it)
+                if (it == th.last_it) gmaxq[it] = max(gmaxq[it], b.fmax);
+        }
+    }
+}
+
+// Runtime mode -> instantiation.
+template <bool kStats>
+__device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
+                                                     const SweepMode &m, const uint16_t *P, const uint16_t *Pold,
+                                                     long long next_bytes, bool old_next, float *fcur, uint8_t *lab_frame,
+                                                     SweepAcc &acc, int (&gmaxq)[kQIter]) {
+    const bool steady = m.update && m.frame && !m.slow && !m.first_mean;
+    if (steady && m.table == 0)
+        pixel_sweep<true, true, true, 0, kStats, true>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+    else if (steady && m.table == 1)
+        pixel_sweep<true, true, true, 1, kStats, true>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+    else if (!m.update)
+        pixel_sweep<false, true, false, 2, kStats, false>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+    else if (m.frame)
+        pixel_sweep<true, true, false, 2, kStats, false>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+    else
+        pixel_sweep<true, false, false, 2, kStats, false>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
 }
 
 // per-warp partial results -> s.red_u[warp * 12 + i]
@@ -679,6 +779,21 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         replicate_edges(s, g, ptid);
         bar_sync(BAR_P, kPThreads);
     }
+    SweepThread th;
+    {
+        const int r0 = ptid / g.qpr, qx = ptid - r0 * g.qpr;
+        th.r0 = r0;
+        th.active = r0 < g.rows_per_it;
+        th.p4_0 = (r0 + g.edge) * W + qx * 4;
+        th.stride = g.rows_per_it * W;
+        th.prefetch = (qx & 15) == 0;
+        th.first_col = g.edge && qx == 0;
+        th.last_col = g.edge && qx == g.qpr - 1;
+        th.perm_x = th.first_col ? 0x3232u : 0x3210u;
+        th.perm_y = th.last_col ? 0x1010u : 0x3210u;
+        const int last_row = g.H - 2 * g.edge - 1;  // owned-row index
+        th.last_it = (th.active && last_row % g.rows_per_it == r0) ? last_row / g.rows_per_it : -1;
+    }
     if (ptid == 0) s.bcast_i[9] = 1;  // the first update of a launch takes the exact path (no background extrema yet)
     bar_sync(BAR_P, kPThreads);
 
@@ -704,16 +819,16 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         }
         const uint16_t *P = is_frame ? frame_ptr(a, clip, t) : nullptr;
         const uint16_t *Pold = (is_frame && t_abs >= kMeanFrames) ? frame_ptr(a, clip, t - kMeanFrames) : nullptr;
-        const bool more = (t + 1 < clip.n_frames);
-        const uint16_t *Pnext = more ? frame_ptr(a, clip, t + 1) : nullptr;
-        const uint16_t *Pold_next = (more && t_abs + 1 >= kMeanFrames) ? frame_ptr(a, clip, t + 1 - kMeanFrames) : nullptr;
+        // linear clips: the next frame (and the next frame leaving the window) lie one frame further on
+        const long long next_bytes = (t + 1 < clip.n_frames && clip.ring_frames == 0) ? (long long)npx * 2 : 0;
         float *fcur = is_frame ? filtered_ptr(a, clip, scratch, t) : nullptr;
         uint8_t *lab_frame = (is_frame && a.labels) ? a.labels + o * npx : nullptr;
 
         // ------------------------------------------------------------ fused sweep (K7 of frame t-1, K1/K8 of frame t)
         SweepAcc acc;
         int gmaxq[kQIter];
-        pixel_sweep(a, s, wt, ptid, m, P, Pold, Pnext, Pold_next, fcur, lab_frame, want_stats, acc, gmaxq);
+        if (want_stats) pixel_sweep_dispatch<true>(a, s, wt, th, m, P, Pold, next_bytes, Pold != nullptr, fcur, lab_frame, acc, gmaxq);
+        else pixel_sweep_dispatch<false>(a, s, wt, th, m, P, Pold, next_bytes, Pold != nullptr, fcur, lab_frame, acc, gmaxq);
         CPT_TICK(ptid == 0, 14);  // sweep issued
         sweep_reduce_store(s, lane, warp, acc, want_stats);
         bar_sync(BAR_P, kPThreads);
@@ -738,21 +853,24 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             }
             if (lane == 0) {
                 if (m.update && changed) average = rint((double)bsum / (double)g.ncrop);  // int(round(np.average(background))), motiondetector.py:232
-                // mode of the NEXT update: the packed keep test needs B + thr < 2^16 and no bound corrections
+                // mode of the NEXT update: the packed keep test needs B + thr < 2^16
                 {
                     const int k_next = min(frames_seen + 1, wt.max_count);
-                    const uint32_t thr_cap = (k_next < wt.linear_upto) ? (uint32_t)k_next + 1u : (__ldg(wt.thr + k_next) & 0xffffu);
-                    s.bcast_i[9] = (bmax + thr_cap > 65535u) || (wt.has_bounds && (int)bmin < wt.max_bound);
+                    const uint32_t thr_cap = (k_next < wt.linear_upto) ? (uint32_t)k_next + 1u
+                                             : ((k_next < kSmemWeights ? s.wthr[k_next] : __ldg(wt.thr + k_next)) & 0xffffu);
+                    s.bcast_i[9] = (bmax + thr_cap > 65535u);
+                    (void)bmin;
                 }
                 if (is_frame) {
                 // avg_change = int(round(np.average(thermal) - background average)), cliptracker.py:103-105
                 int ac;
                 const double avg_int = rint(average);
-                if (avg_int == average && fabs(average) < 1.0e6) {
+                if (avg_int == average && average >= 0.0 && average < 65536.0) {
                     // integer average (always, once the background has changed): round_half_even((sum - avg*n) / n)
                     // in integers; identical to the fp64 expression because the only ties are exact
-                    long long num = (long long)v0 - (long long)avg_int * npx;
-                    long long qd = num / npx, rem = num - qd * npx;
+                    // |sum - avg * n| < 2^31: 32-bit arithmetic
+                    int num = (int)v0 - (int)avg_int * npx;
+                    int qd = num / npx, rem = num - qd * npx;
                     if (rem < 0) { rem += npx; qd -= 1; }
                     if (2 * rem > npx || (2 * rem == npx && (qd & 1))) qd += 1;
                     ac = (int)qd;
@@ -829,7 +947,9 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 for (int dy = -4; dy <= 4; ++dy) {
                     const int yy = ptid + dy - g.edge;  // owned-row index
                     if (yy < 0 || yy >= g.H - 2 * g.edge) continue;
-                    const unsigned long long bits = hot_field(s.hotbits, yy * g.qpr) & rowmask;
+                    // owned row yy = it * rows_per_it + r: its quads are bits [it * kPThreads + r * qpr, + qpr)
+                    const int hit = yy / g.rows_per_it;
+                    const unsigned long long bits = hot_field(s.hotbits, hit * kPThreads + (yy - hit * g.rows_per_it) * g.qpr) & rowmask;
                     near4 |= bits;
                     if (dy >= -2 && dy <= 2) near2 |= bits;
                 }
