@@ -92,6 +92,7 @@ struct WeightTable {
     int linear_upto;  // entries [0, linear_upto) are exactly thr = k + 1, bound = 0 (weight_add == 1)
 };
 constexpr int kSmemWeights = 1024;
+constexpr int kListCap = 1024;  // marked groups per frame handled through the work lists (more: dense sweep)
 
 struct KernelArgs {
     Geometry g;
@@ -126,12 +127,12 @@ struct __align__(16) Smem {
     int32_t bcast_i[16];
     int32_t msg[2][4];         // pixel warps -> component warps, per mask buffer: filtered min, max
     double bcast_d[4];
-    uint32_t hist[256];
     double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
     uint32_t wthr[kSmemWeights];                   // first entries of the clip's keep-test table
     unsigned long long need_u[kMaxH];  // per row, one bit per quad: U is an input of a blur window that can exceed the threshold
     unsigned long long need_b[kMaxH];  // per row, one bit per quad: the blurred output can exceed the threshold
-    uint32_t hotbits[kMaxPx / 4 / 32 + 4];  // one bit per owned quad: some pixel can exceed the threshold
+    uint16_t list_u[kListCap];  // groups of 8 pixels to normalise this frame (need_u)
+    uint16_t list_b[kListCap];  // groups of 8 pixels to blur this frame (need_b)
     int32_t ncomp;
 };
 

@@ -373,7 +373,9 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         prev_fmin = cur_fmin;
         prev_fmax = cur_fmax;
         have_prev = true;
-        // all component threads are done with s.M[buf] (and s.C etc.) -> the pixel warps may refill it
+        // all component threads are done with s.M[buf] (and s.C etc.): hand it back zeroed, the pixel warps only
+        // write the bytes of the groups they blurred
+        for (int i = ctid; i < g.words; i += kCThreads) s.M[buf][i] = 0;
         CPT_TICK(ctid == 0, 12);  // components of the frame
         if (t + 2 < clip.n_frames) bar_arrive(BAR_EMPTY + buf, kThreads);
     }
@@ -385,62 +387,97 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
 // pixel warps
 // ================================================================================================
 
-// K4 first half: 5x5 binomial blur of s.U (fixed point, one rounding, BORDER_REFLECT_101) and
-// threshold `> ith`, 8 pixels per thread in packed 16-bit lanes -> bit rows in s.M[buf].
-__device__ __forceinline__ void blur_threshold(Smem &s, const Geometry &g, int ptid, int buf, int ith) {
+// K4 first half for one group of 8 pixels: 5x5 binomial blur of s.U (fixed point, one rounding,
+// BORDER_REFLECT_101) in packed 16-bit lanes and threshold `> ith` -> one byte of the bit rows in s.M[buf].
+// Only outputs of quads marked in need_b are evaluated: the others cannot exceed the threshold (every input
+// of their window is <= ith) and their windows may reach inputs that were not refreshed.
+__device__ __forceinline__ void blur_group(Smem &s, const Geometry &g, int grp, int buf, int ith) {
     const int W = g.W, H = g.H;
     uint8_t *M8 = reinterpret_cast<uint8_t *>(s.M[buf]);
     const uint32_t T = (ith >= 0 && ith < 255) ? (uint32_t)(((ith + 1) << 8) - 128) : 0u;
-    const bool fast_rows = H >= 4;
-#pragma unroll 1
-    for (int grp = ptid; grp < g.groups; grp += kPThreads) {
-        int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr, x0 = gx * 8;
-        uint32_t bits = 0;
-        if (ith < 0) {
-            bits = 0xffu;
-        } else if (ith < 255 && ((s.need_b[y] >> (2 * gx)) & 3ull)) {
-            // (groups outside need_b cannot exceed the threshold: every input of their window is <= ith)
-            uint32_t V[6] = {0, 0, 0, 0, 0, 0};
-            const bool left_edge = (x0 == 0), right_edge = (x0 + 8 == W);
+    const int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr, x0 = gx * 8;
+    const uint32_t q2 = (uint32_t)(s.need_b[y] >> (2 * gx)) & 3u;
+    uint32_t bits = 0;
+    if (ith < 0) {
+        bits = 0xffu;
+    } else if (ith < 255 && q2) {
+        uint32_t V[6] = {0, 0, 0, 0, 0, 0};
+        const bool left_edge = (x0 == 0), right_edge = (x0 + 8 == W);
 #pragma unroll
-            for (int r = 0; r < 5; ++r) {
-                const uint32_t wgt = (r == 0 || r == 4) ? 1u : ((r == 2) ? 6u : 4u);
-                int yy = y + r - 2;
-                if (fast_rows) {
-                    yy = (yy < 0) ? -yy : yy;
-                    yy = (yy >= H) ? 2 * H - 2 - yy : yy;
-                } else {
-                    yy = reflect101(yy, H);
-                }
-                const uint8_t *row = s.U + yy * W + x0;
-                uint2 m = *reinterpret_cast<const uint2 *>(row);
-                uint32_t lw = left_edge ? 0u : *reinterpret_cast<const uint32_t *>(row - 4);
-                uint32_t rw = right_edge ? 0u : *reinterpret_cast<const uint32_t *>(row + 8);
-                uint32_t lp = left_edge ? __byte_perm(m.x, 0, 0x4142) : __byte_perm(lw, 0, 0x4342);
-                uint32_t rp = right_edge ? __byte_perm(m.y, 0, 0x4142) : __byte_perm(rw, 0, 0x4140);
-                V[0] += wgt * lp;
-                V[1] += wgt * __byte_perm(m.x, 0, 0x4140);
-                V[2] += wgt * __byte_perm(m.x, 0, 0x4342);
-                V[3] += wgt * __byte_perm(m.y, 0, 0x4140);
-                V[4] += wgt * __byte_perm(m.y, 0, 0x4342);
-                V[5] += wgt * rp;
-            }
-            uint32_t odd[5];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) odd[q] = __byte_perm(V[q], V[q + 1], 0x5432);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t sum = V[q] + V[q + 2] + 6u * V[q + 1] + 4u * (odd[q] + odd[q + 1]);
-                bits |= ((sum & 0xffffu) >= T ? 1u : 0u) << (2 * q);
-                bits |= ((sum >> 16) >= T ? 1u : 0u) << (2 * q + 1);
-            }
+        for (int r = 0; r < 5; ++r) {
+            const uint32_t wgt = (r == 0 || r == 4) ? 1u : ((r == 2) ? 6u : 4u);
+            int yy = y + r - 2;
+            yy = (yy < 0) ? -yy : yy;              // H >= 4: one reflection is enough
+            yy = (yy >= H) ? 2 * H - 2 - yy : yy;
+            const uint8_t *row = s.U + yy * W + x0;
+            uint2 m = *reinterpret_cast<const uint2 *>(row);
+            uint32_t lw = left_edge ? 0u : *reinterpret_cast<const uint32_t *>(row - 4);
+            uint32_t rw = right_edge ? 0u : *reinterpret_cast<const uint32_t *>(row + 8);
+            uint32_t lp = left_edge ? __byte_perm(m.x, 0, 0x4142) : __byte_perm(lw, 0, 0x4342);
+            uint32_t rp = right_edge ? __byte_perm(m.y, 0, 0x4142) : __byte_perm(rw, 0, 0x4140);
+            V[0] += wgt * lp;
+            V[1] += wgt * __byte_perm(m.x, 0, 0x4140);
+            V[2] += wgt * __byte_perm(m.x, 0, 0x4342);
+            V[3] += wgt * __byte_perm(m.y, 0, 0x4140);
+            V[4] += wgt * __byte_perm(m.y, 0, 0x4342);
+            V[5] += wgt * rp;
         }
-        if (ith >= 0) {
-            // outputs of a quad that is not marked cannot fire; their windows may reach inputs that were not refreshed
-            const uint32_t q2 = (uint32_t)(s.need_b[y] >> (2 * gx)) & 3u;
-            bits &= ((q2 & 1u) ? 0x0fu : 0u) | ((q2 & 2u) ? 0xf0u : 0u);
+        uint32_t odd[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) odd[q] = __byte_perm(V[q], V[q + 1], 0x5432);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t sum = V[q] + V[q + 2] + 6u * V[q + 1] + 4u * (odd[q] + odd[q + 1]);
+            bits |= ((sum & 0xffffu) >= T ? 1u : 0u) << (2 * q);
+            bits |= ((sum >> 16) >= T ? 1u : 0u) << (2 * q + 1);
         }
-        M8[y * g.row_words * 4 + gx] = (uint8_t)bits;
+        bits &= ((q2 & 1u) ? 0x0fu : 0u) | ((q2 & 2u) ? 0xf0u : 0u);
+    }
+    M8[y * g.row_words * 4 + gx] = (uint8_t)bits;
+}
+
+// K2 for one group of 8 pixels: U = uint8(255 * (G - min) / (max - min)), G = max(P - B - avg_change, 0), in the
+// reference's own fp32 arithmetic (imageprocessing.py:151-169: multiply, then IEEE divide, truncate).
+__device__ __forceinline__ void normalise_group(Smem &s, const uint16_t *P, int grp, int ac, int gmn, int gmx) {
+    const uint4 pv = ldg16(P + grp * 8);  // streamed a moment ago: an L2 hit
+    const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
+    const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+    const bool degenerate = (gmx == gmn);
+    const float range_f = (float)gmx - (float)gmn;
+    const uint32_t degen_val = (gmx == 0) ? 0u : 1u;
+    uint32_t u[8];
+    const int off = -ac;  // G - min = max(F - ac, 0) - gmn
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const int g0 = max(dp2a_us(pw[w], kLoP, dp2a_us(bw[w], kLoN, off)), 0) - gmn;
+        const int g1 = max(dp2a_us(pw[w], kHiP, dp2a_us(bw[w], kHiN, off)), 0) - gmn;
+        u[2 * w] = degenerate ? degen_val : norm_u8(g0, range_f);
+        u[2 * w + 1] = degenerate ? degen_val : norm_u8(g1, range_f);
+    }
+    uint2 w;
+    w.x = u[0] | (u[1] << 8) | (u[2] << 16) | (u[3] << 24);
+    w.y = u[4] | (u[5] << 8) | (u[6] << 16) | (u[7] << 24);
+    *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
+}
+
+// Hot quads (some pixel can exceed the threshold) mark the outputs that may fire (rows +-2, neighbouring quads)
+// and the inputs those outputs read (rows +-4, quads +-2).  Blur weights sum to 256, so nothing else can.
+// Warp-aggregated: `hot` holds the hot quads of ONE row as a bit field; lanes 0..8 of the calling half-warp
+// each OR the dilated field into one of the rows y-4 .. y+4 (32-bit halves: native shared-memory atomics).
+__device__ __forceinline__ void mark_hot_row(Smem &s, const Geometry &g, int y, unsigned long long hot, int dr) {
+    const int r = y + dr;
+    if (hot == 0 || dr < -4 || dr > 4 || r < 0 || r >= g.H) return;
+    const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
+    const unsigned long long um = (hot | (hot << 1) | (hot << 2) | (hot >> 1) | (hot >> 2)) & rowmask;
+    uint32_t *nu = reinterpret_cast<uint32_t *>(&s.need_u[r]);
+    if ((uint32_t)um) atomicOr(nu, (uint32_t)um);
+    if ((uint32_t)(um >> 32)) atomicOr(nu + 1, (uint32_t)(um >> 32));
+    if (dr >= -2 && dr <= 2) {
+        const unsigned long long bm = (hot | (hot << 1) | (hot >> 1)) & rowmask;
+        uint32_t *nb = reinterpret_cast<uint32_t *>(&s.need_b[r]);
+        if ((uint32_t)bm) atomicOr(nb, (uint32_t)bm);
+        if ((uint32_t)(bm >> 32)) atomicOr(nb + 1, (uint32_t)(bm >> 32));
     }
 }
 
@@ -704,15 +741,6 @@ __device__ __forceinline__ void sweep_reduce_store(Smem &s, int lane, int warp, 
     }
 }
 
-// 40-bit row field of the owned-quad hot bits starting at bit `pos`
-__device__ __forceinline__ unsigned long long hot_field(const uint32_t *bits, int pos) {
-    const int w = pos >> 5, sh = pos & 31;
-    const unsigned long long lo = ((unsigned long long)bits[w + 1] << 32) | bits[w];
-    unsigned long long v = lo >> sh;
-    if (sh) v |= (unsigned long long)bits[w + 2] << (64 - sh);
-    return v;
-}
-
 __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int ptid, float *scratch,
                             uint8_t *st_raw) {
     const Geometry &g = a.g;
@@ -852,7 +880,13 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 v5 = __reduce_add_sync(0xffffffffu, in ? r[5] : 0u);
             }
             if (lane == 0) {
-                if (m.update && changed) average = rint((double)bsum / (double)g.ncrop);  // int(round(np.average(background))), motiondetector.py:232
+                if (m.update && changed) {
+                    // int(round(np.average(background))), motiondetector.py:232 -- half to even, in integers
+                    uint32_t qa = bsum / (uint32_t)g.ncrop;
+                    const uint32_t ra = bsum - qa * (uint32_t)g.ncrop;
+                    if (2u * ra > (uint32_t)g.ncrop || (2u * ra == (uint32_t)g.ncrop && (qa & 1u))) qa += 1u;
+                    average = (double)qa;
+                }
                 // mode of the NEXT update: the packed keep test needs B + thr < 2^16
                 {
                     const int k_next = min(frames_seen + 1, wt.max_count);
@@ -879,8 +913,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 }
                 int gmx = max(v2 - ac, 0), gmn = max(v1 - ac, 0);
                 float thr;
-                uint32_t magic = 0;
-                int shift = 0, fth = INT32_MIN;
+                int fth = INT32_MIN;
                 if (gmx == gmn) {
                     thr = (float)clip.background_thresh;  // cliptracker.py:118-119
                 } else {
@@ -888,13 +921,9 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                     thr = __fmul_rn(__fdiv_rn((float)clip.background_thresh, range), 255.0f);
                     unsigned r = (unsigned)(gmx - gmn);
                     if (255ull * r < (1ull << 24)) {
-                        int l = (r == 1) ? 0 : 32 - __clz(r - 1);  // ceil(log2 r)
-                        shift = 24 + l;
-                        // ceil(2^shift / r): the fp64 quotient is within 2^-27 of the truth and the truth is
-                        // either an integer or at least 1/r away from one, so ceil() of it is exact
-                        magic = (uint32_t)ceil(ldexp(1.0, shift) / (double)r);
-                        // a quad can only produce foreground if one of its pixels has U > floor(thr):
-                        // U = floor(255 v / r) >= ith + 1  <=>  v >= ceil((ith + 1) r / 255), v = max(F - ac, 0) - gmn,
+                        // every product is exact in fp32 here, so trunc(fl(255 v / r)) == (255 v) / r and a quad can
+                        // only produce foreground if one of its pixels has U > floor(thr):
+                        // U >= ith + 1  <=>  v >= ceil((ith + 1) r / 255), v = max(F - ac, 0) - gmn,
                         // i.e. F >= fth (the bound is >= 1, so the clamp never matters)
                         int it = (int)floorf(thr);
                         if (it >= 0 && it < 255) fth = (int)(((unsigned)(it + 1) * r + 254u) / 255u) + ac + gmn;
@@ -903,7 +932,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 s.bcast_i[0] = ac; s.bcast_i[1] = gmn; s.bcast_i[2] = gmx;
                 s.bcast_i[3] = v1; s.bcast_i[4] = v2;
                 s.bcast_i[5] = __float_as_int(thr);
-                s.bcast_i[6] = (int)magic; s.bcast_i[7] = shift; s.bcast_i[8] = fth;
+                s.bcast_i[8] = fth;
                 cpt_frame_info fi;
                 fi.threshold = thr; fi.norm_min = gmn; fi.norm_max = gmx; fi.avg_change = ac;
                 fi.filtered_min = v1; fi.filtered_max = v2; fi.n_components = 0;
@@ -915,95 +944,99 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             }
         }
         if (m.update) ++frames_seen;
+        // (idle while warp 0 works) the marks and lists of the previous frame are dead since the sweep barrier
+        if (warp != 0) {
+            const int i = ptid - 32;
+            if (i < g.H) { s.need_u[i] = 0; s.need_b[i] = 0; }
+            if (i == kMaxH) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
+        }
         bar_sync(BAR_P, kPThreads);
         CPT_TICK(ptid == 0, 3);   // scalars + barrier
         if (!is_frame) break;
         const int ac = s.bcast_i[0], gmn = s.bcast_i[1], gmx = s.bcast_i[2];
         const int cur_fmin = s.bcast_i[3], cur_fmax = s.bcast_i[4];
         const float thr = __int_as_float(s.bcast_i[5]);
-        const uint32_t umagic = (uint32_t)s.bcast_i[6];
-        const int ushift = s.bcast_i[7];
         const int fth = s.bcast_i[8];
         const int ith = (int)floorf(thr);
 
-        // ------------------------------------------------------------ hot quads
-        // Blur weights sum to 256, so an output can exceed ith only if some input of its 5x5 window
-        // does.  Hot quads mark the outputs that may fire (rows +-2, neighbouring quads) and the
-        // inputs those outputs read (rows +-4, quads +-2); everything else skips K2/K4 arithmetic.
+        // ------------------------------------------------------------ hot quads -> marks -> work lists
         // (a border row's quads count for the owned row next to them, which only widens the marks)
-        const bool degenerate = (gmx == gmn);
-        const bool no_fg = ith >= 255;
-        const bool all_hot = (fth == INT32_MIN);
-        if (!all_hot) {
+        const bool no_fg = ith >= 255;          // nothing can exceed the threshold: the mask stays empty
+        bool dense = (fth == INT32_MIN);        // no usable bound: every group is normalised and blurred
+        int n_u = 0, n_b = 0;
+        if (!no_fg && !dense) {
+            // a warp's 32 quads of one iteration lie in at most two consecutive rows
+            const int wbase = warp * 32, wr = wbase / g.qpr, wq = wbase - wr * g.qpr;
+            const int n_first = min(32, g.qpr - wq);  // lanes in the first of the two rows
 #pragma unroll
             for (int it = 0; it < kQIter; ++it) {
                 const unsigned mbits = __ballot_sync(0xffffffffu, gmaxq[it] >= fth);  // unowned slots hold INT32_MIN
-                if (lane == 0) s.hotbits[it * kPWarps + warp] = mbits;  // bit (q & 31) of word q >> 5, q = it * kPThreads + ptid
+                if (mbits) {
+                    const int y = wr + it * g.rows_per_it + g.edge;
+                    const unsigned first = (n_first >= 32) ? mbits : (mbits & ((1u << n_first) - 1u));
+                    const unsigned second = (n_first >= 32) ? 0u : (mbits >> n_first);
+                    // lanes 0..8: first row, lanes 16..24: second row; one target row each
+                    if (lane < 16) mark_hot_row(s, g, y, (unsigned long long)first << wq, lane - 4);
+                    else mark_hot_row(s, g, y + 1, (unsigned long long)second, lane - 20);
+                }
             }
             bar_sync(BAR_P, kPThreads);
-            if (ptid < g.H) {
-                const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
-                unsigned long long near2 = 0, near4 = 0;
-                for (int dy = -4; dy <= 4; ++dy) {
-                    const int yy = ptid + dy - g.edge;  // owned-row index
-                    if (yy < 0 || yy >= g.H - 2 * g.edge) continue;
-                    // owned row yy = it * rows_per_it + r: its quads are bits [it * kPThreads + r * qpr, + qpr)
-                    const int hit = yy / g.rows_per_it;
-                    const unsigned long long bits = hot_field(s.hotbits, hit * kPThreads + (yy - hit * g.rows_per_it) * g.qpr) & rowmask;
-                    near4 |= bits;
-                    if (dy >= -2 && dy <= 2) near2 |= bits;
-                }
-                s.need_u[ptid] = (near4 | (near4 << 1) | (near4 << 2) | (near4 >> 1) | (near4 >> 2)) & rowmask;
-                s.need_b[ptid] = (near2 | (near2 << 1) | (near2 >> 1)) & rowmask;
-            }
-        } else if (ptid < g.H) {
-            s.need_u[ptid] = ~0ull;
-            s.need_b[ptid] = ~0ull;
-        }
-        bar_sync(BAR_P, kPThreads);
-        CPT_TICK(ptid == 0, 4);   // hot map + barrier
-        // ------------------------------------------------------------ sweep 2b: U (K2) for the marked groups
-        if (!no_fg) {
-            const float range_f = (float)gmx - (float)gmn;
-            const uint32_t degen_val = (gmx == 0) ? 0u : 1u;
 #pragma unroll
             for (int j = 0; j < kIter; ++j) {
-                int grp = ptid + j * kPThreads;
+                const int grp = ptid + j * kPThreads;
+                bool want_u = false, want_b = false;
                 if (grp < g.groups) {
-                    int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr;
-                    if (!((s.need_u[y] >> (2 * gx)) & 3ull)) continue;
-                    const uint4 pv = ldg16(P + grp * 8);  // just streamed: an L1 / L2 hit
-                    const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
-                    const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
-                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-                    uint32_t u[8];
-                    const int off = -ac;  // G - min = max(F - ac, 0) - gmn
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const int g0 = max(dp2a_us(pw[w], kLoP, dp2a_us(bw[w], kLoN, off)), 0) - gmn;
-                        const int g1 = max(dp2a_us(pw[w], kHiP, dp2a_us(bw[w], kHiN, off)), 0) - gmn;
-                        if (degenerate) {
-                            u[2 * w] = degen_val; u[2 * w + 1] = degen_val;
-                        } else if (umagic) {
-                            u[2 * w] = norm_u8_int(g0, umagic, ushift); u[2 * w + 1] = norm_u8_int(g1, umagic, ushift);
-                        } else {
-                            u[2 * w] = norm_u8(g0, range_f); u[2 * w + 1] = norm_u8(g1, range_f);
-                        }
-                    }
-                    uint2 w;
-                    w.x = u[0] | (u[1] << 8) | (u[2] << 16) | (u[3] << 24);
-                    w.y = u[4] | (u[5] << 8) | (u[6] << 16) | (u[7] << 24);
-                    *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
+                    const int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr;
+                    want_u = (s.need_u[y] >> (2 * gx)) & 3ull;
+                    want_b = (s.need_b[y] >> (2 * gx)) & 3ull;
+                }
+                // one counter bump per warp and list
+                const unsigned mu = __ballot_sync(0xffffffffu, want_u), mb = __ballot_sync(0xffffffffu, want_b);
+                const unsigned below = (1u << lane) - 1u;
+                if (mu) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s.bcast_i[11], __popc(mu));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const int slot = base + __popc(mu & below);
+                    if (want_u && slot < kListCap) s.list_u[slot] = (uint16_t)grp;
+                }
+                if (mb) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s.bcast_i[12], __popc(mb));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const int slot = base + __popc(mb & below);
+                    if (want_b && slot < kListCap) s.list_b[slot] = (uint16_t)grp;
                 }
             }
+            bar_sync(BAR_P, kPThreads);
+            n_u = s.bcast_i[11];
+            n_b = s.bcast_i[12];
+            if (n_u > kListCap || n_b > kListCap) dense = true;  // (the marks stay valid: dense work honours them)
         }
-        bar_sync(BAR_P, kPThreads);
+        CPT_TICK(ptid == 0, 4);   // marks + lists
+        // ------------------------------------------------------------ sweep 2b: U (K2)
+        if (!no_fg) {
+            if (dense) {
+                if (fth == INT32_MIN && ptid < g.H) { s.need_u[ptid] = ~0ull; s.need_b[ptid] = ~0ull; }
+                for (int grp = ptid; grp < g.groups; grp += kPThreads) normalise_group(s, P, grp, ac, gmn, gmx);
+            } else {
+                for (int i = ptid; i < n_u; i += kPThreads) normalise_group(s, P, s.list_u[i], ac, gmn, gmx);
+            }
+            bar_sync(BAR_P, kPThreads);
+        }
         CPT_TICK(ptid == 0, 5);   // sweep 2b + barrier
 
         // ------------------------------------------------------------ blur + threshold (K4) -> s.M[buf]
+        // (the component warps hand the buffer back zeroed)
         if (t >= 2) bar_sync(BAR_EMPTY + buf, kThreads);  // component warps are done with frame t-2's mask
         CPT_TICK(ptid == 0, 6);   // wait for the mask buffer
-        blur_threshold(s, g, ptid, buf, ith);
+        if (!no_fg) {
+            if (dense) {
+                for (int grp = ptid; grp < g.groups; grp += kPThreads) blur_group(s, g, grp, buf, ith);
+            } else {
+                for (int i = ptid; i < n_b; i += kPThreads) blur_group(s, g, s.list_b[i], buf, ith);
+            }
+        }
         if (ptid == 0) { s.msg[buf][0] = cur_fmin; s.msg[buf][1] = cur_fmax; }
         bar_arrive(BAR_FULL + buf, kThreads);
         CPT_TICK(ptid == 0, 7);   // blur
