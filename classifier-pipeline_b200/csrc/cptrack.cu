@@ -12,6 +12,7 @@
 
 namespace cpt {
 __global__ void extract_clips_kernel(const KernelArgs a);
+__global__ void region_variance_kernel(Geometry g, long long total_frames, const float *filtered, cpt_frame_info *info, cpt_region *regions);
 __global__ void background_step_kernel(Geometry g, uint8_t *state, const int32_t *frames, const int *record_index, WeightTable wt);
 __global__ void frame_median_kernel(const uint16_t *frames, int npx, float *out);
 }
@@ -289,7 +290,7 @@ int cpt_debug_phase_cycles(cpt_ctx *c, long long *h_out32, int reset) {
 uint64_t cpt_state_bytes(const cpt_ctx *c) { return c ? cpt::state_bytes(c->g.npx) : 0; }
 
 static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_clips, int n_clips,
-                          const cpt_outputs *out, void *d_state, cudaStream_t stream) {
+                          const cpt_outputs *out, void *d_state, cudaStream_t stream, long long total_frames) {
     if (n_clips == 0) return CPT_OK;
     int grid = std::min(n_clips, c->num_sms);
     if (!out->d_filtered && c->scratch_ctas < (size_t)grid) {
@@ -315,8 +316,16 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     a.work_counter = c->work_counter;
     a.debug = c->debug;
     CUDA_TRY(cudaMemsetAsync(c->work_counter, 0, sizeof(int), stream));
+    // with the filtered images kept and the frame count known, the per-region variances of all frames but the
+    // first of each clip are computed by a second, wide launch
+    a.defer_variance = (out->d_filtered != nullptr && total_frames > 1) ? 1 : 0;
     cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
     CUDA_TRY(cudaGetLastError());
+    if (a.defer_variance) {
+        const unsigned blocks = (unsigned)((total_frames + 7) / 8);
+        cpt::region_variance_kernel<<<blocks, 256, 0, stream>>>(c->g, total_frames, out->d_filtered, out->d_info, out->d_regions);
+        CUDA_TRY(cudaGetLastError());
+    }
     return CPT_OK;
 }
 
@@ -330,7 +339,8 @@ int cpt_extract_batch(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_cl
     if (!c->tables[0].d_thr && !c->tables[1].d_thr && !c->tables[2].d_thr && !c->tables[3].d_thr)
         return fail(CPT_ERR_INVALID, "no weight table set (cpt_set_weight_table)");
     CUDA_TRY(cudaSetDevice(c->device));
-    return launch_extract(c, d_frames, d_clips, n_clips, out, d_state, c->stream);
+    if (out->total_frames < 0) return fail(CPT_ERR_INVALID, "total_frames < 0");
+    return launch_extract(c, d_frames, d_clips, n_clips, out, d_state, c->stream, out->total_frames);
 }
 
 static int ensure_stage(cpt_ctx *c, size_t frames_bytes, size_t out_frames, bool filtered, bool labels) {
@@ -424,8 +434,9 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
         if (ch >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
         cpt_outputs out{c->stage_regions[b], c->stage_info[b], h_filtered ? c->stage_filtered[b] : nullptr,
-                        h_labels ? c->stage_labels[b] : nullptr};
-        rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream);
+                        h_labels ? c->stage_labels[b] : nullptr, sp.out_hi - sp.out_lo};
+        rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream,
+                            sp.out_hi - sp.out_lo);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev_compute[b], c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->ev_compute[b], 0));

@@ -107,6 +107,7 @@ struct KernelArgs {
     uint8_t *state;       // n_clips * state_bytes or nullptr
     int *work_counter;    // zeroed before launch
     long long *debug;     // [gridDim.x][32] phase cycle counters (CPT_PHASE_TIMING builds), else nullptr
+    int defer_variance;   // leave K6 of frames t > 0 to region_variance_kernel (needs `filtered`)
     WeightTable tables[4];
 };
 

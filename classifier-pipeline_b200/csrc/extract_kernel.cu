@@ -113,7 +113,7 @@ struct RunCursor {
 // K4 second half + K5 + K6 for the mask in s.M[buf].  Called by all kCThreads component threads.
 __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry &g, int ctid, int buf, size_t o,
                                     const float *fcur, const float *fprev, int cur_fmin, int cur_fmax, int prev_fmin,
-                                    int prev_fmax, bool have_prev) {
+                                    int prev_fmax, bool have_prev, bool defer_variance) {
     const int W = g.W, lane = ctid & 31, cwarp = ctid >> 5;
     constexpr int kIter = (kMaxWords + kCThreads - 1) / kCThreads;  // 3
     RunCursor rc[kIter];
@@ -304,7 +304,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
     }
     CPT_TICK2(ctid == 0, 26);  // label writes
     // ---- delta-frame variance over each component's bounding box (K6)
-    if (have_prev) {
+    if (have_prev && !defer_variance) {
         const bool exact = 255ll * max(cur_fmax - cur_fmin, prev_fmax - prev_fmin) < (1ll << 24) &&
                            max(max(abs(cur_fmax), abs(cur_fmin)), max(abs(prev_fmax), abs(prev_fmin))) < (1 << 24);
         for (int slot = 0; slot < nslots; ++slot) {
@@ -343,11 +343,14 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             double n = (double)r.width * (double)r.height;
             double mean = s.acc_s[i] / n;
             double var = s.acc_s2[i] / n - mean * mean;
-            r.pixel_variance = (have_prev && var > 0.0) ? var : 0.0;
+            r.pixel_variance = (have_prev && !defer_variance && var > 0.0) ? var : 0.0;
             a.regions[o * g.max_regions + rank] = r;
         }
     }
-    if (ctid == 0) a.info[o].n_components = ncomp;
+    if (ctid == 0) {
+        a.info[o].n_components = ncomp;
+        if (have_prev && defer_variance) a.info[o].reserved[0] = 1;  // region_variance_kernel fills pixel_variance
+    }
 }
 
 __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int ctid, float *scratch,
@@ -368,8 +371,10 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         const int cur_fmin = s.msg[buf][0], cur_fmax = s.msg[buf][1];
         const float *fcur = filtered_ptr(a, clip, scratch, t);
         const float *fprev = (t == 0) ? st_F : filtered_ptr(a, clip, scratch, t - 1);
+        // frames after the first of a launch have both filtered images in the caller's buffer: their variances
+        // are left to region_variance_kernel (a wide second launch) instead of this 7-warp critical path
         components_of_frame(a, s, g, ctid, buf, (size_t)(clip.out_offset + t), fcur, fprev, cur_fmin, cur_fmax, prev_fmin,
-                            prev_fmax, have_prev);
+                            prev_fmax, have_prev, a.defer_variance && t > 0);
         prev_fmin = cur_fmin;
         prev_fmax = cur_fmax;
         have_prev = true;
@@ -1096,6 +1101,46 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
             component_warps(a, s, clip, tid - kPThreads, scratch, st_hdr, st_F);
         }
     }
+}
+
+// K6 for the frames the extraction kernel deferred (info.reserved[0] == 1): per-region variance of the
+// normalised delta frame |norm255(F_t) - norm255(F_t-1)| over the component's bounding box
+// (track/cliptracker.py:249-261,316-318).  One warp per frame; both filtered images are in the output buffer.
+__global__ void __launch_bounds__(256) region_variance_kernel(Geometry g, long long total_frames, const float *filtered,
+                                                              cpt_frame_info *info, cpt_region *regions) {
+    const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (o >= total_frames) return;
+    cpt_frame_info *fi = info + o;
+    if (o == 0 || fi->reserved[0] != 1) return;
+    const int n = min(fi->n_components, g.max_regions);
+    const int cur_fmin = fi->filtered_min, cur_fmax = fi->filtered_max;
+    const int prev_fmin = fi[-1].filtered_min, prev_fmax = fi[-1].filtered_max;
+    const bool exact = 255ll * max(cur_fmax - cur_fmin, prev_fmax - prev_fmin) < (1ll << 24) &&
+                       max(max(abs(cur_fmax), abs(cur_fmin)), max(abs(prev_fmax), abs(prev_fmin))) < (1 << 24);
+    const float *fcur = filtered + (size_t)o * g.npx, *fprev = fcur - g.npx;
+    for (int r = 0; r < n; ++r) {
+        cpt_region *reg = regions + (size_t)o * g.max_regions + r;
+        const int l = reg->x, tp = reg->y, bw = reg->width, bh = reg->height, npix = bw * bh;
+        if (l < 0 || tp < 0 || bw < 1 || bh < 1 || l + bw > g.W || tp + bh > g.H) continue;  // not a record of this launch
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = lane; i < npix; i += 32) {
+            const int yy = i / bw, xx = i - yy * bw, p = (tp + yy) * g.W + l + xx;
+            const int fc = (int)__ldg(fcur + p), fp = (int)__ldg(fprev + p);
+            const float d = fabsf(norm255(fc, cur_fmin, cur_fmax, exact) - norm255(fp, prev_fmin, prev_fmax, exact));
+            s1 += (double)d;
+            s2 += (double)d * (double)d;
+        }
+        for (int off = 16; off; off >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        }
+        if (lane == 0) {
+            const double cnt = (double)npix, mean = s1 / cnt, var = s2 / cnt - mean * mean;
+            reg->pixel_variance = var > 0.0 ? var : 0.0;
+        }
+    }
+    if (lane == 0) fi->reserved[0] = 0;
 }
 
 static_assert(sizeof(Smem) <= 232448, "shared memory budget (227 KB per CTA on sm_100)");

@@ -76,7 +76,7 @@ MOTION_MEAN, MOTION_MEAN_RESTART, MOTION_BACKGROUND, MOTION_DETECT, MOTION_WARME
 class CptOutputs(ctypes.Structure):
     _fields_ = [
         ("d_regions", ctypes.c_void_p), ("d_info", ctypes.c_void_p), ("d_filtered", ctypes.c_void_p),
-        ("d_labels", ctypes.c_void_p),
+        ("d_labels", ctypes.c_void_p), ("total_frames", ctypes.c_int64),
     ]
 
 
@@ -233,8 +233,9 @@ class Context:
     def weight_value(self, slot, count):
         return self.lib.cpt_weight_value(self._h, slot, int(count))
 
-    def extract_batch(self, d_frames, d_clips, n_clips, d_regions, d_info, d_filtered=None, d_labels=None, d_state=None):
-        out = CptOutputs(_ptr(d_regions), _ptr(d_info), _ptr(d_filtered), _ptr(d_labels))
+    def extract_batch(self, d_frames, d_clips, n_clips, d_regions, d_info, d_filtered=None, d_labels=None, d_state=None,
+                      total_frames=0):
+        out = CptOutputs(_ptr(d_regions), _ptr(d_info), _ptr(d_filtered), _ptr(d_labels), int(total_frames))
         check(self.lib.cpt_extract_batch(self._h, _ptr(d_frames), _ptr(d_clips), int(n_clips), ctypes.byref(out), _ptr(d_state)))
 
     def extract_batch_host(self, h_frames, h_clips, total_frames, h_regions, h_info, h_filtered=None, h_labels=None, chunk_clips=0):

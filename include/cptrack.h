@@ -92,6 +92,9 @@ typedef struct {
     cpt_frame_info *d_info;  /* [total_frames] */
     float *d_filtered;       /* [total_frames][H][W]  K1: float32(thermal) - background */
     uint8_t *d_labels;       /* [total_frames][H][W]  K5 label image (0 = background) */
+    int64_t total_frames;    /* frames the per-frame outputs hold (max over clips of out_offset + n_frames); with
+                                d_filtered set it lets a second, wide launch compute the per-region variances.
+                                0 = unknown: they are computed inside the extraction kernel */
 } cpt_outputs;
 
 /* Persistent per-clip state (WeightedBackground + sliding sum), one record per clip:
