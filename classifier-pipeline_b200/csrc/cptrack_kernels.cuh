@@ -130,10 +130,9 @@ struct __align__(16) Smem {
     double bcast_d[4];
     double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
     uint32_t wthr[kSmemWeights];                   // first entries of the clip's keep-test table
-    unsigned long long need_u[kMaxH];  // per row, one bit per quad: U is an input of a blur window that can exceed the threshold
-    unsigned long long need_b[kMaxH];  // per row, one bit per quad: the blurred output can exceed the threshold
+    uint32_t hotbits[kMaxPx / 4 / 32 + 4];  // one bit per owned quad: some pixel can exceed the threshold
     uint16_t list_u[kListCap];  // groups of 8 pixels to normalise this frame (need_u)
-    uint16_t list_b[kListCap];  // groups of 8 pixels to blur this frame (need_b)
+    uint16_t list_b[kListCap];  // groups of 8 pixels to blur this frame: group | quad marks << 14
     int32_t ncomp;
 };
 

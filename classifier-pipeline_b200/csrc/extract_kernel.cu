@@ -394,14 +394,13 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
 
 // K4 first half for one group of 8 pixels: 5x5 binomial blur of s.U (fixed point, one rounding,
 // BORDER_REFLECT_101) in packed 16-bit lanes and threshold `> ith` -> one byte of the bit rows in s.M[buf].
-// Only outputs of quads marked in need_b are evaluated: the others cannot exceed the threshold (every input
+// Only outputs of the marked quads (q2: one bit per quad of the group) are evaluated: the others cannot exceed the threshold (every input
 // of their window is <= ith) and their windows may reach inputs that were not refreshed.
-__device__ __forceinline__ void blur_group(Smem &s, const Geometry &g, int grp, int buf, int ith) {
+__device__ __forceinline__ void blur_group(Smem &s, const Geometry &g, int grp, uint32_t q2, int buf, int ith) {
     const int W = g.W, H = g.H;
     uint8_t *M8 = reinterpret_cast<uint8_t *>(s.M[buf]);
     const uint32_t T = (ith >= 0 && ith < 255) ? (uint32_t)(((ith + 1) << 8) - 128) : 0u;
     const int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr, x0 = gx * 8;
-    const uint32_t q2 = (uint32_t)(s.need_b[y] >> (2 * gx)) & 3u;
     uint32_t bits = 0;
     if (ith < 0) {
         bits = 0xffu;
@@ -466,24 +465,13 @@ __device__ __forceinline__ void normalise_group(Smem &s, const uint16_t *P, int 
     *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
 }
 
-// Hot quads (some pixel can exceed the threshold) mark the outputs that may fire (rows +-2, neighbouring quads)
-// and the inputs those outputs read (rows +-4, quads +-2).  Blur weights sum to 256, so nothing else can.
-// Warp-aggregated: `hot` holds the hot quads of ONE row as a bit field; lanes 0..8 of the calling half-warp
-// each OR the dilated field into one of the rows y-4 .. y+4 (32-bit halves: native shared-memory atomics).
-__device__ __forceinline__ void mark_hot_row(Smem &s, const Geometry &g, int y, unsigned long long hot, int dr) {
-    const int r = y + dr;
-    if (hot == 0 || dr < -4 || dr > 4 || r < 0 || r >= g.H) return;
-    const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
-    const unsigned long long um = (hot | (hot << 1) | (hot << 2) | (hot >> 1) | (hot >> 2)) & rowmask;
-    uint32_t *nu = reinterpret_cast<uint32_t *>(&s.need_u[r]);
-    if ((uint32_t)um) atomicOr(nu, (uint32_t)um);
-    if ((uint32_t)(um >> 32)) atomicOr(nu + 1, (uint32_t)(um >> 32));
-    if (dr >= -2 && dr <= 2) {
-        const unsigned long long bm = (hot | (hot << 1) | (hot >> 1)) & rowmask;
-        uint32_t *nb = reinterpret_cast<uint32_t *>(&s.need_b[r]);
-        if ((uint32_t)bm) atomicOr(nb, (uint32_t)bm);
-        if ((uint32_t)(bm >> 32)) atomicOr(nb + 1, (uint32_t)(bm >> 32));
-    }
+// 40-bit row field of the owned-quad hot bits starting at bit `pos`
+__device__ __forceinline__ unsigned long long hot_field(const uint32_t *bits, int pos) {
+    const int w = pos >> 5, sh = pos & 31;
+    const unsigned long long lo = ((unsigned long long)bits[w + 1] << 32) | bits[w];
+    unsigned long long v = lo >> sh;
+    if (sh) v |= (unsigned long long)bits[w + 2] << (64 - sh);
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -626,36 +614,6 @@ __device__ __forceinline__ int sweep_quad(Smem &s, const WeightTable &wt, const 
     return kFrame ? filter_quad(pw, ow, p4, nb, sv, s.S, fcur, lab_frame, kStats, acc) : INT32_MIN;
 }
 
-// A border row takes the adjacent owned row's background (edge replication); run by that row's owner thread,
-// out of line (two rows of the frame) with its partial results returned by value.
-struct BorderOut {
-    uint32_t psum, fabs_sum;
-    int fmin, fmax, pmin, pmax;
-};
-
-template <bool kUpdate, bool kFrame, bool kStats>
-__device__ __noinline__ BorderOut border_quad(uint16_t *B, uint32_t *S, int pb, uint2 nb, const uint16_t *P, const uint16_t *Pold,
-                                              float *fcur, uint8_t *lab_frame) {
-    SweepAcc acc;
-    if (kUpdate) *reinterpret_cast<uint2 *>(B + pb) = nb;
-    if (kFrame) {
-        const uint2 pw = ldg8(P + pb);
-        const uint2 ow = Pold ? ldg8(Pold + pb) : make_uint2(0, 0);
-        const uint4 sv = *reinterpret_cast<const uint4 *>(S + pb);
-        (void)filter_quad(pw, ow, pb, nb, sv, S, fcur, lab_frame, kStats, acc);
-    }
-    return BorderOut{acc.psum, acc.fabs_sum, acc.fmin, acc.fmax, acc.pmin, acc.pmax};
-}
-
-__device__ __forceinline__ void merge_border(SweepAcc &acc, const BorderOut &b) {
-    acc.psum += b.psum;
-    acc.fabs_sum += b.fabs_sum;
-    acc.fmin = min(acc.fmin, b.fmin);
-    acc.fmax = max(acc.fmax, b.fmax);
-    acc.pmin = min(acc.pmin, b.pmin);
-    acc.pmax = max(acc.pmax, b.pmax);
-}
-
 // kUnrolled: straight-line code with the per-quad maxima in registers (the steady state); otherwise a rolled
 // loop whose maxima go through local memory (first frame, tail pass, exact keep test: once per clip).
 template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled>
@@ -689,19 +647,25 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
             if (it == th.last_it) nb_bottom = nb;
         }
     }
-    if (g.edge && th.active) {
-        if (th.r0 == 0) {
-            const BorderOut b = border_quad<kUpdate, kFrame, kStats>(s.B, s.S, th.p4_0 - g.W, nb_top, P, Pold, fcur, lab_frame);
-            merge_border(acc, b);
-            gmaxq[0] = max(gmaxq[0], b.fmax);  // the quad's only pixels: its max F
-        }
-        if (th.last_it >= 0) {
-            const BorderOut b = border_quad<kUpdate, kFrame, kStats>(s.B, s.S, th.p4_0 + th.last_it * th.stride + g.W, nb_bottom, P,
-                                                                     Pold, fcur, lab_frame);
-            merge_border(acc, b);
+    // A border row takes the adjacent owned row's background (edge replication); run by that row's owner thread.
+    // One rolled body for both rows: two rows of the frame do not deserve straight-line copies.
+    if (g.edge && th.active && (th.r0 == 0 || th.last_it >= 0)) {
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? (th.r0 != 0) : (th.last_it < 0)) continue;
+            const int pb = side == 0 ? th.p4_0 - g.W : th.p4_0 + th.last_it * th.stride + g.W;
+            const uint2 nb = side == 0 ? nb_top : nb_bottom;
+            if (kUpdate) *reinterpret_cast<uint2 *>(s.B + pb) = nb;
+            if (kFrame) {
+                const uint2 pw = ldg8(P + pb);
+                const uint2 ow = Pold ? ldg8(Pold + pb) : make_uint2(0, 0);
+                const uint4 sv = *reinterpret_cast<const uint4 *>(s.S + pb);
+                const int hi = filter_quad(pw, ow, pb, nb, sv, s.S, fcur, lab_frame, kStats, acc);
+                const int slot = side == 0 ? 0 : th.last_it;
 #pragma unroll
-            for (int it = 0; it < kQIter; ++it)
-                if (it == th.last_it) gmaxq[it] = max(gmaxq[it], b.fmax);
+                for (int it = 0; it < kQIter; ++it)
+                    if (it == slot) gmaxq[it] = max(gmaxq[it], hi);
+            }
         }
     }
 }
@@ -767,7 +731,6 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     // ---------------------------------------------------------------- init / resume
     for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
     for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
-    if (ptid < kMaxH) { s.need_u[ptid] = 0; s.need_b[ptid] = 0; }
     if (clip.flags & CPT_CLIP_RESUME) {
         if (ptid == 0) s.bcast_i[10] = 0;
         bar_sync(BAR_P, kPThreads);
@@ -845,7 +808,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             // the update belongs to frame t-1: the mean covers min(t_abs, 45) frames
             const uint32_t cnt = (uint32_t)min(max(t_abs, 1), kMeanFrames);
             m.first_mean = (cnt == 1u);
-            m.magic = m.first_mean ? 0u : (uint32_t)(0x100000000ull / cnt) + 1u;  // exact for S < 2^22, cnt <= 45
+            m.magic = m.first_mean ? 0u : 0xffffffffu / cnt + 1u;  // floor(S / cnt) == umulhi(S, magic): exact for S < 2^22, cnt <= 45
             m.slow = s.bcast_i[9] != 0;
             const int k_cap = frames_seen;  // no weight counter can exceed the number of updates so far
             m.table = (k_cap < wt.linear_upto) ? 0 : ((k_cap < kSmemWeights) ? 1 : 2);
@@ -884,6 +847,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 v4 = __reduce_max_sync(0xffffffffu, in ? (int)r[4] : INT32_MIN);
                 v5 = __reduce_add_sync(0xffffffffu, in ? r[5] : 0u);
             }
+            CPT_TICK(ptid == 0, 15);  // scalars: warp reductions
             if (lane == 0) {
                 if (m.update && changed) {
                     // int(round(np.average(background))), motiondetector.py:232 -- half to even, in integers
@@ -934,6 +898,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                         if (it >= 0 && it < 255) fth = (int)(((unsigned)(it + 1) * r + 254u) / 255u) + ac + gmn;
                     }
                 }
+                CPT_TICK(ptid == 0, 16);  // scalars: lane-0 arithmetic
                 s.bcast_i[0] = ac; s.bcast_i[1] = gmn; s.bcast_i[2] = gmx;
                 s.bcast_i[3] = v1; s.bcast_i[4] = v2;
                 s.bcast_i[5] = __float_as_int(thr);
@@ -949,12 +914,6 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             }
         }
         if (m.update) ++frames_seen;
-        // (idle while warp 0 works) the marks and lists of the previous frame are dead since the sweep barrier
-        if (warp != 0) {
-            const int i = ptid - 32;
-            if (i < g.H) { s.need_u[i] = 0; s.need_b[i] = 0; }
-            if (i == kMaxH) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
-        }
         bar_sync(BAR_P, kPThreads);
         CPT_TICK(ptid == 0, 3);   // scalars + barrier
         if (!is_frame) break;
@@ -964,65 +923,64 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         const int fth = s.bcast_i[8];
         const int ith = (int)floorf(thr);
 
-        // ------------------------------------------------------------ hot quads -> marks -> work lists
-        // (a border row's quads count for the owned row next to them, which only widens the marks)
+        // ------------------------------------------------------------ hot quads -> per-row marks -> work lists
+        // A quad is hot if one of its pixels can exceed the threshold (a border row's quads count for the owned
+        // row next to them, which only widens the marks).  Blur weights sum to 256, so an output can fire only
+        // within rows +-2 / neighbouring quads of a hot quad, and reads U within rows +-4 / quads +-2.
         const bool no_fg = ith >= 255;          // nothing can exceed the threshold: the mask stays empty
         bool dense = (fth == INT32_MIN);        // no usable bound: every group is normalised and blurred
         int n_u = 0, n_b = 0;
         if (!no_fg && !dense) {
-            // a warp's 32 quads of one iteration lie in at most two consecutive rows
-            const int wbase = warp * 32, wr = wbase / g.qpr, wq = wbase - wr * g.qpr;
-            const int n_first = min(32, g.qpr - wq);  // lanes in the first of the two rows
 #pragma unroll
             for (int it = 0; it < kQIter; ++it) {
                 const unsigned mbits = __ballot_sync(0xffffffffu, gmaxq[it] >= fth);  // unowned slots hold INT32_MIN
-                if (mbits) {
-                    const int y = wr + it * g.rows_per_it + g.edge;
-                    const unsigned first = (n_first >= 32) ? mbits : (mbits & ((1u << n_first) - 1u));
-                    const unsigned second = (n_first >= 32) ? 0u : (mbits >> n_first);
-                    // lanes 0..8: first row, lanes 16..24: second row; one target row each
-                    if (lane < 16) mark_hot_row(s, g, y, (unsigned long long)first << wq, lane - 4);
-                    else mark_hot_row(s, g, y + 1, (unsigned long long)second, lane - 20);
-                }
+                if (lane == 0) s.hotbits[it * kPWarps + warp] = mbits;  // bit (q & 31) of word q >> 5, q = it * kPThreads + ptid
             }
+            if (ptid == 0) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
             bar_sync(BAR_P, kPThreads);
+            // two threads per frame row (one per list): OR the hot rows around the row, widen by the neighbouring
+            // quads, and turn the marks into list entries (groups of 8 pixels; a blur entry carries its two quad marks)
+            const int role = ptid >> 7, rrow = ptid & 127;  // role 0: normalise list, role 1: blur list
+            if (role < 2 && rrow < g.H) {
+                const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
+                const int reach = role == 0 ? 4 : 2;
+                unsigned long long near = 0;
 #pragma unroll
-            for (int j = 0; j < kIter; ++j) {
-                const int grp = ptid + j * kPThreads;
-                bool want_u = false, want_b = false;
-                if (grp < g.groups) {
-                    const int y = (int)(((uint32_t)grp * g.gpr_magic) >> 17), gx = grp - y * g.gpr;
-                    want_u = (s.need_u[y] >> (2 * gx)) & 3ull;
-                    want_b = (s.need_b[y] >> (2 * gx)) & 3ull;
+                for (int dy = -4; dy <= 4; ++dy) {
+                    const int yy = rrow + dy - g.edge;  // owned-row index
+                    if (dy < -reach || dy > reach || yy < 0 || yy >= g.H - 2 * g.edge) continue;
+                    // owned row yy = it * rows_per_it + r: its quads are bits [it * kPThreads + r * qpr, + qpr)
+                    const int hit = yy / g.rows_per_it;
+                    near |= hot_field(s.hotbits, hit * kPThreads + (yy - hit * g.rows_per_it) * g.qpr) & rowmask;
                 }
-                // one counter bump per warp and list
-                const unsigned mu = __ballot_sync(0xffffffffu, want_u), mb = __ballot_sync(0xffffffffu, want_b);
-                const unsigned below = (1u << lane) - 1u;
-                if (mu) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s.bcast_i[11], __popc(mu));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const int slot = base + __popc(mu & below);
-                    if (want_u && slot < kListCap) s.list_u[slot] = (uint16_t)grp;
-                }
-                if (mb) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s.bcast_i[12], __popc(mb));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const int slot = base + __popc(mb & below);
-                    if (want_b && slot < kListCap) s.list_b[slot] = (uint16_t)grp;
+                if (near) {
+                    unsigned long long m = near | (near << 1) | (near >> 1);
+                    if (role == 0) m |= (near << 2) | (near >> 2);
+                    m &= rowmask;
+                    // group g of the row is wanted if either of its quads (bits 2g, 2g + 1) is marked
+                    unsigned long long grp_bits = (m | (m >> 1)) & 0x5555555555555555ull;
+                    const int row_grp = rrow * g.gpr;
+                    int base = atomicAdd(&s.bcast_i[11 + role], __popcll(grp_bits));
+                    uint16_t *list = role == 0 ? s.list_u : s.list_b;
+                    while (grp_bits) {
+                        const int bit = __ffsll((long long)grp_bits) - 1;
+                        grp_bits &= grp_bits - 1;
+                        const uint32_t quads = role == 0 ? 0u : (uint32_t)((m >> bit) & 3ull);
+                        if (base < kListCap) list[base] = (uint16_t)((row_grp + (bit >> 1)) | (quads << 14));
+                        ++base;
+                    }
                 }
             }
             bar_sync(BAR_P, kPThreads);
             n_u = s.bcast_i[11];
             n_b = s.bcast_i[12];
-            if (n_u > kListCap || n_b > kListCap) dense = true;  // (the marks stay valid: dense work honours them)
+            // lists overflowed: dense work (every quad evaluated; a superset of the marks, so still exact)
+            if (n_u > kListCap || n_b > kListCap) dense = true;
         }
         CPT_TICK(ptid == 0, 4);   // marks + lists
         // ------------------------------------------------------------ sweep 2b: U (K2)
         if (!no_fg) {
             if (dense) {
-                if (fth == INT32_MIN && ptid < g.H) { s.need_u[ptid] = ~0ull; s.need_b[ptid] = ~0ull; }
                 for (int grp = ptid; grp < g.groups; grp += kPThreads) normalise_group(s, P, grp, ac, gmn, gmx);
             } else {
                 for (int i = ptid; i < n_u; i += kPThreads) normalise_group(s, P, s.list_u[i], ac, gmn, gmx);
@@ -1037,9 +995,12 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         CPT_TICK(ptid == 0, 6);   // wait for the mask buffer
         if (!no_fg) {
             if (dense) {
-                for (int grp = ptid; grp < g.groups; grp += kPThreads) blur_group(s, g, grp, buf, ith);
+                for (int grp = ptid; grp < g.groups; grp += kPThreads) blur_group(s, g, grp, 3u, buf, ith);
             } else {
-                for (int i = ptid; i < n_b; i += kPThreads) blur_group(s, g, s.list_b[i], buf, ith);
+                for (int i = ptid; i < n_b; i += kPThreads) {
+                    const uint32_t e = s.list_b[i];
+                    blur_group(s, g, (int)(e & 0x3fffu), e >> 14, buf, ith);
+                }
             }
         }
         if (ptid == 0) { s.msg[buf][0] = cur_fmin; s.msg[buf][1] = cur_fmax; }

@@ -35,12 +35,12 @@ def main(clips=148, frames=300, exp=0):
     ex.extract_device(d_frames, cl, out=out)
     torch.cuda.synchronize()
     native.check(ex.ctx.lib.cpt_debug_phase_cycles(ex.ctx._h, buf, 0))
-    names = {13: "P s1 first group", 14: "P s1 rest of groups", 2: "P s1 reduce+bar", 3: "P scalars+bar", 4: "P sweep2a+bar", 5: "P sweep2b+bar", 6: "P wait mask buffer", 7: "P blur",
-             8: "P sweep3+bar", 9: "P edges+bar", 11: "C wait mask", 12: "C components",
+    names = {14: "P fused sweep", 2: "P sweep reduce+bar", 15: "P  scalars: reductions", 16: "P  scalars: lane 0 math", 3: "P scalars rest+bar",
+             4: "P marks+lists", 5: "P normalise+bar", 6: "P wait mask buffer", 7: "P blur", 11: "C wait mask", 12: "C components",
              20: "C  close+reset+bar", 21: "C  run starts+bar", 22: "C  unions+bar", 23: "C  roots+bar", 24: "C  run stats+bar",
              25: "C  rank+bar", 26: "C  label writes", 27: "C  variance+bar"}
     total = clips * frames
-    psum = sum(buf[i] for i in list(range(2, 10)) + [13, 14])
+    psum = sum(buf[i] for i in list(range(2, 8)) + [14, 15, 16])
     for i, n in names.items():
         print("{:22s} {:9.0f} cycles/frame".format(n, buf[i] / total))
     print("P total {:.0f} cycles/frame, C total {:.0f}".format(psum / total, (buf[11] + buf[12]) / total))
