@@ -85,6 +85,110 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
 
 
+def measured_traffic(total_frames):
+    """DRAM bytes of one extraction launch, from the committed `ncu --set full` capture (profiles/extract_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per frame of the captured launch, scaled to this launch's frames)."""
+    path = os.path.join(ROOT, "profiles", "extract_traffic.json")
+    try:
+        return float(json.load(open(path))["dram_bytes_per_frame"]) * total_frames
+    except Exception:
+        return None
+
+
+def synthetic_tracks(n_tracks, n_clips, frames, rng, span=45, pick=25):
+    """BASELINE configs[2]: tracks of `span` consecutive frames with drifting boxes inside the crop rectangle
+    (w, h in U(6, 40)); one segment per track = `pick` of its `span` frames (the README's 25-of-45)."""
+    tracks = []
+    for i in range(n_tracks):
+        clip = i % n_clips
+        t0 = int(rng.integers(0, max(frames - span, 1)))
+        n = min(span, frames - t0)
+        w, h = int(rng.integers(6, 41)), int(rng.integers(6, 41))
+        x = rng.integers(1, 159 - w + 1) + np.cumsum(rng.integers(-2, 3, n))
+        y = rng.integers(1, 119 - h + 1) + np.cumsum(rng.integers(-2, 3, n))
+        x = np.clip(x, 1, 159 - w)
+        y = np.clip(y, 1, 119 - h)
+        f = clip * frames + t0 + np.arange(n)
+        regions = np.stack([f, x, y, np.full(n, w), np.full(n, h), np.zeros(n, np.int64)], axis=1)
+        seg = np.sort(rng.choice(f, min(pick, n), replace=False))
+        tracks.append((regions, [seg]))
+    return tracks
+
+
+def bench_preprocess(ex, d_frames, d_filtered, n_clips, frames, n_tracks, steps, torch):
+    """Config C: Interpreter.preprocess_segments for n_tracks tracks (3 launches) on frames resident in HBM."""
+    from classifier_pipeline_b200.batch import BatchPreprocessor
+
+    bp = BatchPreprocessor(ex)
+    rng = np.random.default_rng(77)
+    t_host = time.perf_counter()
+    lim, smp, seg, _ = bp.build_tables(synthetic_tracks(n_tracks, n_clips, frames, rng), seed=1)
+    host_tables_s = time.perf_counter() - t_host
+    d_t = d_frames.reshape(-1, H, W)
+    out = {}
+    crop = (1, 1, W - 2, H - 2)
+    for _ in range(2):
+        bp.run_tables(d_t, d_filtered, lim, smp, seg, n_tracks, crop, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        bp.run_tables(d_t, d_filtered, lim, smp, seg, n_tracks, crop, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n_seg, n_smp = seg.shape[0], len(smp)
+    # algorithmic bytes (SURVEY.md section 8d, medians recomputed): 204800 B written per segment + one full-frame
+    # read per unique track-frame for its median + the crops (thermal u16 + filtered f32)
+    crop_bytes = int((smp["width"].astype(np.int64) * smp["height"] * 6).sum()) + int((lim["width"].astype(np.int64) * lim["height"] * 4).sum())
+    alg_bytes = n_seg * 204800 + n_smp * NPX * 2 + crop_bytes
+    return {
+        "workload": "BASELINE configs[2]: {} tracks x 45 frames, one 25-frame segment each -> ({}, 160, 160, 2) float32".format(n_tracks, n_seg),
+        "segments_per_s": n_seg / (ms * 1e-3), "track_frames_per_s": n_smp / (ms * 1e-3), "ms": ms, "launches_per_pass": 4,
+        "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9, "algorithmic_bytes": alg_bytes, "host_table_build_s": host_tables_s,
+    }
+
+
+class _Window:
+    start = type("T", (), {"dt": "00:00"})()
+    end = type("T", (), {"dt": "00:00"})()
+
+    def use_sunrise_sunset(self):
+        return False
+
+    def inside_window(self):
+        return True
+
+
+def bench_motion(n_frames=400):
+    """Config D: CPTVMotionDetector.process_frame at batch 1 -- host frame in, one fused launch, 32 bytes back."""
+    import types
+
+    from classifier_pipeline_b200.piclassifier.cptvmotiondetector import CPTVMotionDetector
+    from classifier_pipeline_b200.synthetic import make_clip
+
+    pix, _ = make_clip(0, frames=n_frames)
+    cfg = types.SimpleNamespace(
+        motion=types.SimpleNamespace(temp_thresh=2750, delta_thresh=50, count_thresh=3, frame_compare_gap=45, one_diff_only=True,
+                                     trigger_frames=2, edge_pixels=1, warmer_only=True),
+        recorder=types.SimpleNamespace(use_low_power_mode=False, rec_window=_Window(), preview_secs=5, min_secs=5, max_secs=600),
+        location=types.SimpleNamespace())
+    headers = types.SimpleNamespace(model="lepton3", res_x=W, res_y=H, fps=9)
+    CPTVMotionDetector.BACKGROUND_WEIGHT_ADD = 0.1
+    det = CPTVMotionDetector(cfg, None, headers, detect_after=0)
+    frames = [types.SimpleNamespace(pix=pix[t], time_on=10_000_000 + t * 111, last_ffc_time=0) for t in range(n_frames)]
+    lat, moved = [], 0
+    for t, f in enumerate(frames):
+        t0 = time.perf_counter()
+        moved += bool(det.process_frame(f))
+        if t >= 50:
+            lat.append(time.perf_counter() - t0)
+    lat = np.sort(np.array(lat)) * 1e6
+    return {"workload": "BASELINE configs[3]: one stream, batch 1, host frame in / motion flag out", "frames": n_frames,
+            "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]), "max_us": float(lat[-1]),
+            "frames_with_motion": int(moved), "realtime_budget_us": 111111}
+
+
 def cpu_baseline(n_threads, clips_per_thread, frames, pix=None):
     """The C port of the reference path (oracle/) on the host cores, regions-only outputs."""
     from classifier_pipeline_b200.synthetic import clip_model, make_clip
@@ -139,6 +243,8 @@ def main():
     ap.add_argument("--frames", type=int, default=900)
     ap.add_argument("--e2e-clips", type=int, default=0, help="clips per e2e step (0 = auto from host RAM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tracks", type=int, default=10000, help="tracks of the preprocessing measurement (0 = skip)")
+    ap.add_argument("--no-motion", action="store_true")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -209,6 +315,11 @@ def main():
     info = ex.info_numpy(out["info"])
     regions_total = int(np.minimum(info["n_components"], 16).sum())
 
+    # ---- classifier-input preprocessing (configs[2]) on the frames / filtered images still resident in HBM
+    preprocess = None
+    if args.tracks > 0 and rank == 0:
+        preprocess = bench_preprocess(ex, d_frames, out["filtered"], C, T, args.tracks, max(2, min(args.steps, 5)), torch)
+
     # ---- e2e: host frames in, host region lists out, through the C-ABI host call
     e2e = None
     try:
@@ -264,8 +375,14 @@ def main():
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "kernel": "extract_clips_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "peak_source": peak_src,
         },
-        "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary(),
+        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks.summary(),
     }
+    line["roofline"]["traffic"] = measured_traffic(total)
+    line["roofline"]["kernels_per_step"] = ["extract_clips_kernel", "region_variance_kernel"]
+    if preprocess is not None:
+        line["preprocess"] = preprocess
+    if not args.no_motion:
+        line["motion_detector"] = bench_motion()
     if not args.no_cpu_baseline and world >= 1:
         cores = min(os.cpu_count() or 1, 64)
         n_cpu = min(cores, e2e_clips)

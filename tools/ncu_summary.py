@@ -1,5 +1,5 @@
 """Summarise an ncu report (the `--set full` capture of one kernel) into the few numbers DESIGN.md / bench.py cite.
-usage: python tools/ncu_summary.py gpurun_out/prof_X.ncu-rep [frames_in_launch] > profiles/X_summary.txt"""
+usage: python tools/ncu_summary.py gpurun_out/prof_X.ncu-rep [frames_in_launch [traffic.json]] > profiles/X_summary.txt"""
 import csv
 import io
 import subprocess
@@ -17,7 +17,7 @@ WANT = [
 ]
 
 
-def main(path, frames=None):
+def main(path, frames=None, json_out=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
@@ -39,9 +39,14 @@ def main(path, frames=None):
             print("  derived: dram traffic {:.4g} B, duration {:.4g} s, {:.1f} GB/s".format(traffic, dur, traffic / dur / 1e9))
             if frames:
                 print("  derived: {:.0f} B of DRAM traffic per frame ({} frames in the launch); algorithmic 134400 B/frame".format(traffic / frames, frames))
+                if json_out:
+                    import json
+
+                    json.dump({"source": path, "kernel": name, "frames_in_captured_launch": frames, "dram_bytes": traffic,
+                               "dram_bytes_per_frame": traffic / frames, "duration_s": dur}, open(json_out, "w"), indent=1)
         except Exception as e:  # pragma: no cover
             print("  (derived figures unavailable: {})".format(e))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else None)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else None)
