@@ -475,7 +475,8 @@ int cpt_frame_medians(cpt_ctx *c, const uint16_t *d_frames, int64_t n_frames, fl
     if (n_frames < 0 || n_frames > 0x7fffffff) return fail(CPT_ERR_INVALID, "bad n_frames");
     if (n_frames == 0) return CPT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
-    cpt::frame_median_kernel<<<(unsigned)n_frames, 256, (size_t)c->g.npx * sizeof(uint16_t), c->stream>>>(d_frames, c->g.npx, d_medians);
+    const size_t smem = (((size_t)c->g.npx * sizeof(uint16_t) + 15) & ~(size_t)15) + 2048 * sizeof(uint32_t);  // median.cuh bins
+    cpt::frame_median_kernel<<<(unsigned)n_frames, 256, smem, c->stream>>>(d_frames, c->g.npx, d_medians);
     CUDA_TRY(cudaGetLastError());
     return CPT_OK;
 }

@@ -15,6 +15,7 @@
 #include <cfloat>
 
 #include "cptrack_internal.cuh"
+#include "median.cuh"
 
 namespace cpt {
 
@@ -93,63 +94,13 @@ __global__ void __launch_bounds__(128) track_limits_kernel(const float *filtered
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Median (as the sum of the two middle order statistics) of the uint16 values of a rectangle of the frame
-// staged in shared memory: two 256-bin histogram passes (high byte, then low byte within the bucket).
-__device__ int rect_median_sum(const uint16_t *px, int W, int x0, int y0, int w, int h, uint32_t (*hist)[256], int (*sel)[2]) {
-    const int tid = threadIdx.x, n = w * h;
-    for (int i = tid; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) {
-        const int yy = i / w, xx = i - yy * w;
-        atomicAdd(&hist[0][px[(y0 + yy) * W + x0 + xx] >> 8], 1u);
-    }
-    __syncthreads();
-    if (tid < 2) {
-        const int rank = tid == 0 ? (n - 1) / 2 : n / 2;
-        int acc = 0, b = 0;
-        for (; b < 255; ++b) {
-            const int c = (int)hist[0][b];
-            if (rank < acc + c) break;
-            acc += c;
-        }
-        sel[tid][0] = b;
-        sel[tid][1] = rank - acc;
-    }
-    __syncthreads();
-    const int b_lo = sel[0][0], b_hi = sel[1][0];
-    for (int i = tid; i < 256; i += blockDim.x) hist[0][i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) {
-        const int yy = i / w, xx = i - yy * w;
-        const int v = px[(y0 + yy) * W + x0 + xx], hb = v >> 8;
-        if (hb == b_lo) atomicAdd(&hist[0][v & 0xff], 1u);
-        if (hb == b_hi) atomicAdd(&hist[1][v & 0xff], 1u);
-    }
-    __syncthreads();
-    if (tid < 2) {
-        const int rank = sel[tid][1];
-        int acc = 0, b = 0;
-        for (; b < 255; ++b) {
-            const int c = (int)hist[tid][b];
-            if (rank < acc + c) break;
-            acc += c;
-        }
-        sel[tid][1] = (sel[tid][0] << 8) | b;
-    }
-    __syncthreads();
-    const int out = sel[0][1] + sel[1][1];
-    __syncthreads();
-    return out;
-}
-
 // one CTA per unique track-frame
 __global__ void __launch_bounds__(256) sample_median_kernel(const uint16_t *thermal, int W, int H, cpt_sample *samples,
                                                             cpt_track_norm *tracks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *px = reinterpret_cast<uint16_t *>(smem_raw);
-    __shared__ uint32_t hist[2][256];
-    __shared__ int sel[2][2];
+    uint32_t *bins = reinterpret_cast<uint32_t *>(smem_raw + (((size_t)W * H * sizeof(uint16_t) + 15) & ~(size_t)15));
+    __shared__ int red[80];
     cpt_sample *sp = samples + blockIdx.x;
     const cpt_sample r = *sp;
     const int npx = W * H;
@@ -157,10 +108,10 @@ __global__ void __launch_bounds__(256) sample_median_kernel(const uint16_t *ther
     for (int i = threadIdx.x; i < npx / 8; i += blockDim.x) *reinterpret_cast<uint4 *>(px + i * 8) = ldg16(src + i * 8);
     for (int i = (npx / 8) * 8 + threadIdx.x; i < npx; i += blockDim.x) px[i] = src[i];
     __syncthreads();
-    const int frame2 = rect_median_sum(px, W, 0, 0, W, H, hist, sel);  // 2 * median
+    const int frame2 = rect_median_sum(px, W, 0, 0, W, H, bins, red);  // 2 * median
     int crop2 = 0;
     const bool has_crop = r.width > 0 && r.height > 0;
-    if (has_crop) crop2 = rect_median_sum(px, W, r.x, r.y, r.width, r.height, hist, sel);
+    if (has_crop) crop2 = rect_median_sum(px, W, r.x, r.y, r.width, r.height, bins, red);
     if (threadIdx.x == 0) {
         sp->median = 0.5f * (float)frame2;
         // np.median(float32(sub_thermal) - median) <= 0  (interpreter.py:393-399); every value is a multiple of 0.5
@@ -329,7 +280,8 @@ int cpt_preprocess_medians(cpt_ctx *c, const uint16_t *d_thermal, cpt_sample *d_
     if (n_samples == 0) return CPT_OK;
     if (!d_thermal || !d_samples || !d_tracks) return fail(CPT_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    cpt::sample_median_kernel<<<n_samples, 256, (size_t)c->g.npx * sizeof(uint16_t), c->stream>>>(d_thermal, c->g.W, c->g.H,
+    const size_t smem = (((size_t)c->g.npx * sizeof(uint16_t) + 15) & ~(size_t)15) + cpt::kMedianBins * sizeof(uint32_t);
+    cpt::sample_median_kernel<<<n_samples, 256, smem, c->stream>>>(d_thermal, c->g.W, c->g.H,
                                                                                                    d_samples, d_tracks);
     CUDA_TRY(cudaGetLastError());
     return CPT_OK;
