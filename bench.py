@@ -212,8 +212,8 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 64))
-    frames = 200
-    per_thread = 1
+    frames = 900
+    per_thread = 2  # ~3 s of work per step on every host thread
     values = []
     sample = ""
     for step in range(args.warmup + args.steps):
@@ -385,9 +385,9 @@ def main():
         line["motion_detector"] = bench_motion()
     if not args.no_cpu_baseline and world >= 1:
         cores = min(os.cpu_count() or 1, 64)
-        n_cpu = min(cores, e2e_clips)
-        sample = np.ascontiguousarray(h_frames.reshape(e2e_clips, T, H, W)[:n_cpu, : min(T, 300)])
-        v, dt, n_clips = cpu_baseline(cores, 1, 300, pix=sample)
+        n_cpu = min(8 * cores, e2e_clips)  # ~10 s of CPU work: 8 whole clips per host thread
+        sample = np.ascontiguousarray(h_frames.reshape(e2e_clips, T, H, W)[:n_cpu])
+        v, dt, n_clips = cpu_baseline(cores, 1, T, pix=sample)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "first {} clips x {} frames of this run's batch, {:.1f} s".format(n_clips, sample.shape[1], dt)}
     print(json.dumps(line))

@@ -5,8 +5,8 @@ Host-side index bookkeeping only: it decides WHICH 25 frames of a track form a s
 are produced by the preprocessing kernels.  The random draws are made in the reference's order
 (``default_rng(seed)`` for shuffles / padding and the global ``np.random.shuffle`` of the masked
 variant), so a seeded run selects the same frames.  Supported segment types: ALL_RANDOM_MASKED (the
-default), ALL_RANDOM, ALL_RANDOM_NOMIN, IMPORTANT_RANDOM, TOP_RANDOM, ALL_SECTIONS, ALL_SEQUENTIAL and
-IMPORTANT_SEQUENTIAL; the training-only ELONGATION and TOP_SEQUENTIAL types are not part of this path.
+default), ALL_RANDOM, ALL_RANDOM_NOMIN, IMPORTANT_RANDOM, ALL_SECTIONS, ALL_SEQUENTIAL and IMPORTANT_SEQUENTIAL; the training-only ELONGATION and
+TOP_SEQUENTIAL types are not part of this path and TOP_RANDOM is broken in the reference itself.
 """
 import logging
 from enum import Enum
@@ -117,6 +117,10 @@ def get_segments(clip_id, track_id, start_frame, regions, segment_width=25, segm
     for segment_type in segment_types:
         if segment_type in (SegmentType.ELONGATION, SegmentType.TOP_SEQUENTIAL):
             raise NotImplementedError("{} segments are a training-time selection outside this path".format(segment_type))
+        if segment_type == SegmentType.TOP_RANDOM:
+            # the reference sorts the frames into a Python list and then fails on `frames - start_frame`
+            # (datasetstructures.py:1120-1128, 1247): there is no behaviour to reproduce
+            raise NotImplementedError("TOP_RANDOM segments raise TypeError in the reference")
         min_mass = None if segment_type == SegmentType.ALL_RANDOM_NOMIN else segment_min_mass
         usable = _usable_frames(regions, ffc_frames, skip_ffc, frame_min_mass, has_no_mass)
         if fp_frames is not None:
@@ -127,9 +131,6 @@ def get_segments(clip_id, track_id, start_frame, regions, segment_width=25, segm
         usable = np.array(usable)
         min_mass = 1 if min_mass is None else min(min_mass, np.median(mass_history[usable - start_frame]))
         rng = np.random.default_rng(seed=seed)
-        if segment_type == SegmentType.TOP_RANDOM:
-            by_mass = sorted(usable, key=lambda f: mass_history[f - start_frame], reverse=True)[:50]
-            usable = np.array(sorted(by_mass))
         if len(usable) < min_frames and not min_segments:
             stats["too short"] += 1
             continue
