@@ -97,7 +97,9 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
         delete c;
         return nullptr;
     }
-    if (cudaMalloc(&c->work_counter, sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(&c->zero_frame, sizeof(uint16_t) * cpt::kMaxPx) != cudaSuccess ||
+        cudaMemset(c->zero_frame, 0, sizeof(uint16_t) * cpt::kMaxPx) != cudaSuccess ||
+        cudaMalloc(&c->work_counter, sizeof(int)) != cudaSuccess) {
         fail(CPT_ERR_NOMEM, "cudaMalloc failed");
         delete c;
         return nullptr;
@@ -127,6 +129,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     }
     cudaFree(c->scratch);
     cudaFree(c->work_counter);
+    cudaFree(c->zero_frame);
     cudaFree(c->debug);
     cudaFree(c->d_clips);
     cudaFree(c->detect_scratch);
@@ -314,6 +317,7 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     a.state = (uint8_t *)d_state;
     for (int i = 0; i < 4; ++i) a.tables[i] = c->tables[i].device();
     a.work_counter = c->work_counter;
+    a.zero_frame = c->zero_frame;
     a.debug = c->debug;
     CUDA_TRY(cudaMemsetAsync(c->work_counter, 0, sizeof(int), stream));
     // with the filtered images kept and the frame count known, the per-region variances of all frames but the

@@ -50,6 +50,7 @@ struct cpt_ctx {
     float *scratch = nullptr;
     size_t scratch_ctas = 0;
     int *work_counter = nullptr;
+    uint16_t *zero_frame = nullptr;
     long long *debug = nullptr;
     // staging buffers of cpt_extract_batch_host
     void *stage_frames[2] = {nullptr, nullptr};

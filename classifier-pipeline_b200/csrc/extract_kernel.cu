@@ -536,6 +536,7 @@ struct SweepThread {
     bool prefetch;   // first quad of a 128-byte line
     bool first_col, last_col;  // the quad holds a crop-border column (edge == 1)
     uint32_t perm_x, perm_y;   // crop-border columns copy their neighbour (motiondetector.py:239-244)
+    int sel_x, sel_y;          // ... and stay out of the background sum (dp2a selectors)
 };
 
 // keep mask (0xffff per kept pixel) of one packed pair (K7: `background < frame - weight` in table form, see
@@ -573,17 +574,7 @@ __device__ __forceinline__ uint32_t keep_pair(uint32_t b2, uint32_t k2, uint32_t
 // One owned quad: [update] then [frame].  Returns the quad's max F (INT32_MIN without a frame); nb_out = B'.
 template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats>
 __device__ __forceinline__ int sweep_quad(Smem &s, const WeightTable &wt, const SweepThread &th, const SweepMode &m, int p4,
-                                          const uint16_t *P, const uint16_t *Pold, long long next_bytes, bool old_next,
-                                          float *fcur, uint8_t *lab_frame, SweepAcc &acc, uint2 &nb_out) {
-    uint2 pw = make_uint2(0, 0), ow = make_uint2(0, 0);
-    if (kFrame) {
-        pw = ldg8(P + p4);
-        if (Pold) ow = ldg8(Pold + p4);
-        if (th.prefetch && next_bytes) {  // pull the next frame (same layout, next_bytes further on) towards L2
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(P + p4) + next_bytes));
-            if (old_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(Pold + p4) + next_bytes));
-        }
-    }
+                                          uint2 pw, uint2 ow, float *fcur, uint8_t *lab_frame, SweepAcc &acc, uint2 &nb_out) {
     const uint2 bw = *reinterpret_cast<const uint2 *>(s.B + p4);
     const uint4 sv = *reinterpret_cast<const uint4 *>(s.S + p4);
     uint2 nb = bw;
@@ -599,12 +590,10 @@ __device__ __forceinline__ int sweep_quad(Smem &s, const WeightTable &wt, const 
         uint2 nk;
         nk.x = __vadd2(kw.x, 0x00010001u) & keep_x;
         nk.y = __vadd2(kw.y, 0x00010001u) & keep_y;
-        // a border column always equals its neighbour, before and after: it cannot change `changed`, and its
-        // share of the sum is taken out again below
+        // a border column always equals its neighbour, before and after: it cannot change `changed`; the dp2a
+        // selectors leave it out of the sum
         acc.changed |= (nb.x ^ bw.x) | (nb.y ^ bw.y);
-        acc.bsum = (uint32_t)dp2a_us(nb.x, kBoth, dp2a_us(nb.y, kBoth, (int)acc.bsum));
-        if (th.first_col) acc.bsum -= nb.x & 0xffffu;
-        if (th.last_col) acc.bsum -= nb.y >> 16;
+        acc.bsum = (uint32_t)dp2a_us(nb.x, th.sel_x, dp2a_us(nb.y, th.sel_y, (int)acc.bsum));
         *reinterpret_cast<uint2 *>(s.B + p4) = nb;
         *reinterpret_cast<uint2 *>(s.K + p4) = nk;
     }
@@ -614,24 +603,46 @@ __device__ __forceinline__ int sweep_quad(Smem &s, const WeightTable &wt, const 
     return kFrame ? filter_quad(pw, ow, p4, nb, sv, s.S, fcur, lab_frame, kStats, acc) : INT32_MIN;
 }
 
+// The quad's pixels of this frame and of the frame leaving the 45-frame window (a frame of zeros while the window
+// is still filling, so the load is unconditional).
+template <bool kFrame>
+__device__ __forceinline__ void load_quad(int p4, const uint16_t *P, const uint16_t *Pold, uint2 &pw, uint2 &ow) {
+    pw = make_uint2(0, 0);
+    ow = make_uint2(0, 0);
+    if (!kFrame) return;
+    pw = ldg8(P + p4);
+    ow = ldg8(Pold + p4);
+}
+
 // kUnrolled: straight-line code with the per-quad maxima in registers (the steady state); otherwise a rolled
 // loop whose maxima go through local memory (first frame, tail pass, exact keep test: once per clip).
-template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled>
+// kLepton: the geometry is 160x120 with a 1-pixel border (20 rows x 40 quads per iteration), so every offset of the
+// straight-line code is an immediate.
+template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled, bool kLepton>
 __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
-                                            const SweepMode &m, const uint16_t *P, const uint16_t *Pold, long long next_bytes,
-                                            bool old_next, float *fcur, uint8_t *lab_frame, SweepAcc &acc,
-                                            int (&gmaxq)[kQIter]) {
+                                            const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
+                                            uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
     const Geometry &g = a.g;
-    const int owned_rows = g.H - 2 * g.edge;
+    const int owned_rows = kLepton ? 118 : g.H - 2 * g.edge;
+    const int rows_per_it = kLepton ? 20 : g.rows_per_it;
+    const int stride = kLepton ? 20 * 160 : th.stride;
     uint2 nb_top = make_uint2(0, 0), nb_bottom = make_uint2(0, 0);
     if (kUnrolled) {
+        // software pipeline: the global loads of quad it + 1 are in flight while quad it is processed
+        uint2 pw_next, ow_next;
+        load_quad<kFrame>(th.p4_0, P, Pold, pw_next, ow_next);  // (row r0 is always owned when active)
 #pragma unroll
         for (int it = 0; it < kQIter; ++it) {
             gmaxq[it] = INT32_MIN;
-            if (!th.active || th.r0 + it * g.rows_per_it >= owned_rows) continue;
+            // at 160x120 only the last iteration has unowned rows (r0 + 100 < 118)
+            const bool mine = th.active && ((kLepton && it < kQIter - 1) || th.r0 + it * rows_per_it < owned_rows);
+            const uint2 pw = pw_next, ow = ow_next;
+            if (it + 1 < kQIter && th.active && ((kLepton && it + 1 < kQIter - 1) || th.r0 + (it + 1) * rows_per_it < owned_rows))
+                load_quad<kFrame>(th.p4_0 + (it + 1) * stride, P, Pold, pw_next, ow_next);
+            if (!mine) continue;
             uint2 nb;
-            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * th.stride, P, Pold,
-                                                                              next_bytes, old_next, fcur, lab_frame, acc, nb);
+            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * stride, pw, ow, fcur,
+                                                                              lab_frame, acc, nb);
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
@@ -639,10 +650,11 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
 #pragma unroll 1
         for (int it = 0; it < kQIter; ++it) {
             gmaxq[it] = INT32_MIN;
-            if (!th.active || th.r0 + it * g.rows_per_it >= owned_rows) continue;
-            uint2 nb;
-            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * th.stride, P, Pold,
-                                                                              next_bytes, old_next, fcur, lab_frame, acc, nb);
+            if (!th.active || th.r0 + it * rows_per_it >= owned_rows) continue;
+            uint2 nb, pw, ow;
+            load_quad<kFrame>(th.p4_0 + it * stride, P, Pold, pw, ow);
+            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * stride, pw, ow, fcur,
+                                                                              lab_frame, acc, nb);
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
@@ -653,12 +665,12 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
             if (side == 0 ? (th.r0 != 0) : (th.last_it < 0)) continue;
-            const int pb = side == 0 ? th.p4_0 - g.W : th.p4_0 + th.last_it * th.stride + g.W;
+            const int pb = side == 0 ? th.p4_0 - g.W : th.p4_0 + th.last_it * stride + g.W;
             const uint2 nb = side == 0 ? nb_top : nb_bottom;
             if (kUpdate) *reinterpret_cast<uint2 *>(s.B + pb) = nb;
             if (kFrame) {
                 const uint2 pw = ldg8(P + pb);
-                const uint2 ow = Pold ? ldg8(Pold + pb) : make_uint2(0, 0);
+                const uint2 ow = ldg8(Pold + pb);
                 const uint4 sv = *reinterpret_cast<const uint4 *>(s.S + pb);
                 const int hi = filter_quad(pw, ow, pb, nb, sv, s.S, fcur, lab_frame, kStats, acc);
                 const int slot = side == 0 ? 0 : th.last_it;
@@ -673,20 +685,19 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
 // Runtime mode -> instantiation.
 template <bool kStats>
 __device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
-                                                     const SweepMode &m, const uint16_t *P, const uint16_t *Pold,
-                                                     long long next_bytes, bool old_next, float *fcur, uint8_t *lab_frame,
-                                                     SweepAcc &acc, int (&gmaxq)[kQIter]) {
-    const bool steady = m.update && m.frame && !m.slow && !m.first_mean;
+                                                     const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
+                                                     uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
+    const bool steady = m.update && m.frame && !m.slow && !m.first_mean && a.g.W == 160 && a.g.H == 120 && a.g.edge == 1;
     if (steady && m.table == 0)
-        pixel_sweep<true, true, true, 0, kStats, true>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, true, 0, kStats, true, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (steady && m.table == 1)
-        pixel_sweep<true, true, true, 1, kStats, true>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, true, 1, kStats, true, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (!m.update)
-        pixel_sweep<false, true, false, 2, kStats, false>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<false, true, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (m.frame)
-        pixel_sweep<true, true, false, 2, kStats, false>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else
-        pixel_sweep<true, false, false, 2, kStats, false>(a, s, wt, th, m, P, Pold, next_bytes, old_next, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, false, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
 }
 
 // per-warp partial results -> s.red_u[warp * 12 + i]
@@ -787,6 +798,8 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         th.last_col = g.edge && qx == g.qpr - 1;
         th.perm_x = th.first_col ? 0x3232u : 0x3210u;
         th.perm_y = th.last_col ? 0x1010u : 0x3210u;
+        th.sel_x = th.first_col ? kHiP : kBoth;
+        th.sel_y = th.last_col ? kLoP : kBoth;
         const int last_row = g.H - 2 * g.edge - 1;  // owned-row index
         th.last_it = (th.active && last_row % g.rows_per_it == r0) ? last_row / g.rows_per_it : -1;
     }
@@ -814,17 +827,23 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             m.table = (k_cap < wt.linear_upto) ? 0 : ((k_cap < kSmemWeights) ? 1 : 2);
         }
         const uint16_t *P = is_frame ? frame_ptr(a, clip, t) : nullptr;
-        const uint16_t *Pold = (is_frame && t_abs >= kMeanFrames) ? frame_ptr(a, clip, t - kMeanFrames) : nullptr;
-        // linear clips: the next frame (and the next frame leaving the window) lie one frame further on
-        const long long next_bytes = (t + 1 < clip.n_frames && clip.ring_frames == 0) ? (long long)npx * 2 : 0;
+        const bool window_full = t_abs >= kMeanFrames;
+        const uint16_t *Pold = (is_frame && window_full) ? frame_ptr(a, clip, t - kMeanFrames) : a.zero_frame;
+        // linear clips: pull the next frame (and the next frame leaving the window) towards L2 with two bulk prefetches
+        if (ptid == 0 && is_frame && t + 1 < clip.n_frames && clip.ring_frames == 0) {
+            const uint32_t bytes = (uint32_t)npx * 2u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P + npx), "r"(bytes) : "memory");
+            if (t_abs + 1 >= kMeanFrames)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(frame_ptr(a, clip, t + 1 - kMeanFrames)), "r"(bytes) : "memory");
+        }
         float *fcur = is_frame ? filtered_ptr(a, clip, scratch, t) : nullptr;
         uint8_t *lab_frame = (is_frame && a.labels) ? a.labels + o * npx : nullptr;
 
         // ------------------------------------------------------------ fused sweep (K7 of frame t-1, K1/K8 of frame t)
         SweepAcc acc;
         int gmaxq[kQIter];
-        if (want_stats) pixel_sweep_dispatch<true>(a, s, wt, th, m, P, Pold, next_bytes, Pold != nullptr, fcur, lab_frame, acc, gmaxq);
-        else pixel_sweep_dispatch<false>(a, s, wt, th, m, P, Pold, next_bytes, Pold != nullptr, fcur, lab_frame, acc, gmaxq);
+        if (want_stats) pixel_sweep_dispatch<true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        else pixel_sweep_dispatch<false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
         CPT_TICK(ptid == 0, 14);  // sweep issued
         sweep_reduce_store(s, lane, warp, acc, want_stats);
         bar_sync(BAR_P, kPThreads);
