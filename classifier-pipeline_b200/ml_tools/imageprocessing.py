@@ -151,6 +151,23 @@ def detect_objects(image, otsus=False, threshold=30, kernel=(15, 15)):
     return detect.detect_objects(image, otsus=otsus, threshold=threshold, kernel=kernel)
 
 
+def fast_nl_means_denoising(image):
+    """``cv2.fastNlMeansDenoising(np.uint8(image), None)`` as ``ClipTracker._get_filtered_frame`` calls it
+    (track/cliptracker.py:116-117): h = 3, 7x7 template, 21x21 search window; uint8 (H, W) or (N, H, W)."""
+    image = np.ascontiguousarray(np.uint8(image))
+    if image.ndim not in (2, 3):
+        raise ValueError("fast_nl_means_denoising: (H, W) or (N, H, W) uint8 expected")
+    torch = _torch()
+    eng = _engine.get_engine()
+    eng.ctx.use_torch_stream()
+    n = 1 if image.ndim == 2 else image.shape[0]
+    H, W = image.shape[-2:]
+    d_src = torch.from_numpy(image).to(eng.device)
+    d_dst = torch.empty_like(d_src)
+    eng.ctx.nlm_denoise_u8(d_src, W, H, n, d_dst)
+    return d_dst.cpu().numpy()
+
+
 def clear_frame(frame):
     filtered = frame.filtered
     thermal = frame.thermal

@@ -136,6 +136,7 @@ SYMBOLS = {
     "cpt_normalize_f32": (_i, [_vp, _vp, _i64, _d, _d, _d, _i, _vp]),
     "cpt_resize_pad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "cpt_detect_objects_u8": (_i, [_vp, _vp, _i, _i, _d, _i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int32)]),
+    "cpt_nlm_denoise_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cpt_motion_open": (_vp, [_vp, _i, _i, _i, _i]),
     "cpt_motion_close": (None, [_vp]),
     "cpt_motion_store": (_i, [_vp, _vp, _i]),
@@ -281,6 +282,9 @@ class Context:
                                              int(close), int(max_components), _ptr(d_labels), _ptr(d_stats), _ptr(d_centroids),
                                              ctypes.byref(n)))
         return n.value
+
+    def nlm_denoise_u8(self, d_src, width, height, n_frames, d_dst):
+        check(self.lib.cpt_nlm_denoise_u8(self._h, _ptr(d_src), int(width), int(height), int(n_frames), _ptr(d_dst)))
 
     def state_read(self, d_state, clip_index=0, sliding_sum=False):
         bg = np.empty((self.height, self.width), np.int32)

@@ -219,6 +219,11 @@ int cpt_detect_objects_u8(cpt_ctx *ctx, const uint8_t *d_image, int width, int h
                           int close, int max_components, int32_t *d_labels, int32_t *d_stats, double *d_centroids,
                           int32_t *h_count);
 
+/* cv2.fastNlMeansDenoising(uint8, None) (track/cliptracker.py:116-117; h = 3, 7x7 template, 21x21 search), OpenCV's
+ * integer algorithm bit for bit, on n_frames images [n_frames][H][W].  Stand-alone primitive: the batched extractor
+ * does not call it yet (TrackingConfig.denoise must be off there). */
+int cpt_nlm_denoise_u8(cpt_ctx *ctx, const uint8_t *d_src, int width, int height, int n_frames, uint8_t *d_dst);
+
 /* ---- CPTVMotionDetector (piclassifier/cptvmotiondetector.py:14-205), streaming, one launch per frame ----
  * The detector owns a ring of the last ring_frames frames (SlidingWindow of preview_secs * fps + 1 frames), the
  * uint32 running sum (RunningMean over mean_frames = 45) and, for one_diff_only == False, a ring of diff_frames

@@ -125,3 +125,20 @@ def test_preprocess_frame_single_matches_oracle():
         frames.append(out)
     tiled = preprocess_movement(frames, 5, 32, ["thermal", "filtered"])
     np.testing.assert_allclose(tiled, oracle, rtol=1e-6, atol=1e-4)
+
+
+def test_nlm_denoise_matches_oracle_and_reference_fixture():
+    """cv2.fastNlMeansDenoising on the device, bit for bit: against the C oracle (pinned to cv2) on random and
+    structured images of several sizes, and against the reference's own denoised frames where the fixture has them."""
+    from classifier_pipeline_b200.ml_tools import imageprocessing as ip
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(21)
+    for H, W in ((120, 160), (37, 53), (16, 16), (5, 7)):
+        img = rng.integers(0, 60, size=(H, W)).astype(np.uint8)
+        img[H // 3 : H // 3 + max(2, H // 5), W // 4 : W // 4 + max(2, W // 4)] += 150
+        assert np.array_equal(ip.fast_nl_means_denoising(img), orc.nlm_denoise(img))
+    batch = rng.integers(0, 255, size=(3, 60, 80)).astype(np.uint8)
+    got = ip.fast_nl_means_denoising(batch)
+    for i in range(3):
+        assert np.array_equal(got[i], orc.nlm_denoise(batch[i]))
