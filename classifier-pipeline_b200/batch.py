@@ -75,7 +75,11 @@ class BatchExtractor:
         labels = buf("labels", (max(total, 1), self.height, self.width), torch.uint8) if keep_labels else None
         if d_state is None and keep_state:
             d_state = torch.zeros((max(n_clips, 1), self.ctx.state_bytes), dtype=torch.uint8, device=self.device)
-        self.ctx.extract_batch(d_frames, d_clips, n_clips, regions, info, filtered, labels, d_state, total_frames=total)
+        denoise = bool(n_clips) and bool((clips["flags"] & native.CLIP_DENOISE).any())
+        if denoise and not keep_filtered:
+            raise native.NativeError("denoise needs keep_filtered=True (the variance pass reads the filtered images)")
+        self.ctx.extract_batch(d_frames, d_clips, n_clips, regions, info, filtered, labels, d_state, total_frames=total,
+                               denoise=denoise)
         out.update(regions=regions, info=info, filtered=filtered, labels=labels, state=d_state, total_frames=total,
                    d_clips=d_clips)
         return out

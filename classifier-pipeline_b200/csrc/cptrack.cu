@@ -12,6 +12,9 @@
 
 namespace cpt {
 __global__ void extract_clips_kernel(const KernelArgs a);
+__global__ void mask_components_kernel(const KernelArgs a, long long total_frames, const uint8_t *denoised);
+int nlm_launch(cpt_ctx *c, const uint8_t *d_src, int width, int height, long long n_frames, uint8_t *d_dst, const cpt_frame_info *info,
+               cudaStream_t stream);
 __global__ void region_variance_kernel(Geometry g, long long total_frames, const float *filtered, cpt_frame_info *info, cpt_region *regions);
 __global__ void background_step_kernel(Geometry g, uint8_t *state, const int32_t *frames, const int *record_index, WeightTable wt);
 __global__ void frame_median_kernel(const uint16_t *frames, int npx, float *out);
@@ -133,6 +136,8 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     cudaFree(c->debug);
     cudaFree(c->d_clips);
     cudaFree(c->detect_scratch);
+    cudaFree(c->u8_frames[0]);
+    cudaFree(c->u8_frames[1]);
     free_stage(c);
     if (c->events)
         for (int i = 0; i < 2; ++i) {
@@ -323,8 +328,35 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     // with the filtered images kept and the frame count known, the per-region variances of all frames but the
     // first of each clip are computed by a second, wide launch
     a.defer_variance = (out->d_filtered != nullptr && total_frames > 1) ? 1 : 0;
+    if (out->denoise) {
+        // CPT_CLIP_DENOISE clips: normalised images -> cv2.fastNlMeansDenoising -> masks and components, as three
+        // passes over all frames (the recurrence does not depend on the masks)
+        if (total_frames < 1 || !out->d_filtered)
+            return fail(CPT_ERR_INVALID, "denoise needs cpt_outputs.total_frames and d_filtered");
+        const size_t need = (size_t)total_frames * c->g.npx;
+        if (c->u8_bytes < need) {
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            cudaFree(c->u8_frames[0]); cudaFree(c->u8_frames[1]);
+            c->u8_frames[0] = c->u8_frames[1] = nullptr;
+            c->u8_bytes = 0;
+            CUDA_TRY(cudaMalloc(&c->u8_frames[0], need));
+            CUDA_TRY(cudaMalloc(&c->u8_frames[1], need));
+            c->u8_bytes = need;
+        }
+        a.u8_frames = c->u8_frames[0];
+        a.defer_variance = 1;
+    }
     cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
     CUDA_TRY(cudaGetLastError());
+    if (out->denoise) {
+        int rc = cpt::nlm_launch(c, c->u8_frames[0], c->g.W, c->g.H, total_frames, c->u8_frames[1], out->d_info, stream);
+        if (rc) return rc;
+        if (cudaFuncSetAttribute(cpt::mask_components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cpt::Smem)) != cudaSuccess)
+            return fail(CPT_ERR_CUDA, "cannot opt in to shared memory for mask_components_kernel");
+        const int mgrid = (int)std::min<long long>(total_frames, c->num_sms);
+        cpt::mask_components_kernel<<<mgrid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a, total_frames, c->u8_frames[1]);
+        CUDA_TRY(cudaGetLastError());
+    }
     if (a.defer_variance) {
         const unsigned blocks = (unsigned)((total_frames + 7) / 8);
         cpt::region_variance_kernel<<<blocks, 256, 0, stream>>>(c->g, total_frames, out->d_filtered, out->d_info, out->d_regions);
@@ -399,6 +431,7 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
         for (int i = c0; i < c1; ++i) {
             const cpt_clip &k = h_clips[i];
             if (k.flags & CPT_CLIP_RESUME) return fail(CPT_ERR_INVALID, "CPT_CLIP_RESUME is not supported by the host-staged call");
+            if (k.flags & CPT_CLIP_DENOISE) return fail(CPT_ERR_UNSUPPORTED, "CPT_CLIP_DENOISE is not supported by the host-staged call");
             if (k.n_frames < 0 || k.frame_offset < 0 || k.init_offset < 0 || k.out_offset < 0 || k.ring_frames != 0)
                 return fail(CPT_ERR_INVALID, "clip %d: bad offsets", i);
             if (k.out_offset + k.n_frames > total_frames) return fail(CPT_ERR_INVALID, "clip %d: outputs exceed total_frames", i);
@@ -438,7 +471,7 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
         if (ch >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
         cpt_outputs out{c->stage_regions[b], c->stage_info[b], h_filtered ? c->stage_filtered[b] : nullptr,
-                        h_labels ? c->stage_labels[b] : nullptr, sp.out_hi - sp.out_lo};
+                        h_labels ? c->stage_labels[b] : nullptr, sp.out_hi - sp.out_lo, 0};
         rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream,
                             sp.out_hi - sp.out_lo);
         if (rc) return rc;

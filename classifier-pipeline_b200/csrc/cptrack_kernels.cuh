@@ -108,6 +108,7 @@ struct KernelArgs {
     int *work_counter;    // zeroed before launch
     long long *debug;     // [gridDim.x][32] phase cycle counters (CPT_PHASE_TIMING builds), else nullptr
     int defer_variance;   // leave K6 of frames t > 0 to region_variance_kernel (needs `filtered`)
+    uint8_t *u8_frames;   // [total_frames][npx] normalised images of denoise clips (ctx scratch), else nullptr
     const uint16_t *zero_frame;  // npx zeros: stands in for the frame leaving the 45-frame window while it fills
     WeightTable tables[4];
 };

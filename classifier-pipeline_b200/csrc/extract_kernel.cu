@@ -363,7 +363,10 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         prev_fmax = st_hdr->prev_fmax;
         have_prev = st_hdr->have_prev != 0;
     }
-    for (int t = 0; t < clip.n_frames; ++t) {
+    // denoise clips: the pixel warps only emit the normalised image; masks and components come from the
+    // NLM + mask_components passes that follow the launch
+    const int n_here = (clip.flags & CPT_CLIP_DENOISE) ? 0 : clip.n_frames;
+    for (int t = 0; t < n_here; ++t) {
         CPT_TICK_START(ctid == 0);
         const int buf = t & 1;
         bar_sync(BAR_FULL + buf, kThreads);  // mask of frame t is in s.M[buf]
@@ -382,7 +385,7 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         // write the bytes of the groups they blurred
         for (int i = ctid; i < g.words; i += kCThreads) s.M[buf][i] = 0;
         CPT_TICK(ctid == 0, 12);  // components of the frame
-        if (t + 2 < clip.n_frames) bar_arrive(BAR_EMPTY + buf, kThreads);
+        if (t + 2 < n_here) bar_arrive(BAR_EMPTY + buf, kThreads);
     }
     // the saved state (previous filtered frame, header) may be overwritten now
     bar_arrive(BAR_DONE, kThreads);
@@ -442,7 +445,8 @@ __device__ __forceinline__ void blur_group(Smem &s, const Geometry &g, int grp, 
 
 // K2 for one group of 8 pixels: U = uint8(255 * (G - min) / (max - min)), G = max(P - B - avg_change, 0), in the
 // reference's own fp32 arithmetic (imageprocessing.py:151-169: multiply, then IEEE divide, truncate).
-__device__ __forceinline__ void normalise_group(Smem &s, const uint16_t *P, int grp, int ac, int gmn, int gmx) {
+__device__ __forceinline__ void normalise_group(Smem &s, const uint16_t *P, int grp, int ac, int gmn, int gmx,
+                                                uint8_t *u_global = nullptr) {
     const uint4 pv = ldg16(P + grp * 8);  // streamed a moment ago: an L2 hit
     const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
     const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -462,7 +466,8 @@ __device__ __forceinline__ void normalise_group(Smem &s, const uint16_t *P, int 
     uint2 w;
     w.x = u[0] | (u[1] << 8) | (u[2] << 16) | (u[3] << 24);
     w.y = u[4] | (u[5] << 8) | (u[6] << 16) | (u[7] << 24);
-    *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
+    if (u_global) *reinterpret_cast<uint2 *>(u_global + grp * 8) = w;
+    else *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
 }
 
 // 40-bit row field of the owned-quad hot bits starting at bit `pos`
@@ -941,6 +946,18 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         const float thr = __int_as_float(s.bcast_i[5]);
         const int fth = s.bcast_i[8];
         const int ith = (int)floorf(thr);
+        if (clip.flags & CPT_CLIP_DENOISE) {
+            // K3 sits between K2 and K4: emit the whole normalised image; cv2.fastNlMeansDenoising, blur, threshold,
+            // close and components run as separate wide passes over all frames (nlm_denoise_kernel, mask_components_kernel)
+            uint8_t *u_frame = a.u8_frames + o * npx;
+            for (int grp = ptid; grp < g.groups; grp += kPThreads) normalise_group(s, P, grp, ac, gmn, gmx, u_frame);
+            if (ptid == 0) a.info[o].reserved[1] = (t > 0) ? 2 : 1;  // 2: the previous filtered image is frame o - 1
+            prev_fmin = cur_fmin;
+            prev_fmax = cur_fmax;
+            have_prev = 1;
+            bar_sync(BAR_P, kPThreads);  // B is read above and rewritten by the next sweep
+            continue;
+        }
 
         // ------------------------------------------------------------ hot quads -> per-row marks -> work lists
         // A quad is hot if one of its pixels can exceed the threshold (a border row's quads count for the owned
@@ -1080,6 +1097,38 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
             const float *st_F = reinterpret_cast<const float *>(st_raw + sizeof(StateHeader) + (size_t)npx * 8);
             component_warps(a, s, clip, tid - kPThreads, scratch, st_hdr, st_F);
         }
+    }
+}
+
+// Second half of the frame pipeline for denoise clips (info.reserved[1] != 0): the denoised normalised image of every
+// frame -> K4 (blur, threshold, close) -> K5 (components, statistics, labels); the variances are left to
+// region_variance_kernel.  One CTA per frame at a time; same roles, shared-memory layout and code as the
+// persistent kernel, without the recurrence.
+__global__ void __launch_bounds__(kThreads, 1) mask_components_kernel(const KernelArgs a, long long total_frames,
+                                                                      const uint8_t *denoised) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    const Geometry &g = a.g;
+    const int tid = threadIdx.x;
+    for (long long o = blockIdx.x; o < total_frames; o += gridDim.x) {
+        const int marker = a.info[o].reserved[1];
+        if (marker == 0) continue;  // (uniform: every thread reads the same record)
+        const uint8_t *u = denoised + (size_t)o * g.npx;
+        for (int i = tid; i < g.npx / 16; i += kThreads) reinterpret_cast<uint4 *>(s.U)[i] = __ldg(reinterpret_cast<const uint4 *>(u) + i);
+        __syncthreads();
+        const int ith = (int)floorf(a.info[o].threshold);
+        if (tid < kPThreads)
+            for (int grp = tid; grp < g.groups; grp += kPThreads) blur_group(s, g, grp, 3u, 0, ith);
+        __syncthreads();
+        if (tid >= kPThreads) {
+            const bool have_prev = marker == 2;
+            const float *fcur = a.filtered + (size_t)o * g.npx;
+            const int fmin = a.info[o].filtered_min, fmax = a.info[o].filtered_max;
+            components_of_frame(a, s, g, tid - kPThreads, 0, (size_t)o, fcur, have_prev ? fcur - g.npx : fcur, fmin, fmax,
+                                have_prev ? a.info[o - 1].filtered_min : 0, have_prev ? a.info[o - 1].filtered_max : 0, have_prev, true);
+        }
+        __syncthreads();
+        if (tid == 0) a.info[o].reserved[1] = 0;
     }
 }
 

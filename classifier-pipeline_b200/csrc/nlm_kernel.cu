@@ -8,6 +8,7 @@
 // differences of the tile + template border are formed once and box-summed separably (4 ops per pixel and offset
 // instead of 49).  Compute bound by design (441 offsets): this is the stand-alone primitive; fusing it into the
 // persistent extraction kernel is the next step.
+#include <algorithm>
 #include <cmath>
 
 #include "cptrack_internal.cuh"
@@ -27,7 +28,9 @@ __device__ __forceinline__ int nlm_reflect(int p, int n) {
     return p;
 }
 
-__global__ void __launch_bounds__(256) nlm_denoise_kernel(const uint8_t *src, int W, int H, uint8_t *dst) {
+// info != nullptr: only the frames the extraction kernel marked for denoising (reserved[1] != 0) are processed
+__global__ void __launch_bounds__(256) nlm_denoise_kernel(const uint8_t *src, int W, int H, uint8_t *dst, const cpt_frame_info *info) {
+    if (info && info[blockIdx.z].reserved[1] == 0) return;
     __shared__ uint8_t ext[kNlmExt][kNlmExt + 2];
     __shared__ uint32_t sq[kNlmSq][kNlmSq + 1];
     __shared__ uint32_t hs[kNlmSq][kNlmTile + 1];
@@ -77,13 +80,9 @@ __global__ void __launch_bounds__(256) nlm_denoise_kernel(const uint8_t *src, in
 
 using cpt::fail;
 
-extern "C" {
+namespace cpt {
 
-int cpt_nlm_denoise_u8(cpt_ctx *c, const uint8_t *d_src, int width, int height, int n_frames, uint8_t *d_dst) {
-    if (!c || !d_src || !d_dst) return fail(CPT_ERR_INVALID, "null argument");
-    if (width < 1 || height < 1 || n_frames < 0 || n_frames > 65535) return fail(CPT_ERR_INVALID, "bad size");
-    if (n_frames == 0) return CPT_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+int nlm_prepare(cpt_ctx *c) {
     if (!c->nlm_table_ready) {
         // OpenCV FastNlMeansDenoisingInvoker: fixed_point_mult = INT_MAX / (21 * 21 * 255); template 49 -> shift 6
         const int fpm = 2147483647 / (21 * 21 * 255);
@@ -99,10 +98,33 @@ int cpt_nlm_denoise_u8(cpt_ctx *c, const uint8_t *d_src, int width, int height, 
         CUDA_TRY(cudaMemcpyToSymbol(cpt::c_nlm_weights, table, sizeof(table)));
         c->nlm_table_ready = true;
     }
-    dim3 grid((width + cpt::kNlmTile - 1) / cpt::kNlmTile, (height + cpt::kNlmTile - 1) / cpt::kNlmTile, n_frames);
-    cpt::nlm_denoise_kernel<<<grid, 256, 0, c->stream>>>(d_src, width, height, d_dst);
+    return CPT_OK;
+}
+
+int nlm_launch(cpt_ctx *c, const uint8_t *d_src, int width, int height, long long n_frames, uint8_t *d_dst, const cpt_frame_info *info,
+               cudaStream_t stream) {
+    int rc = nlm_prepare(c);
+    if (rc) return rc;
+    for (long long f0 = 0; f0 < n_frames; f0 += 65535) {  // gridDim.z limit
+        const int nz = (int)std::min<long long>(65535, n_frames - f0);
+        dim3 grid((width + kNlmTile - 1) / kNlmTile, (height + kNlmTile - 1) / kNlmTile, nz);
+        nlm_denoise_kernel<<<grid, 256, 0, stream>>>(d_src + (size_t)f0 * width * height, width, height, d_dst + (size_t)f0 * width * height,
+                                                       info ? info + f0 : nullptr);
+    }
     CUDA_TRY(cudaGetLastError());
     return CPT_OK;
+}
+
+}  // namespace cpt
+
+extern "C" {
+
+int cpt_nlm_denoise_u8(cpt_ctx *c, const uint8_t *d_src, int width, int height, int n_frames, uint8_t *d_dst) {
+    if (!c || !d_src || !d_dst) return fail(CPT_ERR_INVALID, "null argument");
+    if (width < 1 || height < 1 || n_frames < 0) return fail(CPT_ERR_INVALID, "bad size");
+    if (n_frames == 0) return CPT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    return cpt::nlm_launch(c, d_src, width, height, n_frames, d_dst, nullptr, c->stream);
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ CLIP_DENOISE = 4
 CLIP_FRAME_STATS = 8
 MAX_COMPONENTS = 255
 MEAN_FRAMES = 45
-HAS_NLM = False  # cv2.fastNlMeansDenoising kernel not built yet
+HAS_NLM = True  # cv2.fastNlMeansDenoising on the device (batched extraction; not the frame-at-a-time streaming path)
 
 
 class NativeError(RuntimeError):
@@ -76,7 +76,7 @@ MOTION_MEAN, MOTION_MEAN_RESTART, MOTION_BACKGROUND, MOTION_DETECT, MOTION_WARME
 class CptOutputs(ctypes.Structure):
     _fields_ = [
         ("d_regions", ctypes.c_void_p), ("d_info", ctypes.c_void_p), ("d_filtered", ctypes.c_void_p),
-        ("d_labels", ctypes.c_void_p), ("total_frames", ctypes.c_int64),
+        ("d_labels", ctypes.c_void_p), ("total_frames", ctypes.c_int64), ("denoise", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -235,8 +235,8 @@ class Context:
         return self.lib.cpt_weight_value(self._h, slot, int(count))
 
     def extract_batch(self, d_frames, d_clips, n_clips, d_regions, d_info, d_filtered=None, d_labels=None, d_state=None,
-                      total_frames=0):
-        out = CptOutputs(_ptr(d_regions), _ptr(d_info), _ptr(d_filtered), _ptr(d_labels), int(total_frames))
+                      total_frames=0, denoise=False):
+        out = CptOutputs(_ptr(d_regions), _ptr(d_info), _ptr(d_filtered), _ptr(d_labels), int(total_frames), int(bool(denoise)), 0)
         check(self.lib.cpt_extract_batch(self._h, _ptr(d_frames), _ptr(d_clips), int(n_clips), ctypes.byref(out), _ptr(d_state)))
 
     def extract_batch_host(self, h_frames, h_clips, total_frames, h_regions, h_info, h_filtered=None, h_labels=None, chunk_clips=0):

@@ -184,7 +184,8 @@ class ClipTrackExtractor(ClipTracker):
             clips["background_thresh"][i] = clip.background_thresh
             clips["weight_table"][i] = ctx.weight_table(background_alg.weight_add, max_frames=max(max(counts), 1024))
         d_frames = torch.from_numpy(h_frames.view(np.int16)).to(eng.device).view(torch.uint16)
-        out = eng.extract_device(d_frames, clips, keep_filtered=keep_images, keep_labels=keep_images, keep_state=True, out={})
+        denoise = bool(getattr(self.config, "denoise", False))  # the device NLM + variance passes read the filtered images
+        out = eng.extract_device(d_frames, clips, keep_filtered=keep_images or denoise, keep_labels=keep_images, keep_state=True, out={})
         medians = None
         if self.calc_stats and total:
             d_med = torch.empty((total + len(jobs),), dtype=torch.float32, device=eng.device)
@@ -276,6 +277,10 @@ class ClipTrackExtractor(ClipTracker):
         """Track one more frame of a clip (streaming; one kernel launch)."""
         import torch
 
+        if getattr(self.config, "denoise", False):
+            raise native.NativeError(
+                "TrackingConfig.denoise=True is built for whole clips (parse_clip / parse_clips); the frame-at-a-time path "
+                "runs the Pi configuration (denoise: false, pi-classifier.yaml:3)")
         st = self._stream
         if st is None or st["background_alg"] is not self.background_alg:
             st = self._open_stream(clip)

@@ -34,7 +34,7 @@ extern "C" {
 /* clip flags */
 #define CPT_CLIP_UPDATE_BACKGROUND 1u /* ClipTrackExtractor(update_background=True), cliptrackextractor.py:168-176 */
 #define CPT_CLIP_RESUME 2u            /* continue from the state saved in d_state instead of initialising */
-#define CPT_CLIP_DENOISE 4u           /* TrackingConfig.denoise: cv2.fastNlMeansDenoising, cliptracker.py:116-117 */
+#define CPT_CLIP_DENOISE 4u           /* TrackingConfig.denoise: cv2.fastNlMeansDenoising, cliptracker.py:116-117 (set cpt_outputs.denoise too) */
 #define CPT_CLIP_FRAME_STATS 8u       /* ClipStats.add_frame, clip.py:474-487 (min/max/median/mean, sum|filtered|) */
 
 typedef struct cpt_ctx cpt_ctx;
@@ -95,6 +95,10 @@ typedef struct {
     int64_t total_frames;    /* frames the per-frame outputs hold (max over clips of out_offset + n_frames); with
                                 d_filtered set it lets a second, wide launch compute the per-region variances.
                                 0 = unknown: they are computed inside the extraction kernel */
+    int32_t denoise;         /* 1: some clip carries CPT_CLIP_DENOISE -- the normalised images then go through
+                                cv2.fastNlMeansDenoising and the mask / component passes after the recurrence
+                                (needs total_frames and d_filtered; not with CPT_CLIP_RESUME) */
+    int32_t reserved;
 } cpt_outputs;
 
 /* Persistent per-clip state (WeightedBackground + sliding sum), one record per clip:

@@ -117,3 +117,36 @@ def test_weighted_background_object_matches_oracle():
             assert np.array_equal(wb.background, bg.astype(np.float64)), t
             assert np.array_equal(wb.background_weight, w), t
             assert wb.average == avg, t
+
+
+def test_parse_clip_default_config_reproduces_reference_possum_json():
+    """The reference's own regression: tests/clips/possum.txt is extract.py's output for possum.cptv with the DEFAULT
+    config (denoise on).  parse_clip on the device reproduces every track position and both tracking scores."""
+    import json
+
+    from classifier_pipeline_b200.config import Config
+    from classifier_pipeline_b200.ml_tools.tools import CustomJSONEncoder
+    from classifier_pipeline_b200.track.clip import Clip
+    from classifier_pipeline_b200.track.cliptrackextractor import ClipTrackExtractor
+
+    config = Config.get_defaults()
+    assert config.tracking["thermal"].denoise is True
+    ext = ClipTrackExtractor(config.tracking, False, cache_to_disk=False)
+    clip = Clip(config.tracking["thermal"], os.path.join(helpers.GOLDEN, "clips", "possum.cptv"))
+    ext.parse_clip(clip)
+    d, meta = helpers.load_golden("possum_nlm")
+    assert_tracks_match_golden(clip, meta, d)
+    gold = json.load(open(os.path.join(helpers.GOLDEN, "clips", "possum.txt")))
+    got = json.loads(json.dumps(clip.get_metadata(), cls=CustomJSONEncoder))
+    assert len(got["tracks"]) == len(gold["tracks"]) == 2
+    for a, b in zip(got["tracks"], gold["tracks"]):
+        for k in ("id", "start_s", "end_s", "num_frames", "frame_start", "frame_end"):
+            assert a[k] == b[k], k
+        assert a["tracking_score"] == pytest.approx(b["tracking_score"], rel=1e-6)
+        assert len(a["positions"]) == len(b["positions"])
+        for p, q in zip(a["positions"], b["positions"]):
+            for k in q:
+                if k == "pixel_variance":
+                    assert p[k] == pytest.approx(q[k], abs=0.011)
+                else:
+                    assert p[k] == q[k], k

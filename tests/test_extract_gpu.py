@@ -230,3 +230,57 @@ def test_extreme_frames(extractor):
             assert np.array_equal(out["labels"][:T].cpu().numpy(), o["labels"]), name
         st = extractor.ctx.state_read(out["state"], 0)
         assert np.array_equal(st["background"], o["final_bg"]), name
+
+
+@pytest.mark.parametrize("name", ["possum_nlm", "hedgehog_nlm", "synth4_nlm"])
+def test_denoise_pipeline_matches_oracle_and_reference(extractor, name):
+    """TrackingConfig.denoise=True (the reference's default): normalise -> cv2.fastNlMeansDenoising -> blur ->
+    threshold -> close -> components as device passes; labels / stats bit-exact vs the oracle and the reference."""
+    from classifier_pipeline_b200 import native
+    from oracle import oracle as orc
+
+    d, meta = helpers.load_golden(name)
+    init, tracked = helpers.clip_input(name)
+    T = len(tracked)
+    p = orc.make_params(background_thresh=meta["background_thresh"], weight_add=meta["weight_add"], max_comp=32, denoise=True)
+    o = orc.extract_clip(tracked, init, p)
+    out = _run_device(extractor, init, tracked, meta["background_thresh"], meta["weight_add"],
+                      flags=native.CLIP_UPDATE_BACKGROUND | native.CLIP_DENOISE)
+    _compare_with_oracle(extractor, out, o, T, meta["weight_add"])
+    assert np.array_equal(out["labels"][:T].cpu().numpy(), d["labels"])
+    regions = extractor.regions_numpy(out["regions"])[:T]
+    for t, (gs, gc) in enumerate(helpers.golden_components(d)):
+        r = regions[t, : len(gs)]
+        assert np.array_equal(np.stack([r["x"], r["y"], r["width"], r["height"], r["area"]], axis=1), gs)
+
+
+def test_mixed_batch_denoise_and_plain(extractor):
+    """Clips with and without CPT_CLIP_DENOISE in one launch."""
+    import torch
+    from classifier_pipeline_b200 import native
+    from classifier_pipeline_b200.batch import linear_clips
+    from classifier_pipeline_b200.synthetic import clip_model, make_clip
+    from oracle import oracle as orc
+
+    lengths = [30, 24, 30]
+    pix = [make_clip(40 + i, frames=n)[0] for i, n in enumerate(lengths)]
+    frames = np.concatenate(pix)
+    bts = [clip_model(40 + i)[2] for i in range(3)]
+    was = [clip_model(40 + i)[3] for i in range(3)]
+    slots = [extractor.ctx.weight_table(w, max_frames=4096) for w in was]
+    clips = linear_clips(lengths, np.array(bts), np.array(slots))
+    clips["flags"][1] |= native.CLIP_DENOISE
+    d_frames = torch.from_numpy(frames.view(np.int16)).cuda().view(torch.uint16)
+    out = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, out={})
+    torch.cuda.synchronize()
+    labels = out["labels"].cpu().numpy()
+    info = extractor.info_numpy(out["info"])
+    regions = extractor.regions_numpy(out["regions"])
+    for i, n in enumerate(lengths):
+        o0 = int(clips["out_offset"][i])
+        o = orc.extract_clip(pix[i], pix[i][0], orc.make_params(background_thresh=bts[i], weight_add=was[i], max_comp=32, denoise=(i == 1)))
+        assert np.array_equal(labels[o0 : o0 + n], o["labels"]), i
+        assert np.array_equal(info["n_components"][o0 : o0 + n], o["ncomp"]), i
+        for t in range(n):
+            k = int(o["ncomp"][t])
+            np.testing.assert_allclose(regions[o0 + t, :k]["pixel_variance"], o["var"][t, :k], rtol=1e-6, atol=1e-6)
