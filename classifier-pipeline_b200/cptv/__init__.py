@@ -1,3 +1,3 @@
-from .reader import CptvReader, CptvFrame, CptvHeader, read_clip, unpack_deltas
+from .reader import CptvReader, CptvFrame, CptvHeader, decode_clips_device, read_clip, unpack_deltas
 
-__all__ = ["CptvReader", "CptvFrame", "CptvHeader", "read_clip", "unpack_deltas"]
+__all__ = ["CptvReader", "CptvFrame", "CptvHeader", "decode_clips_device", "read_clip", "unpack_deltas"]

@@ -202,6 +202,31 @@ class CptvReader:
         background = bool(fields["g"][0]) if "g" in fields else False
         return CptvFrame(pix, time_on, last_ffc, temp_c, ffc_temp, background)
 
+    def index_frames(self):
+        """Walk every frame section from the start of the file WITHOUT decoding pixels.
+
+        Returns ``(stream bytes, table, frames)``: the inflated stream, one ``(payload_offset, bit_width)`` row per
+        frame for ``cpt_cptv_decode`` and the frames' metadata as ``CptvFrame`` objects with ``pix = None``."""
+        saved = self._pos
+        try:
+            self._pos = 5
+            self._read_fields("H")
+            table, frames = [], []
+            while True:
+                fields = self._read_fields("F")
+                if fields is None:
+                    break
+                size = _u("I", fields["f"])
+                table.append((self._pos, fields["w"][0]))
+                self._pos += size
+                frames.append(CptvFrame(
+                    None, _u("I", fields["t"]) if "t" in fields else None, _u("I", fields["c"]) if "c" in fields else None,
+                    _u("f", fields["a"]) if "a" in fields else None, _u("f", fields["b"]) if "b" in fields else None,
+                    bool(fields["g"][0]) if "g" in fields else False))
+            return self._buf, table, frames
+        finally:
+            self._pos = saved
+
     def __iter__(self):
         return self
 
@@ -216,3 +241,40 @@ def read_clip(path):
     """Decode a whole file → (header, list of frames)."""
     reader = CptvReader(path)
     return reader.get_header(), list(reader)
+
+
+def decode_clips_device(engine, readers):
+    """Decode every frame of several clips on the device (csrc/cptv_kernels.cu).
+
+    ``readers``: ``CptvReader`` objects of clips that share the engine's resolution.  Returns ``(d_frames, clip_first,
+    frames)``: a CUDA uint16 tensor ``(total_frames, H, W)`` with the clips back to back, the first frame index of
+    every clip (length n + 1) and, per clip, the frames' metadata objects (``pix`` filled by the caller if wanted)."""
+    import torch
+
+    from .. import native
+
+    streams, rows, clip_first, frames = [], [], [0], []
+    base = 0
+    for r in readers:
+        h = r.get_header()
+        if (h.x_resolution, h.y_resolution) != (engine.width, engine.height):
+            raise ValueError("clip resolution {}x{} does not match the engine".format(h.x_resolution, h.y_resolution))
+        buf, table, fr = r.index_frames()
+        for off, w in table:
+            if not 1 <= w <= 24:
+                raise ValueError("unsupported CPTV bit width {}".format(w))
+            rows.append((base + off, w, 0))
+        streams.append(buf)
+        base += len(buf)
+        clip_first.append(clip_first[-1] + len(table))
+        frames.append(fr)
+    total = clip_first[-1]
+    host = np.frombuffer(b"".join(streams) + b"\0\0\0\0", dtype=np.uint8)  # the last window may read 3 bytes past the end
+    d_stream = torch.from_numpy(host.copy()).to(engine.device)
+    table = np.array(rows, dtype=native.CPTV_FRAME_DTYPE) if rows else np.zeros(0, native.CPTV_FRAME_DTYPE)
+    d_table = torch.from_numpy(table.view(np.uint8).reshape(-1).copy()).to(engine.device)
+    d_first = torch.tensor(clip_first, dtype=torch.int32, device=engine.device)
+    d_frames = torch.empty((max(total, 1), engine.height, engine.width), dtype=torch.uint16, device=engine.device)
+    engine.ctx.use_torch_stream()
+    engine.ctx.cptv_decode(d_stream, d_table, total, d_first, len(readers), d_frames)
+    return d_frames, clip_first, frames

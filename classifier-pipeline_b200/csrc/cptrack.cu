@@ -136,6 +136,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     cudaFree(c->debug);
     cudaFree(c->d_clips);
     cudaFree(c->detect_scratch);
+    cudaFree(c->cptv_scratch);
     cudaFree(c->u8_frames[0]);
     cudaFree(c->u8_frames[1]);
     free_stage(c);

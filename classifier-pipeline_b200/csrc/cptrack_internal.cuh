@@ -70,6 +70,8 @@ struct cpt_ctx {
     size_t detect_scratch_bytes = 0;
     uint8_t *u8_frames[2] = {nullptr, nullptr};  // normalised / denoised images of the denoise pipeline
     size_t u8_bytes = 0;
+    void *cptv_scratch = nullptr;  // per-frame change images of cpt_cptv_decode
+    size_t cptv_scratch_bytes = 0;
     bool nlm_table_ready = false;  // cpt_nlm_denoise_u8 uploaded its weight table (constant memory of this device)
 };
 

@@ -99,6 +99,7 @@ SAMPLE_DTYPE = np.dtype(
     [("frame", "<i8"), ("x", "<i4"), ("y", "<i4"), ("width", "<i4"), ("height", "<i4"), ("track", "<i4"), ("median", "<f4")]
 )
 TRACK_NORM_DTYPE = np.dtype([("filtered_min", "<f4"), ("filtered_max", "<f4"), ("clip_at_zero", "<i4"), ("has_limits", "<i4")])
+CPTV_FRAME_DTYPE = np.dtype([("payload_offset", "<u8"), ("bit_width", "<i4"), ("reserved", "<i4")])
 assert SAMPLE_DTYPE.itemsize == ctypes.sizeof(CptSample) == 32
 assert TRACK_NORM_DTYPE.itemsize == ctypes.sizeof(CptTrackNorm) == 16
 assert REGION_DTYPE.itemsize == ctypes.sizeof(CptRegion) == 40
@@ -137,6 +138,7 @@ SYMBOLS = {
     "cpt_resize_pad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "cpt_detect_objects_u8": (_i, [_vp, _vp, _i, _i, _d, _i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cpt_nlm_denoise_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "cpt_cptv_decode": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp]),
     "cpt_motion_open": (_vp, [_vp, _i, _i, _i, _i]),
     "cpt_motion_close": (None, [_vp]),
     "cpt_motion_store": (_i, [_vp, _vp, _i]),
@@ -285,6 +287,9 @@ class Context:
 
     def nlm_denoise_u8(self, d_src, width, height, n_frames, d_dst):
         check(self.lib.cpt_nlm_denoise_u8(self._h, _ptr(d_src), int(width), int(height), int(n_frames), _ptr(d_dst)))
+
+    def cptv_decode(self, d_stream, d_table, n_frames, d_clip_first, n_clips, d_frames):
+        check(self.lib.cpt_cptv_decode(self._h, _ptr(d_stream), _ptr(d_table), int(n_frames), _ptr(d_clip_first), int(n_clips), _ptr(d_frames)))
 
     def state_read(self, d_state, clip_index=0, sliding_sum=False):
         bg = np.empty((self.height, self.width), np.int32)

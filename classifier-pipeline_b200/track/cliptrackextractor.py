@@ -63,6 +63,7 @@ class ClipTrackExtractor(ClipTracker):
         self.calculate_filtered = calculate_filtered
         self.weighting_percent = 1
         self.device = device
+        self.device_decode = True  # decode CPTV files on the device when this package's reader opens them
         self._stream = None  # streaming session (process_frame)
 
     @property
@@ -116,6 +117,10 @@ class ClipTrackExtractor(ClipTracker):
         from .track import Track
 
         jobs = []
+        readers = []
+        # CPTV files read with this package's own reader are decoded on the device (csrc/cptv_kernels.cu): the host
+        # only inflates the stream and walks the section headers
+        device_decode = self.device_decode and self.reader_factory is ClipTrackExtractor.reader_factory
         for clip in clips:
             reader = self.init_clip(clip)
             if clip.background is None:
@@ -124,6 +129,10 @@ class ClipTrackExtractor(ClipTracker):
             # the reference re-opens the file (cliptrackextractor.py:160): the first frame is tracked too
             reader = self.reader_factory(clip.source_file)
             reader.get_header()
+            if device_decode:
+                readers.append(reader)
+                jobs.append((clip, self.background_alg, None))
+                continue
             frames = []
             while True:
                 frame = reader.next_frame()
@@ -133,7 +142,10 @@ class ClipTrackExtractor(ClipTracker):
                     continue
                 frames.append(frame)
             jobs.append((clip, self.background_alg, frames))
-        results = self._run_batch(jobs)
+        device_frames = None
+        if device_decode and jobs:
+            jobs, device_frames = self._decode_on_device(jobs, readers, process_background)
+        results = self._run_batch(jobs, device_frames)
         for (clip, background_alg, frames), res in zip(jobs, results):
             self.background_alg = background_alg
             Track._track_id = 1
@@ -155,7 +167,33 @@ class ClipTrackExtractor(ClipTracker):
             flags |= native.CLIP_DENOISE
         return flags
 
-    def _run_batch(self, jobs):
+    def _decode_on_device(self, jobs, readers, process_background):
+        """Decode the clips' frames on the device; returns the jobs with their frame objects (pixels copied back for
+        the host-side ``Clip`` objects) and ``(d_frames, init_offsets, frame_offsets)`` for the extraction launch."""
+        from ..cptv import decode_clips_device
+
+        clip0 = jobs[0][0]
+        eng = _engine.get_engine(self.device, clip0.res_x, clip0.res_y, clip0.config.edge_pixels)
+        d_frames, clip_first, all_frames = decode_clips_device(eng, readers)
+        pix = d_frames.cpu().numpy()
+        out_jobs, init_offsets, frame_offsets = [], [], []
+        for i, ((clip, background_alg, _), frames) in enumerate(zip(jobs, all_frames)):
+            first = clip_first[i]
+            for k, f in enumerate(frames):
+                f.pix = pix[first + k]
+            # tracked frames must be contiguous on the device: background frames only ever lead the file
+            skip = 0
+            if not process_background:
+                while skip < len(frames) and frames[skip].background_frame:
+                    skip += 1
+                if any(f.background_frame for f in frames[skip:]):
+                    raise NotImplementedError("background frames after the first tracked frame")
+            out_jobs.append((clip, background_alg, frames[skip:]))
+            init_offsets.append(first)
+            frame_offsets.append(first + skip)
+        return out_jobs, (d_frames, init_offsets, frame_offsets)
+
+    def _run_batch(self, jobs, device_frames=None):
         """One launch over every clip of ``jobs``; per clip a dict of host arrays for its frames."""
         import torch
 
@@ -170,26 +208,35 @@ class ClipTrackExtractor(ClipTracker):
         counts = [len(frames) for _, _, frames in jobs]
         total = sum(counts)
         keep_images = self.keep_frames or self.calculate_filtered
-        # frame layout: [init frame of clip 0][tracked frames of clip 0][init frame of clip 1]...
-        h_frames = np.empty((total + len(jobs), res_y, res_x), np.uint16)
         clips = linear_clips(counts, 0, 0, flags=self._flags())
-        pos = 0
         for i, (clip, background_alg, frames) in enumerate(jobs):
-            h_frames[pos] = clip.background if clip.background.dtype == np.uint16 else np.uint16(clip.background)
-            clips["init_offset"][i] = pos
-            clips["frame_offset"][i] = pos + 1
-            for t, frame in enumerate(frames):
-                h_frames[pos + 1 + t] = frame.pix
-            pos += 1 + counts[i]
             clips["background_thresh"][i] = clip.background_thresh
             clips["weight_table"][i] = ctx.weight_table(background_alg.weight_add, max_frames=max(max(counts), 1024))
-        d_frames = torch.from_numpy(h_frames.view(np.int16)).to(eng.device).view(torch.uint16)
+        if device_frames is not None:
+            # frames decoded on the device: the first frame of the file initialises the background where it lies
+            d_frames, init_offsets, frame_offsets = device_frames
+            clips["init_offset"] = init_offsets
+            clips["frame_offset"] = frame_offsets
+            n_input = int(d_frames.shape[0])
+        else:
+            # frame layout: [init frame of clip 0][tracked frames of clip 0][init frame of clip 1]...
+            h_frames = np.empty((total + len(jobs), res_y, res_x), np.uint16)
+            pos = 0
+            for i, (clip, background_alg, frames) in enumerate(jobs):
+                h_frames[pos] = clip.background if clip.background.dtype == np.uint16 else np.uint16(clip.background)
+                clips["init_offset"][i] = pos
+                clips["frame_offset"][i] = pos + 1
+                for t, frame in enumerate(frames):
+                    h_frames[pos + 1 + t] = frame.pix
+                pos += 1 + counts[i]
+            d_frames = torch.from_numpy(h_frames.view(np.int16)).to(eng.device).view(torch.uint16)
+            n_input = total + len(jobs)
         denoise = bool(getattr(self.config, "denoise", False))  # the device NLM + variance passes read the filtered images
         out = eng.extract_device(d_frames, clips, keep_filtered=keep_images or denoise, keep_labels=keep_images, keep_state=True, out={})
         medians = None
         if self.calc_stats and total:
-            d_med = torch.empty((total + len(jobs),), dtype=torch.float32, device=eng.device)
-            ctx.frame_medians(d_frames, total + len(jobs), d_med)
+            d_med = torch.empty((n_input,), dtype=torch.float32, device=eng.device)
+            ctx.frame_medians(d_frames, n_input, d_med)
             medians = d_med.cpu().numpy()
         regions = eng.regions_numpy(out["regions"])
         info = eng.info_numpy(out["info"])

@@ -228,6 +228,18 @@ int cpt_detect_objects_u8(cpt_ctx *ctx, const uint8_t *d_image, int width, int h
  * does not call it yet (TrackingConfig.denoise must be off there). */
 int cpt_nlm_denoise_u8(cpt_ctx *ctx, const uint8_t *d_src, int width, int height, int n_frames, uint8_t *d_dst);
 
+/* ---- CPTV v2 frame decode (what cptv_rs_python_bindings.CptvReader.next_frame does per pixel;
+ * track/cliptrackextractor.py:108-129,160-165).  The host inflates the gzip stream and walks the section headers;
+ * d_stream is the inflated byte stream, one cpt_cptv_frame per frame section (in file order, clips back to back),
+ * d_clip_first [n_clips + 1] the first frame index of every clip.  d_frames [n_frames][H][W] uint16. */
+typedef struct {
+    uint64_t payload_offset; /* byte offset of the frame payload (int32 start value, then packed deltas) */
+    int32_t bit_width;       /* field 'w': bits per packed delta (1..24), MSB first, two's complement */
+    int32_t reserved;
+} cpt_cptv_frame;
+int cpt_cptv_decode(cpt_ctx *ctx, const uint8_t *d_stream, const cpt_cptv_frame *d_table, int n_frames,
+                    const int32_t *d_clip_first, int n_clips, uint16_t *d_frames);
+
 /* ---- CPTVMotionDetector (piclassifier/cptvmotiondetector.py:14-205), streaming, one launch per frame ----
  * The detector owns a ring of the last ring_frames frames (SlidingWindow of preview_secs * fps + 1 frames), the
  * uint32 running sum (RunningMean over mean_frames = 45) and, for one_diff_only == False, a ring of diff_frames
