@@ -307,7 +307,7 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         cudaFree(c->scratch);
         c->scratch = nullptr;
         size_t ctas = (size_t)std::max(grid, c->num_sms);
-        CUDA_TRY(cudaMalloc(&c->scratch, ctas * 4 * c->g.npx * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&c->scratch, ctas * 8 * c->g.npx * sizeof(float)));
         c->scratch_ctas = ctas;
     }
     cpt::KernelArgs a{};

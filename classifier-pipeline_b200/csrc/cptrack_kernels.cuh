@@ -23,14 +23,24 @@
 
 namespace cpt {
 
-constexpr int kThreads = 1024;
-constexpr int kWarps = kThreads / 32;
-// warp-specialised pipeline: pixel warps stream frames (sweeps, blur, background update) while the
-// component warps label the previous frame's mask
-constexpr int kPThreads = 800;                  // 25 warps: 2400 groups of 8 pixels = 3 per thread at 160x120
+// warp-specialised pipeline over consecutive frames: sweep warps (the recurrence), mask warps (scalars, work lists,
+// normalise, blur) and component warps (labelling)
+#ifndef CPT_EXP
+#define CPT_EXP 0
+#endif
+#if CPT_EXP == 1
+constexpr int kPThreads = 320;                  // 10 sweep warps: 8 rows x 40 quads per iteration at 160 pixels
+#elif CPT_EXP == 2
+constexpr int kPThreads = 480;                  // 15 sweep warps: 12 rows x 40 quads
+#else
+constexpr int kPThreads = 640;                  // 20 sweep warps: 16 rows x 40 quads per iteration at 160 pixels
+#endif
 constexpr int kPWarps = kPThreads / 32;
-constexpr int kCThreads = kThreads - kPThreads; // 7 warps
+constexpr int kMThreads = 128;                  // 4 mask warps
+constexpr int kCThreads = 256;                  // 8 component warps
 constexpr int kCWarps = kCThreads / 32;
+constexpr int kThreads = kPThreads + kMThreads + kCThreads;
+constexpr int kWarps = kThreads / 32;
 constexpr int kMaxPx = 19200;
 constexpr int kQIter = (kMaxPx / 4 + kPThreads - 1) / kPThreads;  // 6 quads of 4 pixels per pixel thread
 constexpr int kMaxW = 160;
@@ -113,6 +123,15 @@ struct KernelArgs {
     WeightTable tables[4];
 };
 
+// sweep -> mask warps: what one frame's sweep found
+struct FrameMsg {
+    uint32_t red[12];  // sum P, min F, max F, min P, max P, sum |F|, sum B, changed, min B, max B
+    int32_t qref;      // reference value the per-quad maxima in Smem::qmax8 are stored against
+    int32_t update;    // the sweep applied a background update
+    int32_t is_frame;  // 0: tail pass (update only)
+    int32_t pad;
+};
+
 struct __align__(16) Smem {
     uint32_t S[kMaxPx];        // sliding sum of the last <=45 frames
     uint16_t B[kMaxPx];        // background (integer valued)
@@ -132,7 +151,14 @@ struct __align__(16) Smem {
     double bcast_d[4];
     double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
     uint32_t wthr[kSmemWeights];                   // first entries of the clip's keep-test table
-    uint32_t hotbits[kMaxPx / 4 / 32 + 4];  // one bit per owned quad: some pixel can exceed the threshold
+    // per owned quad q = it * kPThreads + ptid (= owned row * qpr + column quad): clamp(max F - qref, -128, 127) + 128,
+    // written by the sweep warps at the end of a frame, turned into hot64 by the mask warps
+    uint8_t qmax8[kQIter * kPThreads];
+    unsigned long long hot64[kMaxH];  // per owned row, one bit per quad: some pixel can exceed the threshold
+    FrameMsg fm[2];
+    int32_t fth_latest;      // last bound the mask warps computed (INT32_MIN: none yet): the next qref
+    int32_t final_prev[3];   // filtered min / max of the last frame, have_prev (for the state record)
+    double init_average, final_average;
     uint16_t list_u[kListCap];  // groups of 8 pixels to normalise this frame (need_u)
     uint16_t list_b[kListCap];  // groups of 8 pixels to blur this frame: group | quad marks << 14
     int32_t ncomp;

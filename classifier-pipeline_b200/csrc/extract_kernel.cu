@@ -1,10 +1,11 @@
 // extract_kernel.cu -- the persistent per-clip extraction kernel (see cptrack_kernels.cuh).
 //
-// One CTA per clip, 1024 threads in two roles that run concurrently on different frames:
-//   pixel warps (25):     frame t+1: sweeps over the pixels (K1, K2, K4 blur/threshold, K7)
-//   component warps (7):  frame t:   close, run-based labelling, statistics, variance (K4, K5, K6)
-// The thresholded mask is handed over through a double-buffered bit image with named barriers
-// (full/empty per buffer); everything else the two roles touch is disjoint shared memory.
+// One CTA per clip, 1024 threads in three roles that run concurrently on consecutive frames:
+//   sweep warps (20):     frame t+2: the recurrence -- background update of the previous frame fused with K1 / K7 sum / K8
+//   mask warps (4):       frame t+1: scalars (K2), hot quads -> work lists, normalise (K2), blur + threshold (K4)
+//   component warps (8):  frame t:   close, run-based labelling, statistics, variance (K4, K5, K6)
+// Messages (frame sums + hot-quad ballots, then the thresholded bit image) are double buffered and handed over
+// with named barriers (full / empty per buffer); everything else the roles touch is disjoint shared memory.
 #include "cptrack_kernels.cuh"
 
 namespace cpt {
@@ -23,6 +24,7 @@ namespace {
             tick_last_ = now_;                                                                \
         }                                                                                     \
     } while (0)
+#define CPT_COUNT(cond, i, v) do { if ((cond) && a.debug) atomicAdd((unsigned long long *)&a.debug[blockIdx.x * 32 + (i)], (unsigned long long)(v)); } while (0)
 #define CPT_TICK_START2(cond) long long tick2_last_ = clock64(); (void)tick2_last_
 #define CPT_TICK2(cond, i)                                                                    \
     do {                                                                                      \
@@ -33,13 +35,20 @@ namespace {
         }                                                                                     \
     } while (0)
 #else
+#define CPT_COUNT(cond, i, v) do { } while (0)
 #define CPT_TICK_START2(cond) do { } while (0)
 #define CPT_TICK2(cond, i) do { } while (0)
 #define CPT_TICK_START(cond) do { } while (0)
 #define CPT_TICK(cond, i) do { } while (0)
 #endif
 
-enum : int { BAR_P = 1, BAR_C = 2, BAR_FULL = 3 /* +buffer */, BAR_EMPTY = 5 /* +buffer */, BAR_DONE = 7 };
+enum : int {
+    BAR_P = 1, BAR_M = 2, BAR_C = 3,               // inside a role
+    BAR_SM_FULL = 4, BAR_SM_EMPTY = 6,             // sweep -> mask warps (+buffer)
+    BAR_FULL = 8, BAR_EMPTY = 10,                  // mask -> component warps (+buffer)
+    BAR_DONE = 12, BAR_INIT = 13,
+    BAR_QFREE = 14                                 // mask -> sweep warps: Smem::qmax8 has been consumed
+};
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -65,9 +74,9 @@ __device__ __forceinline__ const uint16_t *frame_ptr(const KernelArgs &a, const 
 }
 
 __device__ __forceinline__ float *filtered_ptr(const KernelArgs &a, const cpt_clip &c, float *scratch, int t) {
-    // frame t's fp32 filtered image: the caller's output, or a 4-deep per-CTA ring (the pixel warps may
-    // run two frames ahead of the component warps, which read frames t and t-1)
-    return a.filtered ? a.filtered + (size_t)(c.out_offset + t) * a.g.npx : scratch + (size_t)(t & 3) * a.g.npx;
+    // frame t's fp32 filtered image: the caller's output, or an 8-deep per-CTA ring (the sweep warps may run four
+    // frames ahead of the component warps, which read frames t and t-1)
+    return a.filtered ? a.filtered + (size_t)(c.out_offset + t) * a.g.npx : scratch + (size_t)(t & 7) * a.g.npx;
 }
 
 // Replicate the edge_pixels border of B from the crop interior (motiondetector.py:239-244 copies rows,
@@ -366,10 +375,11 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
     // denoise clips: the pixel warps only emit the normalised image; masks and components come from the
     // NLM + mask_components passes that follow the launch
     const int n_here = (clip.flags & CPT_CLIP_DENOISE) ? 0 : clip.n_frames;
+    bar_sync(BAR_INIT, kThreads);
     for (int t = 0; t < n_here; ++t) {
         CPT_TICK_START(ctid == 0);
         const int buf = t & 1;
-        bar_sync(BAR_FULL + buf, kThreads);  // mask of frame t is in s.M[buf]
+        bar_sync(BAR_FULL + buf, kMThreads + kCThreads);  // mask of frame t is in s.M[buf]
         CPT_TICK(ctid == 0, 11);  // waiting for a mask
         const int cur_fmin = s.msg[buf][0], cur_fmax = s.msg[buf][1];
         const float *fcur = filtered_ptr(a, clip, scratch, t);
@@ -385,7 +395,7 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         // write the bytes of the groups they blurred
         for (int i = ctid; i < g.words; i += kCThreads) s.M[buf][i] = 0;
         CPT_TICK(ctid == 0, 12);  // components of the frame
-        if (t + 2 < n_here) bar_arrive(BAR_EMPTY + buf, kThreads);
+        if (t + 2 < n_here) bar_arrive(BAR_EMPTY + buf, kMThreads + kCThreads);
     }
     // the saved state (previous filtered frame, header) may be overwritten now
     bar_arrive(BAR_DONE, kThreads);
@@ -443,25 +453,26 @@ __device__ __forceinline__ void blur_group(Smem &s, const Geometry &g, int grp, 
     M8[y * g.row_words * 4 + gx] = (uint8_t)bits;
 }
 
-// K2 for one group of 8 pixels: U = uint8(255 * (G - min) / (max - min)), G = max(P - B - avg_change, 0), in the
-// reference's own fp32 arithmetic (imageprocessing.py:151-169: multiply, then IEEE divide, truncate).
-__device__ __forceinline__ void normalise_group(Smem &s, const uint16_t *P, int grp, int ac, int gmn, int gmx,
-                                                uint8_t *u_global = nullptr) {
-    const uint4 pv = ldg16(P + grp * 8);  // streamed a moment ago: an L2 hit
-    const uint4 bv = *reinterpret_cast<const uint4 *>(s.B + grp * 8);
-    const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
-    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+// K2 for one group of 8 pixels: U = uint8(255 * (G - min) / (max - min)), G = max(F - avg_change, 0) with F the
+// filtered image the sweep wrote (exact integers), in the reference's own fp32 arithmetic
+// (imageprocessing.py:151-169: multiply, then IEEE divide, truncate).
+__device__ __forceinline__ void normalise_values(Smem &s, const float4 f0, const float4 f1, int grp, int ac, int gmn, int gmx,
+                                                 uint32_t nmagic, int nshift, uint8_t *u_global = nullptr) {
+    const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
     const bool degenerate = (gmx == gmn);
     const float range_f = (float)gmx - (float)gmn;
     const uint32_t degen_val = (gmx == 0) ? 0u : 1u;
     uint32_t u[8];
-    const int off = -ac;  // G - min = max(F - ac, 0) - gmn
+    if (nmagic) {
+        // exact integer form of the fp32 quotient (see norm_u8_int): no divide on the mask warps' critical path
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const int g0 = max(dp2a_us(pw[w], kLoP, dp2a_us(bw[w], kLoN, off)), 0) - gmn;
-        const int g1 = max(dp2a_us(pw[w], kHiP, dp2a_us(bw[w], kHiN, off)), 0) - gmn;
-        u[2 * w] = degenerate ? degen_val : norm_u8(g0, range_f);
-        u[2 * w + 1] = degenerate ? degen_val : norm_u8(g1, range_f);
+        for (int i = 0; i < 8; ++i) u[i] = norm_u8_int(max((int)fv[i] - ac, 0) - gmn, nmagic, nshift);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int gv = max((int)fv[i] - ac, 0) - gmn;  // G - min
+            u[i] = degenerate ? degen_val : norm_u8(gv, range_f);
+        }
     }
     uint2 w;
     w.x = u[0] | (u[1] << 8) | (u[2] << 16) | (u[3] << 24);
@@ -470,13 +481,11 @@ __device__ __forceinline__ void normalise_group(Smem &s, const uint16_t *P, int 
     else *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
 }
 
-// 40-bit row field of the owned-quad hot bits starting at bit `pos`
-__device__ __forceinline__ unsigned long long hot_field(const uint32_t *bits, int pos) {
-    const int w = pos >> 5, sh = pos & 31;
-    const unsigned long long lo = ((unsigned long long)bits[w + 1] << 32) | bits[w];
-    unsigned long long v = lo >> sh;
-    if (sh) v |= (unsigned long long)bits[w + 2] << (64 - sh);
-    return v;
+__device__ __forceinline__ void normalise_group(Smem &s, const float *F, int grp, int ac, int gmn, int gmx,
+                                                uint32_t nmagic, int nshift, uint8_t *u_global = nullptr) {
+    // written by the sweep warps of this CTA a moment ago: plain (coherent) loads, an L2 hit
+    const float4 f0 = *reinterpret_cast<const float4 *>(F + grp * 8), f1 = *reinterpret_cast<const float4 *>(F + grp * 8 + 4);
+    normalise_values(s, f0, f1, grp, ac, gmn, gmx, nmagic, nshift, u_global);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -629,8 +638,11 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
                                             uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
     const Geometry &g = a.g;
     const int owned_rows = kLepton ? 118 : g.H - 2 * g.edge;
-    const int rows_per_it = kLepton ? 20 : g.rows_per_it;
-    const int stride = kLepton ? 20 * 160 : th.stride;
+    constexpr int kLeptonRows = kPThreads / 40;  // rows per iteration at 160 pixels
+    // every thread owns a row in iterations [0, kLeptonFull): r0 + it * rows < 118 for all r0 < rows
+    constexpr int kLeptonFull = (118 - kLeptonRows) / kLeptonRows + 1;
+    const int rows_per_it = kLepton ? kLeptonRows : g.rows_per_it;
+    const int stride = kLepton ? kLeptonRows * 160 : th.stride;
     uint2 nb_top = make_uint2(0, 0), nb_bottom = make_uint2(0, 0);
     if (kUnrolled) {
         // software pipeline: the global loads of quad it + 1 are in flight while quad it is processed
@@ -639,10 +651,9 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
 #pragma unroll
         for (int it = 0; it < kQIter; ++it) {
             gmaxq[it] = INT32_MIN;
-            // at 160x120 only the last iteration has unowned rows (r0 + 100 < 118)
-            const bool mine = th.active && ((kLepton && it < kQIter - 1) || th.r0 + it * rows_per_it < owned_rows);
+            const bool mine = th.active && ((kLepton && it < kLeptonFull) || th.r0 + it * rows_per_it < owned_rows);
             const uint2 pw = pw_next, ow = ow_next;
-            if (it + 1 < kQIter && th.active && ((kLepton && it + 1 < kQIter - 1) || th.r0 + (it + 1) * rows_per_it < owned_rows))
+            if (it + 1 < kQIter && th.active && ((kLepton && it + 1 < kLeptonFull) || th.r0 + (it + 1) * rows_per_it < owned_rows))
                 load_quad<kFrame>(th.p4_0 + (it + 1) * stride, P, Pold, pw_next, ow_next);
             if (!mine) continue;
             uint2 nb;
@@ -693,10 +704,15 @@ __device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &
                                                      const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
                                                      uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
     const bool steady = m.update && m.frame && !m.slow && !m.first_mean && a.g.W == 160 && a.g.H == 120 && a.g.edge == 1;
+#if CPT_EXP == 3
+    constexpr bool kUnroll = false;
+#else
+    constexpr bool kUnroll = true;
+#endif
     if (steady && m.table == 0)
-        pixel_sweep<true, true, true, 0, kStats, true, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, true, 0, kStats, kUnroll, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (steady && m.table == 1)
-        pixel_sweep<true, true, true, 1, kStats, true, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, true, 1, kStats, kUnroll, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (!m.update)
         pixel_sweep<false, true, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (m.frame)
@@ -705,28 +721,43 @@ __device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &
         pixel_sweep<true, false, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
 }
 
-// per-warp partial results -> s.red_u[warp * 12 + i]
-__device__ __forceinline__ void sweep_reduce_store(Smem &s, int lane, int warp, const SweepAcc &acc, bool want_stats) {
+// a frame's sums / extrema, folded by the sweep warps (one shared-memory atomic per value and warp)
+__device__ __forceinline__ void frame_msg_reset(FrameMsg &fm) {
+    uint32_t *r = fm.red;
+    r[0] = 0; r[1] = (uint32_t)INT32_MAX; r[2] = (uint32_t)INT32_MIN; r[3] = (uint32_t)INT32_MAX; r[4] = (uint32_t)INT32_MIN;
+    r[5] = 0; r[6] = 0; r[7] = 0; r[8] = 0xffffffffu; r[9] = 0;
+}
+
+__device__ __forceinline__ uint32_t sweep_reduce_store(FrameMsg &fm, int lane, const SweepAcc &acc, bool want_stats) {
     const uint32_t psum = __reduce_add_sync(0xffffffffu, acc.psum), bsum = __reduce_add_sync(0xffffffffu, acc.bsum);
     const uint32_t changed = __reduce_or_sync(0xffffffffu, acc.changed);
     const int fmin = __reduce_min_sync(0xffffffffu, acc.fmin), fmax = __reduce_max_sync(0xffffffffu, acc.fmax);
     const uint32_t bmin = __reduce_min_sync(0xffffffffu, min(acc.bmin2 & 0xffffu, acc.bmin2 >> 16));
     const uint32_t bmax = __reduce_max_sync(0xffffffffu, max(acc.bmax2 & 0xffffu, acc.bmax2 >> 16));
-    int pmin = 0, pmax = 0;
-    uint32_t fabs_sum = 0;
+    uint32_t *r = fm.red;
+    if (lane == 0) atomicAdd(r + 0, psum);
+    if (lane == 1) atomicMin(reinterpret_cast<int *>(r + 1), fmin);
+    if (lane == 2) atomicMax(reinterpret_cast<int *>(r + 2), fmax);
+    if (lane == 6) atomicAdd(r + 6, bsum);
+    if (lane == 7 && changed) atomicOr(r + 7, changed);
+    if (lane == 8) atomicMin(r + 8, bmin);
+    if (lane == 9) atomicMax(r + 9, bmax);
     if (want_stats) {
-        pmin = __reduce_min_sync(0xffffffffu, acc.pmin);
-        pmax = __reduce_max_sync(0xffffffffu, acc.pmax);
-        fabs_sum = __reduce_add_sync(0xffffffffu, acc.fabs_sum);
+        const int pmin = __reduce_min_sync(0xffffffffu, acc.pmin), pmax = __reduce_max_sync(0xffffffffu, acc.pmax);
+        const uint32_t fabs_sum = __reduce_add_sync(0xffffffffu, acc.fabs_sum);
+        if (lane == 3) atomicMin(reinterpret_cast<int *>(r + 3), pmin);
+        if (lane == 4) atomicMax(reinterpret_cast<int *>(r + 4), pmax);
+        if (lane == 5) atomicAdd(r + 5, fabs_sum);
     }
-    if (lane == 0) {
-        uint32_t *r = s.red_u + warp * 12;
-        r[0] = psum; r[1] = (uint32_t)fmin; r[2] = (uint32_t)fmax; r[3] = (uint32_t)pmin; r[4] = (uint32_t)pmax; r[5] = fabs_sum;
-        r[6] = bsum; r[7] = changed; r[8] = bmin; r[9] = bmax;
-    }
+    return bmax;
 }
 
-__device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int ptid, float *scratch,
+// ================================================================================================
+// sweep warps: the recurrence.  Per frame: fused sweep -> fold the frame's sums into the message of the mask
+// warps -> hot-quad ballots against a PREDICTED bound (the mask warps compute the true one; if the prediction
+// turns out too high they fall back to dense work, so the ballots are always a superset) -> next frame.
+// ================================================================================================
+__device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int ptid, float *scratch,
                             uint8_t *st_raw) {
     const Geometry &g = a.g;
     const int lane = ptid & 31, warp = ptid >> 5;
@@ -739,16 +770,14 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     float *st_F = reinterpret_cast<float *>(st_S + npx);
     const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
     const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
-    constexpr int kIter = (kMaxPx / 8 + kPThreads - 1) / kPThreads;  // 3: 8-pixel groups of sweep 2b / blur
-
-    double average = 0.0;  // WeightedBackground.average: only lane 0 of pixel warp 0 uses it
-    int prev_fmin = 0, prev_fmax = 0, have_prev = 0, frames_seen = 0;
+    int frames_seen = 0;
 
     // ---------------------------------------------------------------- init / resume
     for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
     for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
+    if (ptid < 2) frame_msg_reset(s.fm[ptid]);
+    if (ptid == 0) { s.fth_latest = INT32_MIN; s.bcast_i[10] = 0; }
     if (clip.flags & CPT_CLIP_RESUME) {
-        if (ptid == 0) s.bcast_i[10] = 0;
         bar_sync(BAR_P, kPThreads);
         int kmax = 0;
         for (int i = ptid; i < npx; i += kPThreads) {
@@ -760,10 +789,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         }
         kmax = __reduce_max_sync(0xffffffffu, kmax);
         if (lane == 0) atomicMax(&s.bcast_i[10], kmax);
-        average = st_hdr->average;
-        prev_fmin = st_hdr->prev_fmin;
-        prev_fmax = st_hdr->prev_fmax;
-        have_prev = st_hdr->have_prev;
+        if (ptid == 0) s.init_average = st_hdr->average;
         bar_sync(BAR_P, kPThreads);
         // the number of updates applied so far bounds every weight counter; the record may also have been
         // advanced by the stand-alone background kernels, so trust the counters themselves as well
@@ -786,7 +812,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         if (warp == 0) {
             uint32_t v = (lane < kPWarps) ? s.red_u[lane] : 0u;
             v = __reduce_add_sync(0xffffffffu, v);
-            average = (double)v / (double)g.ncrop;  // unrounded (np.average) until the background first changes
+            if (lane == 0) s.init_average = (double)v / (double)g.ncrop;  // unrounded (np.average) until the background first changes
         }
         replicate_edges(s, g, ptid);
         bar_sync(BAR_P, kPThreads);
@@ -808,15 +834,15 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         const int last_row = g.H - 2 * g.edge - 1;  // owned-row index
         th.last_it = (th.active && last_row % g.rows_per_it == r0) ? last_row / g.rows_per_it : -1;
     }
-    if (ptid == 0) s.bcast_i[9] = 1;  // the first update of a launch takes the exact path (no background extrema yet)
-    bar_sync(BAR_P, kPThreads);
+    bar_sync(BAR_INIT, kThreads);  // the state and the initial average are in place: the other roles may start
 
+    bool slow = true;  // the first update of a launch takes the exact path (no background extrema yet)
     // t == n_frames is the tail pass: only the background update of the last frame
     for (int t = 0; t <= clip.n_frames; ++t) {
         CPT_TICK_START(ptid == 0);
         const bool is_frame = t < clip.n_frames;
         const int t_abs = clip.first_frame + t;
-        const int buf = t & 1;
+        const int b = t & 1;
         const size_t o = (size_t)(clip.out_offset + t);
         SweepMode m;
         m.update = update_bg && t > 0;
@@ -827,7 +853,7 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             const uint32_t cnt = (uint32_t)min(max(t_abs, 1), kMeanFrames);
             m.first_mean = (cnt == 1u);
             m.magic = m.first_mean ? 0u : 0xffffffffu / cnt + 1u;  // floor(S / cnt) == umulhi(S, magic): exact for S < 2^22, cnt <= 45
-            m.slow = s.bcast_i[9] != 0;
+            m.slow = slow;
             const int k_cap = frames_seen;  // no weight counter can exceed the number of updates so far
             m.table = (k_cap < wt.linear_upto) ? 0 : ((k_cap < kSmemWeights) ? 1 : 2);
         }
@@ -849,46 +875,107 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         int gmaxq[kQIter];
         if (want_stats) pixel_sweep_dispatch<true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
         else pixel_sweep_dispatch<false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
-        CPT_TICK(ptid == 0, 14);  // sweep issued
-        sweep_reduce_store(s, lane, warp, acc, want_stats);
-        bar_sync(BAR_P, kPThreads);
-        CPT_TICK(ptid == 0, 2);   // sweep reduce + barrier
-        // ------------------------------------------------------------ scalars (K2, K7 average), pixel warp 0
-        if (warp == 0) {
-            const bool in = lane < kPWarps;
-            const uint32_t *r = s.red_u + lane * 12;
-            uint32_t v0 = __reduce_add_sync(0xffffffffu, in ? r[0] : 0u);
-            int v1 = __reduce_min_sync(0xffffffffu, in ? (int)r[1] : INT32_MAX);
-            int v2 = __reduce_max_sync(0xffffffffu, in ? (int)r[2] : INT32_MIN);
-            const uint32_t bsum = __reduce_add_sync(0xffffffffu, in ? r[6] : 0u);
-            const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? r[7] : 0u);
-            const uint32_t bmin = __reduce_min_sync(0xffffffffu, in ? r[8] : 0xffffffffu);
-            const uint32_t bmax = __reduce_max_sync(0xffffffffu, in ? r[9] : 0u);
-            int v3 = 0, v4 = 0;
-            uint32_t v5 = 0;
-            if (want_stats) {
-                v3 = __reduce_min_sync(0xffffffffu, in ? (int)r[3] : INT32_MAX);
-                v4 = __reduce_max_sync(0xffffffffu, in ? (int)r[4] : INT32_MIN);
-                v5 = __reduce_add_sync(0xffffffffu, in ? r[5] : 0u);
+        CPT_TICK(ptid == 0, 14);  // sweep
+        // ------------------------------------------------------------ message to the mask warps
+        if (t >= 2) bar_sync(BAR_SM_EMPTY + b, kPThreads + kMThreads);  // they are done with the message of frame t-2
+        if (t >= 1 && is_frame) bar_sync(BAR_QFREE, kPThreads + kMThreads);  // ... and with the quad maxima of frame t-1
+        CPT_TICK(ptid == 0, 6);   // wait for the message buffer
+        FrameMsg &fm = s.fm[b];
+        const uint32_t warp_bmax = sweep_reduce_store(fm, lane, acc, want_stats);
+        // quad maxima relative to the last bound the mask warps computed (any reference is exact, see mask_warps)
+        const int latest = *(volatile int32_t *)&s.fth_latest;
+        const int qref = (latest == INT32_MIN) ? 0 : latest;
+        if (ptid == 0) {
+            fm.qref = qref;
+            fm.update = m.update;
+            fm.is_frame = is_frame;
+        }
+        {
+            // mode of this warp's NEXT update: the packed keep test needs B + thr < 2^16 for the pixels it owns
+            const int k_next = min(frames_seen + 1, wt.max_count);
+            const uint32_t thr_cap = (k_next < wt.linear_upto) ? (uint32_t)k_next + 1u
+                                     : ((k_next < kSmemWeights ? s.wthr[k_next] : __ldg(wt.thr + k_next)) & 0xffffu);
+            slow = warp_bmax + thr_cap > 65535u;
+        }
+        if (is_frame) {
+            // a border row's quads count for the owned row next to them, which only widens the marks;
+            // unowned slots hold INT32_MIN -> 0
+#pragma unroll
+            for (int it = 0; it < kQIter; ++it) {
+                const int d = min(max(gmaxq[it], qref - 128) - qref, 127) + 128;
+                s.qmax8[it * kPThreads + ptid] = (uint8_t)d;
             }
-            CPT_TICK(ptid == 0, 15);  // scalars: warp reductions
-            if (lane == 0) {
-                if (m.update && changed) {
-                    // int(round(np.average(background))), motiondetector.py:232 -- half to even, in integers
-                    uint32_t qa = bsum / (uint32_t)g.ncrop;
-                    const uint32_t ra = bsum - qa * (uint32_t)g.ncrop;
-                    if (2u * ra > (uint32_t)g.ncrop || (2u * ra == (uint32_t)g.ncrop && (qa & 1u))) qa += 1u;
-                    average = (double)qa;
-                }
-                // mode of the NEXT update: the packed keep test needs B + thr < 2^16
-                {
-                    const int k_next = min(frames_seen + 1, wt.max_count);
-                    const uint32_t thr_cap = (k_next < wt.linear_upto) ? (uint32_t)k_next + 1u
-                                             : ((k_next < kSmemWeights ? s.wthr[k_next] : __ldg(wt.thr + k_next)) & 0xffffu);
-                    s.bcast_i[9] = (bmax + thr_cap > 65535u);
-                    (void)bmin;
-                }
-                if (is_frame) {
+        }
+        if (m.update) ++frames_seen;
+        bar_arrive(BAR_SM_FULL + b, kPThreads + kMThreads);
+        CPT_TICK(ptid == 0, 2);   // message
+    }
+
+    // ---------------------------------------------------------------- save state
+    // (the other roles read the resumed state's filtered frame and header until their last frame is done)
+    bar_sync(BAR_DONE, kThreads);
+    if (st_raw) {
+        for (int i = ptid; i < npx; i += kPThreads) {
+            st_B[i] = s.B[i];
+            st_K[i] = s.K[i];
+            st_S[i] = s.S[i];
+        }
+        if (clip.n_frames > 0) {
+            const float *flast = filtered_ptr(a, clip, scratch, clip.n_frames - 1);
+            for (int i = ptid; i < npx; i += kPThreads) st_F[i] = flast[i];
+        }
+        if (ptid == 0) {
+            st_hdr->average = s.final_average;
+            st_hdr->frames_seen = frames_seen;
+            st_hdr->initialised = 1;
+            st_hdr->prev_fmin = s.final_prev[0];
+            st_hdr->prev_fmax = s.final_prev[1];
+            st_hdr->have_prev = s.final_prev[2];
+        }
+    }
+}
+
+// ================================================================================================
+// mask warps: one frame behind the sweep.  Scalars (K2) from the sweep's message, hot quads -> per-row marks ->
+// work lists, normalise (K2) and blur + threshold (K4) of the listed groups -> bit rows for the component warps.
+// ================================================================================================
+__device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int mtid, float *scratch,
+                           const StateHeader *st_hdr) {
+    const Geometry &g = a.g;
+    const int npx = g.npx;
+    const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
+    const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
+    const bool denoise = clip.flags & CPT_CLIP_DENOISE;
+    bar_sync(BAR_INIT, kThreads);
+    double average = s.init_average;  // WeightedBackground.average: only thread 0 of the role uses it
+    int prev_fmin = 0, prev_fmax = 0, have_prev = 0;
+    if (clip.flags & CPT_CLIP_RESUME) {
+        prev_fmin = st_hdr->prev_fmin;
+        prev_fmax = st_hdr->prev_fmax;
+        have_prev = st_hdr->have_prev;
+    }
+    for (int t = 0; t <= clip.n_frames; ++t) {
+        CPT_TICK_START2(mtid == 0);
+        const bool is_frame = t < clip.n_frames;
+        if (!(update_bg && t > 0) && !is_frame) break;
+        const int b = t & 1;
+        const size_t o = (size_t)(clip.out_offset + t);
+        bar_sync(BAR_SM_FULL + b, kPThreads + kMThreads);  // the sweep of frame t is done
+        CPT_TICK2(mtid == 0, 7);   // waiting for the sweep
+        FrameMsg &fm = s.fm[b];
+        // ------------------------------------------------------------ scalars (K2, K7 average)
+        if (mtid == 0) {
+            const uint32_t v0 = fm.red[0];
+            const int v1 = (int)fm.red[1], v2 = (int)fm.red[2];
+            const uint32_t bsum = fm.red[6], changed = fm.red[7];
+            if (fm.update && changed) {
+                // int(round(np.average(background))), motiondetector.py:232 -- half to even, in integers
+                uint32_t qa = bsum / (uint32_t)g.ncrop;
+                const uint32_t ra = bsum - qa * (uint32_t)g.ncrop;
+                if (2u * ra > (uint32_t)g.ncrop || (2u * ra == (uint32_t)g.ncrop && (qa & 1u))) qa += 1u;
+                average = (double)qa;
+            }
+            if (is_frame) {
                 // avg_change = int(round(np.average(thermal) - background average)), cliptracker.py:103-105
                 int ac;
                 const double avg_int = rint(average);
@@ -907,6 +994,8 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 int gmx = max(v2 - ac, 0), gmn = max(v1 - ac, 0);
                 float thr;
                 int fth = INT32_MIN;
+                uint32_t nmagic = 0;  // 0: the fp32 divide; else (255 v) / r == (255 v * nmagic) >> nshift for 255 v < 2^24
+                int nshift = 0;
                 if (gmx == gmn) {
                     thr = (float)clip.background_thresh;  // cliptracker.py:118-119
                 } else {
@@ -920,156 +1009,201 @@ __device__ void pixel_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                         // i.e. F >= fth (the bound is >= 1, so the clamp never matters)
                         int it = (int)floorf(thr);
                         if (it >= 0 && it < 255) fth = (int)(((unsigned)(it + 1) * r + 254u) / 255u) + ac + gmn;
+                        // Granlund-Montgomery: l = ceil(log2 r), m = ceil(2^(24 + l) / r) < 2^25.  The fp64 quotient is exact
+                        // for powers of two and otherwise at least 1/r >= 2^-17 away from an integer: its ceiling is m.
+                        const int l = (r <= 1u) ? 0 : 32 - __clz((int)(r - 1u));
+                        nshift = 24 + l;
+                        nmagic = (uint32_t)ceil(ldexp(1.0, nshift) / (double)r);
                     }
                 }
-                CPT_TICK(ptid == 0, 16);  // scalars: lane-0 arithmetic
                 s.bcast_i[0] = ac; s.bcast_i[1] = gmn; s.bcast_i[2] = gmx;
                 s.bcast_i[3] = v1; s.bcast_i[4] = v2;
                 s.bcast_i[5] = __float_as_int(thr);
-                s.bcast_i[8] = fth;
+                s.bcast_i[13] = (int)nmagic; s.bcast_i[14] = nshift;
+                // byte threshold for the quad maxima the sweep stored relative to qref (0: no usable bound, dense work):
+                // stored v = clamp(max F - qref, -128, 127) + 128, hot <=> v >= clamp(fth - qref, -127, 127) + 128.
+                // v == 0 means max F <= qref - 128 < fth; v == 255 means max F >= qref + 127 >= fth unless the
+                // threshold was clamped from above, which only widens the marks.
+                {
+                    int tu = 0;
+                    if (fth != INT32_MIN) {
+                        const long long dq = (long long)fth - (long long)fm.qref;
+                        if (dq >= -127) tu = (int)min(dq, 127ll) + 128;
+                    }
+                    s.bcast_i[8] = tu;
+                }
+                if (fth != INT32_MIN) *(volatile int32_t *)&s.fth_latest = fth;
                 cpt_frame_info fi;
                 fi.threshold = thr; fi.norm_min = gmn; fi.norm_max = gmx; fi.avg_change = ac;
                 fi.filtered_min = v1; fi.filtered_max = v2; fi.n_components = 0;
-                fi.thermal_min = v3; fi.thermal_max = v4; fi.thermal_sum = v0;
-                fi.abs_filtered_sum = v5; fi.thermal_median = 0.f;
+                fi.thermal_min = want_stats ? (int)fm.red[3] : 0; fi.thermal_max = want_stats ? (int)fm.red[4] : 0;
+                fi.thermal_sum = v0; fi.abs_filtered_sum = want_stats ? fm.red[5] : 0u; fi.thermal_median = 0.f;
                 fi.background_average = average; fi.reserved[0] = 0; fi.reserved[1] = 0;
                 a.info[o] = fi;
-                }
             }
+            frame_msg_reset(fm);
         }
-        if (m.update) ++frames_seen;
-        bar_sync(BAR_P, kPThreads);
-        CPT_TICK(ptid == 0, 3);   // scalars + barrier
-        if (!is_frame) break;
+        CPT_TICK2(mtid == 0, 16);  // scalars: thread 0
+        bar_sync(BAR_M, kMThreads);
+        CPT_TICK2(mtid == 0, 3);   // scalars + barrier
+        if (!is_frame) break;  // tail pass: only the average
         const int ac = s.bcast_i[0], gmn = s.bcast_i[1], gmx = s.bcast_i[2];
         const int cur_fmin = s.bcast_i[3], cur_fmax = s.bcast_i[4];
         const float thr = __int_as_float(s.bcast_i[5]);
-        const int fth = s.bcast_i[8];
+        const int tu = s.bcast_i[8];
+        const uint32_t nmagic = (uint32_t)s.bcast_i[13];
+        const int nshift = s.bcast_i[14];
         const int ith = (int)floorf(thr);
-        if (clip.flags & CPT_CLIP_DENOISE) {
+        const float *fcur = filtered_ptr(a, clip, scratch, t);
+        // the sweep warps reuse this frame's message buffer two iterations from now, if there is one
+        const bool sweep_comes_back = (t + 2 < clip.n_frames) || (t + 2 == clip.n_frames && update_bg);
+        prev_fmin = cur_fmin;
+        prev_fmax = cur_fmax;
+        have_prev = 1;
+        if (denoise) {
             // K3 sits between K2 and K4: emit the whole normalised image; cv2.fastNlMeansDenoising, blur, threshold,
             // close and components run as separate wide passes over all frames (nlm_denoise_kernel, mask_components_kernel)
             uint8_t *u_frame = a.u8_frames + o * npx;
-            for (int grp = ptid; grp < g.groups; grp += kPThreads) normalise_group(s, P, grp, ac, gmn, gmx, u_frame);
-            if (ptid == 0) a.info[o].reserved[1] = (t > 0) ? 2 : 1;  // 2: the previous filtered image is frame o - 1
-            prev_fmin = cur_fmin;
-            prev_fmax = cur_fmax;
-            have_prev = 1;
-            bar_sync(BAR_P, kPThreads);  // B is read above and rewritten by the next sweep
+            for (int grp = mtid; grp < g.groups; grp += kMThreads) normalise_group(s, fcur, grp, ac, gmn, gmx, nmagic, nshift, u_frame);
+            if (mtid == 0) a.info[o].reserved[1] = (t > 0) ? 2 : 1;  // 2: the previous filtered image is frame o - 1
+            if (sweep_comes_back) bar_arrive(BAR_SM_EMPTY + b, kPThreads + kMThreads);
+            if (t + 1 < clip.n_frames) bar_arrive(BAR_QFREE, kPThreads + kMThreads);
             continue;
         }
 
         // ------------------------------------------------------------ hot quads -> per-row marks -> work lists
-        // A quad is hot if one of its pixels can exceed the threshold (a border row's quads count for the owned
-        // row next to them, which only widens the marks).  Blur weights sum to 256, so an output can fire only
-        // within rows +-2 / neighbouring quads of a hot quad, and reads U within rows +-4 / quads +-2.
-        const bool no_fg = ith >= 255;          // nothing can exceed the threshold: the mask stays empty
-        bool dense = (fth == INT32_MIN);        // no usable bound: every group is normalised and blurred
+        // Blur weights sum to 256, so an output can fire only within rows +-2 / neighbouring quads of a hot quad, and
+        // reads U within rows +-4 / quads +-2.
+        const bool no_fg = ith >= 255;  // nothing can exceed the threshold: the mask stays empty
+        bool dense = tu == 0;           // no usable bound: every group is normalised and blurred
         int n_u = 0, n_b = 0;
+        const int owned = g.H - 2 * g.edge;
         if (!no_fg && !dense) {
-#pragma unroll
-            for (int it = 0; it < kQIter; ++it) {
-                const unsigned mbits = __ballot_sync(0xffffffffu, gmaxq[it] >= fth);  // unowned slots hold INT32_MIN
-                if (lane == 0) s.hotbits[it * kPWarps + warp] = mbits;  // bit (q & 31) of word q >> 5, q = it * kPThreads + ptid
+            // one thread per owned row: its quads' maxima -> one bit per quad
+            for (int oy = mtid; oy < owned; oy += kMThreads) {
+                const int hit = oy / g.rows_per_it;
+                const int pos = hit * kPThreads + (oy - hit * g.rows_per_it) * g.qpr;
+                unsigned long long bits = 0;
+                if (((pos | g.qpr) & 3) == 0) {
+                    const uint32_t *q4 = reinterpret_cast<const uint32_t *>(s.qmax8 + pos);
+                    const uint32_t t4 = (uint32_t)tu * 0x01010101u;
+                    for (int w = 0; w < (g.qpr >> 2); ++w) {
+                        const uint32_t ge = __vcmpgeu4(q4[w], t4) & 0x01010101u;  // byte i -> bit 8 i
+                        bits |= (unsigned long long)((ge * 0x10204080u) >> 28) << (4 * w);  // -> bits 0..3
+                    }
+                } else {
+                    for (int q = 0; q < g.qpr; ++q) bits |= (unsigned long long)(s.qmax8[pos + q] >= tu ? 1u : 0u) << q;
+                }
+                s.hot64[oy] = bits;
             }
-            if (ptid == 0) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
-            bar_sync(BAR_P, kPThreads);
-            // two threads per frame row (one per list): OR the hot rows around the row, widen by the neighbouring
-            // quads, and turn the marks into list entries (groups of 8 pixels; a blur entry carries its two quad marks)
-            const int role = ptid >> 7, rrow = ptid & 127;  // role 0: normalise list, role 1: blur list
-            if (role < 2 && rrow < g.H) {
-                const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
-                const int reach = role == 0 ? 4 : 2;
-                unsigned long long near = 0;
+            if (mtid == 0) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
+            bar_sync(BAR_M, kMThreads);
+        }
+        CPT_TICK2(mtid == 0, 15);  // quad maxima -> hot rows
+        if (t + 1 < clip.n_frames) bar_arrive(BAR_QFREE, kPThreads + kMThreads);  // the next sweep may store its maxima
+        if (!no_fg && !dense) {
+            // one thread per frame row: OR the hot rows around the row, widen by the neighbouring quads, and turn the
+            // marks into list entries (groups of 8 pixels; a blur entry carries its two quad marks)
+            const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
+            for (int rrow = mtid; rrow < g.H; rrow += kMThreads) {
+                unsigned long long near_b = 0, near_u = 0;
 #pragma unroll
                 for (int dy = -4; dy <= 4; ++dy) {
-                    const int yy = rrow + dy - g.edge;  // owned-row index
-                    if (dy < -reach || dy > reach || yy < 0 || yy >= g.H - 2 * g.edge) continue;
-                    // owned row yy = it * rows_per_it + r: its quads are bits [it * kPThreads + r * qpr, + qpr)
-                    const int hit = yy / g.rows_per_it;
-                    near |= hot_field(s.hotbits, hit * kPThreads + (yy - hit * g.rows_per_it) * g.qpr) & rowmask;
+                    const int yy = rrow - g.edge + dy;  // owned-row index
+                    if (yy < 0 || yy >= owned) continue;
+                    const unsigned long long h = s.hot64[yy];
+                    near_u |= h;
+                    if (dy >= -2 && dy <= 2) near_b |= h;
                 }
-                if (near) {
-                    unsigned long long m = near | (near << 1) | (near >> 1);
-                    if (role == 0) m |= (near << 2) | (near >> 2);
-                    m &= rowmask;
+                const int row_grp = rrow * g.gpr;
+                if (near_u) {
+                    const unsigned long long mk = (near_u | (near_u << 1) | (near_u >> 1) | (near_u << 2) | (near_u >> 2)) & rowmask;
                     // group g of the row is wanted if either of its quads (bits 2g, 2g + 1) is marked
-                    unsigned long long grp_bits = (m | (m >> 1)) & 0x5555555555555555ull;
-                    const int row_grp = rrow * g.gpr;
-                    int base = atomicAdd(&s.bcast_i[11 + role], __popcll(grp_bits));
-                    uint16_t *list = role == 0 ? s.list_u : s.list_b;
+                    unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
+                    int base = atomicAdd(&s.bcast_i[11], __popcll(grp_bits));
                     while (grp_bits) {
                         const int bit = __ffsll((long long)grp_bits) - 1;
                         grp_bits &= grp_bits - 1;
-                        const uint32_t quads = role == 0 ? 0u : (uint32_t)((m >> bit) & 3ull);
-                        if (base < kListCap) list[base] = (uint16_t)((row_grp + (bit >> 1)) | (quads << 14));
+                        if (base < kListCap) s.list_u[base] = (uint16_t)(row_grp + (bit >> 1));
+                        ++base;
+                    }
+                }
+                if (near_b) {
+                    const unsigned long long mk = (near_b | (near_b << 1) | (near_b >> 1)) & rowmask;
+                    unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
+                    int base = atomicAdd(&s.bcast_i[12], __popcll(grp_bits));
+                    while (grp_bits) {
+                        const int bit = __ffsll((long long)grp_bits) - 1;
+                        grp_bits &= grp_bits - 1;
+                        const uint32_t quads = (uint32_t)((mk >> bit) & 3ull);
+                        if (base < kListCap) s.list_b[base] = (uint16_t)((row_grp + (bit >> 1)) | (quads << 14));
                         ++base;
                     }
                 }
             }
-            bar_sync(BAR_P, kPThreads);
+            bar_sync(BAR_M, kMThreads);
             n_u = s.bcast_i[11];
             n_b = s.bcast_i[12];
             // lists overflowed: dense work (every quad evaluated; a superset of the marks, so still exact)
             if (n_u > kListCap || n_b > kListCap) dense = true;
         }
-        CPT_TICK(ptid == 0, 4);   // marks + lists
-        // ------------------------------------------------------------ sweep 2b: U (K2)
+        CPT_COUNT(mtid == 0, 28, n_u);
+        CPT_COUNT(mtid == 0, 29, n_b);
+        CPT_COUNT(mtid == 0 && dense, 30, 1);
+        CPT_COUNT(mtid == 0 && no_fg, 31, 1);
+        if (sweep_comes_back) bar_arrive(BAR_SM_EMPTY + b, kPThreads + kMThreads);  // message consumed
+        CPT_TICK2(mtid == 0, 4);   // marks + lists
+        // ------------------------------------------------------------ sweep 2b: U (K2), from the filtered image
         if (!no_fg) {
             if (dense) {
-                for (int grp = ptid; grp < g.groups; grp += kPThreads) normalise_group(s, P, grp, ac, gmn, gmx);
+                for (int grp = mtid; grp < g.groups; grp += kMThreads) normalise_group(s, fcur, grp, ac, gmn, gmx, nmagic, nshift);
             } else {
-                for (int i = ptid; i < n_u; i += kPThreads) normalise_group(s, P, s.list_u[i], ac, gmn, gmx);
+                // all of a thread's loads are in flight before the first value is used (L2 latency paid once)
+                constexpr int kBatch = 4;
+                for (int i0 = mtid; i0 < n_u; i0 += kBatch * kMThreads) {
+                    int grp[kBatch];
+                    float4 f0[kBatch], f1[kBatch];
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) {
+                        const int i = i0 + j * kMThreads;
+                        grp[j] = (i < n_u) ? (int)s.list_u[i] : -1;
+                        if (grp[j] >= 0) {
+                            f0[j] = *reinterpret_cast<const float4 *>(fcur + grp[j] * 8);
+                            f1[j] = *reinterpret_cast<const float4 *>(fcur + grp[j] * 8 + 4);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j)
+                        if (grp[j] >= 0) normalise_values(s, f0[j], f1[j], grp[j], ac, gmn, gmx, nmagic, nshift);
+                }
             }
-            bar_sync(BAR_P, kPThreads);
+            bar_sync(BAR_M, kMThreads);
         }
-        CPT_TICK(ptid == 0, 5);   // sweep 2b + barrier
+        CPT_TICK2(mtid == 0, 5);   // normalise + barrier
 
-        // ------------------------------------------------------------ blur + threshold (K4) -> s.M[buf]
+        // ------------------------------------------------------------ blur + threshold (K4) -> s.M[b]
         // (the component warps hand the buffer back zeroed)
-        if (t >= 2) bar_sync(BAR_EMPTY + buf, kThreads);  // component warps are done with frame t-2's mask
-        CPT_TICK(ptid == 0, 6);   // wait for the mask buffer
+        if (t >= 2) bar_sync(BAR_EMPTY + b, kMThreads + kCThreads);  // component warps are done with frame t-2's mask
+        CPT_TICK2(mtid == 0, 8);   // wait for the mask buffer
         if (!no_fg) {
             if (dense) {
-                for (int grp = ptid; grp < g.groups; grp += kPThreads) blur_group(s, g, grp, 3u, buf, ith);
+                for (int grp = mtid; grp < g.groups; grp += kMThreads) blur_group(s, g, grp, 3u, b, ith);
             } else {
-                for (int i = ptid; i < n_b; i += kPThreads) {
+                for (int i = mtid; i < n_b; i += kMThreads) {
                     const uint32_t e = s.list_b[i];
-                    blur_group(s, g, (int)(e & 0x3fffu), e >> 14, buf, ith);
+                    blur_group(s, g, (int)(e & 0x3fffu), e >> 14, b, ith);
                 }
             }
         }
-        if (ptid == 0) { s.msg[buf][0] = cur_fmin; s.msg[buf][1] = cur_fmax; }
-        bar_arrive(BAR_FULL + buf, kThreads);
-        CPT_TICK(ptid == 0, 7);   // blur
-        prev_fmin = cur_fmin;
-        prev_fmax = cur_fmax;
-        have_prev = 1;
-        // no barrier here: the next sweep touches B / K / S / red_u only, which nothing above still reads
+        if (mtid == 0) { s.msg[b][0] = cur_fmin; s.msg[b][1] = cur_fmax; }
+        bar_arrive(BAR_FULL + b, kMThreads + kCThreads);
+        CPT_TICK2(mtid == 0, 9);   // blur
     }
-
-    // ---------------------------------------------------------------- save state
-    // (the component warps read the resumed state's filtered frame and header until their last frame is done)
-    bar_sync(BAR_DONE, kThreads);
-    if (st_raw) {
-        for (int i = ptid; i < npx; i += kPThreads) {
-            st_B[i] = s.B[i];
-            st_K[i] = s.K[i];
-            st_S[i] = s.S[i];
-        }
-        if (clip.n_frames > 0) {
-            const float *flast = filtered_ptr(a, clip, scratch, clip.n_frames - 1);
-            for (int i = ptid; i < npx; i += kPThreads) st_F[i] = flast[i];
-        }
-        if (ptid == 0) {
-            st_hdr->average = average;
-            st_hdr->frames_seen = frames_seen;
-            st_hdr->initialised = 1;
-            st_hdr->prev_fmin = prev_fmin;
-            st_hdr->prev_fmax = prev_fmax;
-            st_hdr->have_prev = have_prev;
-        }
+    if (mtid == 0) {
+        s.final_average = average;
+        s.final_prev[0] = prev_fmin; s.final_prev[1] = prev_fmax; s.final_prev[2] = have_prev;
     }
+    bar_arrive(BAR_DONE, kThreads);
 }
 
 }  // namespace
@@ -1089,13 +1223,15 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
         if (ci >= a.n_clips) break;
         const cpt_clip clip = a.clips[ci];
         uint8_t *st_raw = a.state ? a.state + (size_t)ci * state_bytes(npx) : nullptr;
-        float *scratch = a.scratch ? a.scratch + (size_t)blockIdx.x * 4 * npx : nullptr;
+        float *scratch = a.scratch ? a.scratch + (size_t)blockIdx.x * 8 * npx : nullptr;
+        const StateHeader *st_hdr = reinterpret_cast<const StateHeader *>(st_raw);
         if (tid < kPThreads) {
-            pixel_warps(a, s, clip, tid, scratch, st_raw);
+            sweep_warps(a, s, clip, tid, scratch, st_raw);
+        } else if (tid < kPThreads + kMThreads) {
+            mask_warps(a, s, clip, tid - kPThreads, scratch, st_hdr);
         } else {
-            const StateHeader *st_hdr = reinterpret_cast<const StateHeader *>(st_raw);
             const float *st_F = reinterpret_cast<const float *>(st_raw + sizeof(StateHeader) + (size_t)npx * 8);
-            component_warps(a, s, clip, tid - kPThreads, scratch, st_hdr, st_F);
+            component_warps(a, s, clip, tid - kPThreads - kMThreads, scratch, st_hdr, st_F);
         }
     }
 }
@@ -1117,14 +1253,14 @@ __global__ void __launch_bounds__(kThreads, 1) mask_components_kernel(const Kern
         for (int i = tid; i < g.npx / 16; i += kThreads) reinterpret_cast<uint4 *>(s.U)[i] = __ldg(reinterpret_cast<const uint4 *>(u) + i);
         __syncthreads();
         const int ith = (int)floorf(a.info[o].threshold);
-        if (tid < kPThreads)
-            for (int grp = tid; grp < g.groups; grp += kPThreads) blur_group(s, g, grp, 3u, 0, ith);
+        if (tid < kThreads - kCThreads)
+            for (int grp = tid; grp < g.groups; grp += kThreads - kCThreads) blur_group(s, g, grp, 3u, 0, ith);
         __syncthreads();
-        if (tid >= kPThreads) {
+        if (tid >= kThreads - kCThreads) {
             const bool have_prev = marker == 2;
             const float *fcur = a.filtered + (size_t)o * g.npx;
             const int fmin = a.info[o].filtered_min, fmax = a.info[o].filtered_max;
-            components_of_frame(a, s, g, tid - kPThreads, 0, (size_t)o, fcur, have_prev ? fcur - g.npx : fcur, fmin, fmax,
+            components_of_frame(a, s, g, tid - (kThreads - kCThreads), 0, (size_t)o, fcur, have_prev ? fcur - g.npx : fcur, fmin, fmax,
                                 have_prev ? a.info[o - 1].filtered_min : 0, have_prev ? a.info[o - 1].filtered_max : 0, have_prev, true);
         }
         __syncthreads();

@@ -35,15 +35,18 @@ def main(clips=148, frames=300, exp=0):
     ex.extract_device(d_frames, cl, out=out)
     torch.cuda.synchronize()
     native.check(ex.ctx.lib.cpt_debug_phase_cycles(ex.ctx._h, buf, 0))
-    names = {14: "P fused sweep", 2: "P sweep reduce+bar", 15: "P  scalars: reductions", 16: "P  scalars: lane 0 math", 3: "P scalars rest+bar",
-             4: "P marks+lists", 5: "P normalise+bar", 6: "P wait mask buffer", 7: "P blur", 11: "C wait mask", 12: "C components",
+    names = {14: "S fused sweep", 6: "S wait msg/qmax free", 2: "S message",
+             7: "M wait sweep", 16: "M scalars thread 0", 3: "M scalars bar", 15: "M quad maxima -> hot rows", 4: "M marks+lists", 5: "M normalise+bar", 8: "M wait mask buffer", 9: "M blur",
+             11: "C wait mask", 12: "C components",
              20: "C  close+reset+bar", 21: "C  run starts+bar", 22: "C  unions+bar", 23: "C  roots+bar", 24: "C  run stats+bar",
              25: "C  rank+bar", 26: "C  label writes", 27: "C  variance+bar"}
     total = clips * frames
-    psum = sum(buf[i] for i in list(range(2, 8)) + [14, 15, 16])
     for i, n in names.items():
         print("{:22s} {:9.0f} cycles/frame".format(n, buf[i] / total))
-    print("P total {:.0f} cycles/frame, C total {:.0f}".format(psum / total, (buf[11] + buf[12]) / total))
+    print("lists: normalise {:.1f} groups/frame, blur {:.1f}; dense frames {:.4f}, no-foreground frames {:.4f}".format(
+        buf[28] / total, buf[29] / total, buf[30] / total, buf[31] / total))
+    print("S total {:.0f} cycles/frame, M total {:.0f}, C total {:.0f}".format(
+        sum(buf[i] for i in (14, 6, 2)) / total, sum(buf[i] for i in (7, 16, 3, 15, 4, 5, 8, 9)) / total, (buf[11] + buf[12]) / total))
 
 
 if __name__ == "__main__":
