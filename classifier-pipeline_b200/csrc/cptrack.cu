@@ -1,4 +1,5 @@
 // cptrack.cu -- C ABI (include/cptrack.h) over the sm_100a kernels.
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -13,6 +14,8 @@
 namespace cpt {
 __global__ void extract_clips_kernel(const KernelArgs a);
 __global__ void mask_components_kernel(const KernelArgs a, long long total_frames, const uint8_t *denoised);
+__global__ void extract_sweep_kernel(const KernelArgs a);
+__global__ void frame_regions_kernel(const KernelArgs a, long long total_frames);
 int nlm_launch(cpt_ctx *c, const uint8_t *d_src, int width, int height, long long n_frames, uint8_t *d_dst, const cpt_frame_info *info,
                cudaStream_t stream);
 __global__ void region_variance_kernel(Geometry g, long long total_frames, const float *filtered, cpt_frame_info *info, cpt_region *regions);
@@ -94,7 +97,11 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     }
     c->stream = c->own_stream;
     if (cudaFuncSetAttribute(cpt::extract_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(cpt::Smem)) != cudaSuccess) {
+                             (int)sizeof(cpt::Smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(cpt::extract_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(cpt::Smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(cpt::frame_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(cpt::FrameSmem)) != cudaSuccess) {
         fail(CPT_ERR_CUDA, "cannot opt in to %zu bytes of shared memory: %s", sizeof(cpt::Smem),
              cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -131,6 +138,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
         cudaFree(t.d_thr);
     }
     cudaFree(c->scratch);
+    cudaFree(c->hot);
     cudaFree(c->work_counter);
     cudaFree(c->zero_frame);
     cudaFree(c->debug);
@@ -347,8 +355,31 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         a.u8_frames = c->u8_frames[0];
         a.defer_variance = 1;
     }
-    cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    // Batch launches that keep the filtered images and carry no per-clip state take the split path: the recurrence as a
+    // persistent sweep kernel, then one CTA per frame for masks / components.  Everything else (streaming, resumed
+    // clips, regions-only launches) runs the single persistent kernel with its three warp roles.
+    static const bool split_allowed = [] { const char *e = getenv("CPT_SPLIT"); return !(e && e[0] == '0'); }();
+    const bool split = split_allowed && d_state == nullptr && out->d_filtered != nullptr && total_frames > 0;
+    if (split) {
+        if (c->hot_frames < (size_t)total_frames) {
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            cudaFree(c->hot);
+            c->hot = nullptr;
+            c->hot_frames = 0;
+            CUDA_TRY(cudaMalloc(&c->hot, (size_t)total_frames * cpt::kHotStride * sizeof(uint32_t)));
+            c->hot_frames = (size_t)total_frames;
+        }
+        a.hot = c->hot;
+        // the valid flag of every output frame starts cleared: frames no clip writes are skipped by the second launch
+        CUDA_TRY(cudaMemsetAsync(c->hot, 0, (size_t)total_frames * cpt::kHotStride * sizeof(uint32_t), stream));
+        cpt::extract_sweep_kernel<<<grid, cpt::kSThreads, sizeof(cpt::Smem), stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        cpt::frame_regions_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::FrameSmem), stream>>>(a, total_frames);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+    }
     if (out->denoise) {
         int rc = cpt::nlm_launch(c, c->u8_frames[0], c->g.W, c->g.H, total_frames, c->u8_frames[1], out->d_info, stream);
         if (rc) return rc;

@@ -49,6 +49,8 @@ struct cpt_ctx {
     cpt::HostWeightTable tables[4];
     float *scratch = nullptr;
     size_t scratch_ctas = 0;
+    uint32_t *hot = nullptr;   // hot-quad words of the split extraction path, [hot_frames][kHotStride]
+    size_t hot_frames = 0;
     int *work_counter = nullptr;
     uint16_t *zero_frame = nullptr;
     long long *debug = nullptr;

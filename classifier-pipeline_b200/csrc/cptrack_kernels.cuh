@@ -32,15 +32,29 @@ namespace cpt {
 constexpr int kPThreads = 320;                  // 10 sweep warps: 8 rows x 40 quads per iteration at 160 pixels
 #elif CPT_EXP == 2
 constexpr int kPThreads = 480;                  // 15 sweep warps: 12 rows x 40 quads
+#elif CPT_EXP == 4
+constexpr int kPThreads = 960;
+#elif CPT_EXP == 5
+constexpr int kPThreads = 800;
 #else
 constexpr int kPThreads = 640;                  // 20 sweep warps: 16 rows x 40 quads per iteration at 160 pixels
 #endif
 constexpr int kPWarps = kPThreads / 32;
+#if CPT_EXP == 4 || CPT_EXP == 5
+constexpr int kMThreads = 32;
+constexpr int kCThreads = 32;
+#else
 constexpr int kMThreads = 128;                  // 4 mask warps
 constexpr int kCThreads = 256;                  // 8 component warps
+#endif
 constexpr int kCWarps = kCThreads / 32;
 constexpr int kThreads = kPThreads + kMThreads + kCThreads;
 constexpr int kWarps = kThreads / 32;
+// split path (batch launches that keep the filtered images and carry no state): extract_sweep_kernel runs the sweep
+// warps plus one scalar warp per clip, frame_regions_kernel then turns every frame into masks / labels / regions with
+// one CTA per frame
+constexpr int kSThreads = kPThreads + 32;
+constexpr int kFThreads = 256;
 constexpr int kMaxPx = 19200;
 constexpr int kQIter = (kMaxPx / 4 + kPThreads - 1) / kPThreads;  // 6 quads of 4 pixels per pixel thread
 constexpr int kMaxW = 160;
@@ -51,6 +65,11 @@ constexpr int kRunsPerRow = kMaxW / 2;          // 80
 constexpr int kMaxRuns = kMaxH * kRunsPerRow;   // 9600
 constexpr int kCompSlots = 256;                 // slot 255 = overflow sink
 constexpr int kMeanFrames = CPT_MEAN_FRAMES;
+// per output frame of the split path: one ballot word per (sweep warp, sweep iteration) -- bit `lane` of word
+// warp * kQIter + it is the hot bit of owned quad it * kPThreads + warp * 32 + lane -- followed by
+// {byte threshold (0: dense), normalise magic, normalise shift, flags (1: valid, 2: first frame of its clip)}
+constexpr int kHotWords = (kQIter * kPWarps + 3) & ~3;  // (the trailer is read and written as one 16-byte vector)
+constexpr int kHotStride = kHotWords + 4;
 constexpr uint16_t kSlotFlag = 0x8000u;
 
 struct Geometry {
@@ -120,12 +139,13 @@ struct KernelArgs {
     int defer_variance;   // leave K6 of frames t > 0 to region_variance_kernel (needs `filtered`)
     uint8_t *u8_frames;   // [total_frames][npx] normalised images of denoise clips (ctx scratch), else nullptr
     const uint16_t *zero_frame;  // npx zeros: stands in for the frame leaving the 45-frame window while it fills
+    uint32_t *hot;        // [total_frames][kHotStride] (split path), else nullptr
     WeightTable tables[4];
 };
 
 // sweep -> mask warps: what one frame's sweep found
 struct FrameMsg {
-    uint32_t red[12];  // sum P, min F, max F, min P, max P, sum |F|, sum B, changed, min B, max B
+    uint32_t red[12];  // sum P, min F, max F, min P, max P, sum |F|, sum B, changed
     int32_t qref;      // reference value the per-quad maxima in Smem::qmax8 are stored against
     int32_t update;    // the sweep applied a background update
     int32_t is_frame;  // 0: tail pass (update only)
@@ -151,16 +171,44 @@ struct __align__(16) Smem {
     double bcast_d[4];
     double acc_s[kCompSlots], acc_s2[kCompSlots];  // per-component sum / sum of squares of the delta frame
     uint32_t wthr[kSmemWeights];                   // first entries of the clip's keep-test table
-    // per owned quad q = it * kPThreads + ptid (= owned row * qpr + column quad): clamp(max F - qref, -128, 127) + 128,
+    // per owned quad q = it * kPThreads + ptid (= owned row * qpr + column quad): max F - qref saturated to int8,
     // written by the sweep warps at the end of a frame, turned into hot64 by the mask warps
-    uint8_t qmax8[kQIter * kPThreads];
+    int8_t qmax8[kQIter * kPThreads];
     unsigned long long hot64[kMaxH];  // per owned row, one bit per quad: some pixel can exceed the threshold
     FrameMsg fm[2];
     int32_t fth_latest;      // last bound the mask warps computed (INT32_MIN: none yet): the next qref
+    int32_t done_frames;     // split path: messages of this clip the scalar warp has finished
+    int32_t tu_pub[2];       // split path: byte threshold of the frame in message buffer b (0: dense)
     int32_t final_prev[3];   // filtered min / max of the last frame, have_prev (for the state record)
     double init_average, final_average;
     uint16_t list_u[kListCap];  // groups of 8 pixels to normalise this frame (need_u)
     uint16_t list_b[kListCap];  // groups of 8 pixels to blur this frame: group | quad marks << 14
+    int32_t ncomp;
+};
+
+// shared memory of frame_regions_kernel (one frame per CTA): the work lists and hot rows are dead once the mask is
+// thresholded, the normalised image once it is blurred, so they share storage with the labelling tables
+struct __align__(16) FrameSmem {
+    union {
+        uint8_t U[kMaxPx];
+        struct { double acc_s[kCompSlots], acc_s2[kCompSlots]; };
+    };
+    union {
+        uint16_t parent[kMaxRuns];
+        struct {
+            uint16_t list_u[kListCap], list_b[kListCap];
+            uint32_t hotw[kHotStride];
+            unsigned long long hot64[kMaxH];
+        };
+    };
+    uint32_t M[1][kMaxWords];
+    uint32_t C[kMaxWords];
+    uint32_t ST[kMaxWords];
+    uint8_t base[kMaxWords + 8];
+    int32_t c_key[kCompSlots], c_area[kCompSlots], c_sx[kCompSlots], c_sy[kCompSlots];
+    int32_t c_l[kCompSlots], c_t[kCompSlots], c_r[kCompSlots], c_b[kCompSlots];
+    uint8_t c_rank[kCompSlots];
+    int32_t bcast_i[16];
     int32_t ncomp;
 };
 
@@ -208,7 +256,8 @@ __device__ __forceinline__ float norm255_f64(float f, double mn, double mx) {
 }
 
 // ---- run bookkeeping on the closed mask ------------------------------------------------------
-__device__ __forceinline__ int run_id(const Smem &s, const Geometry &g, int x, int y) {
+template <class SM>
+__device__ __forceinline__ int run_id(const SM &s, const Geometry &g, int x, int y) {
     int w = y * g.row_words + (x >> 5), b = x & 31;
     uint32_t below = s.ST[w] & (0xffffffffu >> (31 - b));
     return y * kRunsPerRow + (int)s.base[w] + __popc(below) - 1;

@@ -20,17 +20,17 @@ namespace {
     do {                                                                                      \
         if ((cond) && a.debug) {                                                              \
             long long now_ = clock64();                                                       \
-            atomicAdd((unsigned long long *)&a.debug[blockIdx.x * 32 + (i)], (unsigned long long)(now_ - tick_last_)); \
+            atomicAdd((unsigned long long *)&a.debug[(blockIdx.x % 128u) * 32 + (i)], (unsigned long long)(now_ - tick_last_)); \
             tick_last_ = now_;                                                                \
         }                                                                                     \
     } while (0)
-#define CPT_COUNT(cond, i, v) do { if ((cond) && a.debug) atomicAdd((unsigned long long *)&a.debug[blockIdx.x * 32 + (i)], (unsigned long long)(v)); } while (0)
+#define CPT_COUNT(cond, i, v) do { if ((cond) && a.debug) atomicAdd((unsigned long long *)&a.debug[(blockIdx.x % 128u) * 32 + (i)], (unsigned long long)(v)); } while (0)
 #define CPT_TICK_START2(cond) long long tick2_last_ = clock64(); (void)tick2_last_
 #define CPT_TICK2(cond, i)                                                                    \
     do {                                                                                      \
         if ((cond) && a.debug) {                                                              \
             long long now_ = clock64();                                                       \
-            atomicAdd((unsigned long long *)&a.debug[blockIdx.x * 32 + (i)], (unsigned long long)(now_ - tick2_last_)); \
+            atomicAdd((unsigned long long *)&a.debug[(blockIdx.x % 128u) * 32 + (i)], (unsigned long long)(now_ - tick2_last_)); \
             tick2_last_ = now_;                                                               \
         }                                                                                     \
     } while (0)
@@ -50,6 +50,14 @@ enum : int {
     BAR_QFREE = 14                                 // mask -> sweep warps: Smem::qmax8 has been consumed
 };
 
+// quad maximum of a slot the thread does not own / of a pass without a frame: far below any F, and kNoQuad - qref cannot wrap
+constexpr int kNoQuad = -(1 << 30);
+// the byte stored for a quad: max F relative to qref, saturated to int8
+__device__ __forceinline__ int8_t quad_byte(int gmax, int qref) {
+    int d;
+    asm("cvt.sat.s8.s32 %0, %1;" : "=r"(d) : "r"(gmax - qref));
+    return (int8_t)d;
+}
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
@@ -119,19 +127,20 @@ struct RunCursor {
     int y, wi, base;
 };
 
-// K4 second half + K5 + K6 for the mask in s.M[buf].  Called by all kCThreads component threads.
-__device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry &g, int ctid, int buf, size_t o,
+// K4 second half + K5 + K6 for the mask in s.M[buf].  Called by all kT threads of the role (kBar: their named barrier).
+template <class SM, int kT, int kBar>
+__device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &g, int ctid, int buf, size_t o,
                                     const float *fcur, const float *fprev, int cur_fmin, int cur_fmax, int prev_fmin,
                                     int prev_fmax, bool have_prev, bool defer_variance) {
     const int W = g.W, lane = ctid & 31, cwarp = ctid >> 5;
-    constexpr int kIter = (kMaxWords + kCThreads - 1) / kCThreads;  // 3
+    constexpr int kIter = (kMaxWords + kT - 1) / kT;  // 3
     RunCursor rc[kIter];
     bool any = false;
     CPT_TICK_START2(ctid == 0);
     // ---- close: C[y] = M[y-1] | (M[y] & M[y-2]) (C[0] = M[0]); slot tables reset
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
-        int w = ctid + it * kCThreads;
+        int w = ctid + it * kT;
         rc[it].c = 0; rc[it].stw = 0; rc[it].y = 0; rc[it].wi = 0; rc[it].base = 0;
         if (w < g.words) {
             int y = (int)(((uint32_t)w * g.rw_magic) >> 13);
@@ -147,19 +156,19 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             any |= (c != 0);
         }
     }
-    for (int i = ctid; i < kCompSlots; i += kCThreads) {
+    for (int i = ctid; i < kCompSlots; i += kT) {
         s.c_key[i] = INT32_MAX; s.c_area[i] = 0; s.c_sx[i] = 0; s.c_sy[i] = 0;
         s.c_l[i] = INT32_MAX; s.c_t[i] = INT32_MAX; s.c_r[i] = -1; s.c_b[i] = -1;
         s.acc_s[i] = 0.0; s.acc_s2[i] = 0.0;
     }
     if (ctid == 0) s.ncomp = 0;
-    if (!bar_or(BAR_C, kCThreads, any)) return;  // no foreground: info.n_components stays 0
+    if (!bar_or(kBar, kT, any)) return;  // no foreground: info.n_components stays 0
     CPT_TICK2(ctid == 0, 20);  // close + reset + barrier
 
     // ---- run starts and ids
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
-        int w = ctid + it * kCThreads;
+        int w = ctid + it * kT;
         if (w < g.words) {
             const int wi = rc[it].wi, y = rc[it].y;
             uint32_t carry = 0;
@@ -183,12 +192,12 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             }
         }
     }
-    bar_sync(BAR_C, kCThreads);
+    bar_sync(kBar, kT);
     CPT_TICK2(ctid == 0, 21);  // run starts + barrier
     // ---- unions with the row above (8-connectivity)
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
-        int w = ctid + it * kCThreads;
+        int w = ctid + it * kT;
         const uint32_t c = rc[it].c;
         const int y = rc[it].y, wi = rc[it].wi;
         if (w < g.words && y > 0 && c != 0) {
@@ -221,7 +230,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             }
         }
     }
-    bar_sync(BAR_C, kCThreads);
+    bar_sync(kBar, kT);
     CPT_TICK2(ctid == 0, 22);  // unions + barrier
     // ---- roots -> component slots
 #pragma unroll
@@ -238,13 +247,13 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             ++n;
         }
     }
-    bar_sync(BAR_C, kCThreads);
+    bar_sync(kBar, kT);
     CPT_TICK2(ctid == 0, 23);  // roots + barrier
     const int ncomp = s.ncomp;
     // ---- per-run statistics into the slot tables
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
-        int w = ctid + it * kCThreads;
+        int w = ctid + it * kT;
         uint32_t bitsleft = rc[it].stw;
         const uint32_t c = rc[it].c;
         const int y = rc[it].y, wi = rc[it].wi;
@@ -278,17 +287,17 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             atomicMax(&s.c_b[slot], y);
         }
     }
-    bar_sync(BAR_C, kCThreads);
+    bar_sync(kBar, kT);
     CPT_TICK2(ctid == 0, 24);  // run statistics + barrier
     // ---- OpenCV label order: rank by the key of the component's first 2x2 block
     const int nslots = min(ncomp, CPT_MAX_COMPONENTS);
     const int nout = min(nslots, g.max_regions);
-    for (int i = ctid; i < nslots; i += kCThreads) {
+    for (int i = ctid; i < nslots; i += kT) {
         int key = s.c_key[i], rank = 0;
         for (int q = 0; q < nslots; ++q) rank += (s.c_key[q] < key);
         s.c_rank[i] = (uint8_t)rank;
     }
-    bar_sync(BAR_C, kCThreads);
+    bar_sync(kBar, kT);
     CPT_TICK2(ctid == 0, 25);  // rank + barrier
     // ---- label image: the pixel warps already stored zeros for this frame; write the runs
     if (a.labels) {
@@ -322,7 +331,7 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             const int bw = s.c_r[slot] - l + 1, bh = s.c_b[slot] - tp + 1;
             if (cwarp >= bh) continue;
             double s1 = 0.0, s2 = 0.0;
-            for (int yy = tp + cwarp; yy < tp + bh; yy += kCWarps)
+            for (int yy = tp + cwarp; yy < tp + bh; yy += (kT / 32))
                 for (int xx = l + lane; xx < l + bw; xx += 32) {
                     int fc = (int)fcur[yy * W + xx], fp = (int)fprev[yy * W + xx];
                     float d = fabsf(norm255(fc, cur_fmin, cur_fmax, exact) - norm255(fp, prev_fmin, prev_fmax, exact));
@@ -339,9 +348,9 @@ __device__ void components_of_frame(const KernelArgs &a, Smem &s, const Geometry
             }
         }
     }
-    bar_sync(BAR_C, kCThreads);
+    bar_sync(kBar, kT);
     CPT_TICK2(ctid == 0, 27);  // variance + barrier
-    for (int i = ctid; i < nslots; i += kCThreads) {
+    for (int i = ctid; i < nslots; i += kT) {
         const int rank = s.c_rank[i];
         if (rank < nout) {
             cpt_region r;
@@ -386,7 +395,7 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
         const float *fprev = (t == 0) ? st_F : filtered_ptr(a, clip, scratch, t - 1);
         // frames after the first of a launch have both filtered images in the caller's buffer: their variances
         // are left to region_variance_kernel (a wide second launch) instead of this 7-warp critical path
-        components_of_frame(a, s, g, ctid, buf, (size_t)(clip.out_offset + t), fcur, fprev, cur_fmin, cur_fmax, prev_fmin,
+        components_of_frame<Smem, kCThreads, BAR_C>(a, s, g, ctid, buf, (size_t)(clip.out_offset + t), fcur, fprev, cur_fmin, cur_fmax, prev_fmin,
                             prev_fmax, have_prev, a.defer_variance && t > 0);
         prev_fmin = cur_fmin;
         prev_fmax = cur_fmax;
@@ -409,7 +418,8 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
 // BORDER_REFLECT_101) in packed 16-bit lanes and threshold `> ith` -> one byte of the bit rows in s.M[buf].
 // Only outputs of the marked quads (q2: one bit per quad of the group) are evaluated: the others cannot exceed the threshold (every input
 // of their window is <= ith) and their windows may reach inputs that were not refreshed.
-__device__ __forceinline__ void blur_group(Smem &s, const Geometry &g, int grp, uint32_t q2, int buf, int ith) {
+template <class SM>
+__device__ __forceinline__ void blur_group(SM &s, const Geometry &g, int grp, uint32_t q2, int buf, int ith) {
     const int W = g.W, H = g.H;
     uint8_t *M8 = reinterpret_cast<uint8_t *>(s.M[buf]);
     const uint32_t T = (ith >= 0 && ith < 255) ? (uint32_t)(((ith + 1) << 8) - 128) : 0u;
@@ -456,7 +466,8 @@ __device__ __forceinline__ void blur_group(Smem &s, const Geometry &g, int grp, 
 // K2 for one group of 8 pixels: U = uint8(255 * (G - min) / (max - min)), G = max(F - avg_change, 0) with F the
 // filtered image the sweep wrote (exact integers), in the reference's own fp32 arithmetic
 // (imageprocessing.py:151-169: multiply, then IEEE divide, truncate).
-__device__ __forceinline__ void normalise_values(Smem &s, const float4 f0, const float4 f1, int grp, int ac, int gmn, int gmx,
+template <class SM>
+__device__ __forceinline__ void normalise_values(SM &s, const float4 f0, const float4 f1, int grp, int ac, int gmn, int gmx,
                                                  uint32_t nmagic, int nshift, uint8_t *u_global = nullptr) {
     const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
     const bool degenerate = (gmx == gmn);
@@ -481,7 +492,8 @@ __device__ __forceinline__ void normalise_values(Smem &s, const float4 f0, const
     else *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
 }
 
-__device__ __forceinline__ void normalise_group(Smem &s, const float *F, int grp, int ac, int gmn, int gmx,
+template <class SM>
+__device__ __forceinline__ void normalise_group(SM &s, const float *F, int grp, int ac, int gmn, int gmx,
                                                 uint32_t nmagic, int nshift, uint8_t *u_global = nullptr) {
     // written by the sweep warps of this CTA a moment ago: plain (coherent) loads, an L2 hit
     const float4 f0 = *reinterpret_cast<const float4 *>(F + grp * 8), f1 = *reinterpret_cast<const float4 *>(F + grp * 8 + 4);
@@ -508,7 +520,7 @@ struct SweepMode {
 
 struct SweepAcc {
     uint32_t psum = 0, bsum = 0, changed = 0, fabs_sum = 0;
-    uint32_t bmin2 = 0xffffffffu, bmax2 = 0;  // packed uint16 pairs
+    uint32_t bmax2 = 0;  // packed uint16 pair
     int fmin = INT32_MAX, fmax = INT32_MIN, pmin = INT32_MAX, pmax = INT32_MIN;
 };
 
@@ -585,7 +597,7 @@ __device__ __forceinline__ uint32_t keep_pair(uint32_t b2, uint32_t k2, uint32_t
     return (((int)A0 - b0 >= t0) ? 0x0000ffffu : 0u) | (((int)A1 - b1 >= t1) ? 0xffff0000u : 0u);
 }
 
-// One owned quad: [update] then [frame].  Returns the quad's max F (INT32_MIN without a frame); nb_out = B'.
+// One owned quad: [update] then [frame].  Returns the quad's max F (kNoQuad without a frame); nb_out = B'.
 template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats>
 __device__ __forceinline__ int sweep_quad(Smem &s, const WeightTable &wt, const SweepThread &th, const SweepMode &m, int p4,
                                           uint2 pw, uint2 ow, float *fcur, uint8_t *lab_frame, SweepAcc &acc, uint2 &nb_out) {
@@ -611,10 +623,9 @@ __device__ __forceinline__ int sweep_quad(Smem &s, const WeightTable &wt, const 
         *reinterpret_cast<uint2 *>(s.B + p4) = nb;
         *reinterpret_cast<uint2 *>(s.K + p4) = nk;
     }
-    acc.bmin2 = __vminu2(acc.bmin2, __vminu2(nb.x, nb.y));
     acc.bmax2 = __vmaxu2(acc.bmax2, __vmaxu2(nb.x, nb.y));
     nb_out = nb;
-    return kFrame ? filter_quad(pw, ow, p4, nb, sv, s.S, fcur, lab_frame, kStats, acc) : INT32_MIN;
+    return kFrame ? filter_quad(pw, ow, p4, nb, sv, s.S, fcur, lab_frame, kStats, acc) : kNoQuad;
 }
 
 // The quad's pixels of this frame and of the frame leaving the 45-frame window (a frame of zeros while the window
@@ -650,7 +661,7 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
         load_quad<kFrame>(th.p4_0, P, Pold, pw_next, ow_next);  // (row r0 is always owned when active)
 #pragma unroll
         for (int it = 0; it < kQIter; ++it) {
-            gmaxq[it] = INT32_MIN;
+            gmaxq[it] = kNoQuad;
             const bool mine = th.active && ((kLepton && it < kLeptonFull) || th.r0 + it * rows_per_it < owned_rows);
             const uint2 pw = pw_next, ow = ow_next;
             if (it + 1 < kQIter && th.active && ((kLepton && it + 1 < kLeptonFull) || th.r0 + (it + 1) * rows_per_it < owned_rows))
@@ -665,7 +676,7 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
     } else {
 #pragma unroll 1
         for (int it = 0; it < kQIter; ++it) {
-            gmaxq[it] = INT32_MIN;
+            gmaxq[it] = kNoQuad;
             if (!th.active || th.r0 + it * rows_per_it >= owned_rows) continue;
             uint2 nb, pw, ow;
             load_quad<kFrame>(th.p4_0 + it * stride, P, Pold, pw, ow);
@@ -732,7 +743,6 @@ __device__ __forceinline__ uint32_t sweep_reduce_store(FrameMsg &fm, int lane, c
     const uint32_t psum = __reduce_add_sync(0xffffffffu, acc.psum), bsum = __reduce_add_sync(0xffffffffu, acc.bsum);
     const uint32_t changed = __reduce_or_sync(0xffffffffu, acc.changed);
     const int fmin = __reduce_min_sync(0xffffffffu, acc.fmin), fmax = __reduce_max_sync(0xffffffffu, acc.fmax);
-    const uint32_t bmin = __reduce_min_sync(0xffffffffu, min(acc.bmin2 & 0xffffu, acc.bmin2 >> 16));
     const uint32_t bmax = __reduce_max_sync(0xffffffffu, max(acc.bmax2 & 0xffffu, acc.bmax2 >> 16));
     uint32_t *r = fm.red;
     if (lane == 0) atomicAdd(r + 0, psum);
@@ -740,8 +750,6 @@ __device__ __forceinline__ uint32_t sweep_reduce_store(FrameMsg &fm, int lane, c
     if (lane == 2) atomicMax(reinterpret_cast<int *>(r + 2), fmax);
     if (lane == 6) atomicAdd(r + 6, bsum);
     if (lane == 7 && changed) atomicOr(r + 7, changed);
-    if (lane == 8) atomicMin(r + 8, bmin);
-    if (lane == 9) atomicMax(r + 9, bmax);
     if (want_stats) {
         const int pmin = __reduce_min_sync(0xffffffffu, acc.pmin), pmax = __reduce_max_sync(0xffffffffu, acc.pmax);
         const uint32_t fabs_sum = __reduce_add_sync(0xffffffffu, acc.fabs_sum);
@@ -757,8 +765,33 @@ __device__ __forceinline__ uint32_t sweep_reduce_store(FrameMsg &fm, int lane, c
 // warps -> hot-quad ballots against a PREDICTED bound (the mask warps compute the true one; if the prediction
 // turns out too high they fall back to dense work, so the ballots are always a superset) -> next frame.
 // ================================================================================================
+// split path: the quad maxima this thread stored for frame `of` (message buffer bb) against the byte threshold the scalar
+// warp published -> ballot words for frame_regions_kernel (layout: cptrack_kernels.cuh, kHotWords)
+__device__ __forceinline__ void solo_hot_words(const KernelArgs &a, const Smem &s, size_t of, int bb, int ptid, int lane, int warp) {
+    static_assert(kQIter <= 32, "one lane per sweep iteration");
+    const int tu = s.tu_pub[bb];
+    if (tu == 0) return;  // no usable bound: the frame is processed densely
+    uint32_t mine = 0;
+#pragma unroll
+    for (int it = 0; it < kQIter; ++it) {
+        const unsigned mbits = __ballot_sync(0xffffffffu, (int)s.qmax8[it * kPThreads + ptid] >= tu - 128);
+        if (lane == it) mine = mbits;
+    }
+    if (lane < kQIter) a.hot[of * kHotStride + warp * kQIter + lane] = mine;
+}
+
+// split path: wait until the scalar warp has finished `n` messages of this clip
+__device__ __forceinline__ void solo_wait_done(Smem &s, int n) {
+    while (*(volatile int32_t *)&s.done_frames < n) __nanosleep(32);
+    __threadfence_block();
+    __syncwarp();
+}
+
+// kSolo: the split path (extract_sweep_kernel) -- the only other role is the scalar warp, which runs one frame behind
+template <bool kSolo>
 __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int ptid, float *scratch,
                             uint8_t *st_raw) {
+    constexpr int kAll = kSolo ? kSThreads : kThreads;
     const Geometry &g = a.g;
     const int lane = ptid & 31, warp = ptid >> 5;
     const int W = g.W, npx = g.npx;
@@ -776,7 +809,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
     for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
     if (ptid < 2) frame_msg_reset(s.fm[ptid]);
-    if (ptid == 0) { s.fth_latest = INT32_MIN; s.bcast_i[10] = 0; }
+    if (ptid == 0) { s.fth_latest = INT32_MIN; s.bcast_i[10] = 0; s.done_frames = 0; }
     if (clip.flags & CPT_CLIP_RESUME) {
         bar_sync(BAR_P, kPThreads);
         int kmax = 0;
@@ -834,8 +867,9 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         const int last_row = g.H - 2 * g.edge - 1;  // owned-row index
         th.last_it = (th.active && last_row % g.rows_per_it == r0) ? last_row / g.rows_per_it : -1;
     }
-    bar_sync(BAR_INIT, kThreads);  // the state and the initial average are in place: the other roles may start
+    bar_sync(BAR_INIT, kAll);  // the state and the initial average are in place: the other roles may start
 
+    int last_t = -1;
     bool slow = true;  // the first update of a launch takes the exact path (no background extrema yet)
     // t == n_frames is the tail pass: only the background update of the last frame
     for (int t = 0; t <= clip.n_frames; ++t) {
@@ -876,7 +910,42 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         if (want_stats) pixel_sweep_dispatch<true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
         else pixel_sweep_dispatch<false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
         CPT_TICK(ptid == 0, 14);  // sweep
-        // ------------------------------------------------------------ message to the mask warps
+        // ------------------------------------------------------------ message to the mask warps / the scalar warp
+        last_t = t;
+        if (kSolo) {
+            // the scalar warp has had this whole sweep for frame t-1: its byte threshold turns the maxima stored for that
+            // frame into ballot words, and its message buffer (used again at t+1) is free
+            // (a flag, not a barrier: the sweep warps are not forced into lock step at the end of every frame; they can
+            // drift by less than two frames, which also keeps the FULL barriers' phases apart)
+            if (t >= 1) {
+                solo_wait_done(s, t);
+                solo_hot_words(a, s, (size_t)(clip.out_offset + t - 1), b ^ 1, ptid, lane, warp);
+            }
+            CPT_TICK(ptid == 0, 6);   // wait for the scalar warp + ballots
+            FrameMsg &fm = s.fm[b];
+            const uint32_t warp_bmax = sweep_reduce_store(fm, lane, acc, want_stats);
+            const int latest = *(volatile int32_t *)&s.fth_latest;
+            const int qref = (latest == INT32_MIN) ? 0 : latest;
+            if (ptid == 0) {
+                fm.qref = qref;
+                fm.update = m.update;
+                fm.is_frame = is_frame;
+            }
+            {
+                const int k_next = min(frames_seen + 1, wt.max_count);
+                const uint32_t thr_cap = (k_next < wt.linear_upto) ? (uint32_t)k_next + 1u
+                                         : ((k_next < kSmemWeights ? s.wthr[k_next] : __ldg(wt.thr + k_next)) & 0xffffu);
+                slow = warp_bmax + thr_cap > 65535u;
+            }
+            if (is_frame) {
+#pragma unroll
+                for (int it = 0; it < kQIter; ++it) s.qmax8[it * kPThreads + ptid] = quad_byte(gmaxq[it], qref);
+            }
+            if (m.update) ++frames_seen;
+            bar_arrive(BAR_SM_FULL + b, kSThreads);
+            CPT_TICK(ptid == 0, 2);   // message
+            continue;
+        }
         if (t >= 2) bar_sync(BAR_SM_EMPTY + b, kPThreads + kMThreads);  // they are done with the message of frame t-2
         if (t >= 1 && is_frame) bar_sync(BAR_QFREE, kPThreads + kMThreads);  // ... and with the quad maxima of frame t-1
         CPT_TICK(ptid == 0, 6);   // wait for the message buffer
@@ -899,21 +968,22 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         }
         if (is_frame) {
             // a border row's quads count for the owned row next to them, which only widens the marks;
-            // unowned slots hold INT32_MIN -> 0
+            // unowned slots hold kNoQuad -> -128
 #pragma unroll
-            for (int it = 0; it < kQIter; ++it) {
-                const int d = min(max(gmaxq[it], qref - 128) - qref, 127) + 128;
-                s.qmax8[it * kPThreads + ptid] = (uint8_t)d;
-            }
+            for (int it = 0; it < kQIter; ++it) s.qmax8[it * kPThreads + ptid] = quad_byte(gmaxq[it], qref);
         }
         if (m.update) ++frames_seen;
         bar_arrive(BAR_SM_FULL + b, kPThreads + kMThreads);
         CPT_TICK(ptid == 0, 2);   // message
     }
 
+    if (kSolo && last_t >= 0) {
+        solo_wait_done(s, last_t + 1);
+        if (last_t < clip.n_frames) solo_hot_words(a, s, (size_t)(clip.out_offset + last_t), last_t & 1, ptid, lane, warp);
+    }
     // ---------------------------------------------------------------- save state
     // (the other roles read the resumed state's filtered frame and header until their last frame is done)
-    bar_sync(BAR_DONE, kThreads);
+    bar_sync(BAR_DONE, kAll);
     if (st_raw) {
         for (int i = ptid; i < npx; i += kPThreads) {
             st_B[i] = s.B[i];
@@ -933,6 +1003,92 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             st_hdr->have_prev = s.final_prev[2];
         }
     }
+}
+
+// K2 / K7 scalars of one frame from the sweep's message (one thread): WeightedBackground.average, avg_change, the
+// normalisation range, the mapped threshold, the bound F >= fth below which a pixel cannot reach the threshold and the
+// byte threshold for the stored quad maxima.  Writes the frame's info record and s.bcast_i[0..5, 8, 13, 14].
+__device__ __forceinline__ void frame_scalars(const KernelArgs &a, Smem &s, const cpt_clip &clip, FrameMsg &fm, size_t o,
+                                              bool is_frame, bool want_stats, double &average) {
+    const Geometry &g = a.g;
+    const int npx = g.npx;
+    const uint32_t v0 = fm.red[0];
+    const int v1 = (int)fm.red[1], v2 = (int)fm.red[2];
+    const uint32_t bsum = fm.red[6], changed = fm.red[7];
+    if (fm.update && changed) {
+        // int(round(np.average(background))), motiondetector.py:232 -- half to even, in integers
+        uint32_t qa = bsum / (uint32_t)g.ncrop;
+        const uint32_t ra = bsum - qa * (uint32_t)g.ncrop;
+        if (2u * ra > (uint32_t)g.ncrop || (2u * ra == (uint32_t)g.ncrop && (qa & 1u))) qa += 1u;
+        average = (double)qa;
+    }
+    if (is_frame) {
+        // avg_change = int(round(np.average(thermal) - background average)), cliptracker.py:103-105
+        int ac;
+        const double avg_int = rint(average);
+        if (avg_int == average && average >= 0.0 && average < 65536.0) {
+            // integer average (always, once the background has changed): round_half_even((sum - avg*n) / n)
+            // in integers; identical to the fp64 expression because the only ties are exact
+            // |sum - avg * n| < 2^31: 32-bit arithmetic
+            int num = (int)v0 - (int)avg_int * npx;
+            int qd = num / npx, rem = num - qd * npx;
+            if (rem < 0) { rem += npx; qd -= 1; }
+            if (2 * rem > npx || (2 * rem == npx && (qd & 1))) qd += 1;
+            ac = (int)qd;
+        } else {
+            ac = (int)rint((double)v0 / (double)npx - average);
+        }
+        int gmx = max(v2 - ac, 0), gmn = max(v1 - ac, 0);
+        float thr;
+        int fth = INT32_MIN;
+        uint32_t nmagic = 0;  // 0: the fp32 divide; else (255 v) / r == (255 v * nmagic) >> nshift for 255 v < 2^24
+        int nshift = 0;
+        if (gmx == gmn) {
+            thr = (float)clip.background_thresh;  // cliptracker.py:118-119
+        } else {
+            float range = (float)gmx - (float)gmn;
+            thr = __fmul_rn(__fdiv_rn((float)clip.background_thresh, range), 255.0f);
+            unsigned r = (unsigned)(gmx - gmn);
+            if (255ull * r < (1ull << 24)) {
+                // every product is exact in fp32 here, so trunc(fl(255 v / r)) == (255 v) / r and a quad can
+                // only produce foreground if one of its pixels has U > floor(thr):
+                // U >= ith + 1  <=>  v >= ceil((ith + 1) r / 255), v = max(F - ac, 0) - gmn,
+                // i.e. F >= fth (the bound is >= 1, so the clamp never matters)
+                int it = (int)floorf(thr);
+                if (it >= 0 && it < 255) fth = (int)(((unsigned)(it + 1) * r + 254u) / 255u) + ac + gmn;
+                // Granlund-Montgomery: l = ceil(log2 r), m = ceil(2^(24 + l) / r) < 2^25.  The fp64 quotient is exact
+                // for powers of two and otherwise at least 1/r >= 2^-17 away from an integer: its ceiling is m.
+                const int l = (r <= 1u) ? 0 : 32 - __clz((int)(r - 1u));
+                nshift = 24 + l;
+                nmagic = (uint32_t)ceil(ldexp(1.0, nshift) / (double)r);
+            }
+        }
+        s.bcast_i[0] = ac; s.bcast_i[1] = gmn; s.bcast_i[2] = gmx;
+        s.bcast_i[3] = v1; s.bcast_i[4] = v2;
+        s.bcast_i[5] = __float_as_int(thr);
+        s.bcast_i[13] = (int)nmagic; s.bcast_i[14] = nshift;
+        // byte threshold for the quad maxima the sweep stored relative to qref (0: no usable bound, dense work):
+        // stored v = clamp(max F - qref, -128, 127) + 128, hot <=> v >= clamp(fth - qref, -127, 127) + 128.
+        // v == 0 means max F <= qref - 128 < fth; v == 255 means max F >= qref + 127 >= fth unless the
+        // threshold was clamped from above, which only widens the marks.
+        {
+            int tu = 0;
+            if (fth != INT32_MIN) {
+                const long long dq = (long long)fth - (long long)fm.qref;
+                if (dq >= -127) tu = (int)min(dq, 127ll) + 128;
+            }
+            s.bcast_i[8] = tu;
+        }
+        if (fth != INT32_MIN) *(volatile int32_t *)&s.fth_latest = fth;
+        cpt_frame_info fi;
+        fi.threshold = thr; fi.norm_min = gmn; fi.norm_max = gmx; fi.avg_change = ac;
+        fi.filtered_min = v1; fi.filtered_max = v2; fi.n_components = 0;
+        fi.thermal_min = want_stats ? (int)fm.red[3] : 0; fi.thermal_max = want_stats ? (int)fm.red[4] : 0;
+        fi.thermal_sum = v0; fi.abs_filtered_sum = want_stats ? fm.red[5] : 0u; fi.thermal_median = 0.f;
+        fi.background_average = average; fi.reserved[0] = 0; fi.reserved[1] = 0;
+        a.info[o] = fi;
+    }
+    frame_msg_reset(fm);
 }
 
 // ================================================================================================
@@ -964,85 +1120,7 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
         CPT_TICK2(mtid == 0, 7);   // waiting for the sweep
         FrameMsg &fm = s.fm[b];
         // ------------------------------------------------------------ scalars (K2, K7 average)
-        if (mtid == 0) {
-            const uint32_t v0 = fm.red[0];
-            const int v1 = (int)fm.red[1], v2 = (int)fm.red[2];
-            const uint32_t bsum = fm.red[6], changed = fm.red[7];
-            if (fm.update && changed) {
-                // int(round(np.average(background))), motiondetector.py:232 -- half to even, in integers
-                uint32_t qa = bsum / (uint32_t)g.ncrop;
-                const uint32_t ra = bsum - qa * (uint32_t)g.ncrop;
-                if (2u * ra > (uint32_t)g.ncrop || (2u * ra == (uint32_t)g.ncrop && (qa & 1u))) qa += 1u;
-                average = (double)qa;
-            }
-            if (is_frame) {
-                // avg_change = int(round(np.average(thermal) - background average)), cliptracker.py:103-105
-                int ac;
-                const double avg_int = rint(average);
-                if (avg_int == average && average >= 0.0 && average < 65536.0) {
-                    // integer average (always, once the background has changed): round_half_even((sum - avg*n) / n)
-                    // in integers; identical to the fp64 expression because the only ties are exact
-                    // |sum - avg * n| < 2^31: 32-bit arithmetic
-                    int num = (int)v0 - (int)avg_int * npx;
-                    int qd = num / npx, rem = num - qd * npx;
-                    if (rem < 0) { rem += npx; qd -= 1; }
-                    if (2 * rem > npx || (2 * rem == npx && (qd & 1))) qd += 1;
-                    ac = (int)qd;
-                } else {
-                    ac = (int)rint((double)v0 / (double)npx - average);
-                }
-                int gmx = max(v2 - ac, 0), gmn = max(v1 - ac, 0);
-                float thr;
-                int fth = INT32_MIN;
-                uint32_t nmagic = 0;  // 0: the fp32 divide; else (255 v) / r == (255 v * nmagic) >> nshift for 255 v < 2^24
-                int nshift = 0;
-                if (gmx == gmn) {
-                    thr = (float)clip.background_thresh;  // cliptracker.py:118-119
-                } else {
-                    float range = (float)gmx - (float)gmn;
-                    thr = __fmul_rn(__fdiv_rn((float)clip.background_thresh, range), 255.0f);
-                    unsigned r = (unsigned)(gmx - gmn);
-                    if (255ull * r < (1ull << 24)) {
-                        // every product is exact in fp32 here, so trunc(fl(255 v / r)) == (255 v) / r and a quad can
-                        // only produce foreground if one of its pixels has U > floor(thr):
-                        // U >= ith + 1  <=>  v >= ceil((ith + 1) r / 255), v = max(F - ac, 0) - gmn,
-                        // i.e. F >= fth (the bound is >= 1, so the clamp never matters)
-                        int it = (int)floorf(thr);
-                        if (it >= 0 && it < 255) fth = (int)(((unsigned)(it + 1) * r + 254u) / 255u) + ac + gmn;
-                        // Granlund-Montgomery: l = ceil(log2 r), m = ceil(2^(24 + l) / r) < 2^25.  The fp64 quotient is exact
-                        // for powers of two and otherwise at least 1/r >= 2^-17 away from an integer: its ceiling is m.
-                        const int l = (r <= 1u) ? 0 : 32 - __clz((int)(r - 1u));
-                        nshift = 24 + l;
-                        nmagic = (uint32_t)ceil(ldexp(1.0, nshift) / (double)r);
-                    }
-                }
-                s.bcast_i[0] = ac; s.bcast_i[1] = gmn; s.bcast_i[2] = gmx;
-                s.bcast_i[3] = v1; s.bcast_i[4] = v2;
-                s.bcast_i[5] = __float_as_int(thr);
-                s.bcast_i[13] = (int)nmagic; s.bcast_i[14] = nshift;
-                // byte threshold for the quad maxima the sweep stored relative to qref (0: no usable bound, dense work):
-                // stored v = clamp(max F - qref, -128, 127) + 128, hot <=> v >= clamp(fth - qref, -127, 127) + 128.
-                // v == 0 means max F <= qref - 128 < fth; v == 255 means max F >= qref + 127 >= fth unless the
-                // threshold was clamped from above, which only widens the marks.
-                {
-                    int tu = 0;
-                    if (fth != INT32_MIN) {
-                        const long long dq = (long long)fth - (long long)fm.qref;
-                        if (dq >= -127) tu = (int)min(dq, 127ll) + 128;
-                    }
-                    s.bcast_i[8] = tu;
-                }
-                if (fth != INT32_MIN) *(volatile int32_t *)&s.fth_latest = fth;
-                cpt_frame_info fi;
-                fi.threshold = thr; fi.norm_min = gmn; fi.norm_max = gmx; fi.avg_change = ac;
-                fi.filtered_min = v1; fi.filtered_max = v2; fi.n_components = 0;
-                fi.thermal_min = want_stats ? (int)fm.red[3] : 0; fi.thermal_max = want_stats ? (int)fm.red[4] : 0;
-                fi.thermal_sum = v0; fi.abs_filtered_sum = want_stats ? fm.red[5] : 0u; fi.thermal_median = 0.f;
-                fi.background_average = average; fi.reserved[0] = 0; fi.reserved[1] = 0;
-                a.info[o] = fi;
-            }
-            frame_msg_reset(fm);
-        }
+        if (mtid == 0) frame_scalars(a, s, clip, fm, o, is_frame, want_stats, average);
         CPT_TICK2(mtid == 0, 16);  // scalars: thread 0
         bar_sync(BAR_M, kMThreads);
         CPT_TICK2(mtid == 0, 3);   // scalars + barrier
@@ -1088,11 +1166,11 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
                     const uint32_t *q4 = reinterpret_cast<const uint32_t *>(s.qmax8 + pos);
                     const uint32_t t4 = (uint32_t)tu * 0x01010101u;
                     for (int w = 0; w < (g.qpr >> 2); ++w) {
-                        const uint32_t ge = __vcmpgeu4(q4[w], t4) & 0x01010101u;  // byte i -> bit 8 i
+                        const uint32_t ge = __vcmpgeu4(q4[w] ^ 0x80808080u, t4) & 0x01010101u;  // byte i -> bit 8 i
                         bits |= (unsigned long long)((ge * 0x10204080u) >> 28) << (4 * w);  // -> bits 0..3
                     }
                 } else {
-                    for (int q = 0; q < g.qpr; ++q) bits |= (unsigned long long)(s.qmax8[pos + q] >= tu ? 1u : 0u) << q;
+                    for (int q = 0; q < g.qpr; ++q) bits |= (unsigned long long)((int)s.qmax8[pos + q] >= tu - 128 ? 1u : 0u) << q;
                 }
                 s.hot64[oy] = bits;
             }
@@ -1206,6 +1284,51 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
     bar_arrive(BAR_DONE, kThreads);
 }
 
+// ================================================================================================
+// split path, scalar warp: one frame behind the sweep.  Lane 0 turns the sweep's message into the frame's info record,
+// publishes the byte threshold for the sweep warps' ballots and the constants frame_regions_kernel needs.
+// ================================================================================================
+__device__ void scalar_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, int lane) {
+    const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
+    const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
+    const bool denoise = clip.flags & CPT_CLIP_DENOISE;
+    bar_sync(BAR_INIT, kSThreads);
+    double average = s.init_average;
+    int prev_fmin = 0, prev_fmax = 0, have_prev = 0;
+    for (int t = 0; t <= clip.n_frames; ++t) {
+        CPT_TICK_START2(lane == 0);
+        const bool is_frame = t < clip.n_frames;
+        if (!(update_bg && t > 0) && !is_frame) break;
+        const int b = t & 1;
+        const size_t o = (size_t)(clip.out_offset + t);
+        bar_sync(BAR_SM_FULL + b, kSThreads);  // the sweep of frame t is done
+        CPT_TICK2(lane == 0, 7);   // waiting for the sweep
+        if (lane == 0) {
+            frame_scalars(a, s, clip, s.fm[b], o, is_frame, want_stats, average);
+            if (is_frame) {
+                s.tu_pub[b] = s.bcast_i[8];
+                *reinterpret_cast<uint4 *>(a.hot + o * kHotStride + kHotWords) =
+                    make_uint4((uint32_t)s.bcast_i[8], (uint32_t)s.bcast_i[13], (uint32_t)s.bcast_i[14], 1u | (t == 0 ? 2u : 0u));
+                if (denoise) a.info[o].reserved[1] = (t > 0) ? 2 : 1;  // 2: the previous filtered image is frame o - 1
+                prev_fmin = s.bcast_i[3];
+                prev_fmax = s.bcast_i[4];
+                have_prev = 1;
+            }
+        }
+        if (lane == 0) {
+            __threadfence_block();
+            *(volatile int32_t *)&s.done_frames = t + 1;  // message consumed, byte threshold published
+        }
+        __syncwarp();
+        CPT_TICK2(lane == 0, 16);  // scalars
+    }
+    if (lane == 0) {
+        s.final_average = average;
+        s.final_prev[0] = prev_fmin; s.final_prev[1] = prev_fmax; s.final_prev[2] = have_prev;
+    }
+    bar_arrive(BAR_DONE, kSThreads);
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const KernelArgs a) {
@@ -1226,7 +1349,7 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
         float *scratch = a.scratch ? a.scratch + (size_t)blockIdx.x * 8 * npx : nullptr;
         const StateHeader *st_hdr = reinterpret_cast<const StateHeader *>(st_raw);
         if (tid < kPThreads) {
-            sweep_warps(a, s, clip, tid, scratch, st_raw);
+            sweep_warps<false>(a, s, clip, tid, scratch, st_raw);
         } else if (tid < kPThreads + kMThreads) {
             mask_warps(a, s, clip, tid - kPThreads, scratch, st_hdr);
         } else {
@@ -1234,6 +1357,141 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
             component_warps(a, s, clip, tid - kPThreads - kMThreads, scratch, st_hdr, st_F);
         }
     }
+}
+
+// Split path, first launch: the recurrence only.  One persistent CTA per clip: sweep warps + the scalar warp.  Per frame
+// it leaves the filtered image, a zeroed label image, the info record and the hot-quad words in global memory.
+__global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const KernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s.bcast_i[15] = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int ci = s.bcast_i[15];
+        if (ci >= a.n_clips) break;
+        const cpt_clip clip = a.clips[ci];
+        if (tid < kPThreads) sweep_warps<true>(a, s, clip, tid, nullptr, nullptr);
+        else scalar_warp(a, s, clip, tid - kPThreads);
+    }
+}
+
+// Split path, second launch: one CTA per frame.  Hot-quad words -> per-row marks -> work lists -> normalise (K2) ->
+// blur + threshold (K4) -> close -> components, statistics, labels (K5); the variances are left to
+// region_variance_kernel.  Frames are independent here, so the latency of these short dependent phases is hidden by
+// the other frames resident on the SM.
+__global__ void __launch_bounds__(kFThreads, 4) frame_regions_kernel(const KernelArgs a, long long total_frames) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameSmem &s = *reinterpret_cast<FrameSmem *>(smem_raw);
+    const Geometry &g = a.g;
+    const int tid = threadIdx.x;
+    const long long o = blockIdx.x;
+    if (o >= total_frames) return;
+    const uint32_t *hw = a.hot + (size_t)o * kHotStride;
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(hw + kHotWords));
+    if (!(hdr.w & 1u)) return;  // no clip produced this output frame
+    const int tu = (int)hdr.x;
+    const uint32_t nmagic = hdr.y;
+    const int nshift = (int)hdr.z;
+    const bool first_of_clip = hdr.w & 2u;
+    const cpt_frame_info *fi = a.info + o;
+    const float thr = fi->threshold;
+    const int ac = fi->avg_change, gmn = fi->norm_min, gmx = fi->norm_max;
+    const int cur_fmin = fi->filtered_min, cur_fmax = fi->filtered_max;
+    const float *fcur = a.filtered + (size_t)o * g.npx;
+    if (fi->reserved[1]) {
+        // denoise clips: K3 sits between K2 and K4 -- emit the whole normalised image; cv2.fastNlMeansDenoising, blur,
+        // threshold, close and components follow as wide passes (nlm_denoise_kernel, mask_components_kernel)
+        uint8_t *u_frame = a.u8_frames + (size_t)o * g.npx;
+        for (int grp = tid; grp < g.groups; grp += kFThreads) normalise_group(s, fcur, grp, ac, gmn, gmx, nmagic, nshift, u_frame);
+        return;
+    }
+    const int ith = (int)floorf(thr);
+    const bool no_fg = ith >= 255;  // nothing can exceed the threshold: the mask stays empty
+    bool dense = tu == 0;           // no usable bound: every group is normalised and blurred
+    const int owned = g.H - 2 * g.edge;
+    for (int i = tid; i < g.words; i += kFThreads) s.M[0][i] = 0;
+    int n_u = 0, n_b = 0;
+    if (!no_fg && !dense) {
+        for (int i = tid; i < kHotWords; i += kFThreads) s.hotw[i] = __ldg(hw + i);
+        if (tid == 0) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
+        __syncthreads();
+        // one thread per owned row: its quads' bits, spread over the ballot words of the warps that swept it
+        for (int oy = tid; oy < owned; oy += kFThreads) {
+            const int it = oy / g.rows_per_it;
+            const int p0 = (oy - it * g.rows_per_it) * g.qpr;  // sweep thread of the row's first quad
+            const int w0 = p0 >> 5, sh = p0 & 31;
+            unsigned long long bits = (unsigned long long)s.hotw[w0 * kQIter + it] >> sh;
+            if (w0 + 1 < kPWarps) bits |= (unsigned long long)s.hotw[(w0 + 1) * kQIter + it] << (32 - sh);
+            if (sh && w0 + 2 < kPWarps) bits |= (unsigned long long)s.hotw[(w0 + 2) * kQIter + it] << (64 - sh);
+            s.hot64[oy] = bits & ((1ull << g.qpr) - 1ull);
+        }
+        __syncthreads();
+        // one thread per frame row: OR the hot rows around the row, widen by the neighbouring quads, and turn the marks
+        // into list entries (groups of 8 pixels; a blur entry carries its two quad marks).  Blur weights sum to 256, so
+        // an output can fire only within rows +-2 / neighbouring quads of a hot quad, and reads U within rows +-4 / quads +-2.
+        const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
+        for (int rrow = tid; rrow < g.H; rrow += kFThreads) {
+            unsigned long long near_b = 0, near_u = 0;
+#pragma unroll
+            for (int dy = -4; dy <= 4; ++dy) {
+                const int yy = rrow - g.edge + dy;  // owned-row index
+                if (yy < 0 || yy >= owned) continue;
+                const unsigned long long h = s.hot64[yy];
+                near_u |= h;
+                if (dy >= -2 && dy <= 2) near_b |= h;
+            }
+            const int row_grp = rrow * g.gpr;
+            if (near_u) {
+                const unsigned long long mk = (near_u | (near_u << 1) | (near_u >> 1) | (near_u << 2) | (near_u >> 2)) & rowmask;
+                unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
+                int base = atomicAdd(&s.bcast_i[11], __popcll(grp_bits));
+                while (grp_bits) {
+                    const int bit = __ffsll((long long)grp_bits) - 1;
+                    grp_bits &= grp_bits - 1;
+                    if (base < kListCap) s.list_u[base] = (uint16_t)(row_grp + (bit >> 1));
+                    ++base;
+                }
+            }
+            if (near_b) {
+                const unsigned long long mk = (near_b | (near_b << 1) | (near_b >> 1)) & rowmask;
+                unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
+                int base = atomicAdd(&s.bcast_i[12], __popcll(grp_bits));
+                while (grp_bits) {
+                    const int bit = __ffsll((long long)grp_bits) - 1;
+                    grp_bits &= grp_bits - 1;
+                    const uint32_t quads = (uint32_t)((mk >> bit) & 3ull);
+                    if (base < kListCap) s.list_b[base] = (uint16_t)((row_grp + (bit >> 1)) | (quads << 14));
+                    ++base;
+                }
+            }
+        }
+        __syncthreads();
+        n_u = s.bcast_i[11];
+        n_b = s.bcast_i[12];
+        // lists overflowed: dense work (every quad evaluated; a superset of the marks, so still exact)
+        if (n_u > kListCap || n_b > kListCap) dense = true;
+    }
+    if (!no_fg) {
+        if (dense) {
+            for (int grp = tid; grp < g.groups; grp += kFThreads) normalise_group(s, fcur, grp, ac, gmn, gmx, nmagic, nshift);
+        } else {
+            for (int i = tid; i < n_u; i += kFThreads) normalise_group(s, fcur, (int)s.list_u[i], ac, gmn, gmx, nmagic, nshift);
+        }
+        __syncthreads();
+        if (dense) {
+            for (int grp = tid; grp < g.groups; grp += kFThreads) blur_group(s, g, grp, 3u, 0, ith);
+        } else {
+            for (int i = tid; i < n_b; i += kFThreads) {
+                const uint32_t e = s.list_b[i];
+                blur_group(s, g, (int)(e & 0x3fffu), e >> 14, 0, ith);
+            }
+        }
+    }
+    __syncthreads();  // mask complete; lists, hot rows and U are dead from here on
+    const bool have_prev = !first_of_clip;
+    components_of_frame<FrameSmem, kFThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, cur_fmin, cur_fmax, 0, 0, have_prev, true);
 }
 
 // Second half of the frame pipeline for denoise clips (info.reserved[1] != 0): the denoised normalised image of every
@@ -1260,7 +1518,7 @@ __global__ void __launch_bounds__(kThreads, 1) mask_components_kernel(const Kern
             const bool have_prev = marker == 2;
             const float *fcur = a.filtered + (size_t)o * g.npx;
             const int fmin = a.info[o].filtered_min, fmax = a.info[o].filtered_max;
-            components_of_frame(a, s, g, tid - (kThreads - kCThreads), 0, (size_t)o, fcur, have_prev ? fcur - g.npx : fcur, fmin, fmax,
+            components_of_frame<Smem, kCThreads, BAR_C>(a, s, g, tid - (kThreads - kCThreads), 0, (size_t)o, fcur, have_prev ? fcur - g.npx : fcur, fmin, fmax,
                                 have_prev ? a.info[o - 1].filtered_min : 0, have_prev ? a.info[o - 1].filtered_max : 0, have_prev, true);
         }
         __syncthreads();
