@@ -76,6 +76,7 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     g.rw_magic = ((1u << 13) + g.row_words - 1) / g.row_words;
     g.qpr = width / 4;
     g.rows_per_it = cpt::kPThreads / g.qpr;
+    g.balanced = (width == 160 && height == 120 && edge_pixels == 1 && cpt::kPThreads == 640) ? 1 : 0;
     if ((height - 2 * edge_pixels + g.rows_per_it - 1) / g.rows_per_it > cpt::kQIter) {
         fail(CPT_ERR_INVALID, "unsupported geometry %dx%d: too many sweep iterations", width, height);
         delete c;
@@ -139,6 +140,8 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     }
     cudaFree(c->scratch);
     cudaFree(c->hot);
+    for (int i = 0; i < 5; ++i)
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     cudaFree(c->work_counter);
     cudaFree(c->zero_frame);
     cudaFree(c->debug);
@@ -304,6 +307,22 @@ int cpt_debug_phase_cycles(cpt_ctx *c, long long *h_out32, int reset) {
     return CPT_OK;
 }
 
+int cpt_debug_kernel_times(cpt_ctx *c, int enable, float *h_ms4) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (enable && !c->ev_k[0])
+        for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&c->ev_k[i]));
+    if (h_ms4) {
+        for (int i = 0; i < 4; ++i) h_ms4[i] = 0.f;
+        if (c->timed_valid) {
+            CUDA_TRY(cudaEventSynchronize(c->ev_k[4]));
+            for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&h_ms4[i], c->ev_k[i], c->ev_k[i + 1]));
+        }
+    }
+    c->time_kernels = enable != 0;
+    return CPT_OK;
+}
+
 uint64_t cpt_state_bytes(const cpt_ctx *c) { return c ? cpt::state_bytes(c->g.npx) : 0; }
 
 static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_clips, int n_clips,
@@ -358,6 +377,8 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     // Batch launches that keep the filtered images and carry no per-clip state take the split path: the recurrence as a
     // persistent sweep kernel, then one CTA per frame for masks / components.  Everything else (streaming, resumed
     // clips, regions-only launches) runs the single persistent kernel with its three warp roles.
+    const bool timed = c->time_kernels && c->ev_k[0];
+    if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[0], stream));
     static const bool split_allowed = [] { const char *e = getenv("CPT_SPLIT"); return !(e && e[0] == '0'); }();
     const bool split = split_allowed && d_state == nullptr && out->d_filtered != nullptr && total_frames > 0;
     if (split) {
@@ -374,12 +395,15 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         CUDA_TRY(cudaMemsetAsync(c->hot, 0, (size_t)total_frames * cpt::kHotStride * sizeof(uint32_t), stream));
         cpt::extract_sweep_kernel<<<grid, cpt::kSThreads, sizeof(cpt::Smem), stream>>>(a);
         CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[1], stream));
         cpt::frame_regions_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::FrameSmem), stream>>>(a, total_frames);
         CUDA_TRY(cudaGetLastError());
     } else {
         cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
         CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[1], stream));
     }
+    if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[2], stream));
     if (out->denoise) {
         int rc = cpt::nlm_launch(c, c->u8_frames[0], c->g.W, c->g.H, total_frames, c->u8_frames[1], out->d_info, stream);
         if (rc) return rc;
@@ -389,10 +413,15 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         cpt::mask_components_kernel<<<mgrid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a, total_frames, c->u8_frames[1]);
         CUDA_TRY(cudaGetLastError());
     }
+    if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[3], stream));
     if (a.defer_variance) {
         const unsigned blocks = (unsigned)((total_frames + 7) / 8);
         cpt::region_variance_kernel<<<blocks, 256, 0, stream>>>(c->g, total_frames, out->d_filtered, out->d_info, out->d_regions);
         CUDA_TRY(cudaGetLastError());
+    }
+    if (timed) {
+        CUDA_TRY(cudaEventRecord(c->ev_k[4], stream));
+        c->timed_valid = true;
     }
     return CPT_OK;
 }

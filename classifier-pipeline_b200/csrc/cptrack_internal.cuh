@@ -51,6 +51,9 @@ struct cpt_ctx {
     size_t scratch_ctas = 0;
     uint32_t *hot = nullptr;   // hot-quad words of the split extraction path, [hot_frames][kHotStride]
     size_t hot_frames = 0;
+    bool time_kernels = false;  // cpt_debug_kernel_times
+    bool timed_valid = false;
+    cudaEvent_t ev_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int *work_counter = nullptr;
     uint16_t *zero_frame = nullptr;
     long long *debug = nullptr;

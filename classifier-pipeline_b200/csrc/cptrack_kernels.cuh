@@ -87,8 +87,19 @@ struct Geometry {
     // quads of 4 pixels: the unit of the fused pixel sweep.  Rows edge .. H-1-edge are "owned"; the owner of
     // the first / last owned row also produces the border rows above / below it.
     int qpr;             // quads per row = W/4
-    int rows_per_it;     // owned rows the pixel threads cover per sweep iteration = kPThreads / qpr (20 at 160 pixels)
+    int rows_per_it;     // owned rows the pixel threads cover per sweep iteration = kPThreads / qpr (16 at 160 pixels)
+    int balanced;        // 160x120, edge 1, 16 row groups: two rows are remapped to even out the border rows (owned_row_slot)
 };
+
+// sweep slot (iteration, row group) that processes owned row oy; its quads are sweep threads r * qpr .. r * qpr + qpr - 1
+__host__ __device__ inline void owned_row_slot(const Geometry &g, int oy, int &it, int &r) {
+    it = oy / g.rows_per_it;
+    r = oy - it * g.rows_per_it;
+    if (g.balanced) {
+        if (oy == 112) { it = 7; r = 6; }
+        else if (oy == 5) { it = 7; r = 7; }
+    }
+}
 
 // Per-clip persistent record in global memory (cpt_state_bytes()).
 struct StateHeader {
@@ -186,20 +197,20 @@ struct __align__(16) Smem {
     int32_t ncomp;
 };
 
-// shared memory of frame_regions_kernel (one frame per CTA): the work lists and hot rows are dead once the mask is
-// thresholded, the normalised image once it is blurred, so they share storage with the labelling tables
+// shared memory of frame_regions_kernel (one frame per CTA): the normalised image, the work lists and the hot rows are
+// dead once the mask is thresholded, so they share storage with the labelling tables (5 CTAs per SM)
 struct __align__(16) FrameSmem {
     union {
-        uint8_t U[kMaxPx];
-        struct { double acc_s[kCompSlots], acc_s2[kCompSlots]; };
+        uint8_t U[kMaxPx];          // until the mask is thresholded
+        uint16_t parent[kMaxRuns];  // from the run starts on
     };
     union {
-        uint16_t parent[kMaxRuns];
-        struct {
+        struct {                    // until the mask is thresholded
             uint16_t list_u[kListCap], list_b[kListCap];
             uint32_t hotw[kHotStride];
             unsigned long long hot64[kMaxH];
         };
+        struct { double acc_s[kCompSlots], acc_s2[kCompSlots]; };  // in-kernel variance sums (labelling phase)
     };
     uint32_t M[1][kMaxWords];
     uint32_t C[kMaxWords];

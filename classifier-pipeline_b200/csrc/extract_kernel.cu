@@ -527,15 +527,18 @@ struct SweepAcc {
 __device__ __forceinline__ uint2 ldg8(const void *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
 
 // K1 + sliding sum + statistics of one quad against the packed background words nb (2 x 2 pixels)
+template <bool kSlide = true>
 __device__ __forceinline__ int filter_quad(uint2 pw, uint2 ow, int p4, uint2 nb, uint4 sv, uint32_t *S, float *fcur,
                                            uint8_t *lab_frame, bool want_stats, SweepAcc &acc) {
     const int f0 = dp2a_us(pw.x, kLoP, dp2a_us(nb.x, kLoN, 0)), f1 = dp2a_us(pw.x, kHiP, dp2a_us(nb.x, kHiN, 0));
     const int f2 = dp2a_us(pw.y, kLoP, dp2a_us(nb.y, kLoN, 0)), f3 = dp2a_us(pw.y, kHiP, dp2a_us(nb.y, kHiN, 0));
-    sv.x = (uint32_t)dp2a_us(pw.x, kLoP, dp2a_us(ow.x, kLoN, (int)sv.x));
-    sv.y = (uint32_t)dp2a_us(pw.x, kHiP, dp2a_us(ow.x, kHiN, (int)sv.y));
-    sv.z = (uint32_t)dp2a_us(pw.y, kLoP, dp2a_us(ow.y, kLoN, (int)sv.z));
-    sv.w = (uint32_t)dp2a_us(pw.y, kHiP, dp2a_us(ow.y, kHiN, (int)sv.w));
-    *reinterpret_cast<uint4 *>(S + p4) = sv;
+    if (kSlide) {
+        sv.x = (uint32_t)dp2a_us(pw.x, kLoP, dp2a_us(ow.x, kLoN, (int)sv.x));
+        sv.y = (uint32_t)dp2a_us(pw.x, kHiP, dp2a_us(ow.x, kHiN, (int)sv.y));
+        sv.z = (uint32_t)dp2a_us(pw.y, kLoP, dp2a_us(ow.y, kLoN, (int)sv.z));
+        sv.w = (uint32_t)dp2a_us(pw.y, kHiP, dp2a_us(ow.y, kHiN, (int)sv.w));
+        *reinterpret_cast<uint4 *>(S + p4) = sv;
+    }
     acc.psum = (uint32_t)dp2a_us(pw.x, kBoth, dp2a_us(pw.y, kBoth, (int)acc.psum));
     const int lo = min(min(f0, f1), min(f2, f3)), hi = max(max(f0, f1), max(f2, f3));
     acc.fmin = min(acc.fmin, lo);
@@ -558,6 +561,9 @@ struct SweepThread {
     int stride;      // pixels between its consecutive quads (rows_per_it * W)
     int r0;          // owned-row index of the first quad
     int last_it;     // iteration that holds the last owned row, if this thread owns it; else -1
+    int p4_last;     // pixel index of the thread's quad in the last iteration (kQIter - 1), see sweep_thread_init
+    bool has_last;   // the thread has a quad in the last iteration
+    bool skip0;      // the thread's quad of iteration 0 was handed to another thread (balanced 160x120 mapping)
     bool active;     // ptid < rows_per_it * qpr
     bool prefetch;   // first quad of a 128-byte line
     bool first_col, last_col;  // the quad holds a crop-border column (edge == 1)
@@ -639,6 +645,18 @@ __device__ __forceinline__ void load_quad(int p4, const uint16_t *P, const uint1
     ow = ldg8(Pold + p4);
 }
 
+// Which quads a sweep thread processes: iteration `it` covers owned row r0 + it * rows_per_it, except that the last
+// iteration's quad may have been remapped and the first one handed away (SweepThread::p4_last / has_last / skip0).
+template <bool kLepton>
+__device__ __forceinline__ bool sweep_mine(const SweepThread &th, int it, int rows_per_it, int owned_rows) {
+    if (it == kQIter - 1) return th.has_last;
+    if (it == 0) return th.active && !th.skip0 && (kLepton || th.r0 < owned_rows);
+    return th.active && (kLepton || th.r0 + it * rows_per_it < owned_rows);  // 160x120: iterations 1 .. kQIter - 2 are full
+}
+__device__ __forceinline__ int sweep_p4(const SweepThread &th, int it, int stride) {
+    return it == kQIter - 1 ? th.p4_last : th.p4_0 + it * stride;
+}
+
 // kUnrolled: straight-line code with the per-quad maxima in registers (the steady state); otherwise a rolled
 // loop whose maxima go through local memory (first frame, tail pass, exact keep test: once per clip).
 // kLepton: the geometry is 160x120 with a 1-pixel border (20 rows x 40 quads per iteration), so every offset of the
@@ -650,38 +668,44 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
     const Geometry &g = a.g;
     const int owned_rows = kLepton ? 118 : g.H - 2 * g.edge;
     constexpr int kLeptonRows = kPThreads / 40;  // rows per iteration at 160 pixels
-    // every thread owns a row in iterations [0, kLeptonFull): r0 + it * rows < 118 for all r0 < rows
-    constexpr int kLeptonFull = (118 - kLeptonRows) / kLeptonRows + 1;
+    static_assert((118 - kLeptonRows) / kLeptonRows + 1 >= kQIter - 1, "160x120: only the last iteration is partial");
     const int rows_per_it = kLepton ? kLeptonRows : g.rows_per_it;
     const int stride = kLepton ? kLeptonRows * 160 : th.stride;
     uint2 nb_top = make_uint2(0, 0), nb_bottom = make_uint2(0, 0);
     if (kUnrolled) {
         // software pipeline: the global loads of quad it + 1 are in flight while quad it is processed
+        // (two quads ahead, or the next frame's first quad across the message, cost registers the 80-register budget of
+        // 21 warps does not have: measured slower)
         uint2 pw_next, ow_next;
-        load_quad<kFrame>(th.p4_0, P, Pold, pw_next, ow_next);  // (row r0 is always owned when active)
+        if (sweep_mine<kLepton>(th, 0, rows_per_it, owned_rows)) load_quad<kFrame>(th.p4_0, P, Pold, pw_next, ow_next);
 #pragma unroll
         for (int it = 0; it < kQIter; ++it) {
             gmaxq[it] = kNoQuad;
-            const bool mine = th.active && ((kLepton && it < kLeptonFull) || th.r0 + it * rows_per_it < owned_rows);
+            const bool mine = sweep_mine<kLepton>(th, it, rows_per_it, owned_rows);
             const uint2 pw = pw_next, ow = ow_next;
-            if (it + 1 < kQIter && th.active && ((kLepton && it + 1 < kLeptonFull) || th.r0 + (it + 1) * rows_per_it < owned_rows))
-                load_quad<kFrame>(th.p4_0 + (it + 1) * stride, P, Pold, pw_next, ow_next);
+            if (it + 1 < kQIter && sweep_mine<kLepton>(th, it + 1, rows_per_it, owned_rows))
+                load_quad<kFrame>(sweep_p4(th, it + 1, stride), P, Pold, pw_next, ow_next);
             if (!mine) continue;
             uint2 nb;
-            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * stride, pw, ow, fcur,
+            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw, ow, fcur,
                                                                               lab_frame, acc, nb);
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
     } else {
+#pragma unroll
+        for (int j = 0; j < kQIter; ++j) gmaxq[j] = kNoQuad;
 #pragma unroll 1
         for (int it = 0; it < kQIter; ++it) {
-            gmaxq[it] = kNoQuad;
-            if (!th.active || th.r0 + it * rows_per_it >= owned_rows) continue;
+            if (!sweep_mine<false>(th, it, rows_per_it, owned_rows)) continue;
             uint2 nb, pw, ow;
-            load_quad<kFrame>(th.p4_0 + it * stride, P, Pold, pw, ow);
-            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, th.p4_0 + it * stride, pw, ow, fcur,
-                                                                              lab_frame, acc, nb);
+            load_quad<kFrame>(sweep_p4(th, it, stride), P, Pold, pw, ow);
+            const int hi = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw, ow, fcur,
+                                                                                lab_frame, acc, nb);
+            // (selects, not an indexed store: the maxima stay in registers in every instantiation)
+#pragma unroll
+            for (int j = 0; j < kQIter; ++j)
+                if (j == it) gmaxq[j] = hi;
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
@@ -696,10 +720,9 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
             const uint2 nb = side == 0 ? nb_top : nb_bottom;
             if (kUpdate) *reinterpret_cast<uint2 *>(s.B + pb) = nb;
             if (kFrame) {
+                // (a border pixel's background is a copy of its neighbour's: its sliding sum is never used)
                 const uint2 pw = ldg8(P + pb);
-                const uint2 ow = ldg8(Pold + pb);
-                const uint4 sv = *reinterpret_cast<const uint4 *>(s.S + pb);
-                const int hi = filter_quad(pw, ow, pb, nb, sv, s.S, fcur, lab_frame, kStats, acc);
+                const int hi = filter_quad<false>(pw, make_uint2(0, 0), pb, nb, make_uint4(0, 0, 0, 0), s.S, fcur, lab_frame, kStats, acc);
                 const int slot = side == 0 ? 0 : th.last_it;
 #pragma unroll
                 for (int it = 0; it < kQIter; ++it)
@@ -782,7 +805,7 @@ __device__ __forceinline__ void solo_hot_words(const KernelArgs &a, const Smem &
 
 // split path: wait until the scalar warp has finished `n` messages of this clip
 __device__ __forceinline__ void solo_wait_done(Smem &s, int n) {
-    while (*(volatile int32_t *)&s.done_frames < n) __nanosleep(32);
+    while (*(volatile int32_t *)&s.done_frames < n) __nanosleep(200);
     __threadfence_block();
     __syncwarp();
 }
@@ -866,6 +889,18 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         th.sel_y = th.last_col ? kLoP : kBoth;
         const int last_row = g.H - 2 * g.edge - 1;  // owned-row index
         th.last_it = (th.active && last_row % g.rows_per_it == r0) ? last_row / g.rows_per_it : -1;
+        th.has_last = th.active && r0 + (kQIter - 1) * g.rows_per_it <= last_row;
+        th.p4_last = th.p4_0 + (kQIter - 1) * th.stride;
+        th.skip0 = false;
+        if (g.balanced) {
+            // 160x120: 118 owned rows + 2 border rows over 16 row groups.  The owners of the first and last owned row also
+            // produce a border row, so each hands one of its rows to a group whose last iteration is free: no thread
+            // has more than 8 quads per frame (owned_row_slot() is the inverse map).
+            if (r0 == 0) th.has_last = false;                                          // row 113 (owned 112) -> group 6
+            if (r0 == 6) { th.has_last = true; th.p4_last = (112 + g.edge) * W + qx * 4; }
+            if (r0 == 5) th.skip0 = true;                                              // row 6 (owned 5) -> group 7
+            if (r0 == 7) { th.has_last = true; th.p4_last = (5 + g.edge) * W + qx * 4; }
+        }
     }
     bar_sync(BAR_INIT, kAll);  // the state and the initial average are in place: the other roles may start
 
@@ -1159,8 +1194,9 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
         if (!no_fg && !dense) {
             // one thread per owned row: its quads' maxima -> one bit per quad
             for (int oy = mtid; oy < owned; oy += kMThreads) {
-                const int hit = oy / g.rows_per_it;
-                const int pos = hit * kPThreads + (oy - hit * g.rows_per_it) * g.qpr;
+                int hit, hr;
+                owned_row_slot(g, oy, hit, hr);
+                const int pos = hit * kPThreads + hr * g.qpr;
                 unsigned long long bits = 0;
                 if (((pos | g.qpr) & 3) == 0) {
                     const uint32_t *q4 = reinterpret_cast<const uint32_t *>(s.qmax8 + pos);
@@ -1381,7 +1417,7 @@ __global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const Kerne
 // blur + threshold (K4) -> close -> components, statistics, labels (K5); the variances are left to
 // region_variance_kernel.  Frames are independent here, so the latency of these short dependent phases is hidden by
 // the other frames resident on the SM.
-__global__ void __launch_bounds__(kFThreads, 4) frame_regions_kernel(const KernelArgs a, long long total_frames) {
+__global__ void __launch_bounds__(kFThreads, 5) frame_regions_kernel(const KernelArgs a, long long total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrameSmem &s = *reinterpret_cast<FrameSmem *>(smem_raw);
     const Geometry &g = a.g;
@@ -1419,8 +1455,9 @@ __global__ void __launch_bounds__(kFThreads, 4) frame_regions_kernel(const Kerne
         __syncthreads();
         // one thread per owned row: its quads' bits, spread over the ballot words of the warps that swept it
         for (int oy = tid; oy < owned; oy += kFThreads) {
-            const int it = oy / g.rows_per_it;
-            const int p0 = (oy - it * g.rows_per_it) * g.qpr;  // sweep thread of the row's first quad
+            int it, hr;
+            owned_row_slot(g, oy, it, hr);
+            const int p0 = hr * g.qpr;  // sweep thread of the row's first quad
             const int w0 = p0 >> 5, sh = p0 & 31;
             unsigned long long bits = (unsigned long long)s.hotw[w0 * kQIter + it] >> sh;
             if (w0 + 1 < kPWarps) bits |= (unsigned long long)s.hotw[(w0 + 1) * kQIter + it] << (32 - sh);
