@@ -15,7 +15,8 @@ namespace cpt {
 __global__ void extract_clips_kernel(const KernelArgs a);
 __global__ void mask_components_kernel(const KernelArgs a, long long total_frames, const uint8_t *denoised);
 __global__ void extract_sweep_kernel(const KernelArgs a);
-__global__ void frame_regions_kernel(const KernelArgs a, long long total_frames);
+__global__ void frame_mask_kernel(const KernelArgs a, long long total_frames);
+__global__ void frame_components_kernel(const KernelArgs a, long long total_frames);
 int nlm_launch(cpt_ctx *c, const uint8_t *d_src, int width, int height, long long n_frames, uint8_t *d_dst, const cpt_frame_info *info,
                cudaStream_t stream);
 __global__ void region_variance_kernel(Geometry g, long long total_frames, const float *filtered, cpt_frame_info *info, cpt_region *regions);
@@ -101,8 +102,10 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
                              (int)sizeof(cpt::Smem)) != cudaSuccess ||
         cudaFuncSetAttribute(cpt::extract_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(cpt::Smem)) != cudaSuccess ||
-        cudaFuncSetAttribute(cpt::frame_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(cpt::FrameSmem)) != cudaSuccess) {
+        cudaFuncSetAttribute(cpt::frame_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(cpt::MaskSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(cpt::frame_components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(cpt::CompSmem)) != cudaSuccess) {
         fail(CPT_ERR_CUDA, "cannot opt in to %zu bytes of shared memory: %s", sizeof(cpt::Smem),
              cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -140,6 +143,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     }
     cudaFree(c->scratch);
     cudaFree(c->hot);
+    cudaFree(c->maskbits);
     for (int i = 0; i < 5; ++i)
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     cudaFree(c->work_counter);
@@ -385,18 +389,23 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         if (c->hot_frames < (size_t)total_frames) {
             CUDA_TRY(cudaStreamSynchronize(stream));
             cudaFree(c->hot);
-            c->hot = nullptr;
+            cudaFree(c->maskbits);
+            c->hot = c->maskbits = nullptr;
             c->hot_frames = 0;
             CUDA_TRY(cudaMalloc(&c->hot, (size_t)total_frames * cpt::kHotStride * sizeof(uint32_t)));
+            CUDA_TRY(cudaMalloc(&c->maskbits, (size_t)total_frames * cpt::kMaxWords * sizeof(uint32_t)));
             c->hot_frames = (size_t)total_frames;
         }
         a.hot = c->hot;
+        a.maskbits = c->maskbits;
         // the valid flag of every output frame starts cleared: frames no clip writes are skipped by the second launch
         CUDA_TRY(cudaMemsetAsync(c->hot, 0, (size_t)total_frames * cpt::kHotStride * sizeof(uint32_t), stream));
         cpt::extract_sweep_kernel<<<grid, cpt::kSThreads, sizeof(cpt::Smem), stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[1], stream));
-        cpt::frame_regions_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::FrameSmem), stream>>>(a, total_frames);
+        cpt::frame_mask_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::MaskSmem), stream>>>(a, total_frames);
+        CUDA_TRY(cudaGetLastError());
+        cpt::frame_components_kernel<<<(unsigned)total_frames, cpt::kGThreads, sizeof(cpt::CompSmem), stream>>>(a, total_frames);
         CUDA_TRY(cudaGetLastError());
     } else {
         cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);

@@ -50,6 +50,7 @@ struct cpt_ctx {
     float *scratch = nullptr;
     size_t scratch_ctas = 0;
     uint32_t *hot = nullptr;   // hot-quad words of the split extraction path, [hot_frames][kHotStride]
+    uint32_t *maskbits = nullptr;  // thresholded masks between frame_mask_kernel and frame_components_kernel
     size_t hot_frames = 0;
     bool time_kernels = false;  // cpt_debug_kernel_times
     bool timed_valid = false;

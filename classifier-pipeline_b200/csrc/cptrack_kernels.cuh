@@ -21,13 +21,14 @@
 
 #include "../../include/cptrack.h"
 
+#ifndef CPT_EXP
+#define CPT_EXP 0
+#endif
+
 namespace cpt {
 
 // warp-specialised pipeline over consecutive frames: sweep warps (the recurrence), mask warps (scalars, work lists,
 // normalise, blur) and component warps (labelling)
-#ifndef CPT_EXP
-#define CPT_EXP 0
-#endif
 #if CPT_EXP == 1
 constexpr int kPThreads = 320;                  // 10 sweep warps: 8 rows x 40 quads per iteration at 160 pixels
 #elif CPT_EXP == 2
@@ -51,10 +52,15 @@ constexpr int kCWarps = kCThreads / 32;
 constexpr int kThreads = kPThreads + kMThreads + kCThreads;
 constexpr int kWarps = kThreads / 32;
 // split path (batch launches that keep the filtered images and carry no state): extract_sweep_kernel runs the sweep
-// warps plus one scalar warp per clip, frame_regions_kernel then turns every frame into masks / labels / regions with
-// one CTA per frame
+// warps plus one scalar warp per clip; frame_mask_kernel and frame_components_kernel then turn every frame into its
+// mask and its labels / regions with one CTA per frame
 constexpr int kSThreads = kPThreads + 32;
-constexpr int kFThreads = 256;
+#if CPT_EXP == 6
+constexpr int kFThreads = 192, kGThreads = 128;
+#else
+constexpr int kFThreads = 256;   // frame_mask_kernel
+constexpr int kGThreads = 256;   // frame_components_kernel
+#endif
 constexpr int kMaxPx = 19200;
 constexpr int kQIter = (kMaxPx / 4 + kPThreads - 1) / kPThreads;  // 6 quads of 4 pixels per pixel thread
 constexpr int kMaxW = 160;
@@ -151,6 +157,7 @@ struct KernelArgs {
     uint8_t *u8_frames;   // [total_frames][npx] normalised images of denoise clips (ctx scratch), else nullptr
     const uint16_t *zero_frame;  // npx zeros: stands in for the frame leaving the 45-frame window while it fills
     uint32_t *hot;        // [total_frames][kHotStride] (split path), else nullptr
+    uint32_t *maskbits;   // [total_frames][kMaxWords] thresholded masks between the two per-frame kernels (split path)
     WeightTable tables[4];
 };
 
@@ -197,20 +204,23 @@ struct __align__(16) Smem {
     int32_t ncomp;
 };
 
-// shared memory of frame_regions_kernel (one frame per CTA): the normalised image, the work lists and the hot rows are
-// dead once the mask is thresholded, so they share storage with the labelling tables (5 CTAs per SM)
-struct __align__(16) FrameSmem {
+// shared memory of frame_mask_kernel (one frame per CTA: marks -> work lists -> normalise -> blur + threshold)
+struct __align__(16) MaskSmem {
+    uint8_t U[kMaxPx];
+    uint16_t list_u[kListCap], list_b[kListCap];
+    uint32_t hotw[kHotStride];
+    unsigned long long hot64[kMaxH];
+    uint32_t M[1][kMaxWords];
+    int32_t bcast_i[16];
+};
+
+// shared memory of frame_components_kernel (one frame per CTA: close -> components, statistics, labels)
+struct __align__(16) CompSmem {
     union {
-        uint8_t U[kMaxPx];          // until the mask is thresholded
-        uint16_t parent[kMaxRuns];  // from the run starts on
-    };
-    union {
-        struct {                    // until the mask is thresholded
-            uint16_t list_u[kListCap], list_b[kListCap];
-            uint32_t hotw[kHotStride];
-            unsigned long long hot64[kMaxH];
-        };
-        struct { double acc_s[kCompSlots], acc_s2[kCompSlots]; };  // in-kernel variance sums (labelling phase)
+        uint16_t parent[kMaxRuns];
+        // in-kernel variance sums: never live here (this kernel always defers the variances to region_variance_kernel;
+        // components_of_frame only zeroes them before the run starts are written)
+        struct { double acc_s[kCompSlots], acc_s2[kCompSlots]; };
     };
     uint32_t M[1][kMaxWords];
     uint32_t C[kMaxWords];

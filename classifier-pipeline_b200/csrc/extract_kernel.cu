@@ -169,7 +169,7 @@ __device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
         int w = ctid + it * kT;
-        if (w < g.words) {
+        if (w < g.words && rc[it].c != 0) {  // (ST / base of an empty word are never looked up)
             const int wi = rc[it].wi, y = rc[it].y;
             uint32_t carry = 0;
             int base = 0;
@@ -314,9 +314,20 @@ __device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &
                 ++n;
                 int slot = s.parent[id] & 0xff;
                 uint8_t lab = (slot < CPT_MAX_COMPONENTS) ? (uint8_t)(s.c_rank[slot] + 1) : (uint8_t)255;
-                uint8_t *row = lab_frame + y * W;
-                int x = wi * 32 + b;
-                while (x < W && ((s.C[y * g.row_words + (x >> 5)] >> (x & 31)) & 1u)) row[x++] = lab;
+                const int w = y * g.row_words + wi;
+                uint32_t inv = ~(rc[it].c >> b);
+                int len = (inv == 0) ? 32 : (__ffs(inv) - 1);
+                if (b + len >= 32) {  // run continues into the following words
+                    len = 32 - b;
+                    for (int q = wi + 1; q < g.row_words; ++q) {
+                        uint32_t cn = ~s.C[w - wi + q];
+                        if (cn == 0) { len += 32; continue; }
+                        len += __ffs(cn) - 1;
+                        break;
+                    }
+                }
+                uint8_t *px = lab_frame + y * W + wi * 32 + b;
+                for (int k = 0; k < len; ++k) px[k] = lab;
             }
         }
     }
@@ -789,7 +800,7 @@ __device__ __forceinline__ uint32_t sweep_reduce_store(FrameMsg &fm, int lane, c
 // turns out too high they fall back to dense work, so the ballots are always a superset) -> next frame.
 // ================================================================================================
 // split path: the quad maxima this thread stored for frame `of` (message buffer bb) against the byte threshold the scalar
-// warp published -> ballot words for frame_regions_kernel (layout: cptrack_kernels.cuh, kHotWords)
+// warp published -> ballot words for frame_mask_kernel (layout: cptrack_kernels.cuh, kHotWords)
 __device__ __forceinline__ void solo_hot_words(const KernelArgs &a, const Smem &s, size_t of, int bb, int ptid, int lane, int warp) {
     static_assert(kQIter <= 32, "one lane per sweep iteration");
     const int tu = s.tu_pub[bb];
@@ -1322,7 +1333,7 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
 
 // ================================================================================================
 // split path, scalar warp: one frame behind the sweep.  Lane 0 turns the sweep's message into the frame's info record,
-// publishes the byte threshold for the sweep warps' ballots and the constants frame_regions_kernel needs.
+// publishes the byte threshold for the sweep warps' ballots and the constants the per-frame kernels need.
 // ================================================================================================
 __device__ void scalar_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, int lane) {
     const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
@@ -1414,29 +1425,30 @@ __global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const Kerne
 }
 
 // Split path, second launch: one CTA per frame.  Hot-quad words -> per-row marks -> work lists -> normalise (K2) ->
-// blur + threshold (K4) -> close -> components, statistics, labels (K5); the variances are left to
-// region_variance_kernel.  Frames are independent here, so the latency of these short dependent phases is hidden by
-// the other frames resident on the SM.
-__global__ void __launch_bounds__(kFThreads, 5) frame_regions_kernel(const KernelArgs a, long long total_frames) {
+// blur + threshold (K4) -> the frame's mask as bit rows in global memory.  Frames are independent here, so the latency
+// of these short dependent phases is hidden by the other frames resident on the SM (8 CTAs).
+__global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelArgs a, long long total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FrameSmem &s = *reinterpret_cast<FrameSmem *>(smem_raw);
+    MaskSmem &s = *reinterpret_cast<MaskSmem *>(smem_raw);
     const Geometry &g = a.g;
     const int tid = threadIdx.x;
     const long long o = blockIdx.x;
     if (o >= total_frames) return;
     const uint32_t *hw = a.hot + (size_t)o * kHotStride;
+    const cpt_frame_info *fi = a.info + o;
+    // (independent loads first: the trailer, the info record and this thread's ballot word are all in flight together)
     const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(hw + kHotWords));
+    const float thr = fi->threshold;
+    const int ac = fi->avg_change, gmn = fi->norm_min, gmx = fi->norm_max;
+    const int dn_marker = fi->reserved[1];
+    const uint32_t my_hot = tid < kHotWords ? __ldg(hw + tid) : 0u;
+    static_assert(kHotWords <= kFThreads, "one ballot word per thread");
     if (!(hdr.w & 1u)) return;  // no clip produced this output frame
     const int tu = (int)hdr.x;
     const uint32_t nmagic = hdr.y;
     const int nshift = (int)hdr.z;
-    const bool first_of_clip = hdr.w & 2u;
-    const cpt_frame_info *fi = a.info + o;
-    const float thr = fi->threshold;
-    const int ac = fi->avg_change, gmn = fi->norm_min, gmx = fi->norm_max;
-    const int cur_fmin = fi->filtered_min, cur_fmax = fi->filtered_max;
     const float *fcur = a.filtered + (size_t)o * g.npx;
-    if (fi->reserved[1]) {
+    if (dn_marker) {
         // denoise clips: K3 sits between K2 and K4 -- emit the whole normalised image; cv2.fastNlMeansDenoising, blur,
         // threshold, close and components follow as wide passes (nlm_denoise_kernel, mask_components_kernel)
         uint8_t *u_frame = a.u8_frames + (size_t)o * g.npx;
@@ -1447,10 +1459,14 @@ __global__ void __launch_bounds__(kFThreads, 5) frame_regions_kernel(const Kerne
     const bool no_fg = ith >= 255;  // nothing can exceed the threshold: the mask stays empty
     bool dense = tu == 0;           // no usable bound: every group is normalised and blurred
     const int owned = g.H - 2 * g.edge;
-    for (int i = tid; i < g.words; i += kFThreads) s.M[0][i] = 0;
+    if ((g.words & 3) == 0) {
+        for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(s.M[0])[i] = make_uint4(0, 0, 0, 0);
+    } else {
+        for (int i = tid; i < g.words; i += kFThreads) s.M[0][i] = 0;
+    }
     int n_u = 0, n_b = 0;
     if (!no_fg && !dense) {
-        for (int i = tid; i < kHotWords; i += kFThreads) s.hotw[i] = __ldg(hw + i);
+        if (tid < kHotWords) s.hotw[tid] = my_hot;
         if (tid == 0) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
         __syncthreads();
         // one thread per owned row: its quads' bits, spread over the ballot words of the warps that swept it
@@ -1526,9 +1542,49 @@ __global__ void __launch_bounds__(kFThreads, 5) frame_regions_kernel(const Kerne
             }
         }
     }
-    __syncthreads();  // mask complete; lists, hot rows and U are dead from here on
-    const bool have_prev = !first_of_clip;
-    components_of_frame<FrameSmem, kFThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, cur_fmin, cur_fmax, 0, 0, have_prev, true);
+    __syncthreads();
+    uint32_t *mout = a.maskbits + (size_t)o * kMaxWords;
+    if ((g.words & 3) == 0) {
+        for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
+    } else {
+        for (int i = tid; i < g.words; i += kFThreads) mout[i] = s.M[0][i];
+    }
+}
+
+// Split path, third launch: one CTA per frame.  The frame's mask -> close -> components, statistics, labels (K4, K5); the
+// variances are left to region_variance_kernel.
+__global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const KernelArgs a, long long total_frames) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CompSmem &s = *reinterpret_cast<CompSmem *>(smem_raw);
+    const Geometry &g = a.g;
+    const int tid = threadIdx.x;
+    const long long o = blockIdx.x;
+    if (o >= total_frames) return;
+    const cpt_frame_info *fi = a.info + o;
+    const uint32_t *min_ = a.maskbits + (size_t)o * kMaxWords;
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(a.hot + (size_t)o * kHotStride + kHotWords));
+    const int dn_marker = fi->reserved[1];
+    if (!(hdr.w & 1u)) return;  // no clip produced this output frame (its mask words were never written)
+    if (dn_marker) return;      // denoise clips: mask_components_kernel
+    bool any = false;
+    if ((g.words & 3) == 0) {
+        for (int i = tid; i < g.words / 4; i += kGThreads) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(min_) + i);
+            reinterpret_cast<uint4 *>(s.M[0])[i] = w;
+            any |= ((w.x | w.y | w.z | w.w) != 0);
+        }
+    } else {
+        for (int i = tid; i < g.words; i += kGThreads) {
+            const uint32_t w = min_[i];
+            s.M[0][i] = w;
+            any |= (w != 0);
+        }
+    }
+    if (!__syncthreads_or(any)) return;  // empty mask: info.n_components stays 0
+    const float *fcur = a.filtered + (size_t)o * g.npx;
+    const bool have_prev = !(hdr.w & 2u);  // not the first frame of its clip
+    components_of_frame<CompSmem, kGThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, fi->filtered_min, fi->filtered_max, 0, 0,
+                                                 have_prev, true);
 }
 
 // Second half of the frame pipeline for denoise clips (info.reserved[1] != 0): the denoised normalised image of every

@@ -137,7 +137,7 @@ int cpt_debug_phase_cycles(cpt_ctx *ctx, long long *h_out32, int reset);
 /* Diagnostics: with enable != 0, every following cpt_extract_batch call brackets its launches with CUDA events on the
  * ctx stream.  h_ms4 (may be NULL) receives the durations of the last timed call in milliseconds after synchronising:
  * [0] the recurrence kernel (extract_sweep_kernel, or extract_clips_kernel on the single-kernel path), [1]
- * frame_regions_kernel (0 on the single-kernel path), [2] the denoise passes, [3] region_variance_kernel. */
+ * frame_mask_kernel + frame_components_kernel (0 on the single-kernel path), [2] the denoise passes, [3] region_variance_kernel. */
 int cpt_debug_kernel_times(cpt_ctx *ctx, int enable, float *h_ms4);
 
 /* Bytes of one per-clip state record for this ctx's geometry. */
