@@ -195,7 +195,8 @@ struct __align__(16) Smem {
     unsigned long long hot64[kMaxH];  // per owned row, one bit per quad: some pixel can exceed the threshold
     FrameMsg fm[2];
     int32_t fth_latest;      // last bound the mask warps computed (INT32_MIN: none yet): the next qref
-    int32_t done_frames;     // split path: messages of this clip the scalar warp has finished
+    unsigned long long done_bar[2];  // split path: mbarrier per message buffer, one phase per message the scalar warp finishes
+    int32_t done_bar_live;
     int32_t tu_pub[2];       // split path: byte threshold of the frame in message buffer b (0: dense)
     int32_t final_prev[3];   // filtered min / max of the last frame, have_prev (for the state record)
     double init_average, final_average;

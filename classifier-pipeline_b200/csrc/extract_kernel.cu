@@ -687,6 +687,28 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
         // software pipeline: the global loads of quad it + 1 are in flight while quad it is processed
         // (two quads ahead, or the next frame's first quad across the message, cost registers the 80-register budget of
         // 21 warps does not have: measured slower)
+#if CPT_EXP == 7
+        // the frame's pixels two quads ahead, the pixels leaving the window (needed later in the iteration) one quad ahead
+        uint2 pwq[2], ow_next;
+        if (sweep_mine<kLepton>(th, 0, rows_per_it, owned_rows)) load_quad<kFrame>(th.p4_0, P, Pold, pwq[0], ow_next);
+        if (kFrame && sweep_mine<kLepton>(th, 1, rows_per_it, owned_rows)) pwq[1] = ldg8(P + sweep_p4(th, 1, stride));
+#pragma unroll
+        for (int it = 0; it < kQIter; ++it) {
+            gmaxq[it] = kNoQuad;
+            const bool mine = sweep_mine<kLepton>(th, it, rows_per_it, owned_rows);
+            const uint2 pw = pwq[it & 1], ow = ow_next;
+            if (kFrame && it + 2 < kQIter && sweep_mine<kLepton>(th, it + 2, rows_per_it, owned_rows))
+                pwq[it & 1] = ldg8(P + sweep_p4(th, it + 2, stride));
+            if (kFrame && it + 1 < kQIter && sweep_mine<kLepton>(th, it + 1, rows_per_it, owned_rows))
+                ow_next = ldg8(Pold + sweep_p4(th, it + 1, stride));
+            if (!mine) continue;
+            uint2 nb;
+            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw, ow, fcur,
+                                                                              lab_frame, acc, nb);
+            if (it == 0) nb_top = nb;
+            if (it == th.last_it) nb_bottom = nb;
+        }
+#else
         uint2 pw_next, ow_next;
         if (sweep_mine<kLepton>(th, 0, rows_per_it, owned_rows)) load_quad<kFrame>(th.p4_0, P, Pold, pw_next, ow_next);
 #pragma unroll
@@ -703,6 +725,7 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
+#endif
     } else {
 #pragma unroll
         for (int j = 0; j < kQIter; ++j) gmaxq[j] = kNoQuad;
@@ -814,11 +837,33 @@ __device__ __forceinline__ void solo_hot_words(const KernelArgs &a, const Smem &
     if (lane < kQIter) a.hot[of * kHotStride + warp * kQIter + lane] = mine;
 }
 
-// split path: wait until the scalar warp has finished `n` messages of this clip
-__device__ __forceinline__ void solo_wait_done(Smem &s, int n) {
-    while (*(volatile int32_t *)&s.done_frames < n) __nanosleep(200);
-    __threadfence_block();
-    __syncwarp();
+// split path: the scalar warp signals "message f of this clip consumed, byte threshold published" on the shared-memory
+// barrier of the message's buffer (f & 1, one arrival per phase); a sweep warp that is ahead of it waits there in
+// hardware instead of spinning on a flag (a spinning warp takes issue slots from the warps it is waiting for)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// wait until the scalar warp has finished message f of this clip
+__device__ __forceinline__ void solo_wait_done(Smem &s, int f) {
+    mbar_wait(&s.done_bar[f & 1], (uint32_t)(f >> 1) & 1u);
 }
 
 // kSolo: the split path (extract_sweep_kernel) -- the only other role is the scalar warp, which runs one frame behind
@@ -843,7 +888,17 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
     for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
     if (ptid < 2) frame_msg_reset(s.fm[ptid]);
-    if (ptid == 0) { s.fth_latest = INT32_MIN; s.bcast_i[10] = 0; s.done_frames = 0; }
+    if (ptid == 0) {
+        s.fth_latest = INT32_MIN;
+        s.bcast_i[10] = 0;
+        if (kSolo) {
+            // fresh phase counters for this clip (every thread of the CTA is between clips here)
+            if (s.done_bar_live) { mbar_inval(&s.done_bar[0]); mbar_inval(&s.done_bar[1]); }
+            mbar_init(&s.done_bar[0], 1);
+            mbar_init(&s.done_bar[1], 1);
+            s.done_bar_live = 1;
+        }
+    }
     if (clip.flags & CPT_CLIP_RESUME) {
         bar_sync(BAR_P, kPThreads);
         int kmax = 0;
@@ -964,7 +1019,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             // (a flag, not a barrier: the sweep warps are not forced into lock step at the end of every frame; they can
             // drift by less than two frames, which also keeps the FULL barriers' phases apart)
             if (t >= 1) {
-                solo_wait_done(s, t);
+                solo_wait_done(s, t - 1);
                 solo_hot_words(a, s, (size_t)(clip.out_offset + t - 1), b ^ 1, ptid, lane, warp);
             }
             CPT_TICK(ptid == 0, 6);   // wait for the scalar warp + ballots
@@ -1024,7 +1079,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     }
 
     if (kSolo && last_t >= 0) {
-        solo_wait_done(s, last_t + 1);
+        solo_wait_done(s, last_t);
         if (last_t < clip.n_frames) solo_hot_words(a, s, (size_t)(clip.out_offset + last_t), last_t & 1, ptid, lane, warp);
     }
     // ---------------------------------------------------------------- save state
@@ -1362,10 +1417,7 @@ __device__ void scalar_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 have_prev = 1;
             }
         }
-        if (lane == 0) {
-            __threadfence_block();
-            *(volatile int32_t *)&s.done_frames = t + 1;  // message consumed, byte threshold published
-        }
+        if (lane == 0) mbar_arrive(&s.done_bar[b]);  // message consumed, byte threshold published (release)
         __syncwarp();
         CPT_TICK2(lane == 0, 16);  // scalars
     }
@@ -1412,6 +1464,7 @@ __global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const Kerne
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &s = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
+    if (tid == 0) s.done_bar_live = 0;
     while (true) {
         __syncthreads();
         if (tid == 0) s.bcast_i[15] = atomicAdd(a.work_counter, 1);
