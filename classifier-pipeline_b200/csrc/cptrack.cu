@@ -77,7 +77,18 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     g.rw_magic = ((1u << 13) + g.row_words - 1) / g.row_words;
     g.qpr = width / 4;
     g.rows_per_it = cpt::kPThreads / g.qpr;
-    g.balanced = (width == 160 && height == 120 && edge_pixels == 1 && cpt::kPThreads == 640) ? 1 : 0;
+    g.balanced = 0;
+    g.bal_a_oy = g.bal_a_r = g.bal_b_oy = g.bal_b_r = -1;
+    if (width == 160 && height == 120 && edge_pixels == 1) {
+        const int R = g.rows_per_it, last = height - 2 * edge_pixels - 1, li = cpt::kQIter - 1;
+        const int fr = last + 1 - li * R;  // first row group without a row of its own in the last iteration
+        const int rb = last % R;           // row group of the last owned row
+        if (last / R == li && li * R <= last && rb != 0 && fr > rb && fr + 1 < R) {
+            g.balanced = 1;
+            g.bal_a_oy = li * R; g.bal_a_r = fr;     // group 0 (top border row) hands over its last row
+            g.bal_b_oy = rb; g.bal_b_r = fr + 1;     // group rb (bottom border row) hands over its first row
+        }
+    }
     if ((height - 2 * edge_pixels + g.rows_per_it - 1) / g.rows_per_it > cpt::kQIter) {
         fail(CPT_ERR_INVALID, "unsupported geometry %dx%d: too many sweep iterations", width, height);
         delete c;

@@ -37,6 +37,8 @@ constexpr int kPThreads = 480;                  // 15 sweep warps: 12 rows x 40 
 constexpr int kPThreads = 960;
 #elif CPT_EXP == 5
 constexpr int kPThreads = 800;
+#elif CPT_EXP == 8 || CPT_EXP == 9
+constexpr int kPThreads = 608;                  // 19 sweep warps: 15 rows x 40 quads per iteration (8 threads idle)
 #else
 constexpr int kPThreads = 640;                  // 20 sweep warps: 16 rows x 40 quads per iteration at 160 pixels
 #endif
@@ -94,7 +96,10 @@ struct Geometry {
     // the first / last owned row also produces the border rows above / below it.
     int qpr;             // quads per row = W/4
     int rows_per_it;     // owned rows the pixel threads cover per sweep iteration = kPThreads / qpr (16 at 160 pixels)
-    int balanced;        // 160x120, edge 1, 16 row groups: two rows are remapped to even out the border rows (owned_row_slot)
+    // 160x120, edge 1: the owners of the first and last owned row also produce a border row, so two rows are remapped to
+    // row groups whose last iteration is free (owned_row_slot): owned row bal_a_oy -> group bal_a_r, bal_b_oy -> bal_b_r
+    int balanced;
+    int bal_a_oy, bal_a_r, bal_b_oy, bal_b_r;
 };
 
 // sweep slot (iteration, row group) that processes owned row oy; its quads are sweep threads r * qpr .. r * qpr + qpr - 1
@@ -102,8 +107,8 @@ __host__ __device__ inline void owned_row_slot(const Geometry &g, int oy, int &i
     it = oy / g.rows_per_it;
     r = oy - it * g.rows_per_it;
     if (g.balanced) {
-        if (oy == 112) { it = 7; r = 6; }
-        else if (oy == 5) { it = 7; r = 7; }
+        if (oy == g.bal_a_oy) { it = kQIter - 1; r = g.bal_a_r; }
+        else if (oy == g.bal_b_oy) { it = kQIter - 1; r = g.bal_b_r; }
     }
 }
 
@@ -217,16 +222,18 @@ struct __align__(16) MaskSmem {
 
 // shared memory of frame_components_kernel (one frame per CTA: close -> components, statistics, labels)
 struct __align__(16) CompSmem {
+    uint16_t parent[kMaxRuns];
+    uint32_t C[kMaxWords];
     union {
-        uint16_t parent[kMaxRuns];
-        // in-kernel variance sums: never live here (this kernel always defers the variances to region_variance_kernel;
-        // components_of_frame only zeroes them before the run starts are written)
+        // the mask (read by the close) and the run-start bits / per-word run counts (read by the unions) ...
+        struct {
+            uint32_t M[1][kMaxWords];
+            uint32_t ST[kMaxWords];
+            uint8_t base[kMaxWords + 8];
+        };
+        // ... then the variance sums (components_of_frame zeroes them after the unions)
         struct { double acc_s[kCompSlots], acc_s2[kCompSlots]; };
     };
-    uint32_t M[1][kMaxWords];
-    uint32_t C[kMaxWords];
-    uint32_t ST[kMaxWords];
-    uint8_t base[kMaxWords + 8];
     int32_t c_key[kCompSlots], c_area[kCompSlots], c_sx[kCompSlots], c_sy[kCompSlots];
     int32_t c_l[kCompSlots], c_t[kCompSlots], c_r[kCompSlots], c_b[kCompSlots];
     uint8_t c_rank[kCompSlots];

@@ -159,7 +159,6 @@ __device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &
     for (int i = ctid; i < kCompSlots; i += kT) {
         s.c_key[i] = INT32_MAX; s.c_area[i] = 0; s.c_sx[i] = 0; s.c_sy[i] = 0;
         s.c_l[i] = INT32_MAX; s.c_t[i] = INT32_MAX; s.c_r[i] = -1; s.c_b[i] = -1;
-        s.acc_s[i] = 0.0; s.acc_s2[i] = 0.0;
     }
     if (ctid == 0) s.ncomp = 0;
     if (!bar_or(kBar, kT, any)) return;  // no foreground: info.n_components stays 0
@@ -232,7 +231,9 @@ __device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &
     }
     bar_sync(kBar, kT);
     CPT_TICK2(ctid == 0, 22);  // unions + barrier
-    // ---- roots -> component slots
+    // ---- roots -> component slots (and the variance sums: in frame_components_kernel they live where the mask and the
+    // run-start bits were, both dead once the unions are done)
+    for (int i = ctid; i < kCompSlots; i += kT) { s.acc_s[i] = 0.0; s.acc_s2[i] = 0.0; }
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
         uint32_t bitsleft = rc[it].stw;
@@ -687,28 +688,6 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
         // software pipeline: the global loads of quad it + 1 are in flight while quad it is processed
         // (two quads ahead, or the next frame's first quad across the message, cost registers the 80-register budget of
         // 21 warps does not have: measured slower)
-#if CPT_EXP == 7
-        // the frame's pixels two quads ahead, the pixels leaving the window (needed later in the iteration) one quad ahead
-        uint2 pwq[2], ow_next;
-        if (sweep_mine<kLepton>(th, 0, rows_per_it, owned_rows)) load_quad<kFrame>(th.p4_0, P, Pold, pwq[0], ow_next);
-        if (kFrame && sweep_mine<kLepton>(th, 1, rows_per_it, owned_rows)) pwq[1] = ldg8(P + sweep_p4(th, 1, stride));
-#pragma unroll
-        for (int it = 0; it < kQIter; ++it) {
-            gmaxq[it] = kNoQuad;
-            const bool mine = sweep_mine<kLepton>(th, it, rows_per_it, owned_rows);
-            const uint2 pw = pwq[it & 1], ow = ow_next;
-            if (kFrame && it + 2 < kQIter && sweep_mine<kLepton>(th, it + 2, rows_per_it, owned_rows))
-                pwq[it & 1] = ldg8(P + sweep_p4(th, it + 2, stride));
-            if (kFrame && it + 1 < kQIter && sweep_mine<kLepton>(th, it + 1, rows_per_it, owned_rows))
-                ow_next = ldg8(Pold + sweep_p4(th, it + 1, stride));
-            if (!mine) continue;
-            uint2 nb;
-            gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw, ow, fcur,
-                                                                              lab_frame, acc, nb);
-            if (it == 0) nb_top = nb;
-            if (it == th.last_it) nb_bottom = nb;
-        }
-#else
         uint2 pw_next, ow_next;
         if (sweep_mine<kLepton>(th, 0, rows_per_it, owned_rows)) load_quad<kFrame>(th.p4_0, P, Pold, pw_next, ow_next);
 #pragma unroll
@@ -725,7 +704,6 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
-#endif
     } else {
 #pragma unroll
         for (int j = 0; j < kQIter; ++j) gmaxq[j] = kNoQuad;
@@ -959,13 +937,13 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         th.p4_last = th.p4_0 + (kQIter - 1) * th.stride;
         th.skip0 = false;
         if (g.balanced) {
-            // 160x120: 118 owned rows + 2 border rows over 16 row groups.  The owners of the first and last owned row also
-            // produce a border row, so each hands one of its rows to a group whose last iteration is free: no thread
-            // has more than 8 quads per frame (owned_row_slot() is the inverse map).
-            if (r0 == 0) th.has_last = false;                                          // row 113 (owned 112) -> group 6
-            if (r0 == 6) { th.has_last = true; th.p4_last = (112 + g.edge) * W + qx * 4; }
-            if (r0 == 5) th.skip0 = true;                                              // row 6 (owned 5) -> group 7
-            if (r0 == 7) { th.has_last = true; th.p4_last = (5 + g.edge) * W + qx * 4; }
+            // 160x120: 118 owned rows + 2 border rows.  The owners of the first and last owned row also produce a border
+            // row, so each hands one of its rows to a group whose last iteration is free: no thread has more than 8
+            // quads per frame (owned_row_slot() is the inverse map).
+            if (r0 == 0) th.has_last = false;
+            if (r0 == g.bal_a_r) { th.has_last = true; th.p4_last = (g.bal_a_oy + g.edge) * W + qx * 4; }
+            if (r0 == g.bal_b_oy) th.skip0 = true;  // (the last owned row's group index equals its first row's index)
+            if (r0 == g.bal_b_r) { th.has_last = true; th.p4_last = (g.bal_b_oy + g.edge) * W + qx * 4; }
         }
     }
     bar_sync(BAR_INIT, kAll);  // the state and the initial average are in place: the other roles may start
@@ -1636,6 +1614,7 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
     if (!__syncthreads_or(any)) return;  // empty mask: info.n_components stays 0
     const float *fcur = a.filtered + (size_t)o * g.npx;
     const bool have_prev = !(hdr.w & 2u);  // not the first frame of its clip
+    // (computing the variances here was measured slower than the separate wide pass: +4.1 ms against 2.6 ms)
     components_of_frame<CompSmem, kGThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, fi->filtered_min, fi->filtered_max, 0, 0,
                                                  have_prev, true);
 }
