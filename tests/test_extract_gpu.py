@@ -20,7 +20,7 @@ def extractor():
     return BatchExtractor(device=0, max_regions=32)
 
 
-def _run_device(extractor, init, tracked, bt, weight_add, flags=None):
+def _run_device(extractor, init, tracked, bt, weight_add, flags=None, keep_state=True):
     import torch
     from classifier_pipeline_b200 import native
     from classifier_pipeline_b200.batch import linear_clips
@@ -32,12 +32,14 @@ def _run_device(extractor, init, tracked, bt, weight_add, flags=None):
     clips["frame_offset"] = 1
     clips["init_offset"] = 0
     clips["out_offset"] = 0
-    out = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, keep_state=True)
+    # keep_state=True: the single persistent kernel (three warp roles); without a state record the launch takes the
+    # split path (sweep kernel + per-frame kernels), see DESIGN.md section 3.1
+    out = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, keep_state=keep_state, out={})
     torch.cuda.synchronize()
     return out
 
 
-def _compare_with_oracle(extractor, out, o, T, slot_weight_add):
+def _compare_with_oracle(extractor, out, o, T, slot_weight_add, with_state=True):
     regions = extractor.regions_numpy(out["regions"])[:T]
     info = extractor.info_numpy(out["info"])[:T]
     assert np.array_equal(out["filtered"][:T].cpu().numpy(), o["filtered"])
@@ -53,6 +55,8 @@ def _compare_with_oracle(extractor, out, o, T, slot_weight_add):
         got = np.stack([r["x"], r["y"], r["width"], r["height"], r["area"], r["sum_x"], r["sum_y"], r["key"]], axis=1)
         assert np.array_equal(got, o["comp"][t, :n]), t
         np.testing.assert_allclose(r["pixel_variance"], o["var"][t, :n], rtol=1e-6, atol=1e-6)
+    if not with_state:
+        return
     st = extractor.ctx.state_read(out["state"], 0)
     assert np.array_equal(st["background"], o["final_bg"])
     assert st["average"] == o["final_avg"]
@@ -86,6 +90,64 @@ def test_kernel_matches_oracle_and_reference(extractor, name):
     for row in d["regions"]:
         t, rid, var = int(row[0]), int(row[7]), row[6]
         assert regions[t, rid]["pixel_variance"] == pytest.approx(var, rel=2e-4, abs=1e-4)
+
+
+@pytest.mark.parametrize("name", RAW)
+def test_split_path_matches_oracle_and_reference(extractor, name):
+    """The same clips through the split path (no state record: extract_sweep_kernel + frame_mask_kernel +
+    frame_components_kernel + region_variance_kernel)."""
+    from oracle import oracle as orc
+
+    d, meta = helpers.load_golden(name)
+    init, tracked = helpers.clip_input(name)
+    T = len(tracked)
+    p = orc.make_params(background_thresh=meta["background_thresh"], weight_add=meta["weight_add"], max_comp=32)
+    o = orc.extract_clip(tracked, init, p)
+    out = _run_device(extractor, init, tracked, meta["background_thresh"], meta["weight_add"], keep_state=False)
+    _compare_with_oracle(extractor, out, o, T, meta["weight_add"], with_state=False)
+    assert np.array_equal(out["labels"][:T].cpu().numpy(), d["labels"])
+    bg = helpers.golden_background(d)
+    assert np.array_equal(out["filtered"][:T].cpu().numpy(), (tracked.astype(np.int64) - bg).astype(np.float32))
+
+
+def test_split_and_single_kernel_paths_agree_on_a_ragged_batch(extractor):
+    """Both launch plans, same ragged batch (empty clip, one-frame clip, clips around the 45-frame window, unused output
+    frames between clips): every output identical, variances included."""
+    import torch
+    from classifier_pipeline_b200.batch import linear_clips
+    from classifier_pipeline_b200.synthetic import clip_model, make_clip
+
+    lengths = [50, 0, 17, 64, 1, 46, 45, 90, 2, 131]
+    pix = [make_clip(40 + i, frames=max(n, 1))[0][:n] for i, n in enumerate(lengths)]
+    frames = np.concatenate([p for p in pix if len(p)])
+    bts = np.array([clip_model(40 + i)[2] for i in range(len(lengths))])
+    slots = np.array([extractor.ctx.weight_table(clip_model(40 + i)[3], max_frames=4096) for i in range(len(lengths))])
+    clips = linear_clips(lengths, bts, slots)
+    clips["out_offset"] += 3 * np.arange(len(lengths))  # gaps: output frames no clip writes
+    d_frames = torch.from_numpy(frames.view(np.int16)).cuda().view(torch.uint16)
+    outs = []
+    for keep_state in (True, False):
+        o = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, keep_state=keep_state, out={})
+        torch.cuda.synchronize()
+        outs.append(o)
+    a, b = outs
+    ia, ib = extractor.info_numpy(a["info"]), extractor.info_numpy(b["info"])
+    ra, rb = extractor.regions_numpy(a["regions"]), extractor.regions_numpy(b["regions"])
+    fa, fb = a["filtered"].cpu().numpy(), b["filtered"].cpu().numpy()
+    la, lb = a["labels"].cpu().numpy(), b["labels"].cpu().numpy()
+    seen = 0
+    for i, n in enumerate(lengths):
+        o0 = int(clips["out_offset"][i])
+        sl = slice(o0, o0 + n)
+        assert np.array_equal(fa[sl], fb[sl]) and np.array_equal(la[sl], lb[sl]), i
+        for f in ("threshold", "norm_min", "norm_max", "avg_change", "filtered_min", "filtered_max", "n_components", "thermal_sum", "background_average"):
+            assert np.array_equal(ia[f][sl], ib[f][sl]), (i, f)
+        for t in range(o0, o0 + n):
+            k = min(int(ia["n_components"][t]), extractor.max_regions)
+            seen += k
+            for f in ("x", "y", "width", "height", "area", "sum_x", "sum_y", "key", "pixel_variance"):
+                assert np.array_equal(ra[t, :k][f], rb[t, :k][f]), (i, t, f)
+    assert seen > 50
 
 
 def test_batch_of_ragged_clips_matches_single_clip_runs(extractor):
