@@ -56,7 +56,7 @@ constexpr int kWarps = kThreads / 32;
 // split path (batch launches that keep the filtered images and carry no state): extract_sweep_kernel runs the sweep
 // warps plus one scalar warp per clip; frame_mask_kernel and frame_components_kernel then turn every frame into its
 // mask and its labels / regions with one CTA per frame
-constexpr int kSThreads = kPThreads + 32;
+constexpr int kSThreads = kPThreads + 64;  // sweep warps + scalar warp + producer warp
 #if CPT_EXP == 6
 constexpr int kFThreads = 192, kGThreads = 128;
 #else

@@ -512,6 +512,82 @@ __device__ __forceinline__ void normalise_group(SM &s, const float *F, int grp, 
     normalise_values(s, f0, f1, grp, ac, gmn, gmx, nmagic, nshift, u_global);
 }
 
+// split path: the scalar warp signals "message f of this clip consumed, byte threshold published" on the shared-memory
+// barrier of the message's buffer (f & 1, one arrival per phase); a sweep warp that is ahead of it waits there in
+// hardware instead of spinning on a flag (a spinning warp takes issue slots from the warps it is waiting for)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D): bytes a multiple of 16, both addresses 16-byte aligned; completion is
+// counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Split path: the frame rows of one sweep iteration (P and the rows of the frame leaving the window) are staged in shared
+// memory by a producer warp, kStages iterations ahead of the sweep warps (full / empty mbarrier per stage).  The ring
+// lives in the part of Smem only the mask / component warps of the single-kernel path use.
+constexpr int kStages = 5;
+constexpr int kStageHalf = kPThreads * 8 + 2 * kMaxW;  // rows_per_it * W <= 4 * kPThreads pixels, plus one remapped row
+constexpr int kStageBytes = 2 * kStageHalf;  // P rows, then P_old rows
+struct SoloStage {
+    uint8_t data[kStages][kStageBytes];
+    unsigned long long full[kStages], empty[kStages];
+};
+static_assert(kStageHalf % 16 == 0, "bulk copies need 16-byte alignment");
+static_assert(sizeof(SoloStage) <= offsetof(Smem, c_rank) - offsetof(Smem, U), "the staging ring overlays U .. c_b");
+static_assert(offsetof(Smem, U) % 128 == 0, "staging ring alignment");
+__device__ __forceinline__ SoloStage &solo_stage(Smem &s) { return *reinterpret_cast<SoloStage *>(s.U); }
+
+// where a frame's iterations sit in the ring: iteration it of this frame is use number k0 + (s0 + it) / kStages of
+// stage (s0 + it) % kStages
+struct StageCtx {
+    int s0, k0, n_it;
+};
+static_assert(kStages - 1 + kQIter - 1 < 3 * kStages, "stage index by at most two subtractions");
+
+// the quad of iteration `it` from the ring (all threads of the warp call this; the warp releases the stage once read)
+template <bool kFrame>
+__device__ __forceinline__ void stage_load(Smem &s, const StageCtx &sc, int it, bool mine, int l4, int lane, uint2 &pw, uint2 &ow) {
+    pw = make_uint2(0, 0);
+    ow = make_uint2(0, 0);
+    if (!kFrame || it >= sc.n_it) return;
+    SoloStage &st = solo_stage(s);
+    const int q = sc.s0 + it;
+    const int wrap = q >= 2 * kStages ? 2 : (q >= kStages ? 1 : 0);
+    const int stage = q - wrap * kStages;
+    mbar_wait(&st.full[stage], (uint32_t)(sc.k0 + wrap) & 1u);
+    if (mine) {
+        pw = *reinterpret_cast<const uint2 *>(st.data[stage] + l4 * 2);
+        ow = *reinterpret_cast<const uint2 *>(st.data[stage] + kStageHalf + l4 * 2);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&st.empty[stage]);  // (release: the loads above have completed)
+}
+
 // ------------------------------------------------------------------------------------------------
 // The fused pixel sweep.  For every owned quad (4 pixels) in one pass over the on-chip state:
 //   [update]  WeightedBackground.process_frame for the PREVIOUS frame (K7): A = floor(S / cnt),
@@ -576,6 +652,8 @@ struct SweepThread {
     int p4_last;     // pixel index of the thread's quad in the last iteration (kQIter - 1), see sweep_thread_init
     bool has_last;   // the thread has a quad in the last iteration
     bool skip0;      // the thread's quad of iteration 0 was handed to another thread (balanced 160x120 mapping)
+    int l4_0, l4_last;  // split path: the quad's pixel offset inside the staged rows of an iteration (last iteration: l4_last)
+    int lane;
     bool active;     // ptid < rows_per_it * qpr
     bool prefetch;   // first quad of a 128-byte line
     bool first_col, last_col;  // the quad holds a crop-border column (edge == 1)
@@ -673,10 +751,11 @@ __device__ __forceinline__ int sweep_p4(const SweepThread &th, int it, int strid
 // loop whose maxima go through local memory (first frame, tail pass, exact keep test: once per clip).
 // kLepton: the geometry is 160x120 with a 1-pixel border (20 rows x 40 quads per iteration), so every offset of the
 // straight-line code is an immediate.
-template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled, bool kLepton>
+// kSolo: the split path -- the quads come from the staging ring (stage_load) instead of global memory.
+template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled, bool kLepton, bool kSolo>
 __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
                                             const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
-                                            uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
+                                            uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter], const StageCtx &sc) {
     const Geometry &g = a.g;
     const int owned_rows = kLepton ? 118 : g.H - 2 * g.edge;
     constexpr int kLeptonRows = kPThreads / 40;  // rows per iteration at 160 pixels
@@ -685,6 +764,22 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
     const int stride = kLepton ? kLeptonRows * 160 : th.stride;
     uint2 nb_top = make_uint2(0, 0), nb_bottom = make_uint2(0, 0);
     if (kUnrolled) {
+        if (kSolo) {
+            // the border rows' pixels: two global loads per frame for two row groups, in flight across the whole sweep
+            uint2 pw_it, ow_it;
+#pragma unroll
+            for (int it = 0; it < kQIter; ++it) {
+                gmaxq[it] = kNoQuad;
+                const bool mine = sweep_mine<kLepton>(th, it, rows_per_it, owned_rows);
+                stage_load<kFrame>(s, sc, it, mine, it == kQIter - 1 ? th.l4_last : th.l4_0, th.lane, pw_it, ow_it);
+                if (!mine) continue;
+                uint2 nb;
+                gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw_it, ow_it,
+                                                                                  fcur, lab_frame, acc, nb);
+                if (it == 0) nb_top = nb;
+                if (it == th.last_it) nb_bottom = nb;
+            }
+        } else {
         // software pipeline: the global loads of quad it + 1 are in flight while quad it is processed
         // (two quads ahead, or the next frame's first quad across the message, cost registers the 80-register budget of
         // 21 warps does not have: measured slower)
@@ -704,14 +799,17 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < kQIter; ++j) gmaxq[j] = kNoQuad;
 #pragma unroll 1
         for (int it = 0; it < kQIter; ++it) {
-            if (!sweep_mine<false>(th, it, rows_per_it, owned_rows)) continue;
+            const bool mine_it = sweep_mine<false>(th, it, rows_per_it, owned_rows);
             uint2 nb, pw, ow;
-            load_quad<kFrame>(sweep_p4(th, it, stride), P, Pold, pw, ow);
+            if (kSolo) stage_load<kFrame>(s, sc, it, mine_it, it == kQIter - 1 ? th.l4_last : th.l4_0, th.lane, pw, ow);
+            if (!mine_it) continue;
+            if (!kSolo) load_quad<kFrame>(sweep_p4(th, it, stride), P, Pold, pw, ow);
             const int hi = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw, ow, fcur,
                                                                                 lab_frame, acc, nb);
             // (selects, not an indexed store: the maxima stay in registers in every instantiation)
@@ -745,10 +843,10 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
 }
 
 // Runtime mode -> instantiation.
-template <bool kStats>
+template <bool kStats, bool kSolo>
 __device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
                                                      const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
-                                                     uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
+                                                     uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter], const StageCtx &sc) {
     const bool steady = m.update && m.frame && !m.slow && !m.first_mean && a.g.W == 160 && a.g.H == 120 && a.g.edge == 1;
 #if CPT_EXP == 3
     constexpr bool kUnroll = false;
@@ -756,15 +854,15 @@ __device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &
     constexpr bool kUnroll = true;
 #endif
     if (steady && m.table == 0)
-        pixel_sweep<true, true, true, 0, kStats, kUnroll, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, true, 0, kStats, kUnroll, true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
     else if (steady && m.table == 1)
-        pixel_sweep<true, true, true, 1, kStats, kUnroll, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, true, 1, kStats, kUnroll, true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
     else if (!m.update)
-        pixel_sweep<false, true, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<false, true, false, 2, kStats, false, false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
     else if (m.frame)
-        pixel_sweep<true, true, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, true, false, 2, kStats, false, false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
     else
-        pixel_sweep<true, false, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        pixel_sweep<true, false, false, 2, kStats, false, false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
 }
 
 // a frame's sums / extrema, folded by the sweep warps (one shared-memory atomic per value and warp)
@@ -815,30 +913,6 @@ __device__ __forceinline__ void solo_hot_words(const KernelArgs &a, const Smem &
     if (lane < kQIter) a.hot[of * kHotStride + warp * kQIter + lane] = mine;
 }
 
-// split path: the scalar warp signals "message f of this clip consumed, byte threshold published" on the shared-memory
-// barrier of the message's buffer (f & 1, one arrival per phase); a sweep warp that is ahead of it waits there in
-// hardware instead of spinning on a flag (a spinning warp takes issue slots from the warps it is waiting for)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra.uni WAIT_DONE;\n"
-        "bra.uni WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 // wait until the scalar warp has finished message f of this clip
 __device__ __forceinline__ void solo_wait_done(Smem &s, int f) {
     mbar_wait(&s.done_bar[f & 1], (uint32_t)(f >> 1) & 1u);
@@ -863,7 +937,9 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     int frames_seen = 0;
 
     // ---------------------------------------------------------------- init / resume
-    for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
+    const int n_it = (g.H - 2 * g.edge + g.rows_per_it - 1) / g.rows_per_it;  // sweep iterations that hold rows
+    if (!kSolo)
+        for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
     for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
     if (ptid < 2) frame_msg_reset(s.fm[ptid]);
     if (ptid == 0) {
@@ -871,9 +947,19 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         s.bcast_i[10] = 0;
         if (kSolo) {
             // fresh phase counters for this clip (every thread of the CTA is between clips here)
-            if (s.done_bar_live) { mbar_inval(&s.done_bar[0]); mbar_inval(&s.done_bar[1]); }
+            SoloStage &st = solo_stage(s);
+            if (s.done_bar_live) {
+                mbar_inval(&s.done_bar[0]);
+                mbar_inval(&s.done_bar[1]);
+                for (int i = 0; i < kStages; ++i) { mbar_inval(&st.full[i]); mbar_inval(&st.empty[i]); }
+            }
             mbar_init(&s.done_bar[0], 1);
             mbar_init(&s.done_bar[1], 1);
+            for (int i = 0; i < kStages; ++i) {
+                mbar_init(&st.full[i], 1);         // the producer's arrive.expect_tx
+                mbar_init(&st.empty[i], kPWarps);  // one arrival per sweep warp
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             s.done_bar_live = 1;
         }
     }
@@ -936,14 +1022,21 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         th.has_last = th.active && r0 + (kQIter - 1) * g.rows_per_it <= last_row;
         th.p4_last = th.p4_0 + (kQIter - 1) * th.stride;
         th.skip0 = false;
+        th.l4_0 = th.l4_last = r0 * W + qx * 4;
+        th.lane = lane;
         if (g.balanced) {
             // 160x120: 118 owned rows + 2 border rows.  The owners of the first and last owned row also produce a border
             // row, so each hands one of its rows to a group whose last iteration is free: no thread has more than 8
             // quads per frame (owned_row_slot() is the inverse map).
             if (r0 == 0) th.has_last = false;
-            if (r0 == g.bal_a_r) { th.has_last = true; th.p4_last = (g.bal_a_oy + g.edge) * W + qx * 4; }
+            if (r0 == g.bal_a_r) { th.has_last = true; th.p4_last = (g.bal_a_oy + g.edge) * W + qx * 4; th.l4_last = qx * 4; }
             if (r0 == g.bal_b_oy) th.skip0 = true;  // (the last owned row's group index equals its first row's index)
-            if (r0 == g.bal_b_r) { th.has_last = true; th.p4_last = (g.bal_b_oy + g.edge) * W + qx * 4; }
+            // (the producer appends that row after the last iteration's own rows)
+            if (r0 == g.bal_b_r) {
+                th.has_last = true;
+                th.p4_last = (g.bal_b_oy + g.edge) * W + qx * 4;
+                th.l4_last = (g.H - 2 * g.edge - (kQIter - 1) * g.rows_per_it) * W + qx * 4;
+            }
         }
     }
     bar_sync(BAR_INIT, kAll);  // the state and the initial average are in place: the other roles may start
@@ -986,8 +1079,12 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         // ------------------------------------------------------------ fused sweep (K7 of frame t-1, K1/K8 of frame t)
         SweepAcc acc;
         int gmaxq[kQIter];
-        if (want_stats) pixel_sweep_dispatch<true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
-        else pixel_sweep_dispatch<false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        StageCtx sc;
+        sc.n_it = n_it;
+        sc.s0 = (t * n_it) % kStages;  // (every t < n_frames is a frame: frame t's iterations are uses t * n_it ...)
+        sc.k0 = (t * n_it) / kStages;
+        if (want_stats) pixel_sweep_dispatch<true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
+        else pixel_sweep_dispatch<false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
         CPT_TICK(ptid == 0, 14);  // sweep
         // ------------------------------------------------------------ message to the mask warps / the scalar warp
         last_t = t;
@@ -1021,7 +1118,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
                 for (int it = 0; it < kQIter; ++it) s.qmax8[it * kPThreads + ptid] = quad_byte(gmaxq[it], qref);
             }
             if (m.update) ++frames_seen;
-            bar_arrive(BAR_SM_FULL + b, kSThreads);
+            bar_arrive(BAR_SM_FULL + b, kPThreads + 32);
             CPT_TICK(ptid == 0, 2);   // message
             continue;
         }
@@ -1381,7 +1478,7 @@ __device__ void scalar_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         if (!(update_bg && t > 0) && !is_frame) break;
         const int b = t & 1;
         const size_t o = (size_t)(clip.out_offset + t);
-        bar_sync(BAR_SM_FULL + b, kSThreads);  // the sweep of frame t is done
+        bar_sync(BAR_SM_FULL + b, kPThreads + 32);  // the sweep of frame t is done
         CPT_TICK2(lane == 0, 7);   // waiting for the sweep
         if (lane == 0) {
             frame_scalars(a, s, clip, s.fm[b], o, is_frame, want_stats, average);
@@ -1436,6 +1533,46 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
     }
 }
 
+// ================================================================================================
+// split path, producer warp: one elected lane keeps the staging ring full -- per frame and sweep iteration the rows the
+// sweep warps are about to read, from the frame and from the frame leaving the 45-frame window (zeros while the
+// window fills), as 1-D bulk copies (TMA) that complete on the stage's mbarrier.
+// ================================================================================================
+__device__ void producer_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, int lane) {
+    const Geometry &g = a.g;
+    bar_sync(BAR_INIT, kSThreads);
+    if (lane == 0) {
+        SoloStage &st = solo_stage(s);
+        const int owned = g.H - 2 * g.edge, R = g.rows_per_it;
+        const int n_it = (owned + R - 1) / R;
+        const uint32_t row_bytes = (uint32_t)g.W * 2u;
+        int use = 0;  // uses of the ring so far: stage use % kStages, its (use / kStages)-th use
+        for (int t = 0; t < clip.n_frames; ++t) {
+            const int t_abs = clip.first_frame + t;
+            const uint16_t *P = frame_ptr(a, clip, t);
+            const uint16_t *Pold = (t_abs >= kMeanFrames) ? frame_ptr(a, clip, t - kMeanFrames) : a.zero_frame;
+            for (int it = 0; it < n_it; ++it, ++use) {
+                const int stage = use % kStages, k = use / kStages;
+                if (k > 0) mbar_wait(&st.empty[stage], (uint32_t)(k - 1) & 1u);  // every sweep warp has read its previous use
+                const int row0 = g.edge + it * R, rows = min(R, owned - it * R);
+                const uint32_t bytes = (uint32_t)rows * row_bytes;
+                const bool extra = g.balanced && it == kQIter - 1;  // the remapped row rides behind the last iteration's own rows
+                mbar_arrive_expect_tx(&st.full[stage], 2u * (bytes + (extra ? row_bytes : 0u)));
+                uint8_t *dst = st.data[stage];
+                bulk_g2s(dst, P + (size_t)row0 * g.W, bytes, &st.full[stage]);
+                bulk_g2s(dst + kStageHalf, Pold + (size_t)row0 * g.W, bytes, &st.full[stage]);
+                if (extra) {
+                    const size_t rx = (size_t)(g.bal_b_oy + g.edge) * g.W;
+                    bulk_g2s(dst + bytes, P + rx, row_bytes, &st.full[stage]);
+                    bulk_g2s(dst + kStageHalf + bytes, Pold + rx, row_bytes, &st.full[stage]);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    bar_arrive(BAR_DONE, kSThreads);
+}
+
 // Split path, first launch: the recurrence only.  One persistent CTA per clip: sweep warps + the scalar warp.  Per frame
 // it leaves the filtered image, a zeroed label image, the info record and the hot-quad words in global memory.
 __global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const KernelArgs a) {
@@ -1451,7 +1588,8 @@ __global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const Kerne
         if (ci >= a.n_clips) break;
         const cpt_clip clip = a.clips[ci];
         if (tid < kPThreads) sweep_warps<true>(a, s, clip, tid, nullptr, nullptr);
-        else scalar_warp(a, s, clip, tid - kPThreads);
+        else if (tid < kPThreads + 32) scalar_warp(a, s, clip, tid - kPThreads);
+        else producer_warp(a, s, clip, tid - kPThreads - 32);
     }
 }
 
