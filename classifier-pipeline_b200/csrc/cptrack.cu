@@ -395,7 +395,8 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     const bool timed = c->time_kernels && c->ev_k[0];
     if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[0], stream));
     static const bool split_allowed = [] { const char *e = getenv("CPT_SPLIT"); return !(e && e[0] == '0'); }();
-    const bool split = split_allowed && d_state == nullptr && out->d_filtered != nullptr && total_frames > 0;
+    // (the sweep kernel stages frame rows with 16-byte bulk copies: rows must be a multiple of 8 pixels)
+    const bool split = split_allowed && d_state == nullptr && out->d_filtered != nullptr && total_frames > 0 && c->g.W % 8 == 0;
     if (split) {
         if (c->hot_frames < (size_t)total_frames) {
             CUDA_TRY(cudaStreamSynchronize(stream));

@@ -75,7 +75,7 @@ constexpr int kCompSlots = 256;                 // slot 255 = overflow sink
 constexpr int kMeanFrames = CPT_MEAN_FRAMES;
 // per output frame of the split path: one ballot word per (sweep warp, sweep iteration) -- bit `lane` of word
 // warp * kQIter + it is the hot bit of owned quad it * kPThreads + warp * 32 + lane -- followed by
-// {byte threshold (0: dense), normalise magic, normalise shift, flags (1: valid, 2: first frame of its clip)}
+// {byte threshold (0: dense), normalise magic, normalise shift, flags (1: valid, 2: first frame of its clip, 4: empty mask)}
 constexpr int kHotWords = (kQIter * kPWarps + 3) & ~3;  // (the trailer is read and written as one 16-byte vector)
 constexpr int kHotStride = kHotWords + 4;
 constexpr uint16_t kSlotFlag = 0x8000u;

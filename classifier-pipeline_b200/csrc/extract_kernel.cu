@@ -156,11 +156,13 @@ __device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &
             any |= (c != 0);
         }
     }
-    for (int i = ctid; i < kCompSlots; i += kT) {
+    // (a component's slot is initialised by the thread that allocates it; only the overflow sink is reset here)
+    if (ctid == 0) {
+        s.ncomp = 0;
+        const int i = CPT_MAX_COMPONENTS;
         s.c_key[i] = INT32_MAX; s.c_area[i] = 0; s.c_sx[i] = 0; s.c_sy[i] = 0;
         s.c_l[i] = INT32_MAX; s.c_t[i] = INT32_MAX; s.c_r[i] = -1; s.c_b[i] = -1;
     }
-    if (ctid == 0) s.ncomp = 0;
     if (!bar_or(kBar, kT, any)) return;  // no foreground: info.n_components stays 0
     CPT_TICK2(ctid == 0, 20);  // close + reset + barrier
 
@@ -233,7 +235,6 @@ __device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &
     CPT_TICK2(ctid == 0, 22);  // unions + barrier
     // ---- roots -> component slots (and the variance sums: in frame_components_kernel they live where the mask and the
     // run-start bits were, both dead once the unions are done)
-    for (int i = ctid; i < kCompSlots; i += kT) { s.acc_s[i] = 0.0; s.acc_s2[i] = 0.0; }
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
         uint32_t bitsleft = rc[it].stw;
@@ -243,6 +244,11 @@ __device__ void components_of_frame(const KernelArgs &a, SM &s, const Geometry &
             int id = rc[it].y * kRunsPerRow + rc[it].base + n;
             if (s.parent[id] == id) {
                 int slot = atomicAdd(&s.ncomp, 1);
+                if (slot < CPT_MAX_COMPONENTS) {
+                    s.c_key[slot] = INT32_MAX; s.c_area[slot] = 0; s.c_sx[slot] = 0; s.c_sy[slot] = 0;
+                    s.c_l[slot] = INT32_MAX; s.c_t[slot] = INT32_MAX; s.c_r[slot] = -1; s.c_b[slot] = -1;
+                    s.acc_s[slot] = 0.0; s.acc_s2[slot] = 0.0;
+                }
                 s.parent[id] = (uint16_t)(kSlotFlag | (slot < CPT_MAX_COMPONENTS ? slot : CPT_MAX_COMPONENTS));
             }
             ++n;
@@ -893,6 +899,30 @@ __device__ __forceinline__ uint32_t sweep_reduce_store(FrameMsg &fm, int lane, c
     return bmax;
 }
 
+// split path: the warp's partial results as one row of the message buffer's table (Smem::red_u viewed as
+// [2][kPWarps][8]); the scalar warp folds the rows, so the sweep warps issue no atomics.  Returns the warp's background maximum.
+__device__ __forceinline__ uint32_t sweep_reduce_partials(uint32_t *row, int lane, const SweepAcc &acc, bool want_stats) {
+    const uint32_t psum = __reduce_add_sync(0xffffffffu, acc.psum), bsum = __reduce_add_sync(0xffffffffu, acc.bsum);
+    const uint32_t changed = __reduce_or_sync(0xffffffffu, acc.changed);
+    const int fmin = __reduce_min_sync(0xffffffffu, acc.fmin), fmax = __reduce_max_sync(0xffffffffu, acc.fmax);
+    const uint32_t bmax = __reduce_max_sync(0xffffffffu, max(acc.bmax2 & 0xffffu, acc.bmax2 >> 16));
+    uint32_t v = psum;                       // slot order: FrameMsg::red[0..7]
+    v = lane == 1 ? (uint32_t)fmin : v;
+    v = lane == 2 ? (uint32_t)fmax : v;
+    v = lane == 6 ? bsum : v;
+    v = lane == 7 ? changed : v;
+    if (want_stats) {
+        const int pmin = __reduce_min_sync(0xffffffffu, acc.pmin), pmax = __reduce_max_sync(0xffffffffu, acc.pmax);
+        const uint32_t fabs_sum = __reduce_add_sync(0xffffffffu, acc.fabs_sum);
+        v = lane == 3 ? (uint32_t)pmin : v;
+        v = lane == 4 ? (uint32_t)pmax : v;
+        v = lane == 5 ? fabs_sum : v;
+    }
+    if (lane < 8) row[lane] = v;
+    return bmax;
+}
+static_assert(2 * kPWarps * 8 <= kWarps * 12, "the partial-result table fits Smem::red_u");
+
 // ================================================================================================
 // sweep warps: the recurrence.  Per frame: fused sweep -> fold the frame's sums into the message of the mask
 // warps -> hot-quad ballots against a PREDICTED bound (the mask warps compute the true one; if the prediction
@@ -1042,6 +1072,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     bar_sync(BAR_INIT, kAll);  // the state and the initial average are in place: the other roles may start
 
     int last_t = -1;
+    uint32_t magic_cnt = 0, magic_val = 0;
     bool slow = true;  // the first update of a launch takes the exact path (no background extrema yet)
     // t == n_frames is the tail pass: only the background update of the last frame
     for (int t = 0; t <= clip.n_frames; ++t) {
@@ -1058,7 +1089,12 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             // the update belongs to frame t-1: the mean covers min(t_abs, 45) frames
             const uint32_t cnt = (uint32_t)min(max(t_abs, 1), kMeanFrames);
             m.first_mean = (cnt == 1u);
-            m.magic = m.first_mean ? 0u : 0xffffffffu / cnt + 1u;  // floor(S / cnt) == umulhi(S, magic): exact for S < 2^22, cnt <= 45
+            // floor(S / cnt) == umulhi(S, magic): exact for S < 2^22, cnt <= 45 (the count saturates: one division per clip then)
+            if (cnt != magic_cnt) {
+                magic_cnt = cnt;
+                magic_val = (cnt == 1u) ? 0u : 0xffffffffu / cnt + 1u;
+            }
+            m.magic = magic_val;
             m.slow = slow;
             const int k_cap = frames_seen;  // no weight counter can exceed the number of updates so far
             m.table = (k_cap < wt.linear_upto) ? 0 : ((k_cap < kSmemWeights) ? 1 : 2);
@@ -1099,7 +1135,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
             }
             CPT_TICK(ptid == 0, 6);   // wait for the scalar warp + ballots
             FrameMsg &fm = s.fm[b];
-            const uint32_t warp_bmax = sweep_reduce_store(fm, lane, acc, want_stats);
+            const uint32_t warp_bmax = sweep_reduce_partials(s.red_u + (b * kPWarps + warp) * 8, lane, acc, want_stats);
             const int latest = *(volatile int32_t *)&s.fth_latest;
             const int qref = (latest == INT32_MIN) ? 0 : latest;
             if (ptid == 0) {
@@ -1480,6 +1516,28 @@ __device__ void scalar_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         const size_t o = (size_t)(clip.out_offset + t);
         bar_sync(BAR_SM_FULL + b, kPThreads + 32);  // the sweep of frame t is done
         CPT_TICK2(lane == 0, 7);   // waiting for the sweep
+        {
+            // fold the sweep warps' partial results (one row per warp) into the message
+            const uint32_t *row = s.red_u + (b * kPWarps + lane) * 8;
+            const bool in = lane < kPWarps;
+            const uint32_t psum = __reduce_add_sync(0xffffffffu, in ? row[0] : 0u);
+            const int fmin = __reduce_min_sync(0xffffffffu, in ? (int)row[1] : INT32_MAX);
+            const int fmax = __reduce_max_sync(0xffffffffu, in ? (int)row[2] : INT32_MIN);
+            const uint32_t bsum = __reduce_add_sync(0xffffffffu, in ? row[6] : 0u);
+            const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? row[7] : 0u);
+            int pmin = 0, pmax = 0;
+            uint32_t fabs_sum = 0;
+            if (want_stats) {
+                pmin = __reduce_min_sync(0xffffffffu, in ? (int)row[3] : INT32_MAX);
+                pmax = __reduce_max_sync(0xffffffffu, in ? (int)row[4] : INT32_MIN);
+                fabs_sum = __reduce_add_sync(0xffffffffu, in ? row[5] : 0u);
+            }
+            if (lane == 0) {
+                uint32_t *r = s.fm[b].red;
+                r[0] = psum; r[1] = (uint32_t)fmin; r[2] = (uint32_t)fmax; r[3] = (uint32_t)pmin; r[4] = (uint32_t)pmax;
+                r[5] = fabs_sum; r[6] = bsum; r[7] = changed;
+            }
+        }
         if (lane == 0) {
             frame_scalars(a, s, clip, s.fm[b], o, is_frame, want_stats, average);
             if (is_frame) {
@@ -1712,9 +1770,27 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
         }
     }
     __syncthreads();
+    // an empty mask (frames without an animal) is only flagged: frame_components_kernel leaves at once
     uint32_t *mout = a.maskbits + (size_t)o * kMaxWords;
-    if ((g.words & 3) == 0) {
-        for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
+    const bool vec = (g.words & 3) == 0;
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    if (vec && tid < g.words / 4) mine = reinterpret_cast<const uint4 *>(s.M[0])[tid];
+    bool any = (mine.x | mine.y | mine.z | mine.w) != 0;
+    if (vec) {
+        for (int i = tid + kFThreads; i < g.words / 4; i += kFThreads) {
+            const uint4 w = reinterpret_cast<const uint4 *>(s.M[0])[i];
+            any |= (w.x | w.y | w.z | w.w) != 0;
+        }
+    } else {
+        for (int i = tid; i < g.words; i += kFThreads) any |= s.M[0][i] != 0;
+    }
+    if (!__syncthreads_or(any)) {
+        if (tid == 0) a.hot[(size_t)o * kHotStride + kHotWords + 3] = hdr.w | 4u;
+        return;
+    }
+    if (vec) {
+        if (tid < g.words / 4) reinterpret_cast<uint4 *>(mout)[tid] = mine;
+        for (int i = tid + kFThreads; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
     } else {
         for (int i = tid; i < g.words; i += kFThreads) mout[i] = s.M[0][i];
     }
@@ -1734,6 +1810,7 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
     const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(a.hot + (size_t)o * kHotStride + kHotWords));
     const int dn_marker = fi->reserved[1];
     if (!(hdr.w & 1u)) return;  // no clip produced this output frame (its mask words were never written)
+    if (hdr.w & 4u) return;     // empty mask (flagged by frame_mask_kernel): info.n_components stays 0
     if (dn_marker) return;      // denoise clips: mask_components_kernel
     bool any = false;
     if ((g.words & 3) == 0) {
