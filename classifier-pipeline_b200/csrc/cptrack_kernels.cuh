@@ -188,7 +188,7 @@ struct __align__(16) Smem {
     int32_t c_key[kCompSlots], c_area[kCompSlots], c_sx[kCompSlots], c_sy[kCompSlots];
     int32_t c_l[kCompSlots], c_t[kCompSlots], c_r[kCompSlots], c_b[kCompSlots];
     uint8_t c_rank[kCompSlots];
-    uint32_t red_u[kWarps * 12];
+    uint32_t red_u[(kWarps * 12 > 2 * kPWarps * 8) ? kWarps * 12 : 2 * kPWarps * 8];  // per-warp partial results
     int32_t bcast_i[16];
     int32_t msg[2][4];         // pixel warps -> component warps, per mask buffer: filtered min, max
     double bcast_d[4];
