@@ -37,10 +37,12 @@ constexpr int kPThreads = 480;                  // 15 sweep warps: 12 rows x 40 
 constexpr int kPThreads = 960;
 #elif CPT_EXP == 5
 constexpr int kPThreads = 800;
-#elif CPT_EXP == 8 || CPT_EXP == 9
-constexpr int kPThreads = 608;                  // 19 sweep warps: 15 rows x 40 quads per iteration (8 threads idle)
+#elif CPT_EXP == 10
+constexpr int kPThreads = 640;                  // 20 sweep warps: 16 row groups, 7 or 8 quads per thread (34.2 -> 35.5 ms)
 #else
-constexpr int kPThreads = 640;                  // 20 sweep warps: 16 rows x 40 quads per iteration at 160 pixels
+// 19 sweep warps: 15 rows x 40 quads per iteration at 160 pixels (the last 8 threads idle).  120 rows / 15 row groups = 8
+// quads for every thread once the two border rows are balanced (Geometry::balanced): no warp is ever ahead of another.
+constexpr int kPThreads = 608;
 #endif
 constexpr int kPWarps = kPThreads / 32;
 #if CPT_EXP == 4 || CPT_EXP == 5

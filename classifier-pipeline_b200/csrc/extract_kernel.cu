@@ -531,16 +531,19 @@ __device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// (the suspend-time hint keeps a waiting warp asleep instead of re-issuing try_wait: a spinning warp takes issue slots from
+// the warps it is waiting for)
+constexpr uint32_t kWaitHintNs = 4000;
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra.uni WAIT_DONE;\n"
         "bra.uni WAIT_LOOP;\n"
         "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
