@@ -575,6 +575,7 @@ __device__ __forceinline__ SoloStage &solo_stage(Smem &s) { return *reinterpret_
 // stage (s0 + it) % kStages
 struct StageCtx {
     int s0, k0, n_it;
+    long long *debug;  // phase-timing builds
 };
 static_assert(kStages - 1 + kQIter - 1 < 3 * kStages, "stage index by at most two subtractions");
 
@@ -588,7 +589,13 @@ __device__ __forceinline__ void stage_load(Smem &s, const StageCtx &sc, int it, 
     const int q = sc.s0 + it;
     const int wrap = q >= 2 * kStages ? 2 : (q >= kStages ? 1 : 0);
     const int stage = q - wrap * kStages;
+#ifdef CPT_PHASE_TIMING
+    const long long w0_ = clock64();
+#endif
     mbar_wait(&st.full[stage], (uint32_t)(sc.k0 + wrap) & 1u);
+#ifdef CPT_PHASE_TIMING
+    if (threadIdx.x == 0 && sc.debug) atomicAdd((unsigned long long *)&sc.debug[(blockIdx.x % 128u) * 32 + 5], (unsigned long long)(clock64() - w0_));
+#endif
     if (mine) {
         pw = *reinterpret_cast<const uint2 *>(st.data[stage] + l4 * 2);
         ow = *reinterpret_cast<const uint2 *>(st.data[stage] + kStageHalf + l4 * 2);
@@ -1120,6 +1127,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         int gmaxq[kQIter];
         StageCtx sc;
         sc.n_it = n_it;
+        sc.debug = a.debug;
         sc.s0 = (t * n_it) % kStages;  // (every t < n_frames is a frame: frame t's iterations are uses t * n_it ...)
         sc.k0 = (t * n_it) / kStages;
         if (want_stats) pixel_sweep_dispatch<true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
@@ -1614,7 +1622,9 @@ __device__ void producer_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip
             const uint16_t *Pold = (t_abs >= kMeanFrames) ? frame_ptr(a, clip, t - kMeanFrames) : a.zero_frame;
             for (int it = 0; it < n_it; ++it, ++use) {
                 const int stage = use % kStages, k = use / kStages;
+                CPT_TICK_START2(true);
                 if (k > 0) mbar_wait(&st.empty[stage], (uint32_t)(k - 1) & 1u);  // every sweep warp has read its previous use
+                CPT_TICK2(true, 8);   // producer: waiting for a free stage
                 const int row0 = g.edge + it * R, rows = min(R, owned - it * R);
                 const uint32_t bytes = (uint32_t)rows * row_bytes;
                 const bool extra = g.balanced && it == kQIter - 1;  // the remapped row rides behind the last iteration's own rows
@@ -1627,6 +1637,7 @@ __device__ void producer_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip
                     bulk_g2s(dst + bytes, P + rx, row_bytes, &st.full[stage]);
                     bulk_g2s(dst + kStageHalf + bytes, Pold + rx, row_bytes, &st.full[stage]);
                 }
+                CPT_TICK2(true, 9);   // producer: issuing the copies
             }
         }
     }

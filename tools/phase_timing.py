@@ -35,8 +35,9 @@ def main(clips=148, frames=300, exp=0):
     ex.extract_device(d_frames, cl, out=out)
     torch.cuda.synchronize()
     native.check(ex.ctx.lib.cpt_debug_phase_cycles(ex.ctx._h, buf, 0))
-    names = {14: "S fused sweep", 6: "S wait scalars + ballots", 2: "S message",
-             7: "M wait sweep", 16: "M scalars thread 0", 3: "M scalars bar", 15: "M quad maxima -> hot rows", 4: "M marks+lists", 5: "M normalise+bar", 8: "M wait mask buffer", 9: "M blur",
+    names = {14: "S fused sweep", 5: "S  of which: waiting for staged rows", 6: "S wait scalars + ballots", 2: "S message",
+             8: "producer: wait free stage", 9: "producer: issue copies",
+             7: "M wait sweep", 16: "M scalars thread 0", 3: "M scalars bar", 15: "M quad maxima -> hot rows", 4: "M marks+lists",
              11: "C wait mask", 12: "C components",
              20: "C  close+reset+bar", 21: "C  run starts+bar", 22: "C  unions+bar", 23: "C  roots+bar", 24: "C  run stats+bar",
              25: "C  rank+bar", 26: "C  label writes", 27: "C  variance+bar"}
