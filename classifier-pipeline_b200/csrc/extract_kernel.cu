@@ -974,6 +974,7 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     float *st_F = reinterpret_cast<float *>(st_S + npx);
     const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
     const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
+    const bool skip_first_update = clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE;
     int frames_seen = 0;
 
     // ---------------------------------------------------------------- init / resume
@@ -1092,7 +1093,8 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         const int b = t & 1;
         const size_t o = (size_t)(clip.out_offset + t);
         SweepMode m;
-        m.update = update_bg && t > 0;
+        // (rawdb.py:84-122: no update follows the frame that initialised the background when it is also the first kept frame)
+        m.update = update_bg && t > 0 && !(skip_first_update && t_abs == 1);
         m.frame = is_frame;
         if (!m.update && !m.frame) break;
         {
@@ -1336,7 +1338,7 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
     for (int t = 0; t <= clip.n_frames; ++t) {
         CPT_TICK_START2(mtid == 0);
         const bool is_frame = t < clip.n_frames;
-        if (!(update_bg && t > 0) && !is_frame) break;
+        if (!(update_bg && t > 0 && !((clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE) && clip.first_frame + t == 1)) && !is_frame) break;
         const int b = t & 1;
         const size_t o = (size_t)(clip.out_offset + t);
         bar_sync(BAR_SM_FULL + b, kPThreads + kMThreads);  // the sweep of frame t is done
@@ -1522,7 +1524,7 @@ __device__ void scalar_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     for (int t = 0; t <= clip.n_frames; ++t) {
         CPT_TICK_START2(lane == 0);
         const bool is_frame = t < clip.n_frames;
-        if (!(update_bg && t > 0) && !is_frame) break;
+        if (!(update_bg && t > 0 && !((clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE) && clip.first_frame + t == 1)) && !is_frame) break;
         const int b = t & 1;
         const size_t o = (size_t)(clip.out_offset + t);
         bar_sync(BAR_SM_FULL + b, kPThreads + 32);  // the sweep of frame t is done

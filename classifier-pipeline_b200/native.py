@@ -16,6 +16,7 @@ CLIP_UPDATE_BACKGROUND = 1
 CLIP_RESUME = 2
 CLIP_DENOISE = 4
 CLIP_FRAME_STATS = 8
+CLIP_SKIP_FIRST_UPDATE = 16
 MAX_COMPONENTS = 255
 MEAN_FRAMES = 45
 HAS_NLM = True  # cv2.fastNlMeansDenoising on the device (batched extraction; not the frame-at-a-time streaming path)

@@ -36,6 +36,8 @@ extern "C" {
 #define CPT_CLIP_RESUME 2u            /* continue from the state saved in d_state instead of initialising */
 #define CPT_CLIP_DENOISE 4u           /* TrackingConfig.denoise: cv2.fastNlMeansDenoising, cliptracker.py:116-117 (set cpt_outputs.denoise too) */
 #define CPT_CLIP_FRAME_STATS 8u       /* ClipStats.add_frame, clip.py:474-487 (min/max/median/mean, sum|filtered|) */
+#define CPT_CLIP_SKIP_FIRST_UPDATE 16u /* RawDatabase.load_frames, ml_tools/rawdb.py:84-122: the frame that initialised the
+                                          background is also the first kept frame and is not followed by a background update */
 
 typedef struct cpt_ctx cpt_ctx;
 
