@@ -342,7 +342,8 @@ def main():
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 16 << 30
-    e2e_clips = args.e2e_clips or int(max(8, min(C, (avail // 4) // (T * NPX * 2), 256)))
+    # (every rank pins its own staging copy at the same time: share the host's free memory between the ranks)
+    e2e_clips = args.e2e_clips or int(max(8, min(C, (avail // (4 * world)) // (T * NPX * 2), 256)))
     h_frames = native.pinned_empty((e2e_clips * T, H, W), np.uint16)
     h_frames[:] = d_frames.view(torch.int16)[:e2e_clips].reshape(-1, H, W).cpu().numpy().view(np.uint16)
     e_clips = linear_clips([T] * e2e_clips, bts[:e2e_clips], wts[:e2e_clips])

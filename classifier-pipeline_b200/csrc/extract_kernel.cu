@@ -1903,8 +1903,9 @@ __global__ void __launch_bounds__(256) region_variance_kernel(Geometry g, long l
         const int l = reg->x, tp = reg->y, bw = reg->width, bh = reg->height, npix = bw * bh;
         if (l < 0 || tp < 0 || bw < 1 || bh < 1 || l + bw > g.W || tp + bh > g.H) continue;  // not a record of this launch
         double s1 = 0.0, s2 = 0.0;
+        const uint32_t rcp = 0xffffffffu / (uint32_t)bw + 1u;  // i / bw == umulhi(i, rcp) for i * bw < 2^32
         for (int i = lane; i < npix; i += 32) {
-            const int yy = i / bw, xx = i - yy * bw, p = (tp + yy) * g.W + l + xx;
+            const int yy = bw == 1 ? i : (int)__umulhi((uint32_t)i, rcp), xx = i - yy * bw, p = (tp + yy) * g.W + l + xx;  // (rcp wraps to 0 for bw == 1)
             const int fc = (int)__ldg(fcur + p), fp = (int)__ldg(fprev + p);
             const float d = fabsf(norm255(fc, cur_fmin, cur_fmax, exact) - norm255(fp, prev_fmin, prev_fmax, exact));
             s1 += (double)d;
