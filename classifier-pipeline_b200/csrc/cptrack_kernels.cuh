@@ -1,20 +1,24 @@
-// cptrack_kernels.cuh -- sm_100a kernels for thermal-clip track extraction.
+// cptrack_kernels.cuh -- sm_100a kernels for thermal-clip track extraction (DESIGN.md section 3.1).
 //
-// One persistent CTA per clip.  The whole per-clip recurrence state of the reference
-// (WeightedBackground: background + per-pixel weight counter, the 45-frame sliding sum that
-// replaces np.mean(get_last_x(45)), piclassifier/motiondetector.py:178-248 and
-// track/cliptrackextractor.py:168-176) stays resident in shared memory for the life of the clip;
-// frames stream through once from HBM (uint16, 16-byte vector loads), and each frame emits
-//   filtered fp32 (K1), the uint8 label image (K5) and a compact region list (K5/K6).
-// Per-frame stages:
-//   sweep 1   F = P - B, sum P, min/max F, sliding sum update                       (K1, K7, K8)
-//   scalars   avg_change, normalisation range, mapped threshold                     (K2)
-//   sweep 2   U = uint8(255*(G-min)/(max-min))                                      (K2)
-//   stencil   5x5 binomial blur in packed 16-bit lanes, threshold -> bit rows       (K4)
-//   close     C[y] = M[y-1] | (M[y] & M[y-2]) on 32-bit row words                   (K4)
-//   label     run-based union-find on the bit rows, OpenCV label order              (K5)
-//   regions   bbox / area / centroid sums per component, delta-frame variance       (K5, K6)
-//   sweep 3   weighted background update + edge replication                         (K7)
+// The per-clip recurrence of the reference (WeightedBackground: background + per-pixel weight counter, the 45-frame
+// sliding sum that replaces np.mean(get_last_x(45)), piclassifier/motiondetector.py:178-248 and
+// track/cliptrackextractor.py:168-176) runs in one persistent CTA per clip with its whole state resident in shared
+// memory; frames stream through once from HBM and each frame emits filtered fp32 (K1), the uint8 label image (K5) and
+// a compact region list (K5/K6).  Stages of a frame:
+//   fused sweep   weighted background update of the previous frame (K7), then F = P - B, sliding sum, sum P,
+//                 min/max F, per-quad maxima of F                                               (K1, K7, K8)
+//   scalars       avg_change, normalisation range, mapped threshold, bound below which no pixel can fire  (K2)
+//   marks         hot quads -> rows of marks -> work lists of 8-pixel groups
+//   normalise     U = uint8(255*(G-min)/(max-min)) for the listed groups                        (K2)
+//   blur          5x5 binomial blur in packed 16-bit lanes, threshold -> bit rows               (K4)
+//   close         C[y] = M[y-1] | (M[y] & M[y-2]) on 32-bit row words                           (K4)
+//   label         run-based union-find on the bit rows, OpenCV label order                      (K5)
+//   regions       bbox / area / centroid sums per component, delta-frame variance               (K5, K6)
+// Two launch plans share these device functions:
+//   split path (batch launches that keep the filtered images, no state): extract_sweep_kernel (sweep warps + scalar warp
+//     + producer warp per clip) -> frame_mask_kernel -> frame_components_kernel (one CTA per frame) -> region_variance_kernel
+//   single kernel (streaming, resumed clips, regions-only): extract_clips_kernel, the stages as three warp roles
+//     (sweep / mask / component warps) running concurrently on consecutive frames of the clip
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,23 +33,20 @@ namespace cpt {
 
 // warp-specialised pipeline over consecutive frames: sweep warps (the recurrence), mask warps (scalars, work lists,
 // normalise, blur) and component warps (labelling)
-#if CPT_EXP == 1
-constexpr int kPThreads = 320;                  // 10 sweep warps: 8 rows x 40 quads per iteration at 160 pixels
-#elif CPT_EXP == 2
-constexpr int kPThreads = 480;                  // 15 sweep warps: 12 rows x 40 quads
-#elif CPT_EXP == 4
-constexpr int kPThreads = 960;
+// Sweep-warp count (tools/gpu_exp.sh builds -DCPT_EXP=<n> variants for A/B runs; the measured alternatives are in
+// DESIGN.md section 7).  640 = 16 row groups (7 or 8 quads per thread), 800 = 20 groups (split path only: the single
+// persistent kernel cannot hold 25 + 4 + 8 warps).
+#if CPT_EXP == 10
+constexpr int kPThreads = 640;
 #elif CPT_EXP == 5
 constexpr int kPThreads = 800;
-#elif CPT_EXP == 10
-constexpr int kPThreads = 640;                  // 20 sweep warps: 16 row groups, 7 or 8 quads per thread (34.2 -> 35.5 ms)
 #else
 // 19 sweep warps: 15 rows x 40 quads per iteration at 160 pixels (the last 8 threads idle).  120 rows / 15 row groups = 8
 // quads for every thread once the two border rows are balanced (Geometry::balanced): no warp is ever ahead of another.
 constexpr int kPThreads = 608;
 #endif
 constexpr int kPWarps = kPThreads / 32;
-#if CPT_EXP == 4 || CPT_EXP == 5
+#if CPT_EXP == 5
 constexpr int kMThreads = 32;
 constexpr int kCThreads = 32;
 #else
@@ -59,12 +60,8 @@ constexpr int kWarps = kThreads / 32;
 // warps plus one scalar warp per clip; frame_mask_kernel and frame_components_kernel then turn every frame into its
 // mask and its labels / regions with one CTA per frame
 constexpr int kSThreads = kPThreads + 64;  // sweep warps + scalar warp + producer warp
-#if CPT_EXP == 6
-constexpr int kFThreads = 192, kGThreads = 128;
-#else
 constexpr int kFThreads = 256;   // frame_mask_kernel
 constexpr int kGThreads = 256;   // frame_components_kernel
-#endif
 constexpr int kMaxPx = 19200;
 constexpr int kQIter = (kMaxPx / 4 + kPThreads - 1) / kPThreads;  // 6 quads of 4 pixels per pixel thread
 constexpr int kMaxW = 160;

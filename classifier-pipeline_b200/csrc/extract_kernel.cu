@@ -1,11 +1,14 @@
-// extract_kernel.cu -- the persistent per-clip extraction kernel (see cptrack_kernels.cuh).
+// extract_kernel.cu -- the extraction kernels (launch plans and stages: cptrack_kernels.cuh).
 //
-// One CTA per clip, 1024 threads in three roles that run concurrently on consecutive frames:
-//   sweep warps (20):     frame t+2: the recurrence -- background update of the previous frame fused with K1 / K7 sum / K8
+// extract_clips_kernel: one CTA per clip, three roles that run concurrently on consecutive frames:
+//   sweep warps (19):     frame t+2: the recurrence -- background update of the previous frame fused with K1 / K7 sum / K8
 //   mask warps (4):       frame t+1: scalars (K2), hot quads -> work lists, normalise (K2), blur + threshold (K4)
 //   component warps (8):  frame t:   close, run-based labelling, statistics, variance (K4, K5, K6)
-// Messages (frame sums + hot-quad ballots, then the thresholded bit image) are double buffered and handed over
-// with named barriers (full / empty per buffer); everything else the roles touch is disjoint shared memory.
+//   Messages (frame sums + per-quad maxima, then the thresholded bit image) are double buffered and handed over
+//   with named barriers (full / empty per buffer); everything else the roles touch is disjoint shared memory.
+// extract_sweep_kernel: the same sweep warps on their own, plus a scalar warp (one frame behind: info record, byte
+//   threshold for the hot-quad ballots) and a producer warp (TMA bulk copies of the frame rows into a shared-memory ring);
+//   frame_mask_kernel / frame_components_kernel / region_variance_kernel then do the per-frame stages one CTA (warp) per frame.
 #include "cptrack_kernels.cuh"
 
 namespace cpt {
@@ -864,11 +867,7 @@ __device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &
                                                      const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
                                                      uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter], const StageCtx &sc) {
     const bool steady = m.update && m.frame && !m.slow && !m.first_mean && a.g.W == 160 && a.g.H == 120 && a.g.edge == 1;
-#if CPT_EXP == 3
-    constexpr bool kUnroll = false;
-#else
     constexpr bool kUnroll = true;
-#endif
     if (steady && m.table == 0)
         pixel_sweep<true, true, true, 0, kStats, kUnroll, true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
     else if (steady && m.table == 1)
