@@ -78,8 +78,9 @@ class BatchExtractor:
         denoise = bool(n_clips) and bool((clips["flags"] & native.CLIP_DENOISE).any())
         if denoise and not keep_filtered:
             raise native.NativeError("denoise needs keep_filtered=True (the variance pass reads the filtered images)")
+        no_resume = not (bool(n_clips) and bool((clips["flags"] & native.CLIP_RESUME).any()))
         self.ctx.extract_batch(d_frames, d_clips, n_clips, regions, info, filtered, labels, d_state, total_frames=total,
-                               denoise=denoise)
+                               denoise=denoise, no_resume=no_resume)
         out.update(regions=regions, info=info, filtered=filtered, labels=labels, state=d_state, total_frames=total,
                    d_clips=d_clips)
         return out

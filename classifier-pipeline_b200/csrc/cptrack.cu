@@ -322,6 +322,12 @@ int cpt_debug_phase_cycles(cpt_ctx *c, long long *h_out32, int reset) {
     return CPT_OK;
 }
 
+int cpt_debug_force_single_kernel(cpt_ctx *c, int enable) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    c->force_single = enable != 0;
+    return CPT_OK;
+}
+
 int cpt_debug_kernel_times(cpt_ctx *c, int enable, float *h_ms4) {
     if (!c) return fail(CPT_ERR_INVALID, "null ctx");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -390,13 +396,15 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         a.defer_variance = 1;
     }
     // Batch launches that keep the filtered images and carry no per-clip state take the split path: the recurrence as a
-    // persistent sweep kernel, then one CTA per frame for masks / components.  Everything else (streaming, resumed
-    // clips, regions-only launches) runs the single persistent kernel with its three warp roles.
+    // persistent sweep kernel, then one CTA per frame for masks / components.  A state record may be written (not
+    // resumed from).  Everything else (streaming, resumed clips, regions-only launches) runs the single persistent
+    // kernel with its three warp roles.
     const bool timed = c->time_kernels && c->ev_k[0];
     if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[0], stream));
     static const bool split_allowed = [] { const char *e = getenv("CPT_SPLIT"); return !(e && e[0] == '0'); }();
     // (the sweep kernel stages frame rows with 16-byte bulk copies: rows must be a multiple of 8 pixels)
-    const bool split = split_allowed && d_state == nullptr && out->d_filtered != nullptr && total_frames > 0 && c->g.W % 8 == 0;
+    const bool split = split_allowed && !c->force_single && (d_state == nullptr || out->no_resume) && out->d_filtered != nullptr &&
+                       total_frames > 0 && c->g.W % 8 == 0;
     if (split) {
         if (c->hot_frames < (size_t)total_frames) {
             CUDA_TRY(cudaStreamSynchronize(stream));

@@ -52,6 +52,7 @@ struct cpt_ctx {
     uint32_t *hot = nullptr;   // hot-quad words of the split extraction path, [hot_frames][kHotStride]
     uint32_t *maskbits = nullptr;  // thresholded masks between frame_mask_kernel and frame_components_kernel
     size_t hot_frames = 0;
+    bool force_single = false;  // cpt_debug_force_single_kernel
     bool time_kernels = false;  // cpt_debug_kernel_times
     bool timed_valid = false;
     cudaEvent_t ev_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

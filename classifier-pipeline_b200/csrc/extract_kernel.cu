@@ -1660,7 +1660,8 @@ __global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const Kerne
         const int ci = s.bcast_i[15];
         if (ci >= a.n_clips) break;
         const cpt_clip clip = a.clips[ci];
-        if (tid < kPThreads) sweep_warps<true>(a, s, clip, tid, nullptr, nullptr);
+        uint8_t *st_raw = a.state ? a.state + (size_t)ci * state_bytes(a.g.npx) : nullptr;  // written at the end of the clip
+        if (tid < kPThreads) sweep_warps<true>(a, s, clip, tid, nullptr, st_raw);
         else if (tid < kPThreads + 32) scalar_warp(a, s, clip, tid - kPThreads);
         else producer_warp(a, s, clip, tid - kPThreads - 32);
     }

@@ -77,7 +77,7 @@ MOTION_MEAN, MOTION_MEAN_RESTART, MOTION_BACKGROUND, MOTION_DETECT, MOTION_WARME
 class CptOutputs(ctypes.Structure):
     _fields_ = [
         ("d_regions", ctypes.c_void_p), ("d_info", ctypes.c_void_p), ("d_filtered", ctypes.c_void_p),
-        ("d_labels", ctypes.c_void_p), ("total_frames", ctypes.c_int64), ("denoise", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("d_labels", ctypes.c_void_p), ("total_frames", ctypes.c_int64), ("denoise", ctypes.c_int32), ("no_resume", ctypes.c_int32),
     ]
 
 
@@ -121,6 +121,7 @@ SYMBOLS = {
     "cpt_build_weight_table": (_i, [_d, _i, _vp, _vp]),
     "cpt_debug_phase_cycles": (_i, [_vp, _vp, _i]),
     "cpt_debug_kernel_times": (_i, [_vp, _i, _vp]),
+    "cpt_debug_force_single_kernel": (_i, [_vp, _i]),
     "cpt_device_alloc": (_i, [_vp, ctypes.POINTER(_vp), _u64]),
     "cpt_device_free": (_i, [_vp, _vp]),
     "cpt_host_alloc_pinned": (_i, [ctypes.POINTER(_vp), _u64]),
@@ -239,9 +240,14 @@ class Context:
         return self.lib.cpt_weight_value(self._h, slot, int(count))
 
     def extract_batch(self, d_frames, d_clips, n_clips, d_regions, d_info, d_filtered=None, d_labels=None, d_state=None,
-                      total_frames=0, denoise=False):
-        out = CptOutputs(_ptr(d_regions), _ptr(d_info), _ptr(d_filtered), _ptr(d_labels), int(total_frames), int(bool(denoise)), 0)
+                      total_frames=0, denoise=False, no_resume=False):
+        out = CptOutputs(_ptr(d_regions), _ptr(d_info), _ptr(d_filtered), _ptr(d_labels), int(total_frames), int(bool(denoise)),
+                         int(bool(no_resume)))
         check(self.lib.cpt_extract_batch(self._h, _ptr(d_frames), _ptr(d_clips), int(n_clips), ctypes.byref(out), _ptr(d_state)))
+
+    def force_single_kernel(self, enable=True):
+        """Tests / diagnostics: run the single persistent kernel also where the split plan would apply."""
+        check(self.lib.cpt_debug_force_single_kernel(self._h, int(bool(enable))))
 
     def extract_batch_host(self, h_frames, h_clips, total_frames, h_regions, h_info, h_filtered=None, h_labels=None, chunk_clips=0):
         check(

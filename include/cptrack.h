@@ -100,7 +100,8 @@ typedef struct {
     int32_t denoise;         /* 1: some clip carries CPT_CLIP_DENOISE -- the normalised images then go through
                                 cv2.fastNlMeansDenoising and the mask / component passes after the recurrence
                                 (needs total_frames and d_filtered; not with CPT_CLIP_RESUME) */
-    int32_t reserved;
+    int32_t no_resume;       /* 1: no clip of this launch carries CPT_CLIP_RESUME (d_state, if given, is only written).
+                                Lets a launch with a state record take the split plan of DESIGN.md section 3.1; 0 is always safe */
 } cpt_outputs;
 
 /* Persistent per-clip state (WeightedBackground + sliding sum), one record per clip:
@@ -141,6 +142,10 @@ int cpt_debug_phase_cycles(cpt_ctx *ctx, long long *h_out32, int reset);
  * [0] the recurrence kernel (extract_sweep_kernel, or extract_clips_kernel on the single-kernel path), [1]
  * frame_mask_kernel + frame_components_kernel (0 on the single-kernel path), [2] the denoise passes, [3] region_variance_kernel. */
 int cpt_debug_kernel_times(cpt_ctx *ctx, int enable, float *h_ms4);
+
+/* Diagnostics / tests: with enable != 0 every extraction launch of this ctx runs the single persistent kernel, also where
+ * the split plan would apply (both plans produce identical results). */
+int cpt_debug_force_single_kernel(cpt_ctx *ctx, int enable);
 
 /* Bytes of one per-clip state record for this ctx's geometry. */
 uint64_t cpt_state_bytes(const cpt_ctx *ctx);

@@ -32,8 +32,8 @@ def _run_device(extractor, init, tracked, bt, weight_add, flags=None, keep_state
     clips["frame_offset"] = 1
     clips["init_offset"] = 0
     clips["out_offset"] = 0
-    # keep_state=True: the single persistent kernel (three warp roles); without a state record the launch takes the
-    # split path (sweep kernel + per-frame kernels), see DESIGN.md section 3.1
+    # (with or without a state record the launch takes the split plan -- sweep kernel + per-frame kernels -- unless the
+    # `plan` fixture forces the single persistent kernel)
     out = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, keep_state=keep_state, out={})
     torch.cuda.synchronize()
     return out
@@ -66,8 +66,17 @@ def _compare_with_oracle(extractor, out, o, T, slot_weight_add, with_state=True)
     assert st["frames_seen"] == T
 
 
+@pytest.fixture(params=["split", "single"])
+def plan(request, extractor):
+    """Both launch plans of DESIGN.md section 3.1: batch launches that keep the filtered images take the split plan unless the
+    ctx is told to run the single persistent kernel."""
+    extractor.ctx.force_single_kernel(request.param == "single")
+    yield request.param
+    extractor.ctx.force_single_kernel(False)
+
+
 @pytest.mark.parametrize("name", RAW)
-def test_kernel_matches_oracle_and_reference(extractor, name):
+def test_kernel_matches_oracle_and_reference(extractor, name, plan):
     from oracle import oracle as orc
 
     d, meta = helpers.load_golden(name)
@@ -126,11 +135,16 @@ def test_split_and_single_kernel_paths_agree_on_a_ragged_batch(extractor):
     clips["out_offset"] += 3 * np.arange(len(lengths))  # gaps: output frames no clip writes
     d_frames = torch.from_numpy(frames.view(np.int16)).cuda().view(torch.uint16)
     outs = []
-    for keep_state in (True, False):
-        o = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, keep_state=keep_state, out={})
-        torch.cuda.synchronize()
-        outs.append(o)
+    try:
+        for single in (True, False):
+            extractor.ctx.force_single_kernel(single)
+            o = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, keep_state=True, out={})
+            torch.cuda.synchronize()
+            outs.append(o)
+    finally:
+        extractor.ctx.force_single_kernel(False)
     a, b = outs
+    assert torch.equal(a["state"], b["state"])  # the saved per-clip records (background, counters, sums, last filtered image)
     ia, ib = extractor.info_numpy(a["info"]), extractor.info_numpy(b["info"])
     ra, rb = extractor.regions_numpy(a["regions"]), extractor.regions_numpy(b["regions"])
     fa, fb = a["filtered"].cpu().numpy(), b["filtered"].cpu().numpy()
@@ -150,7 +164,7 @@ def test_split_and_single_kernel_paths_agree_on_a_ragged_batch(extractor):
     assert seen > 50
 
 
-def test_batch_of_ragged_clips_matches_single_clip_runs(extractor):
+def test_batch_of_ragged_clips_matches_single_clip_runs(extractor, plan):
     """Clips are independent: a ragged batch (incl. an empty clip) equals per-clip oracle runs."""
     import torch
     from classifier_pipeline_b200 import native
