@@ -360,3 +360,48 @@ def test_mixed_batch_denoise_and_plain(extractor):
         for t in range(n):
             k = int(o["ncomp"][t])
             np.testing.assert_allclose(regions[o0 + t, :k]["pixel_variance"], o["var"][t, :k], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("geom", [(80, 64, 1), (128, 96, 1), (152, 40, 1), (160, 120, 0)])
+@pytest.mark.parametrize("single", [False, True])
+def test_other_geometries_match_the_oracle(geom, single):
+    """The generic (rolled, unbalanced) sweep, generic staging chunks and generic hot-row extraction: frames that are not
+    160x120 with a 1-pixel border, under both launch plans."""
+    import torch
+    from classifier_pipeline_b200.batch import BatchExtractor, linear_clips
+    from classifier_pipeline_b200.synthetic import make_clip
+    from oracle import oracle as orc
+
+    W, H, edge = geom
+    ex = BatchExtractor(device=0, width=W, height=H, edge_pixels=edge, max_regions=32)
+    ex.ctx.force_single_kernel(single)
+    lengths = [60, 3, 47]
+    pix = [make_clip(70 + i, frames=n, width=W, height=H)[0] for i, n in enumerate(lengths)]
+    slot = ex.ctx.weight_table(0.1, max_frames=1024)
+    clips = linear_clips(lengths, 20, slot)
+    d_frames = torch.from_numpy(np.concatenate(pix).view(np.int16)).cuda().view(torch.uint16)
+    out = ex.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, keep_state=True, out={})
+    torch.cuda.synchronize()
+    regions = ex.regions_numpy(out["regions"])
+    info = ex.info_numpy(out["info"])
+    filtered = out["filtered"].cpu().numpy()
+    labels = out["labels"].cpu().numpy()
+    p = orc.make_params(W=W, H=H, edge=edge, background_thresh=20, weight_add=0.1, max_comp=32)
+    seen = 0
+    for i, n in enumerate(lengths):
+        o0 = int(clips["out_offset"][i])
+        o = orc.extract_clip(pix[i], pix[i][0], p)
+        assert np.array_equal(filtered[o0 : o0 + n], o["filtered"]), i
+        assert np.array_equal(labels[o0 : o0 + n], o["labels"]), i
+        assert np.array_equal(info["n_components"][o0 : o0 + n], o["ncomp"]), i
+        assert np.array_equal(info["threshold"][o0 : o0 + n], o["thresh"]), i
+        for t in range(n):
+            k = int(o["ncomp"][t])
+            seen += k
+            r = regions[o0 + t, :k]
+            got = np.stack([r["x"], r["y"], r["width"], r["height"], r["area"], r["sum_x"], r["sum_y"], r["key"]], axis=1)
+            assert np.array_equal(got, o["comp"][t, :k])
+            np.testing.assert_allclose(r["pixel_variance"], o["var"][t, :k], rtol=1e-6, atol=1e-6)
+        st = ex.ctx.state_read(out["state"], i)
+        assert np.array_equal(st["background"], o["final_bg"]), i
+    assert seen > 0
