@@ -73,12 +73,6 @@ __device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
     return r != 0;
 }
 
-__device__ __forceinline__ int reflect101(int p, int n) {
-    if (n == 1) return 0;
-    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * n - 2 - p;
-    return p;
-}
-
 __device__ __forceinline__ const uint16_t *frame_ptr(const KernelArgs &a, const cpt_clip &c, int t) {
     int64_t idx = c.ring_frames ? (int64_t)((c.first_frame + t) % c.ring_frames) : (int64_t)t;
     return a.frames + (size_t)(c.frame_offset + idx) * a.g.npx;
