@@ -1825,6 +1825,31 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
     }
 }
 
+// K6 for one region record: variance of |norm255(F_t) - norm255(F_t-1)| over the component's bounding box; one warp.
+// (one summation order everywhere it is used, so both launch plans give identical bits)
+__device__ __forceinline__ void region_variance_warp(const Geometry &g, cpt_region *reg, const float *fcur, const float *fprev, int cur_fmin,
+                                                     int cur_fmax, int prev_fmin, int prev_fmax, bool exact, int lane) {
+    const int l = reg->x, tp = reg->y, bw = reg->width, bh = reg->height, npix = bw * bh;
+    if (l < 0 || tp < 0 || bw < 1 || bh < 1 || l + bw > g.W || tp + bh > g.H) return;  // not a record of this launch
+    double s1 = 0.0, s2 = 0.0;
+    const uint32_t rcp = 0xffffffffu / (uint32_t)bw + 1u;  // i / bw == umulhi(i, rcp) for i * bw < 2^32
+    for (int i = lane; i < npix; i += 32) {
+        const int yy = bw == 1 ? i : (int)__umulhi((uint32_t)i, rcp), xx = i - yy * bw, p = (tp + yy) * g.W + l + xx;  // (rcp wraps to 0 for bw == 1)
+        const int fc = (int)__ldg(fcur + p), fp = (int)__ldg(fprev + p);
+        const float d = fabsf(norm255(fc, cur_fmin, cur_fmax, exact) - norm255(fp, prev_fmin, prev_fmax, exact));
+        s1 += (double)d;
+        s2 += (double)d * (double)d;
+    }
+    for (int off = 16; off; off >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) {
+        const double cnt = (double)npix, mean = s1 / cnt, var = s2 / cnt - mean * mean;
+        reg->pixel_variance = var > 0.0 ? var : 0.0;
+    }
+}
+
 // Split path, third launch: one CTA per frame.  The frame's mask -> close -> components, statistics, labels (K4, K5); the
 // variances are left to region_variance_kernel.
 __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const KernelArgs a, long long total_frames) {
@@ -1858,7 +1883,9 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
     if (!__syncthreads_or(any)) return;  // empty mask: info.n_components stays 0
     const float *fcur = a.filtered + (size_t)o * g.npx;
     const bool have_prev = !(hdr.w & 2u);  // not the first frame of its clip
-    // (computing the variances here was measured slower than the separate wide pass: +4.1 ms against 2.6 ms)
+    // (variances in this kernel were measured slower than the separate wide pass, whose warps hide the cold reads of
+    // the filtered images: components_of_frame's own path +4.1 ms, one warp per region record as a tail here +7.9 ms,
+    // against the 2.4 ms of region_variance_kernel)
     components_of_frame<CompSmem, kGThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, fi->filtered_min, fi->filtered_max, 0, 0,
                                                  have_prev, true);
 }
@@ -1911,28 +1938,8 @@ __global__ void __launch_bounds__(256) region_variance_kernel(Geometry g, long l
     const bool exact = 255ll * max(cur_fmax - cur_fmin, prev_fmax - prev_fmin) < (1ll << 24) &&
                        max(max(abs(cur_fmax), abs(cur_fmin)), max(abs(prev_fmax), abs(prev_fmin))) < (1 << 24);
     const float *fcur = filtered + (size_t)o * g.npx, *fprev = fcur - g.npx;
-    for (int r = 0; r < n; ++r) {
-        cpt_region *reg = regions + (size_t)o * g.max_regions + r;
-        const int l = reg->x, tp = reg->y, bw = reg->width, bh = reg->height, npix = bw * bh;
-        if (l < 0 || tp < 0 || bw < 1 || bh < 1 || l + bw > g.W || tp + bh > g.H) continue;  // not a record of this launch
-        double s1 = 0.0, s2 = 0.0;
-        const uint32_t rcp = 0xffffffffu / (uint32_t)bw + 1u;  // i / bw == umulhi(i, rcp) for i * bw < 2^32
-        for (int i = lane; i < npix; i += 32) {
-            const int yy = bw == 1 ? i : (int)__umulhi((uint32_t)i, rcp), xx = i - yy * bw, p = (tp + yy) * g.W + l + xx;  // (rcp wraps to 0 for bw == 1)
-            const int fc = (int)__ldg(fcur + p), fp = (int)__ldg(fprev + p);
-            const float d = fabsf(norm255(fc, cur_fmin, cur_fmax, exact) - norm255(fp, prev_fmin, prev_fmax, exact));
-            s1 += (double)d;
-            s2 += (double)d * (double)d;
-        }
-        for (int off = 16; off; off >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-        }
-        if (lane == 0) {
-            const double cnt = (double)npix, mean = s1 / cnt, var = s2 / cnt - mean * mean;
-            reg->pixel_variance = var > 0.0 ? var : 0.0;
-        }
-    }
+    for (int r = 0; r < n; ++r)
+        region_variance_warp(g, regions + (size_t)o * g.max_regions + r, fcur, fprev, cur_fmin, cur_fmax, prev_fmin, prev_fmax, exact, lane);
     if (lane == 0) fi->reserved[0] = 0;
 }
 
