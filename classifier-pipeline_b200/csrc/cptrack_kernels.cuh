@@ -34,19 +34,24 @@ namespace cpt {
 // warp-specialised pipeline over consecutive frames: sweep warps (the recurrence), mask warps (scalars, work lists,
 // normalise, blur) and component warps (labelling)
 // Sweep-warp count (tools/gpu_exp.sh builds -DCPT_EXP=<n> variants for A/B runs; the measured alternatives are in
-// DESIGN.md section 7).  640 = 16 row groups (7 or 8 quads per thread), 800 = 20 groups (split path only: the single
-// persistent kernel cannot hold 25 + 4 + 8 warps).
+// DESIGN.md section 7).  640 = 16 row groups (7 or 8 quads per thread); 480 / 800 / 960 = 12 / 20 / 24 balanced groups of
+// 10 / 6 / 5 quads (800 and 960: split path only -- the single persistent kernel cannot hold that many warps next to
+// its mask and component warps, so those builds shrink the two roles to placeholders).
 #if CPT_EXP == 10
 constexpr int kPThreads = 640;
 #elif CPT_EXP == 5
 constexpr int kPThreads = 800;
+#elif CPT_EXP == 4
+constexpr int kPThreads = 960;
+#elif CPT_EXP == 2
+constexpr int kPThreads = 480;
 #else
 // 19 sweep warps: 15 rows x 40 quads per iteration at 160 pixels (the last 8 threads idle).  120 rows / 15 row groups = 8
 // quads for every thread once the two border rows are balanced (Geometry::balanced): no warp is ever ahead of another.
 constexpr int kPThreads = 608;
 #endif
 constexpr int kPWarps = kPThreads / 32;
-#if CPT_EXP == 5
+#if CPT_EXP == 5 || CPT_EXP == 4
 constexpr int kMThreads = 32;
 constexpr int kCThreads = 32;
 #else

@@ -574,7 +574,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // Split path: the frame rows of one sweep iteration (P and the rows of the frame leaving the window) are staged in shared
 // memory by a producer warp, kStages iterations ahead of the sweep warps (full / empty mbarrier per stage).  The ring
 // lives in the part of Smem only the mask / component warps of the single-kernel path use.
-constexpr int kStages = (kPThreads > 640) ? 4 : 5;
+constexpr int kStages = kPThreads > 800 ? 3 : (kPThreads > 640 ? 4 : (kPThreads < 600 ? 6 : 5));
 constexpr int kStageHalf = kPThreads * 8 + 2 * kMaxW;  // rows_per_it * W <= 4 * kPThreads pixels, plus one remapped row
 constexpr int kStageBytes = 2 * kStageHalf;  // P rows, then P_old rows
 struct SoloStage {
