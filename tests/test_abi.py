@@ -67,3 +67,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_clip_flags_match_header():
+    """The Python constants of the clip flags are the header's #defines."""
+    from classifier_pipeline_b200 import native
+
+    text = open(os.path.join(ROOT, "include", "cptrack.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+CPT_CLIP_([A-Z_]+)\s+(\d+)u", text)}
+    assert set(flags) >= {"UPDATE_BACKGROUND", "RESUME", "DENOISE", "FRAME_STATS", "SKIP_FIRST_UPDATE"}
+    for name, value in flags.items():
+        assert getattr(native, "CLIP_" + name) == value, name
+    assert len(set(flags.values())) == len(flags) and all(v & (v - 1) == 0 for v in flags.values())
