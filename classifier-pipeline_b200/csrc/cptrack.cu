@@ -14,7 +14,9 @@
 namespace cpt {
 __global__ void extract_clips_kernel(const KernelArgs a);
 __global__ void mask_components_kernel(const KernelArgs a, long long total_frames, const uint8_t *denoised);
-__global__ void extract_sweep_kernel(const KernelArgs a);
+__global__ void strip_sweep_kernel(const KernelArgs a);
+__global__ void frame_scalars_kernel(const KernelArgs a);
+size_t strip_sweep_smem_bytes();
 __global__ void frame_mask_kernel(const KernelArgs a, long long total_frames);
 __global__ void frame_components_kernel(const KernelArgs a, long long total_frames);
 int nlm_launch(cpt_ctx *c, const uint8_t *d_src, int width, int height, long long n_frames, uint8_t *d_dst, const cpt_frame_info *info,
@@ -76,6 +78,12 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     g.gpr_magic = ((1u << 17) + g.gpr - 1) / g.gpr;
     g.rw_magic = ((1u << 13) + g.row_words - 1) / g.row_words;
     g.qpr = width / 4;
+    {
+        // strips of whole rows, at most kStripPxMax pixels, split evenly (a border row and the owned row next to it always
+        // share a strip: every strip has at least two rows)
+        const int rmax = std::max(cpt::kStripPxMax / width, 1);
+        g.n_strips = (height + rmax - 1) / rmax;
+    }
     g.rows_per_it = cpt::kPThreads / g.qpr;
     g.balanced = 0;
     g.bal_a_oy = g.bal_a_r = g.bal_b_oy = g.bal_b_r = -1;
@@ -111,8 +119,8 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
     c->stream = c->own_stream;
     if (cudaFuncSetAttribute(cpt::extract_clips_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(cpt::Smem)) != cudaSuccess ||
-        cudaFuncSetAttribute(cpt::extract_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(cpt::Smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(cpt::strip_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)cpt::strip_sweep_smem_bytes()) != cudaSuccess ||
         cudaFuncSetAttribute(cpt::frame_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(cpt::MaskSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(cpt::frame_components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -153,9 +161,11 @@ void cpt_ctx_destroy(cpt_ctx *c) {
         cudaFree(t.d_thr);
     }
     cudaFree(c->scratch);
-    cudaFree(c->hot);
+    cudaFree(c->qbytes);
+    cudaFree(c->prec);
+    cudaFree(c->fhdr);
     cudaFree(c->maskbits);
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 6; ++i)
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     cudaFree(c->work_counter);
     cudaFree(c->zero_frame);
@@ -331,13 +341,29 @@ int cpt_debug_force_single_kernel(cpt_ctx *c, int enable) {
 int cpt_debug_kernel_times(cpt_ctx *c, int enable, float *h_ms4) {
     if (!c) return fail(CPT_ERR_INVALID, "null ctx");
     CUDA_TRY(cudaSetDevice(c->device));
-    if (enable && !c->ev_k[0])
-        for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&c->ev_k[i]));
+    float ms5[5];
+    int rc = cpt_debug_kernel_times_ex(c, enable, h_ms4 ? ms5 : nullptr, 5);
+    if (rc) return rc;
     if (h_ms4) {
-        for (int i = 0; i < 4; ++i) h_ms4[i] = 0.f;
+        h_ms4[0] = ms5[0];
+        h_ms4[1] = ms5[1] + ms5[2];
+        h_ms4[2] = ms5[3];
+        h_ms4[3] = ms5[4];
+    }
+    return CPT_OK;
+}
+
+int cpt_debug_kernel_times_ex(cpt_ctx *c, int enable, float *h_ms, int n) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    if (h_ms && (n < 1 || n > 5)) return fail(CPT_ERR_INVALID, "n must be in [1,5]");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (enable && !c->ev_k[0])
+        for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&c->ev_k[i]));
+    if (h_ms) {
+        for (int i = 0; i < n; ++i) h_ms[i] = 0.f;
         if (c->timed_valid) {
-            CUDA_TRY(cudaEventSynchronize(c->ev_k[4]));
-            for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&h_ms4[i], c->ev_k[i], c->ev_k[i + 1]));
+            CUDA_TRY(cudaEventSynchronize(c->ev_k[5]));
+            for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&h_ms[i], c->ev_k[i], c->ev_k[i + 1]));
         }
     }
     c->time_kernels = enable != 0;
@@ -406,23 +432,35 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     const bool split = split_allowed && !c->force_single && (d_state == nullptr || out->no_resume) && out->d_filtered != nullptr &&
                        total_frames > 0 && c->g.W % 8 == 0;
     if (split) {
-        if (c->hot_frames < (size_t)total_frames) {
+        const size_t qb_frame = (size_t)c->g.H * c->g.qpr;
+        if (c->split_frames < (size_t)total_frames || c->split_clips < (size_t)n_clips) {
             CUDA_TRY(cudaStreamSynchronize(stream));
-            cudaFree(c->hot);
-            cudaFree(c->maskbits);
-            c->hot = c->maskbits = nullptr;
-            c->hot_frames = 0;
-            CUDA_TRY(cudaMalloc(&c->hot, (size_t)total_frames * cpt::kHotStride * sizeof(uint32_t)));
-            CUDA_TRY(cudaMalloc(&c->maskbits, (size_t)total_frames * cpt::kMaxWords * sizeof(uint32_t)));
-            c->hot_frames = (size_t)total_frames;
+            cudaFree(c->qbytes); cudaFree(c->prec); cudaFree(c->fhdr); cudaFree(c->maskbits);
+            c->qbytes = nullptr; c->prec = nullptr; c->fhdr = nullptr; c->maskbits = nullptr;
+            c->split_frames = c->split_clips = 0;
+            const size_t nf = std::max(c->split_frames, (size_t)total_frames), nc = std::max(c->split_clips, (size_t)n_clips);
+            CUDA_TRY(cudaMalloc(&c->qbytes, nf * qb_frame));
+            CUDA_TRY(cudaMalloc(&c->prec, (nf + nc) * c->g.n_strips * sizeof(cpt::StripRec)));
+            CUDA_TRY(cudaMalloc(&c->fhdr, nf * sizeof(cpt::FrameHdr)));
+            CUDA_TRY(cudaMalloc(&c->maskbits, nf * cpt::kMaxWords * sizeof(uint32_t)));
+            c->split_frames = nf;
+            c->split_clips = nc;
         }
-        a.hot = c->hot;
+        a.qbytes = c->qbytes;
+        a.prec = c->prec;
+        a.fhdr = c->fhdr;
         a.maskbits = c->maskbits;
-        // the valid flag of every output frame starts cleared: frames no clip writes are skipped by the second launch
-        CUDA_TRY(cudaMemsetAsync(c->hot, 0, (size_t)total_frames * cpt::kHotStride * sizeof(uint32_t), stream));
-        cpt::extract_sweep_kernel<<<grid, cpt::kSThreads, sizeof(cpt::Smem), stream>>>(a);
+        a.total_frames = total_frames;
+        // the valid flag of every output frame starts cleared: frames no clip writes are skipped by the per-frame launches
+        CUDA_TRY(cudaMemsetAsync(c->fhdr, 0, (size_t)total_frames * sizeof(cpt::FrameHdr), stream));
+        const long long units = (long long)n_clips * c->g.n_strips;
+        const int sgrid = (int)std::min<long long>(units, c->num_sms);
+        cpt::strip_sweep_kernel<<<sgrid, cpt::kStripThreads, cpt::strip_sweep_smem_bytes(), stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[1], stream));
+        cpt::frame_scalars_kernel<<<(n_clips + 3) / 4, 128, 0, stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[2], stream));
         cpt::frame_mask_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::MaskSmem), stream>>>(a, total_frames);
         CUDA_TRY(cudaGetLastError());
         cpt::frame_components_kernel<<<(unsigned)total_frames, cpt::kGThreads, sizeof(cpt::CompSmem), stream>>>(a, total_frames);
@@ -430,9 +468,12 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     } else {
         cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
         CUDA_TRY(cudaGetLastError());
-        if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[1], stream));
+        if (timed) {
+            CUDA_TRY(cudaEventRecord(c->ev_k[1], stream));
+            CUDA_TRY(cudaEventRecord(c->ev_k[2], stream));
+        }
     }
-    if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[2], stream));
+    if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[3], stream));
     if (out->denoise) {
         int rc = cpt::nlm_launch(c, c->u8_frames[0], c->g.W, c->g.H, total_frames, c->u8_frames[1], out->d_info, stream);
         if (rc) return rc;
@@ -442,14 +483,14 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         cpt::mask_components_kernel<<<mgrid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a, total_frames, c->u8_frames[1]);
         CUDA_TRY(cudaGetLastError());
     }
-    if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[3], stream));
+    if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[4], stream));
     if (a.defer_variance) {
         const unsigned blocks = (unsigned)((total_frames + 7) / 8);
         cpt::region_variance_kernel<<<blocks, 256, 0, stream>>>(c->g, total_frames, out->d_filtered, out->d_info, out->d_regions);
         CUDA_TRY(cudaGetLastError());
     }
     if (timed) {
-        CUDA_TRY(cudaEventRecord(c->ev_k[4], stream));
+        CUDA_TRY(cudaEventRecord(c->ev_k[5], stream));
         c->timed_valid = true;
     }
     return CPT_OK;

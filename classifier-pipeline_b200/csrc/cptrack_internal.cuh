@@ -49,13 +49,17 @@ struct cpt_ctx {
     cpt::HostWeightTable tables[4];
     float *scratch = nullptr;
     size_t scratch_ctas = 0;
-    uint32_t *hot = nullptr;   // hot-quad words of the split extraction path, [hot_frames][kHotStride]
-    uint32_t *maskbits = nullptr;  // thresholded masks between frame_mask_kernel and frame_components_kernel
-    size_t hot_frames = 0;
+    // scratch of the split extraction path (grown on demand): quad bytes, strip pass records, per-frame headers and the
+    // thresholded masks between frame_mask_kernel and frame_components_kernel
+    int8_t *qbytes = nullptr;
+    cpt::StripRec *prec = nullptr;
+    cpt::FrameHdr *fhdr = nullptr;
+    uint32_t *maskbits = nullptr;
+    size_t split_frames = 0, split_clips = 0;
     bool force_single = false;  // cpt_debug_force_single_kernel
     bool time_kernels = false;  // cpt_debug_kernel_times
     bool timed_valid = false;
-    cudaEvent_t ev_k[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_k[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int *work_counter = nullptr;
     uint16_t *zero_frame = nullptr;
     long long *debug = nullptr;

@@ -104,6 +104,9 @@ struct Geometry {
     // row groups whose last iteration is free (owned_row_slot): owned row bal_a_oy -> group bal_a_r, bal_b_oy -> bal_b_r
     int balanced;
     int bal_a_oy, bal_a_r, bal_b_oy, bal_b_r;
+    // strip sweep (strip_sweep.cu): the frame is cut into n_strips bands of whole rows, strip s = rows
+    // [s * H / n_strips, (s + 1) * H / n_strips), at most kStripPxMax pixels each
+    int n_strips;
 };
 
 // sweep slot (iteration, row group) that processes owned row oy; its quads are sweep threads r * qpr .. r * qpr + qpr - 1
@@ -147,6 +150,33 @@ struct WeightTable {
     int linear_upto;  // entries [0, linear_upto) are exactly thr = k + 1, bound = 0 (weight_add == 1)
 };
 constexpr int kSmemWeights = 1024;
+
+// ---- strip sweep (split path, strip_sweep.cu) -------------------------------------------------
+constexpr int kStripPxMax = 1920;   // pixels of one strip (12 rows at 160 pixels): 480 quads, one per consumer thread
+constexpr int kMaxStrips = 16;
+constexpr int kStripThreads = kStripPxMax / 4 + 32;  // one consumer thread per quad + the producer warp
+// What one strip CTA found in one pass (frame t, or the tail pass that only applies the last background update), folded
+// over its warps.  [pass][strip] in global memory; frame_scalars_kernel folds the strips of a frame.
+struct StripRec {
+    uint32_t psum;     // sum of the strip's thermal pixels
+    int32_t fmin, fmax;  // extrema of filtered = thermal - background over the strip
+    int32_t nbsum;     // minus the sum of the background over the strip's crop pixels (after this pass's update)
+    int32_t pmin, pmax;  // thermal extrema (CPT_CLIP_FRAME_STATS)
+    uint32_t fabs_sum; // sum |filtered| (CPT_CLIP_FRAME_STATS)
+    int32_t ref_changed;  // (reference the strip's quad bytes were stored against) << 1 | (some background pixel changed)
+};
+static_assert(sizeof(StripRec) == 32, "two 16-byte vectors");
+// Per output frame, written by frame_scalars_kernel for the per-frame kernels.
+struct FrameHdr {
+    uint32_t nmagic;   // (255 v) / range == (255 v * nmagic) >> nshift; 0: the fp32 divide
+    int32_t nshift;
+    uint32_t flags;    // 1: valid, 2: first frame of its clip, 4: empty mask, 8: dense (no usable bound for the quad bytes)
+    uint32_t hot_strips;  // bit s: strip s may hold a hot quad
+    int16_t theta[kMaxStrips];  // quad byte b of strip s is hot <=> b >= theta[s]
+};
+static_assert(sizeof(FrameHdr) == 48, "three 16-byte vectors");
+constexpr uint32_t kHdrValid = 1u, kHdrFirst = 2u, kHdrEmpty = 4u, kHdrDense = 8u;
+constexpr int kQuadRefBias = 64;    // a strip's quad bytes are stored against (its min filtered value some frames ago) + bias
 constexpr int kListCap = 1024;  // marked groups per frame handled through the work lists (more: dense sweep)
 
 struct KernelArgs {
@@ -167,6 +197,11 @@ struct KernelArgs {
     const uint16_t *zero_frame;  // npx zeros: stands in for the frame leaving the 45-frame window while it fills
     uint32_t *hot;        // [total_frames][kHotStride] (split path), else nullptr
     uint32_t *maskbits;   // [total_frames][kMaxWords] thresholded masks between the two per-frame kernels (split path)
+    // strip sweep outputs (split path)
+    int8_t *qbytes;       // [total_frames][H][qpr] per quad: max filtered - strip reference, saturated to int8
+    StripRec *prec;       // [total_frames + n_clips][n_strips]: pass records (clip ci's tail pass at total_frames + ci)
+    FrameHdr *fhdr;       // [total_frames]
+    long long total_frames;
     WeightTable tables[4];
 };
 
@@ -218,7 +253,7 @@ struct __align__(16) Smem {
 struct __align__(16) MaskSmem {
     uint8_t U[kMaxPx];
     uint16_t list_u[kListCap], list_b[kListCap];
-    uint32_t hotw[kHotStride];
+    int16_t theta[kMaxStrips];
     unsigned long long hot64[kMaxH];
     uint32_t M[1][kMaxWords];
     int32_t bcast_i[16];

@@ -1521,70 +1521,6 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
     bar_arrive(BAR_DONE, kThreads);
 }
 
-// ================================================================================================
-// split path, scalar warp: one frame behind the sweep.  Lane 0 turns the sweep's message into the frame's info record,
-// publishes the byte threshold for the sweep warps' ballots and the constants the per-frame kernels need.
-// ================================================================================================
-__device__ void scalar_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, int lane) {
-    const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
-    const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
-    const bool denoise = clip.flags & CPT_CLIP_DENOISE;
-    bar_sync(BAR_INIT, kSThreads);
-    double average = s.init_average;
-    int prev_fmin = 0, prev_fmax = 0, have_prev = 0;
-    for (int t = 0; t <= clip.n_frames; ++t) {
-        CPT_TICK_START2(lane == 0);
-        const bool is_frame = t < clip.n_frames;
-        if (!(update_bg && t > 0 && !((clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE) && clip.first_frame + t == 1)) && !is_frame) break;
-        const int b = t & 1;
-        const size_t o = (size_t)(clip.out_offset + t);
-        bar_sync(BAR_SM_FULL + b, kPThreads + 32);  // the sweep of frame t is done
-        CPT_TICK2(lane == 0, 7);   // waiting for the sweep
-        {
-            // fold the sweep warps' partial results (one row per warp) into the message
-            const uint32_t *row = s.red_u + (b * kPWarps + lane) * 8;
-            const bool in = lane < kPWarps;
-            const uint32_t psum = __reduce_add_sync(0xffffffffu, in ? row[0] : 0u);
-            const int fmin = __reduce_min_sync(0xffffffffu, in ? (int)row[1] : INT32_MAX);
-            const int fmax = __reduce_max_sync(0xffffffffu, in ? (int)row[2] : INT32_MIN);
-            const uint32_t bsum = __reduce_add_sync(0xffffffffu, in ? row[6] : 0u);
-            const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? row[7] : 0u);
-            int pmin = 0, pmax = 0;
-            uint32_t fabs_sum = 0;
-            if (want_stats) {
-                pmin = __reduce_min_sync(0xffffffffu, in ? (int)row[3] : INT32_MAX);
-                pmax = __reduce_max_sync(0xffffffffu, in ? (int)row[4] : INT32_MIN);
-                fabs_sum = __reduce_add_sync(0xffffffffu, in ? row[5] : 0u);
-            }
-            if (lane == 0) {
-                uint32_t *r = s.fm[b].red;
-                r[0] = psum; r[1] = (uint32_t)fmin; r[2] = (uint32_t)fmax; r[3] = (uint32_t)pmin; r[4] = (uint32_t)pmax;
-                r[5] = fabs_sum; r[6] = bsum; r[7] = changed;
-            }
-        }
-        if (lane == 0) {
-            frame_scalars(a, s, clip, s.fm[b], o, is_frame, want_stats, average);
-            if (is_frame) {
-                s.tu_pub[b] = s.bcast_i[8];
-                *reinterpret_cast<uint4 *>(a.hot + o * kHotStride + kHotWords) =
-                    make_uint4((uint32_t)s.bcast_i[8], (uint32_t)s.bcast_i[13], (uint32_t)s.bcast_i[14], 1u | (t == 0 ? 2u : 0u));
-                if (denoise) a.info[o].reserved[1] = (t > 0) ? 2 : 1;  // 2: the previous filtered image is frame o - 1
-                prev_fmin = s.bcast_i[3];
-                prev_fmax = s.bcast_i[4];
-                have_prev = 1;
-            }
-        }
-        if (lane == 0) mbar_arrive(&s.done_bar[b]);  // message consumed, byte threshold published (release)
-        __syncwarp();
-        CPT_TICK2(lane == 0, 16);  // scalars
-    }
-    if (lane == 0) {
-        s.final_average = average;
-        s.final_prev[0] = prev_fmin; s.final_prev[1] = prev_fmax; s.final_prev[2] = have_prev;
-    }
-    bar_arrive(BAR_DONE, kSThreads);
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const KernelArgs a) {
@@ -1615,69 +1551,26 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
     }
 }
 
-// ================================================================================================
-// split path, producer warp: one elected lane keeps the staging ring full -- per frame and sweep iteration the rows the
-// sweep warps are about to read, from the frame and from the frame leaving the 45-frame window (zeros while the
-// window fills), as 1-D bulk copies (TMA) that complete on the stage's mbarrier.
-// ================================================================================================
-__device__ void producer_warp(const KernelArgs &a, Smem &s, const cpt_clip &clip, int lane) {
-    const Geometry &g = a.g;
-    bar_sync(BAR_INIT, kSThreads);
-    if (lane == 0) {
-        SoloStage &st = solo_stage(s);
-        const int owned = g.H - 2 * g.edge, R = g.rows_per_it;
-        const int n_it = (owned + R - 1) / R;
-        const uint32_t row_bytes = (uint32_t)g.W * 2u;
-        const unsigned long long pol_keep = l2_policy_keep(), pol_drop = l2_policy_drop();
-        int use = 0;  // uses of the ring so far: stage use % kStages, its (use / kStages)-th use
-        for (int t = 0; t < clip.n_frames; ++t) {
-            const int t_abs = clip.first_frame + t;
-            const uint16_t *P = frame_ptr(a, clip, t);
-            const uint16_t *Pold = (t_abs >= kMeanFrames) ? frame_ptr(a, clip, t - kMeanFrames) : a.zero_frame;
-            for (int it = 0; it < n_it; ++it, ++use) {
-                const int stage = use % kStages, k = use / kStages;
-                CPT_TICK_START2(true);
-                if (k > 0) mbar_wait(&st.empty[stage], (uint32_t)(k - 1) & 1u);  // every sweep warp has read its previous use
-                CPT_TICK2(true, 8);   // producer: waiting for a free stage
-                const int row0 = g.edge + it * R, rows = min(R, owned - it * R);
-                const uint32_t bytes = (uint32_t)rows * row_bytes;
-                const bool extra = g.balanced && it == kQIter - 1;  // the remapped row rides behind the last iteration's own rows
-                mbar_arrive_expect_tx(&st.full[stage], 2u * (bytes + (extra ? row_bytes : 0u)));
-                uint8_t *dst = st.data[stage];
-                bulk_g2s_hint(dst, P + (size_t)row0 * g.W, bytes, &st.full[stage], pol_keep);
-                bulk_g2s_hint(dst + kStageHalf, Pold + (size_t)row0 * g.W, bytes, &st.full[stage], pol_drop);
-                if (extra) {
-                    const size_t rx = (size_t)(g.bal_b_oy + g.edge) * g.W;
-                    bulk_g2s(dst + bytes, P + rx, row_bytes, &st.full[stage]);
-                    bulk_g2s(dst + kStageHalf + bytes, Pold + rx, row_bytes, &st.full[stage]);
-                }
-                CPT_TICK2(true, 9);   // producer: issuing the copies
-            }
+// One image row of quad bytes (strip_sweep_kernel) against its strip's byte threshold: bit q = quad q may hold a pixel
+// that reaches the threshold.
+__device__ __forceinline__ unsigned long long quad_row_bits(const Geometry &g, const int8_t *qb, const int16_t *theta,
+                                                            uint32_t hot_strips, int y) {
+    const int sidx = ((y + 1) * g.n_strips - 1) / g.H;  // strip s holds rows [s * H / n, (s + 1) * H / n)
+    if (!((hot_strips >> sidx) & 1u)) return 0ull;
+    const int th = theta[sidx];
+    const int8_t *row = qb + y * g.qpr;
+    unsigned long long bits = 0;
+    if ((g.qpr & 3) == 0) {
+        const uint32_t t4 = (uint32_t)(th + 128) * 0x01010101u;
+        for (int w = 0; w < (g.qpr >> 2); ++w) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(row) + w);
+            const uint32_t ge = __vcmpgeu4(v ^ 0x80808080u, t4) & 0x01010101u;           // byte i -> bit 8 i
+            bits |= (unsigned long long)((ge * 0x10204080u) >> 28) << (4 * w);           // -> bits 0..3
         }
+    } else {
+        for (int q = 0; q < g.qpr; ++q) bits |= (unsigned long long)((int)row[q] >= th ? 1u : 0u) << q;
     }
-    __syncwarp();
-    bar_arrive(BAR_DONE, kSThreads);
-}
-
-// Split path, first launch: the recurrence only.  One persistent CTA per clip: sweep warps + the scalar warp.  Per frame
-// it leaves the filtered image, a zeroed label image, the info record and the hot-quad words in global memory.
-__global__ void __launch_bounds__(kSThreads, 1) extract_sweep_kernel(const KernelArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
-    const int tid = threadIdx.x;
-    if (tid == 0) s.done_bar_live = 0;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s.bcast_i[15] = atomicAdd(a.work_counter, 1);
-        __syncthreads();
-        const int ci = s.bcast_i[15];
-        if (ci >= a.n_clips) break;
-        const cpt_clip clip = a.clips[ci];
-        uint8_t *st_raw = a.state ? a.state + (size_t)ci * state_bytes(a.g.npx) : nullptr;  // written at the end of the clip
-        if (tid < kPThreads) sweep_warps<true>(a, s, clip, tid, nullptr, st_raw);
-        else if (tid < kPThreads + 32) scalar_warp(a, s, clip, tid - kPThreads);
-        else producer_warp(a, s, clip, tid - kPThreads - 32);
-    }
+    return bits;
 }
 
 // Split path, second launch: one CTA per frame.  Hot-quad words -> per-row marks -> work lists -> normalise (K2) ->
@@ -1690,19 +1583,16 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
     const int tid = threadIdx.x;
     const long long o = blockIdx.x;
     if (o >= total_frames) return;
-    const uint32_t *hw = a.hot + (size_t)o * kHotStride;
+    const FrameHdr *fh = a.fhdr + o;
     const cpt_frame_info *fi = a.info + o;
-    // (independent loads first: the trailer, the info record and this thread's ballot word are all in flight together)
-    const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(hw + kHotWords));
+    // (independent loads first: the header and the info record are in flight together)
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(fh));  // nmagic, nshift, flags, hot_strips
     const float thr = fi->threshold;
     const int ac = fi->avg_change, gmn = fi->norm_min, gmx = fi->norm_max;
     const int dn_marker = fi->reserved[1];
-    const uint32_t my_hot = tid < kHotWords ? __ldg(hw + tid) : 0u;
-    static_assert(kHotWords <= kFThreads, "one ballot word per thread");
-    if (!(hdr.w & 1u)) return;  // no clip produced this output frame
-    const int tu = (int)hdr.x;
-    const uint32_t nmagic = hdr.y;
-    const int nshift = (int)hdr.z;
+    if (!(hdr.z & kHdrValid)) return;  // no clip produced this output frame
+    const uint32_t nmagic = hdr.x;
+    const int nshift = (int)hdr.y;
     const float *fcur = a.filtered + (size_t)o * g.npx;
     if (dn_marker) {
         // denoise clips: K3 sits between K2 and K4 -- emit the whole normalised image; cv2.fastNlMeansDenoising, blur,
@@ -1713,7 +1603,7 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
     }
     const int ith = (int)floorf(thr);
     const bool no_fg = ith >= 255;  // nothing can exceed the threshold: the mask stays empty
-    bool dense = tu == 0;           // no usable bound: every group is normalised and blurred
+    bool dense = (hdr.z & kHdrDense) != 0;  // no usable bound: every group is normalised and blurred
     const int owned = g.H - 2 * g.edge;
     if ((g.words & 3) == 0) {
         for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(s.M[0])[i] = make_uint4(0, 0, 0, 0);
@@ -1722,19 +1612,17 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
     }
     int n_u = 0, n_b = 0;
     if (!no_fg && !dense) {
-        if (tid < kHotWords) s.hotw[tid] = my_hot;
+        if (tid < kMaxStrips) s.theta[tid] = fh->theta[tid];
         if (tid == 0) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
         __syncthreads();
-        // one thread per owned row: its quads' bits, spread over the ballot words of the warps that swept it
+        // one thread per owned row: its quads' bytes against the strip's byte threshold -> one bit per quad (a border
+        // row's quads count for the owned row next to it, which only widens the marks)
+        const int8_t *qb = a.qbytes + (size_t)o * (g.H * g.qpr);
         for (int oy = tid; oy < owned; oy += kFThreads) {
-            int it, hr;
-            owned_row_slot(g, oy, it, hr);
-            const int p0 = hr * g.qpr;  // sweep thread of the row's first quad
-            const int w0 = p0 >> 5, sh = p0 & 31;
-            unsigned long long bits = (unsigned long long)s.hotw[w0 * kQIter + it] >> sh;
-            if (w0 + 1 < kPWarps) bits |= (unsigned long long)s.hotw[(w0 + 1) * kQIter + it] << (32 - sh);
-            if (sh && w0 + 2 < kPWarps) bits |= (unsigned long long)s.hotw[(w0 + 2) * kQIter + it] << (64 - sh);
-            s.hot64[oy] = bits & ((1ull << g.qpr) - 1ull);
+            unsigned long long bits = quad_row_bits(g, qb, s.theta, hdr.w, oy + g.edge);
+            if (g.edge && oy == 0) bits |= quad_row_bits(g, qb, s.theta, hdr.w, 0);
+            if (g.edge && oy == owned - 1) bits |= quad_row_bits(g, qb, s.theta, hdr.w, g.H - 1);
+            s.hot64[oy] = bits;
         }
         __syncthreads();
         // one thread per frame row: OR the hot rows around the row, widen by the neighbouring quads, and turn the marks
@@ -1814,7 +1702,7 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
         for (int i = tid; i < g.words; i += kFThreads) any |= s.M[0][i] != 0;
     }
     if (!__syncthreads_or(any)) {
-        if (tid == 0) a.hot[(size_t)o * kHotStride + kHotWords + 3] = hdr.w | 4u;
+        if (tid == 0) a.fhdr[o].flags = hdr.z | kHdrEmpty;
         return;
     }
     if (vec) {
@@ -1861,10 +1749,10 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
     if (o >= total_frames) return;
     const cpt_frame_info *fi = a.info + o;
     const uint32_t *min_ = a.maskbits + (size_t)o * kMaxWords;
-    const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(a.hot + (size_t)o * kHotStride + kHotWords));
+    const uint32_t hflags = a.fhdr[o].flags;  // (plain load: frame_mask_kernel may have set the empty-mask flag)
     const int dn_marker = fi->reserved[1];
-    if (!(hdr.w & 1u)) return;  // no clip produced this output frame (its mask words were never written)
-    if (hdr.w & 4u) return;     // empty mask (flagged by frame_mask_kernel): info.n_components stays 0
+    if (!(hflags & kHdrValid)) return;  // no clip produced this output frame (its mask words were never written)
+    if (hflags & kHdrEmpty) return;     // empty mask (flagged by frame_mask_kernel): info.n_components stays 0
     if (dn_marker) return;      // denoise clips: mask_components_kernel
     bool any = false;
     if ((g.words & 3) == 0) {
@@ -1882,7 +1770,7 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
     }
     if (!__syncthreads_or(any)) return;  // empty mask: info.n_components stays 0
     const float *fcur = a.filtered + (size_t)o * g.npx;
-    const bool have_prev = !(hdr.w & 2u);  // not the first frame of its clip
+    const bool have_prev = !(hflags & kHdrFirst);  // not the first frame of its clip
     // (variances in this kernel were measured slower than the separate wide pass, whose warps hide the cold reads of
     // the filtered images: components_of_frame's own path +4.1 ms, one warp per region record as a tail here +7.9 ms,
     // against the 2.4 ms of region_variance_kernel)

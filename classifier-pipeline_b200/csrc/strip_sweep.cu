@@ -1,0 +1,642 @@
+// strip_sweep.cu -- the recurrence of the split extraction path, cut into row strips.
+//
+// The per-pixel recurrence of the reference (WeightedBackground keep test + 45-frame sliding mean,
+// piclassifier/motiondetector.py:197-244, track/cliptrackextractor.py:168-176) never looks at another pixel: only the
+// per-frame scalars (mean of the frame, extrema of filtered, mean of the background) couple the pixels of a frame, and
+// those are only needed by the later per-frame stages.  So a clip is cut into n_strips bands of whole rows and every
+// (clip, strip) pair is an independent work unit of strip_sweep_kernel:
+//   * one CTA per unit, 15 consumer warps + 1 producer warp; a consumer thread owns ONE quad (4 pixels) for the whole
+//     clip: background B, weight counter k and sliding sum S of its pixels live in registers from the first frame to the
+//     last -- no per-frame state traffic at all;
+//   * the strip's rows of the last 45 frames (the window of the sliding mean) plus kLead frames of read-ahead sit in a
+//     shared-memory ring filled by the producer warp with one 1-D TMA bulk copy per frame (full mbarriers); the frame
+//     leaving the window is read from that ring, so every frame is read from HBM exactly once and never again;
+//   * per frame a consumer writes its filtered quad (fp32), the zeroed label bytes and one byte per quad (max filtered
+//     relative to a strip reference, for the hot-quad test of the per-frame kernels); the warps' partial sums go through
+//     a small shared-memory table to the producer warp, which folds them into the strip's pass record in global memory
+//     before it issues the next bulk copy (done mbarriers).
+// frame_scalars_kernel (one warp per clip) then folds the strips' records into the per-frame scalars of
+// ClipTracker._get_filtered_frame (track/cliptracker.py:93-122): WeightedBackground.average (a running value: scanned over
+// the frames with warp ballots), avg_change, the normalisation range, the mapped threshold, the integer normalise
+// constants and the per-strip byte thresholds.
+#include <type_traits>
+
+#include "cptrack_kernels.cuh"
+#include "sm100_primitives.cuh"
+
+namespace cpt {
+
+namespace {
+
+using namespace prim;
+
+constexpr int kLead = 7;                             // frames the producer runs ahead of the slowest consumer warp
+constexpr int kRingSlots = kMeanFrames + kLead;      // 52 frames of the strip's rows
+constexpr int kSlotBytes = kStripPxMax * 2;          // 3840
+constexpr int kConsWarps = kStripPxMax / 4 / 32;     // 15
+constexpr int kConsThreads = kConsWarps * 32;        // 480
+constexpr int kBarRing = 8;                          // full / done barriers and stat rows are reused every 8 passes
+static_assert(kBarRing > kLead, "a barrier is reused only after every warp has passed its previous use");
+static_assert(kStripThreads == kConsThreads + 32, "consumer warps + the producer warp");
+constexpr int kStripTable = 4096;                    // first entries of the clip's keep-test table
+constexpr int kRefDefault = kQuadRefBias;            // reference of the first kLead frames (filtered starts near 0)
+
+struct __align__(128) StripSmem {
+    uint8_t ring[kRingSlots][kSlotBytes];
+    uint32_t wthr[kStripTable];
+    uint32_t stat[kBarRing][kConsWarps][8];  // per pass and warp: psum, fmin, fmax, nbsum, pmin, pmax, fabs, changed
+    int32_t ref_ring[16];                    // byte reference published with pass t, used by pass t + kLead
+    unsigned long long full[kBarRing], done[kBarRing];
+    int32_t unit;
+};
+static_assert(sizeof(StripSmem) <= 232448, "shared memory budget (227 KB per CTA on sm_100)");
+
+// what is uniform over the CTA in one pass
+struct PassCtx {
+    bool update, is_frame, window_full, first_mean;
+    uint32_t magic;              // floor(S / cnt) == umulhi(S, magic)
+    uint32_t cur_off, old_off;   // ring slots (byte offsets) of frame t and of frame t - 45
+    unsigned long long *full;
+    uint32_t parity;
+    const int32_t *ref_slot;     // reference for this frame's quad bytes, published by the producer (nullptr: the default)
+};
+
+struct StripThread {
+    bool active, border_row, first_col, last_col;
+    int off_src, off_out;  // byte offsets of the quad inside a ring slot: the row its state follows / the row it outputs
+    float *fptr;           // the thread's quad in this frame's outputs (advanced by the caller after every frame)
+    uint8_t *lptr;
+    int8_t *qptr;
+};
+
+// A thread's pixels: nB = -background, S = sliding sum, kv = weight counter k -- or, while the keep test is the linear one
+// (thr = k + 1, weight_add == 1), v = nB - k: then keep <=> A - B >= k + 1 <=> v > -A, and both outcomes fold into
+// v' = max(v - 1, -A) (kept: k + 1; reset: background = A, k = 0).  k = nB - v either way (the same formula converts back).
+struct QuadState {
+    int nB[4], kv[4], f[4];
+    uint32_t S[4];
+    bool lin;
+};
+
+struct PassOut {
+    uint32_t psum;
+    int fmin, fmax, bs, chg, pmin, pmax;
+    uint32_t fabs_sum;
+};
+
+__device__ __forceinline__ uint2 lds8(const uint8_t *p) { return *reinterpret_cast<const uint2 *>(p); }
+
+// One pass of one quad: [update] WeightedBackground.process_frame for the previous frame (A = floor(S / cnt); keep <=>
+// B < A - w_k in the table form of cptrack_kernels.cuh; B' = keep ? B : A, k' = keep ? k + 1 : 0), then [frame] K1 of this
+// frame against B' (F = P - B', S += P - P_old) with the frame's sums.  State is unpacked 32-bit integers.
+// kTab: 0 thr = k + 1 (weight_add == 1; QuadState::lin form), 1 table in shared memory, 2 table in shared + global memory.
+// kSteady: update && frame && window full && cnt == 45 are compile-time facts.
+template <int kTab, bool kStats, bool kSteady>
+__device__ __forceinline__ void strip_pass(StripSmem &s, const WeightTable &wt, const PassCtx &pc, const StripThread &th,
+                                           QuadState &q, PassOut &po) {
+    const bool is_frame = kSteady || pc.is_frame;
+    uint2 pw = make_uint2(0, 0), pv = make_uint2(0, 0), ow = make_uint2(0, 0);
+    int ref = kRefDefault;
+    if (is_frame) {
+        mbar_wait(pc.full, pc.parity);
+        // (read after the acquire: the producer published it before it issued this frame's copy)
+        if (pc.ref_slot) ref = *(volatile const int32_t *)pc.ref_slot;
+        const uint8_t *cur = &s.ring[0][0] + pc.cur_off;
+        pw = lds8(cur + th.off_src);
+        pv = th.border_row ? lds8(cur + th.off_out) : pw;
+        if (kSteady || pc.window_full) ow = lds8(&s.ring[0][0] + pc.old_off + th.off_src);
+    }
+    int chg = 0;
+    if (kSteady || pc.update) {
+        int nA[4], nn[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nA[i] = -(int)((!kSteady && pc.first_mean) ? q.S[i] : __umulhi(q.S[i], pc.magic));
+        if (kTab == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                nn[i] = q.kv[i] > nA[i] ? q.nB[i] : nA[i];
+                q.kv[i] = __viaddmax_s32(q.kv[i], -1, nA[i]);
+            }
+        } else {
+            int e[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (kTab == 1) e[i] = (int)s.wthr[q.kv[i]];
+                else e[i] = (int)(q.kv[i] < kStripTable ? s.wthr[q.kv[i]] : __ldg(wt.thr + q.kv[i]));
+            }
+            if (wt.has_bounds) {
+                // entries with a bound (the fp64 rounding of A - w_k depends on the magnitude of B) are rare: one vote per quad
+                if (__any_sync(0xffffffffu, (uint32_t)(e[0] | e[1] | e[2] | e[3]) > 0xffffu)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int bound = (int)((uint32_t)e[i] >> 16);
+                        e[i] = (e[i] & 0xffff) - ((-q.nB[i] < bound) ? 1 : 0);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool keep = q.nB[i] - nA[i] >= e[i];  // A - B >= thr
+                nn[i] = keep ? q.nB[i] : nA[i];
+                q.kv[i] = keep ? q.kv[i] + 1 : 0;
+            }
+        }
+        // crop-border columns copy their neighbour (motiondetector.py:239-244); they were equal before, so they add nothing
+        // to `changed` (their own counters only ever feed their own, discarded, keep test)
+        if (th.first_col) nn[0] = nn[1];
+        if (th.last_col) nn[3] = nn[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            chg |= nn[i] ^ q.nB[i];
+            q.nB[i] = nn[i];
+        }
+    }
+    // minus the background sum over the crop pixels of owned rows
+    int bs = q.nB[0] + q.nB[1] + q.nB[2] + q.nB[3];
+    if (th.first_col) bs -= q.nB[0];
+    if (th.last_col) bs -= q.nB[3];
+    if (th.border_row || !th.active) bs = 0;
+    po.bs = bs;
+    po.chg = th.active ? chg : 0;
+    po.psum = 0;
+    po.fmin = INT32_MAX; po.fmax = INT32_MIN; po.pmin = INT32_MAX; po.pmax = INT32_MIN; po.fabs_sum = 0;
+    if (is_frame) {
+        int (&f)[4] = q.f;
+        f[0] = dp2a_us(pv.x, kLoP, q.nB[0]); f[1] = dp2a_us(pv.x, kHiP, q.nB[1]);
+        f[2] = dp2a_us(pv.y, kLoP, q.nB[2]); f[3] = dp2a_us(pv.y, kHiP, q.nB[3]);
+        q.S[0] = (uint32_t)dp2a_us(pw.x, kLoP, dp2a_us(ow.x, kLoN, (int)q.S[0]));
+        q.S[1] = (uint32_t)dp2a_us(pw.x, kHiP, dp2a_us(ow.x, kHiN, (int)q.S[1]));
+        q.S[2] = (uint32_t)dp2a_us(pw.y, kLoP, dp2a_us(ow.y, kLoN, (int)q.S[2]));
+        q.S[3] = (uint32_t)dp2a_us(pw.y, kHiP, dp2a_us(ow.y, kHiN, (int)q.S[3]));
+        const int lo = min(min(f[0], f[1]), min(f[2], f[3])), hi = max(max(f[0], f[1]), max(f[2], f[3]));
+        if (th.active) {
+            po.psum = (uint32_t)dp2a_us(pv.x, kBoth, dp2a_us(pv.y, kBoth, 0));
+            po.fmin = lo;
+            po.fmax = hi;
+            if (kStats) {
+                const int p0 = (int)(pv.x & 0xffffu), p1 = (int)(pv.x >> 16), p2 = (int)(pv.y & 0xffffu), p3 = (int)(pv.y >> 16);
+                po.pmin = min(min(p0, p1), min(p2, p3));
+                po.pmax = max(max(p0, p1), max(p2, p3));
+                po.fabs_sum = (uint32_t)(abs(f[0]) + abs(f[1]) + abs(f[2]) + abs(f[3]));
+            }
+            *reinterpret_cast<float4 *>(th.fptr) = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
+            if (th.lptr) *reinterpret_cast<uint32_t *>(th.lptr) = 0u;
+            int b;
+            asm("cvt.sat.s8.s32 %0, %1;" : "=r"(b) : "r"(hi - ref));
+            *th.qptr = (int8_t)b;
+        }
+    }
+}
+
+// k <-> v = nB - k (QuadState): the same formula both ways.  Border columns restart from k = 0 (their counters are
+// never used; this keeps table indices in range).
+__device__ __forceinline__ void quad_state_form(QuadState &q, const StripThread &th, bool lin) {
+    if (q.lin == lin) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q.kv[i] = q.nB[i] - q.kv[i];
+    if (!lin) {
+        if (th.first_col) q.kv[0] = 0;
+        if (th.last_col) q.kv[3] = 0;
+    }
+    q.lin = lin;
+}
+
+template <bool kStats>
+__device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip &clip, int ci, int y0, int rows, int tid) {
+    const Geometry &g = a.g;
+    const int W = g.W, H = g.H, e = g.edge, qpr = g.qpr, npx = g.npx;
+    const int lane = tid & 31, warp = tid >> 5;
+    const WeightTable wt = a.tables[clip.weight_table & 3];
+    const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
+    const bool skip_first = clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE;
+    const int n = clip.n_frames;
+    StripThread th;
+    th.active = tid < rows * qpr;
+    const int r = th.active ? tid / qpr : 0, qx = th.active ? tid - r * qpr : 0;
+    const int y = y0 + r;
+    const int ys = min(max(y, e), H - 1 - e);  // a border row follows the state of the owned row next to it
+    th.border_row = ys != y;
+    th.first_col = e && qx == 0;
+    th.last_col = e && qx == qpr - 1;
+    th.off_src = ((ys - y0) * W + 4 * qx) * 2;
+    th.off_out = ((y - y0) * W + 4 * qx) * 2;
+    const int pix = y * W + 4 * qx;
+    th.fptr = a.filtered + (size_t)clip.out_offset * npx + pix;
+    th.lptr = a.labels ? a.labels + (size_t)clip.out_offset * npx + pix : nullptr;
+    th.qptr = a.qbytes + (size_t)clip.out_offset * (H * qpr) + (y * qpr + qx);
+    const int qstride = H * qpr;
+
+    // ---- WeightedBackground first call (motiondetector.py:199-212): background = the initialising frame, edges replicated
+    QuadState q;
+    q.lin = false;
+    {
+        const uint16_t *init = a.frames + (size_t)clip.init_offset * npx;
+        const uint2 v = th.active ? __ldg(reinterpret_cast<const uint2 *>(init + ys * W + 4 * qx)) : make_uint2(0, 0);
+        int b0 = (int)(v.x & 0xffffu), b1 = (int)(v.x >> 16), b2 = (int)(v.y & 0xffffu), b3 = (int)(v.y >> 16);
+        if (th.first_col) b0 = b1;
+        if (th.last_col) b3 = b2;
+        q.nB[0] = -b0; q.nB[1] = -b1; q.nB[2] = -b2; q.nB[3] = -b3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { q.kv[i] = 0; q.S[i] = 0; q.f[i] = 0; }
+    }
+
+    int frames_seen = 0;
+    // running ring / barrier positions of pass t
+    uint32_t cur_off = 0, old_off = (uint32_t)kLead * kSlotBytes;  // slot of frame t - 45 == slot of frame t + kLead
+    int bi = 0;            // t % kBarRing
+    uint32_t parity = 0;   // (t / kBarRing) & 1
+    constexpr uint32_t kMagic45 = 0xffffffffu / (uint32_t)kMeanFrames + 1u;
+
+    // one pass; kSteadyPass: frame + update + full window + 45-frame mean
+    auto pass = [&](int t, auto steady_tag) {
+        constexpr bool kSteadyPass = decltype(steady_tag)::value;
+        PassCtx pc;
+        const bool is_frame = kSteadyPass || t < n;
+        const int t_abs = clip.first_frame + t;
+        // (rawdb.py:84-122: no update follows the frame that initialised the background when it is also the first kept frame)
+        pc.update = kSteadyPass || (update_bg && t > 0 && !(skip_first && t_abs == 1));
+        pc.is_frame = is_frame;
+        if (kSteadyPass) {
+            pc.first_mean = false;
+            pc.magic = kMagic45;
+            pc.window_full = true;
+        } else {
+            // the update belongs to frame t-1: the mean covers min(t_abs, 45) frames
+            const uint32_t cnt = (uint32_t)min(max(t_abs, 1), kMeanFrames);
+            pc.first_mean = cnt == 1u;
+            pc.magic = cnt == 1u ? 0u : 0xffffffffu / cnt + 1u;  // exact for S < 2^22, cnt <= 45
+            pc.window_full = t >= kMeanFrames;
+        }
+        pc.cur_off = cur_off;
+        pc.old_off = old_off;
+        pc.full = &s.full[bi];
+        pc.parity = parity;
+        pc.ref_slot = t >= kLead ? &s.ref_ring[(t - kLead) & 15] : nullptr;
+        const int tab = frames_seen < wt.linear_upto ? 0 : (frames_seen < kStripTable ? 1 : 2);
+        quad_state_form(q, th, tab == 0);
+        PassOut po;
+        if (tab == 0) strip_pass<0, kStats, kSteadyPass>(s, wt, pc, th, q, po);
+        else if (tab == 1 && kSteadyPass) strip_pass<1, kStats, kSteadyPass>(s, wt, pc, th, q, po);
+        else strip_pass<2, kStats, kSteadyPass>(s, wt, pc, th, q, po);
+        if (pc.update) ++frames_seen;
+        // ---- the warp's partial results -> its row of the pass table; the producer warp folds the rows
+        {
+            const uint32_t psum = __reduce_add_sync(0xffffffffu, po.psum);
+            const int fmin = __reduce_min_sync(0xffffffffu, po.fmin), fmax = __reduce_max_sync(0xffffffffu, po.fmax);
+            const int bs = __reduce_add_sync(0xffffffffu, po.bs);
+            const bool chg = __any_sync(0xffffffffu, po.chg != 0);
+            int pmin = INT32_MAX, pmax = INT32_MIN;
+            uint32_t fabs_sum = 0;
+            if (kStats) {
+                pmin = __reduce_min_sync(0xffffffffu, po.pmin);
+                pmax = __reduce_max_sync(0xffffffffu, po.pmax);
+                fabs_sum = __reduce_add_sync(0xffffffffu, po.fabs_sum);
+            }
+            if (lane == 0) {
+                uint4 *row = reinterpret_cast<uint4 *>(s.stat[bi][warp]);
+                row[0] = make_uint4(psum, (uint32_t)fmin, (uint32_t)fmax, (uint32_t)bs);
+                row[1] = make_uint4((uint32_t)pmin, (uint32_t)pmax, fabs_sum, chg ? 1u : 0u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.done[bi]);  // (release: the ring reads and the row are done)
+        }
+        if (is_frame) {
+            th.fptr += npx;
+            if (th.lptr) th.lptr += npx;
+            th.qptr += qstride;
+        }
+        cur_off += kSlotBytes;
+        if (cur_off == (uint32_t)kRingSlots * kSlotBytes) cur_off = 0;
+        old_off += kSlotBytes;
+        if (old_off == (uint32_t)kRingSlots * kSlotBytes) old_off = 0;
+        bi = (bi + 1) & (kBarRing - 1);
+        parity ^= (bi == 0) ? 1u : 0u;
+    };
+    using SteadyTag = std::true_type;
+    using GenericTag = std::false_type;
+
+    // passes 0 .. n: frames t < n, then the tail pass (the background update that follows the last frame).  A pass is
+    // steady once the window is full, i.e. for 45 <= t < n when the clip updates its background from its first frame on.
+    const bool can_steady = update_bg && clip.first_frame >= 0;
+    int t = 0;
+    for (; t < min(n, kMeanFrames); ++t) pass(t, GenericTag{});
+    if (can_steady) {
+        for (; t < n; ++t) pass(t, SteadyTag{});
+    } else {
+        for (; t < n; ++t) pass(t, GenericTag{});
+    }
+    if (update_bg && n > 0 && !(skip_first && clip.first_frame + n == 1)) pass(n, GenericTag{});
+
+    // ---- the clip's state record (cpt_state_bytes): background, counters, sliding sums, last filtered image
+    if (a.state && th.active) {
+        quad_state_form(q, th, false);
+        uint8_t *st_raw = a.state + (size_t)ci * state_bytes(npx);
+        uint16_t *st_B = reinterpret_cast<uint16_t *>(st_raw + sizeof(StateHeader));
+        uint16_t *st_K = st_B + npx;
+        uint32_t *st_S = reinterpret_cast<uint32_t *>(st_K + npx);
+        float *st_F = reinterpret_cast<float *>(st_S + npx);
+        uint2 bw, kw;
+        bw.x = (uint32_t)(-q.nB[0]) | ((uint32_t)(-q.nB[1]) << 16);
+        bw.y = (uint32_t)(-q.nB[2]) | ((uint32_t)(-q.nB[3]) << 16);
+        // (a border row / column has no counter of its own: zero, as the crop view of cpt_state_read never shows it)
+        const int k0 = th.first_col ? 0 : q.kv[0], k3 = th.last_col ? 0 : q.kv[3];
+        kw.x = th.border_row ? 0u : ((uint32_t)k0 | ((uint32_t)q.kv[1] << 16));
+        kw.y = th.border_row ? 0u : ((uint32_t)q.kv[2] | ((uint32_t)k3 << 16));
+        *reinterpret_cast<uint2 *>(st_B + pix) = bw;
+        *reinterpret_cast<uint2 *>(st_K + pix) = kw;
+        *reinterpret_cast<uint4 *>(st_S + pix) = th.border_row ? make_uint4(0, 0, 0, 0) : make_uint4(q.S[0], q.S[1], q.S[2], q.S[3]);
+        if (n > 0) *reinterpret_cast<float4 *>(st_F + pix) = make_float4((float)q.f[0], (float)q.f[1], (float)q.f[2], (float)q.f[3]);
+    }
+}
+
+__device__ void strip_producer(const KernelArgs &a, StripSmem &s, const cpt_clip &clip, int ci, int strip, int y0, int rows,
+                               int lane) {
+    const Geometry &g = a.g;
+    const int n = clip.n_frames, NS = g.n_strips;
+    const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
+    const bool skip_first = clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE;
+    const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
+    const uint32_t bytes = (uint32_t)(rows * g.W) * 2u;
+    const unsigned long long policy = l2_policy_evict_first();  // every frame is read exactly once
+    auto issue = [&](int fidx) {
+        if (lane == 0) {
+            const int64_t idx = clip.ring_frames ? (int64_t)((clip.first_frame + fidx) % clip.ring_frames) : (int64_t)fidx;
+            const uint16_t *src = a.frames + (size_t)(clip.frame_offset + idx) * g.npx + (size_t)y0 * g.W;
+            unsigned long long *bar = &s.full[fidx & (kBarRing - 1)];
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s_hint(s.ring[fidx % kRingSlots], src, bytes, bar, policy);
+        }
+    };
+    for (int fidx = 0; fidx < min(kLead, n); ++fidx) issue(fidx);
+    for (int t = 0; t <= n; ++t) {
+        const bool is_frame = t < n;
+        const bool update = update_bg && t > 0 && !(skip_first && clip.first_frame + t == 1);
+        if (!update && !is_frame) break;
+        mbar_wait(&s.done[t & (kBarRing - 1)], (uint32_t)(t / kBarRing) & 1u);  // every consumer warp has finished pass t
+        const uint32_t *row = s.stat[t & (kBarRing - 1)][lane < kConsWarps ? lane : 0];
+        const bool in = lane < kConsWarps;
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(row), r1 = *reinterpret_cast<const uint4 *>(row + 4);
+        StripRec rec;
+        rec.psum = __reduce_add_sync(0xffffffffu, in ? r0.x : 0u);
+        rec.fmin = __reduce_min_sync(0xffffffffu, in ? (int)r0.y : INT32_MAX);
+        rec.fmax = __reduce_max_sync(0xffffffffu, in ? (int)r0.z : INT32_MIN);
+        rec.nbsum = __reduce_add_sync(0xffffffffu, in ? (int)r0.w : 0);
+        rec.pmin = 0; rec.pmax = 0; rec.fabs_sum = 0;
+        if (want_stats) {
+            rec.pmin = __reduce_min_sync(0xffffffffu, in ? (int)r1.x : INT32_MAX);
+            rec.pmax = __reduce_max_sync(0xffffffffu, in ? (int)r1.y : INT32_MIN);
+            rec.fabs_sum = __reduce_add_sync(0xffffffffu, in ? r1.z : 0u);
+        }
+        const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? r1.w : 0u);
+        if (lane == 0) {
+            const int ref = t >= kLead ? s.ref_ring[(t - kLead) & 15] : kRefDefault;  // what pass t's bytes were stored against
+            rec.ref_changed = (int32_t)(((uint32_t)ref << 1) | (changed & 1u));
+            const size_t ri = is_frame ? (size_t)(clip.out_offset + t) : (size_t)(a.total_frames + ci);
+            uint4 *dst = reinterpret_cast<uint4 *>(a.prec + ri * NS + strip);
+            dst[0] = make_uint4(rec.psum, (uint32_t)rec.fmin, (uint32_t)rec.fmax, (uint32_t)rec.nbsum);
+            dst[1] = make_uint4((uint32_t)rec.pmin, (uint32_t)rec.pmax, rec.fabs_sum, (uint32_t)rec.ref_changed);
+            // the reference of pass t + kLead: this strip's filtered minimum now, plus the bias (clamped so that it
+            // survives the shift above)
+            if (is_frame) s.ref_ring[t & 15] = max(min(rec.fmin, 1 << 20), -(1 << 20)) + kQuadRefBias;
+        }
+        __syncwarp();
+        if (t + kLead < n) issue(t + kLead);  // (the arrive.expect_tx releases the reference to the consumers of that frame)
+    }
+}
+
+}  // namespace
+
+// Split path, first launch: the recurrence.  grid = min(units, SMs) persistent CTAs; units = (clip, strip) pairs handed
+// out by an atomic counter, clip-major so that the strips of a clip run side by side.
+__global__ void __launch_bounds__(kStripThreads, 1) strip_sweep_kernel(const KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StripSmem &s = *reinterpret_cast<StripSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const Geometry &g = a.g;
+    const int NS = g.n_strips;
+    bool bars_live = false;
+    while (true) {
+        __syncthreads();  // every thread is done with the previous unit (ring, barriers, table)
+        if (tid == 0) s.unit = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int u = s.unit;
+        if (u >= a.n_clips * NS) break;
+        const int ci = u / NS, strip = u - ci * NS;
+        const cpt_clip clip = a.clips[ci];
+        const int y0 = strip * g.H / NS, rows = (strip + 1) * g.H / NS - y0;
+        if (tid == 0) {
+            if (bars_live)
+                for (int i = 0; i < kBarRing; ++i) { mbar_inval(&s.full[i]); mbar_inval(&s.done[i]); }
+            for (int i = 0; i < kBarRing; ++i) {
+                mbar_init(&s.full[i], 1);           // the producer's arrive.expect_tx
+                mbar_init(&s.done[i], kConsWarps);  // one arrival per consumer warp
+            }
+            mbar_fence_init();
+            bars_live = true;
+        }
+        {
+            const WeightTable wt = a.tables[clip.weight_table & 3];
+            for (int i = tid; i < kStripTable; i += kStripThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
+        }
+        __syncthreads();
+        if (tid < kConsThreads) {
+            if (clip.flags & CPT_CLIP_FRAME_STATS) strip_consumer<true>(a, s, clip, ci, y0, rows, tid);
+            else strip_consumer<false>(a, s, clip, ci, y0, rows, tid);
+        } else {
+            strip_producer(a, s, clip, ci, strip, y0, rows, tid - kConsThreads);
+        }
+    }
+}
+
+size_t strip_sweep_smem_bytes() { return sizeof(StripSmem); }
+
+// ================================================================================================
+// frame_scalars_kernel: one warp per clip, lanes = 32 consecutive passes.
+// ================================================================================================
+namespace {
+
+struct FrameScalars {
+    int ac, gmn, gmx, fth;
+    float thr;
+    uint32_t nmagic;
+    int nshift;
+};
+
+// K2 scalars of one frame (track/cliptracker.py:93-122, imageprocessing.py:151-169) from its sums: avg_change, the
+// normalisation range, the mapped threshold (fp32 as numpy >= 2 evaluates it), the bound F >= fth below which a pixel cannot
+// reach the threshold and the Granlund-Montgomery constants of the integer normalise.
+__device__ __forceinline__ FrameScalars frame_scalars_of(uint32_t psum, int fmin, int fmax, double average, int background_thresh, int npx) {
+    FrameScalars r;
+    // avg_change = int(round(np.average(thermal) - background average)), cliptracker.py:103-105
+    const double avg_int = rint(average);
+    if (avg_int == average && average >= 0.0 && average < 65536.0) {
+        // integer average (always, once the background has changed): round_half_even((sum - avg * n) / n) in integers;
+        // identical to the fp64 expression because the only ties are exact.  |sum - avg * n| < 2^31.
+        const int num = (int)psum - (int)avg_int * npx;
+        int qd = num / npx, rem = num - qd * npx;
+        if (rem < 0) { rem += npx; qd -= 1; }
+        if (2 * rem > npx || (2 * rem == npx && (qd & 1))) qd += 1;
+        r.ac = qd;
+    } else {
+        r.ac = (int)rint((double)psum / (double)npx - average);
+    }
+    r.gmx = max(fmax - r.ac, 0);
+    r.gmn = max(fmin - r.ac, 0);
+    r.fth = INT32_MIN;
+    r.nmagic = 0;  // 0: the fp32 divide; else (255 v) / range == (255 v * nmagic) >> nshift for 255 v < 2^24
+    r.nshift = 0;
+    if (r.gmx == r.gmn) {
+        r.thr = (float)background_thresh;  // cliptracker.py:118-119
+    } else {
+        const float range = (float)r.gmx - (float)r.gmn;
+        r.thr = __fmul_rn(__fdiv_rn((float)background_thresh, range), 255.0f);
+        const unsigned rr = (unsigned)(r.gmx - r.gmn);
+        if (255ull * rr < (1ull << 24)) {
+            // every product is exact in fp32 here, so trunc(fl(255 v / r)) == (255 v) / r and a quad can only produce
+            // foreground if one of its pixels has U > floor(thr):  U >= ith + 1  <=>  v >= ceil((ith + 1) r / 255),
+            // v = max(F - ac, 0) - gmn, i.e. F >= fth (the bound is >= 1, so the clamp never matters)
+            const int it = (int)floorf(r.thr);
+            if (it >= 0 && it < 255) r.fth = (int)(((unsigned)(it + 1) * rr + 254u) / 255u) + r.ac + r.gmn;
+            // Granlund-Montgomery: l = ceil(log2 r), m = ceil(2^(24 + l) / r) < 2^25
+            const int l = (rr <= 1u) ? 0 : 32 - __clz((int)(rr - 1u));
+            r.nshift = 24 + l;
+            r.nmagic = (uint32_t)ceil(ldexp(1.0, r.nshift) / (double)rr);
+        }
+    }
+    return r;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128) frame_scalars_kernel(const KernelArgs a) {
+    const Geometry &g = a.g;
+    const int lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ci >= a.n_clips) return;
+    const cpt_clip clip = a.clips[ci];
+    const int n = clip.n_frames, NS = g.n_strips, npx = g.npx;
+    const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
+    const bool skip_first = clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE;
+    const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
+    const bool denoise = clip.flags & CPT_CLIP_DENOISE;
+    double average = 0.0;  // WeightedBackground.average: carried from pass to pass
+    int frames_seen = 0, last_fmin = 0, last_fmax = 0;
+    if (n == 0) {
+        // no pass ran: the initial average straight from the initialising frame (np.average of the crop, unrounded)
+        const uint16_t *init = a.frames + (size_t)clip.init_offset * npx;
+        uint32_t sum = 0;
+        for (int i = lane; i < npx; i += 32) {
+            const int y = i / g.W, x = i - y * g.W;
+            if (x >= g.edge && x < g.W - g.edge && y >= g.edge && y < g.H - g.edge) sum += __ldg(init + i);
+        }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        average = (double)sum / (double)g.ncrop;
+    }
+    for (int base = 0; base <= n && n > 0; base += 32) {
+        const int t = base + lane;
+        const bool is_frame = t < n;
+        const bool upd = update_bg && t > 0 && t <= n && !(skip_first && clip.first_frame + t == 1);
+        const bool valid = t <= n && (is_frame || upd);
+        const size_t o = (size_t)(clip.out_offset + t);
+        // ---- fold the strips' records of this pass
+        uint32_t psum = 0, fabs_sum = 0, changed = 0;
+        int fmin = INT32_MAX, fmax = INT32_MIN, pmin = INT32_MAX, pmax = INT32_MIN;
+        long long nbsum = 0;
+        int ref_s[kMaxStrips], fmax_s[kMaxStrips];
+        if (valid) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(a.prec + (is_frame ? o : (size_t)(a.total_frames + ci)) * NS);
+#pragma unroll
+            for (int sidx = 0; sidx < kMaxStrips; ++sidx) {
+                ref_s[sidx] = 0;
+                fmax_s[sidx] = INT32_MIN;
+                if (sidx < NS) {
+                    const uint4 r0 = __ldcg(rp + 2 * sidx), r1 = __ldcg(rp + 2 * sidx + 1);
+                    psum += r0.x;
+                    fmin = min(fmin, (int)r0.y);
+                    fmax = max(fmax, (int)r0.z);
+                    nbsum += (int)r0.w;
+                    pmin = min(pmin, (int)r1.x);
+                    pmax = max(pmax, (int)r1.y);
+                    fabs_sum += r1.z;
+                    changed |= r1.w & 1u;
+                    ref_s[sidx] = (int)r1.w >> 1;
+                    fmax_s[sidx] = (int)r0.z;
+                }
+            }
+        }
+        // ---- WeightedBackground.average: set by pass 0 (np.average of the initial crop, unrounded) and by every update
+        // that changed the background (int(round(np.average(background))), motiondetector.py:232, half to even)
+        const uint32_t bsum = (uint32_t)(-nbsum);
+        double mine = 0.0;
+        bool sets = false;
+        if (valid && t == 0) {
+            mine = (double)bsum / (double)g.ncrop;
+            sets = true;
+        } else if (valid && upd && changed) {
+            uint32_t qa = bsum / (uint32_t)g.ncrop;
+            const uint32_t ra = bsum - qa * (uint32_t)g.ncrop;
+            if (2u * ra > (uint32_t)g.ncrop || (2u * ra == (uint32_t)g.ncrop && (qa & 1u))) qa += 1u;
+            mine = (double)qa;
+            sets = true;
+        }
+        const uint32_t set_mask = __ballot_sync(0xffffffffu, sets);
+        const uint32_t below = set_mask & (0xffffffffu >> (31 - lane));  // lanes <= this one
+        const int src = below ? 31 - __clz((int)below) : lane;
+        const double got = __shfl_sync(0xffffffffu, mine, src);
+        const double avg_here = below ? got : average;
+        average = __shfl_sync(0xffffffffu, avg_here, 31);
+        frames_seen += __popc(__ballot_sync(0xffffffffu, valid && upd));
+        if (is_frame) {
+            const FrameScalars fs = frame_scalars_of(psum, fmin, fmax, avg_here, clip.background_thresh, npx);
+            cpt_frame_info fi;
+            fi.background_average = avg_here;
+            fi.threshold = fs.thr; fi.norm_min = fs.gmn; fi.norm_max = fs.gmx; fi.avg_change = fs.ac;
+            fi.filtered_min = fmin; fi.filtered_max = fmax; fi.n_components = 0;
+            fi.thermal_min = want_stats ? pmin : 0; fi.thermal_max = want_stats ? pmax : 0;
+            fi.thermal_sum = psum; fi.abs_filtered_sum = want_stats ? fabs_sum : 0u; fi.thermal_median = 0.f;
+            fi.reserved[0] = 0;
+            fi.reserved[1] = denoise ? ((t > 0) ? 2 : 1) : 0;  // 2: the previous filtered image is frame o - 1
+            a.info[o] = fi;
+            FrameHdr h;
+            h.nmagic = fs.nmagic; h.nshift = fs.nshift;
+            h.flags = kHdrValid | (t == 0 ? kHdrFirst : 0u);
+            h.hot_strips = 0;
+            bool dense = fs.fth == INT32_MIN;
+#pragma unroll
+            for (int sidx = 0; sidx < kMaxStrips; ++sidx) {
+                int th = 127;
+                if (sidx < NS && !dense) {
+                    // stored b = clamp(max F - ref, -128, 127); hot <=> b >= clamp(fth - ref, ., 127): a superset of
+                    // max F >= fth whenever fth - ref >= -127 (else every quad of the strip could be hot: dense frame)
+                    const long long dq = (long long)fs.fth - (long long)ref_s[sidx];
+                    if (dq < -127) dense = true;
+                    th = (int)min(dq, 127ll);
+                    if (fmax_s[sidx] >= fs.fth) h.hot_strips |= 1u << sidx;
+                }
+                h.theta[sidx] = (int16_t)th;
+            }
+            if (dense) { h.flags |= kHdrDense; h.hot_strips = 0xffffffffu; }
+            uint4 *hp = reinterpret_cast<uint4 *>(a.fhdr + o);
+            const uint4 *hs = reinterpret_cast<const uint4 *>(&h);
+            hp[0] = hs[0]; hp[1] = hs[1]; hp[2] = hs[2];
+        }
+        if (t == n - 1) { last_fmin = fmin; last_fmax = fmax; }
+    }
+    if (a.state) {
+        // header of the clip's state record (the strips wrote background, counters, sums and the last filtered image)
+        const int holder = n > 0 ? (n - 1) & 31 : 0;
+        last_fmin = __shfl_sync(0xffffffffu, last_fmin, holder);
+        last_fmax = __shfl_sync(0xffffffffu, last_fmax, holder);
+        if (lane == 0) {
+            StateHeader *hd = reinterpret_cast<StateHeader *>(a.state + (size_t)ci * state_bytes(npx));
+            hd->average = average;
+            hd->frames_seen = frames_seen;
+            hd->initialised = 1;
+            hd->prev_fmin = n > 0 ? last_fmin : 0;
+            hd->prev_fmax = n > 0 ? last_fmax : 0;
+            hd->have_prev = n > 0 ? 1 : 0;
+        }
+    }
+}
+
+}  // namespace cpt

@@ -121,6 +121,7 @@ SYMBOLS = {
     "cpt_build_weight_table": (_i, [_d, _i, _vp, _vp]),
     "cpt_debug_phase_cycles": (_i, [_vp, _vp, _i]),
     "cpt_debug_kernel_times": (_i, [_vp, _i, _vp]),
+    "cpt_debug_kernel_times_ex": (_i, [_vp, _i, _vp, _i]),
     "cpt_debug_force_single_kernel": (_i, [_vp, _i]),
     "cpt_device_alloc": (_i, [_vp, ctypes.POINTER(_vp), _u64]),
     "cpt_device_free": (_i, [_vp, _vp]),

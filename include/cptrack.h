@@ -139,9 +139,13 @@ int cpt_debug_phase_cycles(cpt_ctx *ctx, long long *h_out32, int reset);
 
 /* Diagnostics: with enable != 0, every following cpt_extract_batch call brackets its launches with CUDA events on the
  * ctx stream.  h_ms4 (may be NULL) receives the durations of the last timed call in milliseconds after synchronising:
- * [0] the recurrence kernel (extract_sweep_kernel, or extract_clips_kernel on the single-kernel path), [1]
- * frame_mask_kernel + frame_components_kernel (0 on the single-kernel path), [2] the denoise passes, [3] region_variance_kernel. */
+ * [0] the recurrence kernel (strip_sweep_kernel, or extract_clips_kernel on the single-kernel path), [1]
+ * frame_scalars_kernel + the per-frame mask / component launches (0 on the single-kernel path), [2] the denoise passes,
+ * [3] region_variance_kernel. */
 int cpt_debug_kernel_times(cpt_ctx *ctx, int enable, float *h_ms4);
+/* Same, finer: h_ms[0..n-1], n <= 5: [0] strip_sweep_kernel (the recurrence; extract_clips_kernel on the single-kernel path),
+ * [1] frame_scalars_kernel, [2] the per-frame mask / component launches, [3] the denoise passes, [4] region_variance_kernel. */
+int cpt_debug_kernel_times_ex(cpt_ctx *ctx, int enable, float *h_ms, int n);
 
 /* Diagnostics / tests: with enable != 0 every extraction launch of this ctx runs the single persistent kernel, also where
  * the split plan would apply (both plans produce identical results). */

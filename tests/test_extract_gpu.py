@@ -144,7 +144,16 @@ def test_split_and_single_kernel_paths_agree_on_a_ragged_batch(extractor):
     finally:
         extractor.ctx.force_single_kernel(False)
     a, b = outs
-    assert torch.equal(a["state"], b["state"])  # the saved per-clip records (background, counters, sums, last filtered image)
+    # the saved per-clip records: background, counters (crop view), sliding sums, average, last filtered image
+    npx = 160 * 120
+    for i in range(len(lengths)):
+        sa, sb = extractor.ctx.state_read(a["state"], i, sliding_sum=True), extractor.ctx.state_read(b["state"], i, sliding_sum=True)
+        for f in ("background", "weight_count", "sliding_sum"):
+            assert np.array_equal(sa[f], sb[f]), (i, f)
+        assert sa["average"] == sb["average"] and sa["frames_seen"] == sb["frames_seen"], i
+        if lengths[i]:
+            fa_, fb_ = a["state"][i, 64 + 8 * npx :], b["state"][i, 64 + 8 * npx :]
+            assert torch.equal(fa_, fb_), i
     ia, ib = extractor.info_numpy(a["info"]), extractor.info_numpy(b["info"])
     ra, rb = extractor.regions_numpy(a["regions"]), extractor.regions_numpy(b["regions"])
     fa, fb = a["filtered"].cpu().numpy(), b["filtered"].cpu().numpy()
