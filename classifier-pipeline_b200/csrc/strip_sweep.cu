@@ -43,7 +43,8 @@ constexpr int kRefDefault = kQuadRefBias;            // reference of the first k
 
 struct __align__(128) StripSmem {
     uint8_t ring[kRingSlots][kSlotBytes];
-    uint32_t wthr[kStripTable];
+    uint16_t wthr[kStripTable];              // keep-test thresholds of the clip's table (first entries) ...
+    uint16_t wbnd[kStripTable];              // ... and their bounds (cptrack_kernels.cuh, WeightTable)
     uint32_t stat[kBarRing][kConsWarps][8];  // per pass and warp: psum, fmin, fmax, nbsum, pmin, pmax, fabs, changed
     int32_t ref_ring[16];                    // byte reference published with pass t, used by pass t + kLead
     unsigned long long full[kBarRing], done[kBarRing];
@@ -51,36 +52,39 @@ struct __align__(128) StripSmem {
 };
 static_assert(sizeof(StripSmem) <= 232448, "shared memory budget (227 KB per CTA on sm_100)");
 
-// what is uniform over the CTA in one pass
-struct PassCtx {
-    bool update, is_frame, window_full, first_mean;
-    uint32_t magic;              // floor(S / cnt) == umulhi(S, magic)
-    uint32_t cur_off, old_off;   // ring slots (byte offsets) of frame t and of frame t - 45
-    unsigned long long *full;
-    uint32_t parity;
-    const int32_t *ref_slot;     // reference for this frame's quad bytes, published by the producer (nullptr: the default)
-};
-
-struct StripThread {
-    bool active, border_row, first_col, last_col;
-    int off_src, off_out;  // byte offsets of the quad inside a ring slot: the row its state follows / the row it outputs
-    float *fptr;           // the thread's quad in this frame's outputs (advanced by the caller after every frame)
-    uint8_t *lptr;
-    int8_t *qptr;
-};
-
-// A thread's pixels: nB = -background, S = sliding sum, kv = weight counter k -- or, while the keep test is the linear one
-// (thr = k + 1, weight_add == 1), v = nB - k: then keep <=> A - B >= k + 1 <=> v > -A, and both outcomes fold into
-// v' = max(v - 1, -A) (kept: k + 1; reset: background = A, k = 0).  k = nB - v either way (the same formula converts back).
+// A thread's pixels.  Everything is kept biased by kBias = 0x4B400000 (the bits of 1.5 * 2^23): nb = kBias - background, so
+// that thermal + nb is at once the integer filtered + kBias (ordering, extrema and differences are unaffected) and the bit
+// pattern of the float 12582912 + filtered -- one FADD instead of an integer-to-float conversion per pixel.
+// kv = the weight counter k -- or, while the keep test is the linear one (thr = k + 1, weight_add == 1), v = nb - k: then
+// keep <=> A - B >= k + 1 <=> v > kBias - A, and both outcomes fold into v' = max(v - 1, kBias - A) (kept: k + 1; reset:
+// background = A, k = 0).  k = nb - v either way (the same formula converts back).
+constexpr int kBias = 0x4B400000;
+constexpr float kBiasF = 12582912.0f;
 struct QuadState {
-    int nB[4], kv[4], f[4];
+    int nb[4], kv[4], f[4];
     uint32_t S[4];
     bool lin;
 };
 
+struct StripThread {
+    bool active, border_row, first_col, last_col;
+    const uint8_t *src, *out;  // the quad inside ring slot 0: the row its state follows / the row it outputs
+    int m[4];                  // 1: the pixel counts for the background sum (crop pixel of an owned row)
+    int bs0;                   // -(m[0] + .. + m[3]) * kBias
+    float *fptr;               // the thread's quad in this frame's outputs (advanced after every frame)
+    uint8_t *lptr;
+    int8_t *qptr;
+};
+
+// what is uniform over the CTA in one pass of the generic path
+struct PassCtx {
+    bool update, is_frame, window_full, first_mean;
+    uint32_t magic;              // floor(S / cnt) == umulhi(S, magic)
+};
+
 struct PassOut {
     uint32_t psum;
-    int fmin, fmax, bs, chg, pmin, pmax;
+    int fmin, fmax, bs, chg, pmin, pmax;   // fmin / fmax biased by kBias
     uint32_t fabs_sum;
 };
 
@@ -91,53 +95,50 @@ __device__ __forceinline__ uint2 lds8(const uint8_t *p) { return *reinterpret_ca
 // frame against B' (F = P - B', S += P - P_old) with the frame's sums.  State is unpacked 32-bit integers.
 // kTab: 0 thr = k + 1 (weight_add == 1; QuadState::lin form), 1 table in shared memory, 2 table in shared + global memory.
 // kSteady: update && frame && window full && cnt == 45 are compile-time facts.
-template <int kTab, bool kStats, bool kSteady>
+// bmax: largest bound of the table entries a counter can have reached (bounds only matter for backgrounds below them).
+template <int kTab, bool kStats, bool kSteady, bool kLabels>
 __device__ __forceinline__ void strip_pass(StripSmem &s, const WeightTable &wt, const PassCtx &pc, const StripThread &th,
-                                           QuadState &q, PassOut &po) {
+                                           QuadState &q, PassOut &po, uint32_t cur_off, uint32_t old_off, int refb, int bmax) {
     const bool is_frame = kSteady || pc.is_frame;
     uint2 pw = make_uint2(0, 0), pv = make_uint2(0, 0), ow = make_uint2(0, 0);
-    int ref = kRefDefault;
     if (is_frame) {
-        mbar_wait(pc.full, pc.parity);
-        // (read after the acquire: the producer published it before it issued this frame's copy)
-        if (pc.ref_slot) ref = *(volatile const int32_t *)pc.ref_slot;
-        const uint8_t *cur = &s.ring[0][0] + pc.cur_off;
-        pw = lds8(cur + th.off_src);
-        pv = th.border_row ? lds8(cur + th.off_out) : pw;
-        if (kSteady || pc.window_full) ow = lds8(&s.ring[0][0] + pc.old_off + th.off_src);
+        pw = lds8(th.src + cur_off);
+        pv = th.border_row ? lds8(th.out + cur_off) : pw;
+        if (kSteady || pc.window_full) ow = lds8(th.src + old_off);
     }
     int chg = 0;
     if (kSteady || pc.update) {
-        int nA[4], nn[4];
+        int na[4], nn[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) nA[i] = -(int)((!kSteady && pc.first_mean) ? q.S[i] : __umulhi(q.S[i], pc.magic));
+        for (int i = 0; i < 4; ++i) na[i] = kBias - (int)((!kSteady && pc.first_mean) ? q.S[i] : __umulhi(q.S[i], pc.magic));
         if (kTab == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                nn[i] = q.kv[i] > nA[i] ? q.nB[i] : nA[i];
-                q.kv[i] = __viaddmax_s32(q.kv[i], -1, nA[i]);
+                nn[i] = q.kv[i] > na[i] ? q.nb[i] : na[i];
+                q.kv[i] = __viaddmax_s32(q.kv[i], -1, na[i]);
             }
         } else {
             int e[4];
+            const bool use_global = kTab == 2;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (kTab == 1) e[i] = (int)s.wthr[q.kv[i]];
-                else e[i] = (int)(q.kv[i] < kStripTable ? s.wthr[q.kv[i]] : __ldg(wt.thr + q.kv[i]));
+                if (use_global && q.kv[i] >= kStripTable) e[i] = (int)(__ldg(wt.thr + q.kv[i]) & 0xffffu);
+                else e[i] = (int)s.wthr[q.kv[i]];
             }
-            if (wt.has_bounds) {
-                // entries with a bound (the fp64 rounding of A - w_k depends on the magnitude of B) are rare: one vote per quad
-                if (__any_sync(0xffffffffu, (uint32_t)(e[0] | e[1] | e[2] | e[3]) > 0xffffu)) {
+            // bounds (the fp64 rounding of A - w_k depends on the magnitude of B) only matter for backgrounds below the largest
+            // bound a counter can have reached: one vote per quad, rarely taken
+            const int nbmax = max(max(q.nb[0], q.nb[1]), max(q.nb[2], q.nb[3]));
+            if (__any_sync(0xffffffffu, nbmax + bmax > kBias)) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int bound = (int)((uint32_t)e[i] >> 16);
-                        e[i] = (e[i] & 0xffff) - ((-q.nB[i] < bound) ? 1 : 0);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const int bound = (use_global && q.kv[i] >= kStripTable) ? (int)(__ldg(wt.thr + q.kv[i]) >> 16) : (int)s.wbnd[q.kv[i]];
+                    e[i] -= (q.nb[i] + bound > kBias) ? 1 : 0;   // B < bound
                 }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const bool keep = q.nB[i] - nA[i] >= e[i];  // A - B >= thr
-                nn[i] = keep ? q.nB[i] : nA[i];
+                const bool keep = q.nb[i] - na[i] >= e[i];  // A - B >= thr
+                nn[i] = keep ? q.nb[i] : na[i];
                 q.kv[i] = keep ? q.kv[i] + 1 : 0;
             }
         }
@@ -147,23 +148,21 @@ __device__ __forceinline__ void strip_pass(StripSmem &s, const WeightTable &wt, 
         if (th.last_col) nn[3] = nn[2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            chg |= nn[i] ^ q.nB[i];
-            q.nB[i] = nn[i];
+            chg |= nn[i] ^ q.nb[i];
+            q.nb[i] = nn[i];
         }
     }
-    // minus the background sum over the crop pixels of owned rows
-    int bs = q.nB[0] + q.nB[1] + q.nB[2] + q.nB[3];
-    if (th.first_col) bs -= q.nB[0];
-    if (th.last_col) bs -= q.nB[3];
-    if (th.border_row || !th.active) bs = 0;
-    po.bs = bs;
-    po.chg = th.active ? chg : 0;
+    // minus the background sum over the crop pixels of owned rows (wrapping arithmetic takes the bias out again)
+    po.bs = (int)((uint32_t)q.nb[0] * (uint32_t)th.m[0] +
+                  ((uint32_t)q.nb[1] * (uint32_t)th.m[1] +
+                   ((uint32_t)q.nb[2] * (uint32_t)th.m[2] + ((uint32_t)q.nb[3] * (uint32_t)th.m[3] + (uint32_t)th.bs0))));
+    po.chg = chg;  // (inactive threads follow a real row of the strip: duplicates of real changes)
     po.psum = 0;
     po.fmin = INT32_MAX; po.fmax = INT32_MIN; po.pmin = INT32_MAX; po.pmax = INT32_MIN; po.fabs_sum = 0;
     if (is_frame) {
         int (&f)[4] = q.f;
-        f[0] = dp2a_us(pv.x, kLoP, q.nB[0]); f[1] = dp2a_us(pv.x, kHiP, q.nB[1]);
-        f[2] = dp2a_us(pv.y, kLoP, q.nB[2]); f[3] = dp2a_us(pv.y, kHiP, q.nB[3]);
+        f[0] = dp2a_us(pv.x, kLoP, q.nb[0]); f[1] = dp2a_us(pv.x, kHiP, q.nb[1]);
+        f[2] = dp2a_us(pv.y, kLoP, q.nb[2]); f[3] = dp2a_us(pv.y, kHiP, q.nb[3]);
         q.S[0] = (uint32_t)dp2a_us(pw.x, kLoP, dp2a_us(ow.x, kLoN, (int)q.S[0]));
         q.S[1] = (uint32_t)dp2a_us(pw.x, kHiP, dp2a_us(ow.x, kHiN, (int)q.S[1]));
         q.S[2] = (uint32_t)dp2a_us(pw.y, kLoP, dp2a_us(ow.y, kLoN, (int)q.S[2]));
@@ -177,23 +176,24 @@ __device__ __forceinline__ void strip_pass(StripSmem &s, const WeightTable &wt, 
                 const int p0 = (int)(pv.x & 0xffffu), p1 = (int)(pv.x >> 16), p2 = (int)(pv.y & 0xffffu), p3 = (int)(pv.y >> 16);
                 po.pmin = min(min(p0, p1), min(p2, p3));
                 po.pmax = max(max(p0, p1), max(p2, p3));
-                po.fabs_sum = (uint32_t)(abs(f[0]) + abs(f[1]) + abs(f[2]) + abs(f[3]));
+                po.fabs_sum = (uint32_t)(abs(f[0] - kBias) + abs(f[1] - kBias) + abs(f[2] - kBias) + abs(f[3] - kBias));
             }
-            *reinterpret_cast<float4 *>(th.fptr) = make_float4((float)f[0], (float)f[1], (float)f[2], (float)f[3]);
-            if (th.lptr) *reinterpret_cast<uint32_t *>(th.lptr) = 0u;
+            *reinterpret_cast<float4 *>(th.fptr) = make_float4(__int_as_float(f[0]) - kBiasF, __int_as_float(f[1]) - kBiasF,
+                                                               __int_as_float(f[2]) - kBiasF, __int_as_float(f[3]) - kBiasF);
+            if (kLabels) *reinterpret_cast<uint32_t *>(th.lptr) = 0u;
             int b;
-            asm("cvt.sat.s8.s32 %0, %1;" : "=r"(b) : "r"(hi - ref));
+            asm("cvt.sat.s8.s32 %0, %1;" : "=r"(b) : "r"(hi - refb));
             *th.qptr = (int8_t)b;
         }
     }
 }
 
-// k <-> v = nB - k (QuadState): the same formula both ways.  Border columns restart from k = 0 (their counters are
+// k <-> v = nb - k (QuadState): the same formula both ways.  Border columns restart from k = 0 (their counters are
 // never used; this keeps table indices in range).
 __device__ __forceinline__ void quad_state_form(QuadState &q, const StripThread &th, bool lin) {
     if (q.lin == lin) return;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) q.kv[i] = q.nB[i] - q.kv[i];
+    for (int i = 0; i < 4; ++i) q.kv[i] = q.nb[i] - q.kv[i];
     if (!lin) {
         if (th.first_col) q.kv[0] = 0;
         if (th.last_col) q.kv[3] = 0;
@@ -201,7 +201,42 @@ __device__ __forceinline__ void quad_state_form(QuadState &q, const StripThread 
     q.lin = lin;
 }
 
+// the running positions of a consumer warp: pass t, its ring slots and barriers
+struct PassPos {
+    int t;
+    uint32_t cur_off, old_off;   // ring slots (byte offsets) of frame t and of frame t - 45 (== the slot of frame t + kLead)
+    int frames_seen;             // background updates applied so far: no weight counter can exceed it
+    int bmax;                    // largest bound among the table entries [0, frames_seen]
+};
+
+__device__ __forceinline__ void pass_advance(PassPos &p) {
+    ++p.t;
+    p.cur_off += kSlotBytes;
+    if (p.cur_off == (uint32_t)kRingSlots * kSlotBytes) p.cur_off = 0;
+    p.old_off += kSlotBytes;
+    if (p.old_off == (uint32_t)kRingSlots * kSlotBytes) p.old_off = 0;
+}
+
+// the warp's partial results -> its row of the pass table (the producer warp folds the rows), then the warp's arrival
 template <bool kStats>
+__device__ __forceinline__ void pass_report(StripSmem &s, const PassOut &po, int bi, int warp, int lane) {
+    const uint32_t psum = __reduce_add_sync(0xffffffffu, po.psum);
+    const int fmin = __reduce_min_sync(0xffffffffu, po.fmin), fmax = __reduce_max_sync(0xffffffffu, po.fmax);
+    const int bs = __reduce_add_sync(0xffffffffu, po.bs);
+    const bool chg = __any_sync(0xffffffffu, po.chg != 0);
+    uint4 *row = reinterpret_cast<uint4 *>(s.stat[bi][warp]);
+    if (kStats) {
+        const int pmin = __reduce_min_sync(0xffffffffu, po.pmin), pmax = __reduce_max_sync(0xffffffffu, po.pmax);
+        const uint32_t fabs_sum = __reduce_add_sync(0xffffffffu, po.fabs_sum);
+        if (lane == 0) row[1] = make_uint4((uint32_t)pmin, (uint32_t)pmax, fabs_sum, 0u);
+    }
+    // (psum < 2^23 for a warp: bit 31 carries `changed`)
+    if (lane == 0) row[0] = make_uint4(psum | (chg ? 0x80000000u : 0u), (uint32_t)fmin, (uint32_t)fmax, (uint32_t)bs);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.done[bi]);  // (release: the ring reads and the row are done)
+}
+
+template <bool kStats, bool kLabels>
 __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip &clip, int ci, int y0, int rows, int tid) {
     const Geometry &g = a.g;
     const int W = g.W, H = g.H, e = g.edge, qpr = g.qpr, npx = g.npx;
@@ -218,11 +253,16 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
     th.border_row = ys != y;
     th.first_col = e && qx == 0;
     th.last_col = e && qx == qpr - 1;
-    th.off_src = ((ys - y0) * W + 4 * qx) * 2;
-    th.off_out = ((y - y0) * W + 4 * qx) * 2;
+    th.src = &s.ring[0][0] + ((ys - y0) * W + 4 * qx) * 2;
+    th.out = &s.ring[0][0] + ((y - y0) * W + 4 * qx) * 2;
+    {
+        const int own = (th.active && !th.border_row) ? 1 : 0;
+        th.m[0] = th.first_col ? 0 : own; th.m[1] = own; th.m[2] = own; th.m[3] = th.last_col ? 0 : own;
+        th.bs0 = (int)(0u - (uint32_t)(th.m[0] + th.m[1] + th.m[2] + th.m[3]) * (uint32_t)kBias);
+    }
     const int pix = y * W + 4 * qx;
     th.fptr = a.filtered + (size_t)clip.out_offset * npx + pix;
-    th.lptr = a.labels ? a.labels + (size_t)clip.out_offset * npx + pix : nullptr;
+    th.lptr = a.labels + (size_t)clip.out_offset * npx + pix;   // (only dereferenced with kLabels)
     th.qptr = a.qbytes + (size_t)clip.out_offset * (H * qpr) + (y * qpr + qx);
     const int qstride = H * qpr;
 
@@ -235,97 +275,98 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         int b0 = (int)(v.x & 0xffffu), b1 = (int)(v.x >> 16), b2 = (int)(v.y & 0xffffu), b3 = (int)(v.y >> 16);
         if (th.first_col) b0 = b1;
         if (th.last_col) b3 = b2;
-        q.nB[0] = -b0; q.nB[1] = -b1; q.nB[2] = -b2; q.nB[3] = -b3;
+        q.nb[0] = kBias - b0; q.nb[1] = kBias - b1; q.nb[2] = kBias - b2; q.nb[3] = kBias - b3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { q.kv[i] = 0; q.S[i] = 0; q.f[i] = 0; }
+        for (int i = 0; i < 4; ++i) { q.kv[i] = 0; q.S[i] = 0; q.f[i] = kBias; }
     }
 
-    int frames_seen = 0;
-    // running ring / barrier positions of pass t
-    uint32_t cur_off = 0, old_off = (uint32_t)kLead * kSlotBytes;  // slot of frame t - 45 == slot of frame t + kLead
-    int bi = 0;            // t % kBarRing
-    uint32_t parity = 0;   // (t / kBarRing) & 1
+    PassPos pp;
+    pp.t = 0;
+    pp.cur_off = 0;
+    pp.old_off = (uint32_t)kLead * kSlotBytes;
+    pp.frames_seen = 0;
+    pp.bmax = 0;
     constexpr uint32_t kMagic45 = 0xffffffffu / (uint32_t)kMeanFrames + 1u;
+    auto table_bound = [&](int k) -> int {  // bound of table entry k
+        if (k > wt.max_count) return 0;
+        return k < kStripTable ? (int)s.wbnd[k] : (int)(__ldg(wt.thr + k) >> 16);
+    };
+    auto frame_sync = [&](int t, int &refb) {
+        // the frame's rows are in the ring; the reference its quad bytes are stored against was published by the producer
+        // before it issued the copy (read after the acquire)
+        mbar_wait(&s.full[t & (kBarRing - 1)], (uint32_t)(t >> 3) & 1u);
+        refb = (t >= kLead ? *(volatile const int32_t *)&s.ref_ring[(t - kLead) & 15] : kRefDefault) + kBias;
+    };
+    static_assert(kBarRing == 8, "parity = (t >> 3) & 1");
+    auto after_frame = [&]() {
+        th.fptr += npx;
+        th.lptr += npx;
+        th.qptr += qstride;
+    };
 
-    // one pass; kSteadyPass: frame + update + full window + 45-frame mean
-    auto pass = [&](int t, auto steady_tag) {
-        constexpr bool kSteadyPass = decltype(steady_tag)::value;
+    // ---- generic pass (the first 45 frames, the tail pass, clips that do not update their background)
+    auto generic_pass = [&]() {
+        const int t = pp.t;
         PassCtx pc;
-        const bool is_frame = kSteadyPass || t < n;
+        pc.is_frame = t < n;
         const int t_abs = clip.first_frame + t;
         // (rawdb.py:84-122: no update follows the frame that initialised the background when it is also the first kept frame)
-        pc.update = kSteadyPass || (update_bg && t > 0 && !(skip_first && t_abs == 1));
-        pc.is_frame = is_frame;
-        if (kSteadyPass) {
-            pc.first_mean = false;
-            pc.magic = kMagic45;
-            pc.window_full = true;
-        } else {
-            // the update belongs to frame t-1: the mean covers min(t_abs, 45) frames
-            const uint32_t cnt = (uint32_t)min(max(t_abs, 1), kMeanFrames);
-            pc.first_mean = cnt == 1u;
-            pc.magic = cnt == 1u ? 0u : 0xffffffffu / cnt + 1u;  // exact for S < 2^22, cnt <= 45
-            pc.window_full = t >= kMeanFrames;
-        }
-        pc.cur_off = cur_off;
-        pc.old_off = old_off;
-        pc.full = &s.full[bi];
-        pc.parity = parity;
-        pc.ref_slot = t >= kLead ? &s.ref_ring[(t - kLead) & 15] : nullptr;
-        const int tab = frames_seen < wt.linear_upto ? 0 : (frames_seen < kStripTable ? 1 : 2);
-        quad_state_form(q, th, tab == 0);
+        pc.update = update_bg && t > 0 && !(skip_first && t_abs == 1);
+        // the update belongs to frame t-1: the mean covers min(t_abs, 45) frames
+        const uint32_t cnt = (uint32_t)min(max(t_abs, 1), kMeanFrames);
+        pc.first_mean = cnt == 1u;
+        pc.magic = cnt == 1u ? 0u : 0xffffffffu / cnt + 1u;  // exact for S < 2^22, cnt <= 45
+        pc.window_full = t >= kMeanFrames;
+        int refb = kRefDefault + kBias;
+        if (pc.is_frame) frame_sync(t, refb);
+        const bool lin = pp.frames_seen < wt.linear_upto;
+        quad_state_form(q, th, lin);
         PassOut po;
-        if (tab == 0) strip_pass<0, kStats, kSteadyPass>(s, wt, pc, th, q, po);
-        else if (tab == 1 && kSteadyPass) strip_pass<1, kStats, kSteadyPass>(s, wt, pc, th, q, po);
-        else strip_pass<2, kStats, kSteadyPass>(s, wt, pc, th, q, po);
-        if (pc.update) ++frames_seen;
-        // ---- the warp's partial results -> its row of the pass table; the producer warp folds the rows
-        {
-            const uint32_t psum = __reduce_add_sync(0xffffffffu, po.psum);
-            const int fmin = __reduce_min_sync(0xffffffffu, po.fmin), fmax = __reduce_max_sync(0xffffffffu, po.fmax);
-            const int bs = __reduce_add_sync(0xffffffffu, po.bs);
-            const bool chg = __any_sync(0xffffffffu, po.chg != 0);
-            int pmin = INT32_MAX, pmax = INT32_MIN;
-            uint32_t fabs_sum = 0;
-            if (kStats) {
-                pmin = __reduce_min_sync(0xffffffffu, po.pmin);
-                pmax = __reduce_max_sync(0xffffffffu, po.pmax);
-                fabs_sum = __reduce_add_sync(0xffffffffu, po.fabs_sum);
-            }
-            if (lane == 0) {
-                uint4 *row = reinterpret_cast<uint4 *>(s.stat[bi][warp]);
-                row[0] = make_uint4(psum, (uint32_t)fmin, (uint32_t)fmax, (uint32_t)bs);
-                row[1] = make_uint4((uint32_t)pmin, (uint32_t)pmax, fabs_sum, chg ? 1u : 0u);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.done[bi]);  // (release: the ring reads and the row are done)
+        if (lin) strip_pass<0, kStats, false, kLabels>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax);
+        else strip_pass<2, kStats, false, kLabels>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax);
+        if (pc.update) {
+            ++pp.frames_seen;
+            pp.bmax = max(pp.bmax, table_bound(pp.frames_seen));
         }
-        if (is_frame) {
-            th.fptr += npx;
-            if (th.lptr) th.lptr += npx;
-            th.qptr += qstride;
-        }
-        cur_off += kSlotBytes;
-        if (cur_off == (uint32_t)kRingSlots * kSlotBytes) cur_off = 0;
-        old_off += kSlotBytes;
-        if (old_off == (uint32_t)kRingSlots * kSlotBytes) old_off = 0;
-        bi = (bi + 1) & (kBarRing - 1);
-        parity ^= (bi == 0) ? 1u : 0u;
+        pass_report<kStats>(s, po, t & (kBarRing - 1), warp, lane);
+        if (pc.is_frame) after_frame();
+        pass_advance(pp);
     };
-    using SteadyTag = std::true_type;
-    using GenericTag = std::false_type;
+    // ---- steady passes [pp.t, t_end) with one keep-test form
+    auto steady_passes = [&](int t_end, auto tab_tag) {
+        constexpr int kTab = decltype(tab_tag)::value;
+        quad_state_form(q, th, kTab == 0);
+        if (kTab != 0) pp.bmax = max(pp.bmax, table_bound(pp.frames_seen));
+        PassCtx pc;
+        pc.update = true; pc.is_frame = true; pc.window_full = true; pc.first_mean = false;
+        pc.magic = kMagic45;
+        while (pp.t < t_end) {
+            int refb;
+            frame_sync(pp.t, refb);
+            PassOut po;
+            strip_pass<kTab, kStats, true, kLabels>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax);
+            ++pp.frames_seen;
+            if (kTab != 0) pp.bmax = max(pp.bmax, table_bound(pp.frames_seen));
+            pass_report<kStats>(s, po, pp.t & (kBarRing - 1), warp, lane);
+            after_frame();
+            pass_advance(pp);
+        }
+    };
 
     // passes 0 .. n: frames t < n, then the tail pass (the background update that follows the last frame).  A pass is
     // steady once the window is full, i.e. for 45 <= t < n when the clip updates its background from its first frame on.
     const bool can_steady = update_bg && clip.first_frame >= 0;
-    int t = 0;
-    for (; t < min(n, kMeanFrames); ++t) pass(t, GenericTag{});
-    if (can_steady) {
-        for (; t < n; ++t) pass(t, SteadyTag{});
-    } else {
-        for (; t < n; ++t) pass(t, GenericTag{});
+    while (pp.t < min(n, kMeanFrames)) generic_pass();
+    while (pp.t < n) {
+        if (!can_steady) { generic_pass(); continue; }
+        // the keep-test form changes with the number of updates so far: linear while every reachable entry is k + 1, then the
+        // shared-memory table, then shared + global
+        const int fs = pp.frames_seen;
+        if (fs < wt.linear_upto) steady_passes(min(n, pp.t + (wt.linear_upto - fs)), std::integral_constant<int, 0>{});
+        else if (fs < kStripTable) steady_passes(min(n, pp.t + (kStripTable - fs)), std::integral_constant<int, 1>{});
+        else steady_passes(n, std::integral_constant<int, 2>{});
     }
-    if (update_bg && n > 0 && !(skip_first && clip.first_frame + n == 1)) pass(n, GenericTag{});
+    if (update_bg && n > 0 && !(skip_first && clip.first_frame + n == 1)) generic_pass();
 
     // ---- the clip's state record (cpt_state_bytes): background, counters, sliding sums, last filtered image
     if (a.state && th.active) {
@@ -336,8 +377,8 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         uint32_t *st_S = reinterpret_cast<uint32_t *>(st_K + npx);
         float *st_F = reinterpret_cast<float *>(st_S + npx);
         uint2 bw, kw;
-        bw.x = (uint32_t)(-q.nB[0]) | ((uint32_t)(-q.nB[1]) << 16);
-        bw.y = (uint32_t)(-q.nB[2]) | ((uint32_t)(-q.nB[3]) << 16);
+        bw.x = (uint32_t)(kBias - q.nb[0]) | ((uint32_t)(kBias - q.nb[1]) << 16);
+        bw.y = (uint32_t)(kBias - q.nb[2]) | ((uint32_t)(kBias - q.nb[3]) << 16);
         // (a border row / column has no counter of its own: zero, as the crop view of cpt_state_read never shows it)
         const int k0 = th.first_col ? 0 : q.kv[0], k3 = th.last_col ? 0 : q.kv[3];
         kw.x = th.border_row ? 0u : ((uint32_t)k0 | ((uint32_t)q.kv[1] << 16));
@@ -345,7 +386,9 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         *reinterpret_cast<uint2 *>(st_B + pix) = bw;
         *reinterpret_cast<uint2 *>(st_K + pix) = kw;
         *reinterpret_cast<uint4 *>(st_S + pix) = th.border_row ? make_uint4(0, 0, 0, 0) : make_uint4(q.S[0], q.S[1], q.S[2], q.S[3]);
-        if (n > 0) *reinterpret_cast<float4 *>(st_F + pix) = make_float4((float)q.f[0], (float)q.f[1], (float)q.f[2], (float)q.f[3]);
+        if (n > 0)
+            *reinterpret_cast<float4 *>(st_F + pix) = make_float4((float)(q.f[0] - kBias), (float)(q.f[1] - kBias), (float)(q.f[2] - kBias),
+                                                                  (float)(q.f[3] - kBias));
     }
 }
 
@@ -377,9 +420,11 @@ __device__ void strip_producer(const KernelArgs &a, StripSmem &s, const cpt_clip
         const bool in = lane < kConsWarps;
         const uint4 r0 = *reinterpret_cast<const uint4 *>(row), r1 = *reinterpret_cast<const uint4 *>(row + 4);
         StripRec rec;
-        rec.psum = __reduce_add_sync(0xffffffffu, in ? r0.x : 0u);
-        rec.fmin = __reduce_min_sync(0xffffffffu, in ? (int)r0.y : INT32_MAX);
-        rec.fmax = __reduce_max_sync(0xffffffffu, in ? (int)r0.z : INT32_MIN);
+        rec.psum = __reduce_add_sync(0xffffffffu, in ? (r0.x & 0x7fffffffu) : 0u);
+        // (the consumers' extrema carry the bias of their filtered values; INT32_MAX / INT32_MIN of a pass without a frame wrap,
+        // the record of such a pass is never read for them)
+        rec.fmin = __reduce_min_sync(0xffffffffu, in ? (int)r0.y : INT32_MAX) - kBias;
+        rec.fmax = __reduce_max_sync(0xffffffffu, in ? (int)r0.z : INT32_MIN) - kBias;
         rec.nbsum = __reduce_add_sync(0xffffffffu, in ? (int)r0.w : 0);
         rec.pmin = 0; rec.pmax = 0; rec.fabs_sum = 0;
         if (want_stats) {
@@ -387,7 +432,7 @@ __device__ void strip_producer(const KernelArgs &a, StripSmem &s, const cpt_clip
             rec.pmax = __reduce_max_sync(0xffffffffu, in ? (int)r1.y : INT32_MIN);
             rec.fabs_sum = __reduce_add_sync(0xffffffffu, in ? r1.z : 0u);
         }
-        const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? r1.w : 0u);
+        const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? (r0.x >> 31) : 0u);
         if (lane == 0) {
             const int ref = t >= kLead ? s.ref_ring[(t - kLead) & 15] : kRefDefault;  // what pass t's bytes were stored against
             rec.ref_changed = (int32_t)(((uint32_t)ref << 1) | (changed & 1u));
@@ -436,12 +481,21 @@ __global__ void __launch_bounds__(kStripThreads, 1) strip_sweep_kernel(const Ker
         }
         {
             const WeightTable wt = a.tables[clip.weight_table & 3];
-            for (int i = tid; i < kStripTable; i += kStripThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
+            for (int i = tid; i < kStripTable; i += kStripThreads) {
+                const uint32_t e = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
+                s.wthr[i] = (uint16_t)(e & 0xffffu);
+                s.wbnd[i] = (uint16_t)(e >> 16);
+            }
         }
         __syncthreads();
         if (tid < kConsThreads) {
-            if (clip.flags & CPT_CLIP_FRAME_STATS) strip_consumer<true>(a, s, clip, ci, y0, rows, tid);
-            else strip_consumer<false>(a, s, clip, ci, y0, rows, tid);
+            if (clip.flags & CPT_CLIP_FRAME_STATS) {
+                if (a.labels) strip_consumer<true, true>(a, s, clip, ci, y0, rows, tid);
+                else strip_consumer<true, false>(a, s, clip, ci, y0, rows, tid);
+            } else {
+                if (a.labels) strip_consumer<false, true>(a, s, clip, ci, y0, rows, tid);
+                else strip_consumer<false, false>(a, s, clip, ci, y0, rows, tid);
+            }
         } else {
             strip_producer(a, s, clip, ci, strip, y0, rows, tid - kConsThreads);
         }

@@ -124,11 +124,13 @@ def test_counters_past_the_shared_memory_table(extractor, weight_add, bt, index,
         assert st["weight_count"].max() > 2000  # the counters really went past the shared-memory prefix
 
 
-def test_table_shorter_than_the_clip(extractor):
+def test_table_shorter_than_the_clip():
     """max_frames = 300 on a 700-frame dark-start clip: the device equals the oracle while no counter has reached the
     end of the table; from there counters stop keeping (their background resets) and both launch plans still agree."""
+    from classifier_pipeline_b200.batch import BatchExtractor
     from oracle import oracle as orc
 
+    extractor = BatchExtractor(device=0, max_regions=32)  # (a fresh context: a context keeps the longest table it was asked for)
     T, cap = 700, 300
     pix = _dark_start_clip(202, T, 400)
     runs = []
