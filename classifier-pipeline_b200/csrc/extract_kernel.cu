@@ -1604,6 +1604,11 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
     const int ith = (int)floorf(thr);
     const bool no_fg = ith >= 255;  // nothing can exceed the threshold: the mask stays empty
     bool dense = (hdr.z & kHdrDense) != 0;  // no usable bound: every group is normalised and blurred
+    if (no_fg || (!dense && hdr.w == 0u)) {
+        // nothing can reach the threshold (no strip holds a hot quad): the mask is empty, frame_components_kernel leaves at once
+        if (tid == 0) a.fhdr[o].flags = hdr.z | kHdrEmpty;
+        return;
+    }
     const int owned = g.H - 2 * g.edge;
     if ((g.words & 3) == 0) {
         for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(s.M[0])[i] = make_uint4(0, 0, 0, 0);

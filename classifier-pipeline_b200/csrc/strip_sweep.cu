@@ -39,14 +39,15 @@ constexpr int kBarRing = 8;                          // full / done barriers and
 static_assert(kBarRing > kLead, "a barrier is reused only after every warp has passed its previous use");
 static_assert(kStripThreads == kConsThreads + 32, "consumer warps + the producer warp");
 constexpr int kStripTable = 4096;                    // first entries of the clip's keep-test table
-constexpr int kRefDefault = kQuadRefBias;            // reference of the first kLead frames (filtered starts near 0)
+constexpr int kRefLag = kLead + 1;                    // a frame's quad bytes are stored against the strip minimum kRefLag frames earlier
+constexpr int kRefDefault = kQuadRefBias;            // reference of the first kRefLag frames (filtered starts near 0)
 
 struct __align__(128) StripSmem {
     uint8_t ring[kRingSlots][kSlotBytes];
     uint16_t wthr[kStripTable];              // keep-test thresholds of the clip's table (first entries) ...
     uint16_t wbnd[kStripTable];              // ... and their bounds (cptrack_kernels.cuh, WeightTable)
     uint32_t stat[kBarRing][kConsWarps][8];  // per pass and warp: psum, fmin, fmax, nbsum, pmin, pmax, fabs, changed
-    int32_t ref_ring[16];                    // byte reference published with pass t, used by pass t + kLead
+    int32_t ref_ring[16];                    // byte reference published with pass t, used by pass t + kRefLag
     unsigned long long full[kBarRing], done[kBarRing];
     int32_t unit;
 };
@@ -295,7 +296,7 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         // the frame's rows are in the ring; the reference its quad bytes are stored against was published by the producer
         // before it issued the copy (read after the acquire)
         mbar_wait(&s.full[t & (kBarRing - 1)], (uint32_t)(t >> 3) & 1u);
-        refb = (t >= kLead ? *(volatile const int32_t *)&s.ref_ring[(t - kLead) & 15] : kRefDefault) + kBias;
+        refb = (t >= kRefLag ? *(volatile const int32_t *)&s.ref_ring[(t - kRefLag) & 15] : kRefDefault) + kBias;
     };
     static_assert(kBarRing == 8, "parity = (t >> 3) & 1");
     auto after_frame = [&]() {
@@ -401,51 +402,55 @@ __device__ void strip_producer(const KernelArgs &a, StripSmem &s, const cpt_clip
     const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
     const uint32_t bytes = (uint32_t)(rows * g.W) * 2u;
     const unsigned long long policy = l2_policy_evict_first();  // every frame is read exactly once
+    const bool linear = clip.ring_frames == 0;
+    const uint16_t *lin_src = a.frames + (size_t)clip.frame_offset * g.npx + (size_t)y0 * g.W;  // frame 0 of a linear clip
     auto issue = [&](int fidx) {
         if (lane == 0) {
-            const int64_t idx = clip.ring_frames ? (int64_t)((clip.first_frame + fidx) % clip.ring_frames) : (int64_t)fidx;
-            const uint16_t *src = a.frames + (size_t)(clip.frame_offset + idx) * g.npx + (size_t)y0 * g.W;
+            const uint16_t *src = linear ? lin_src + (size_t)fidx * g.npx
+                                         : a.frames + (size_t)(clip.frame_offset + (clip.first_frame + fidx) % clip.ring_frames) * g.npx + (size_t)y0 * g.W;
             unsigned long long *bar = &s.full[fidx & (kBarRing - 1)];
             mbar_arrive_expect_tx(bar, bytes);
             bulk_g2s_hint(s.ring[fidx % kRingSlots], src, bytes, bar, policy);
         }
     };
     for (int fidx = 0; fidx < min(kLead, n); ++fidx) issue(fidx);
+    uint4 *rec_frame = reinterpret_cast<uint4 *>(a.prec + (size_t)clip.out_offset * NS + strip);  // pass t: + t * NS records
+    uint4 *rec_tail = reinterpret_cast<uint4 *>(a.prec + (size_t)(a.total_frames + ci) * NS + strip);
+    const bool in = lane < kConsWarps;
     for (int t = 0; t <= n; ++t) {
         const bool is_frame = t < n;
         const bool update = update_bg && t > 0 && !(skip_first && clip.first_frame + t == 1);
         if (!update && !is_frame) break;
         mbar_wait(&s.done[t & (kBarRing - 1)], (uint32_t)(t / kBarRing) & 1u);  // every consumer warp has finished pass t
-        const uint32_t *row = s.stat[t & (kBarRing - 1)][lane < kConsWarps ? lane : 0];
-        const bool in = lane < kConsWarps;
-        const uint4 r0 = *reinterpret_cast<const uint4 *>(row), r1 = *reinterpret_cast<const uint4 *>(row + 4);
-        StripRec rec;
-        rec.psum = __reduce_add_sync(0xffffffffu, in ? (r0.x & 0x7fffffffu) : 0u);
-        // (the consumers' extrema carry the bias of their filtered values; INT32_MAX / INT32_MIN of a pass without a frame wrap,
-        // the record of such a pass is never read for them)
-        rec.fmin = __reduce_min_sync(0xffffffffu, in ? (int)r0.y : INT32_MAX) - kBias;
-        rec.fmax = __reduce_max_sync(0xffffffffu, in ? (int)r0.z : INT32_MIN) - kBias;
-        rec.nbsum = __reduce_add_sync(0xffffffffu, in ? (int)r0.w : 0);
-        rec.pmin = 0; rec.pmax = 0; rec.fabs_sum = 0;
-        if (want_stats) {
-            rec.pmin = __reduce_min_sync(0xffffffffu, in ? (int)r1.x : INT32_MAX);
-            rec.pmax = __reduce_max_sync(0xffffffffu, in ? (int)r1.y : INT32_MIN);
-            rec.fabs_sum = __reduce_add_sync(0xffffffffu, in ? r1.z : 0u);
-        }
+        // first the copy of frame t + kLead into the slot pass t has just released (the critical path of the pipeline) ...
+        if (t + kLead < n) issue(t + kLead);  // (the arrive.expect_tx releases the references published so far)
+        // ... then the fold of the warps' rows into the strip's record of pass t
+        const uint32_t *row = s.stat[t & (kBarRing - 1)][in ? lane : 0];
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(row);
+        const uint32_t psum = __reduce_add_sync(0xffffffffu, in ? (r0.x & 0x7fffffffu) : 0u);
+        // (the consumers' extrema carry the bias of their filtered values; the extrema of a pass without a frame are never read)
+        const int fmin = __reduce_min_sync(0xffffffffu, in ? (int)r0.y : INT32_MAX) - kBias;
+        const int fmax = __reduce_max_sync(0xffffffffu, in ? (int)r0.z : INT32_MIN) - kBias;
+        const int nbsum = __reduce_add_sync(0xffffffffu, in ? (int)r0.w : 0);
         const uint32_t changed = __reduce_or_sync(0xffffffffu, in ? (r0.x >> 31) : 0u);
+        int pmin = 0, pmax = 0;
+        uint32_t fabs_sum = 0;
+        if (want_stats) {
+            const uint4 r1 = *reinterpret_cast<const uint4 *>(row + 4);
+            pmin = __reduce_min_sync(0xffffffffu, in ? (int)r1.x : INT32_MAX);
+            pmax = __reduce_max_sync(0xffffffffu, in ? (int)r1.y : INT32_MIN);
+            fabs_sum = __reduce_add_sync(0xffffffffu, in ? r1.z : 0u);
+        }
         if (lane == 0) {
-            const int ref = t >= kLead ? s.ref_ring[(t - kLead) & 15] : kRefDefault;  // what pass t's bytes were stored against
-            rec.ref_changed = (int32_t)(((uint32_t)ref << 1) | (changed & 1u));
-            const size_t ri = is_frame ? (size_t)(clip.out_offset + t) : (size_t)(a.total_frames + ci);
-            uint4 *dst = reinterpret_cast<uint4 *>(a.prec + ri * NS + strip);
-            dst[0] = make_uint4(rec.psum, (uint32_t)rec.fmin, (uint32_t)rec.fmax, (uint32_t)rec.nbsum);
-            dst[1] = make_uint4((uint32_t)rec.pmin, (uint32_t)rec.pmax, rec.fabs_sum, (uint32_t)rec.ref_changed);
-            // the reference of pass t + kLead: this strip's filtered minimum now, plus the bias (clamped so that it
+            const int ref = t >= kRefLag ? s.ref_ring[(t - kRefLag) & 15] : kRefDefault;  // what pass t's bytes were stored against
+            uint4 *dst = is_frame ? rec_frame + (size_t)t * (2 * NS) : rec_tail;
+            dst[0] = make_uint4(psum, (uint32_t)fmin, (uint32_t)fmax, (uint32_t)nbsum);
+            dst[1] = make_uint4((uint32_t)pmin, (uint32_t)pmax, fabs_sum, ((uint32_t)ref << 1) | (changed & 1u));
+            // the reference of pass t + kRefLag: this strip's filtered minimum now, plus the bias (clamped so that it
             // survives the shift above)
-            if (is_frame) s.ref_ring[t & 15] = max(min(rec.fmin, 1 << 20), -(1 << 20)) + kQuadRefBias;
+            if (is_frame) s.ref_ring[t & 15] = max(min(fmin, 1 << 20), -(1 << 20)) + kQuadRefBias;
         }
         __syncwarp();
-        if (t + kLead < n) issue(t + kLead);  // (the arrive.expect_tx releases the reference to the consumers of that frame)
     }
 }
 
