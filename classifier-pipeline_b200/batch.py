@@ -117,6 +117,33 @@ class BatchExtractor:
         return out
 
 
+    def extract_host_packed(self, h_stream, table, clip_first, clips, chunk_clips=0, out=None):
+        """Packed clips in, host records out: the inflated CPTV frame payloads (``h_stream`` uint8, ideally pinned; one
+        ``native.CPTV_FRAME_DTYPE`` row per frame in ``table``; clip i = rows ``clip_first[i]:clip_first[i + 1]``) are
+        staged to the device, decoded there and extracted.  ``clips`` address frames by table row."""
+        h_stream = np.ascontiguousarray(h_stream, dtype=np.uint8)
+        table = np.ascontiguousarray(table, dtype=native.CPTV_FRAME_DTYPE)
+        clip_first = np.ascontiguousarray(clip_first, dtype=np.int64)
+        clips = np.ascontiguousarray(clips)
+        if len(clip_first) != len(clips) + 1:
+            raise ValueError("clip_first must hold len(clips) + 1 rows")
+        total = int((clips["out_offset"] + clips["n_frames"]).max()) if len(clips) else 0
+        out = out if out is not None else {}
+
+        def buf(name, shape, dtype):
+            a = out.get(name)
+            if a is None or a.shape != tuple(shape) or a.dtype != np.dtype(dtype):
+                a = native.pinned_empty(shape, dtype)
+                out[name] = a
+            return a
+
+        regions = buf("regions", (max(total, 1), self.max_regions), native.REGION_DTYPE)
+        info = buf("info", (max(total, 1),), native.INFO_DTYPE)
+        self.ctx.extract_batch_cptv_host(h_stream, table, clip_first, clips, total, regions, info, chunk_clips)
+        out["total_frames"] = total
+        return out
+
+
 def pad_segment_samples(n_frames, tiles, seed=None):
     """Indices into a segment's frame list for its ``tiles`` cells: ``preprocess_movement`` repeats
     randomly chosen frames (seeded generator) when the segment is short, then sorts

@@ -217,6 +217,8 @@ class CptvReader:
                 if fields is None:
                     break
                 size = _u("I", fields["f"])
+                if self._pos + size > len(self._buf):
+                    raise ValueError("CPTV frame section at byte {} is truncated".format(self._pos))
                 table.append((self._pos, fields["w"][0]))
                 self._pos += size
                 frames.append(CptvFrame(
@@ -260,9 +262,14 @@ def decode_clips_device(engine, readers):
         if (h.x_resolution, h.y_resolution) != (engine.width, engine.height):
             raise ValueError("clip resolution {}x{} does not match the engine".format(h.x_resolution, h.y_resolution))
         buf, table, fr = r.index_frames()
+        n_px = h.x_resolution * h.y_resolution
         for off, w in table:
             if not 1 <= w <= 24:
                 raise ValueError("unsupported CPTV bit width {}".format(w))
+            # the payload the device will read must lie inside this clip's stream (a malformed file must not make the
+            # unpack kernel read out of bounds)
+            if off + 4 + ((n_px - 1) * w + 7) // 8 > len(buf):
+                raise ValueError("CPTV frame payload at byte {} runs past the end of the stream".format(off))
             rows.append((base + off, w, 0))
         streams.append(buf)
         base += len(buf)

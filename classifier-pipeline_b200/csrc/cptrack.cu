@@ -19,6 +19,8 @@ __global__ void frame_scalars_kernel(const KernelArgs a);
 size_t strip_sweep_smem_bytes();
 __global__ void frame_mask_kernel(const KernelArgs a, long long total_frames);
 __global__ void frame_components_kernel(const KernelArgs a, long long total_frames);
+int cptv_decode_launch(cpt_ctx *c, const uint8_t *d_stream, const cpt_cptv_frame *d_table, int n_frames, const int32_t *d_clip_first,
+                       int n_clips, uint16_t *d_frames, int32_t *scratch, cudaStream_t stream);
 int nlm_launch(cpt_ctx *c, const uint8_t *d_src, int width, int height, long long n_frames, uint8_t *d_dst, const cpt_frame_info *info,
                cudaStream_t stream);
 __global__ void region_variance_kernel(Geometry g, long long total_frames, const float *filtered, cpt_frame_info *info, cpt_region *regions);
@@ -175,6 +177,11 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     cudaFree(c->cptv_scratch);
     cudaFree(c->u8_frames[0]);
     cudaFree(c->u8_frames[1]);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->pk_stream[i]); cudaFree(c->pk_table[i]); cudaFree(c->pk_first[i]);
+        cudaFreeHost(c->pk_h_table[i]); cudaFreeHost(c->pk_h_first[i]);
+    }
+    cudaFree(c->pk_change);
     free_stage(c);
     if (c->events)
         for (int i = 0; i < 2; ++i) {
@@ -617,6 +624,140 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
                                      cudaMemcpyDeviceToHost, c->d2h_stream));
         if (h_labels)
             CUDA_TRY(cudaMemcpyAsync(h_labels + (size_t)sp.out_lo * npx, c->stage_labels[b], nf * npx, cudaMemcpyDeviceToHost, c->d2h_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_d2h[b], c->d2h_stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPT_OK;
+}
+
+// Host-staged extraction from PACKED clips: the inflated CPTV frame payloads travel over PCIe (about one byte per pixel
+// instead of two), cpt_cptv_decode's kernels rebuild the uint16 frames on the device, the extraction runs on them.
+int cpt_extract_batch_cptv_host(cpt_ctx *c, const uint8_t *h_stream, uint64_t stream_bytes, const cpt_cptv_frame *h_table,
+                                const int64_t *h_clip_first, const cpt_clip *h_clips, int n_clips, int64_t total_frames,
+                                cpt_region *h_regions, cpt_frame_info *h_info, int chunk_clips) {
+    if (!c) return fail(CPT_ERR_INVALID, "null ctx");
+    if (n_clips < 0 || total_frames < 0) return fail(CPT_ERR_INVALID, "negative sizes");
+    if (n_clips == 0) return CPT_OK;
+    if (!h_stream || !h_table || !h_clip_first || !h_clips || !h_regions || !h_info) return fail(CPT_ERR_INVALID, "null host buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (chunk_clips <= 0) chunk_clips = c->num_sms;
+    const size_t npx = c->g.npx;
+    const int n_chunks = (n_clips + chunk_clips - 1) / chunk_clips;
+    // per chunk: the rows of the frame table, the bytes of the stream and the output frames its clips touch
+    struct Span { int64_t row_lo, row_hi, out_lo, out_hi; uint64_t byte_lo, byte_hi; };
+    std::vector<Span> spans(n_chunks);
+    std::vector<cpt_clip> rebased(h_clips, h_clips + n_clips);
+    size_t max_rows = 0, max_out = 0, max_bytes = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int c0 = ch * chunk_clips, c1 = std::min(n_clips, c0 + chunk_clips);
+        Span sp{h_clip_first[c0], h_clip_first[c1], INT64_MAX, 0, UINT64_MAX, 0};
+        if (sp.row_lo < 0 || sp.row_hi < sp.row_lo) return fail(CPT_ERR_INVALID, "clip table rows must ascend");
+        for (int64_t r = sp.row_lo; r < sp.row_hi; ++r) {
+            // every payload must lie inside the stream (a malformed file must not make the device read out of bounds)
+            const cpt_cptv_frame &f = h_table[r];
+            if (f.bit_width < 1 || f.bit_width > 24) return fail(CPT_ERR_INVALID, "frame %lld: unsupported bit width %d", (long long)r, f.bit_width);
+            const uint64_t size = 4 + ((uint64_t)(npx - 1) * (uint64_t)f.bit_width + 7) / 8;
+            if (f.payload_offset > stream_bytes || size > stream_bytes - f.payload_offset)
+                return fail(CPT_ERR_INVALID, "frame %lld: payload outside the stream", (long long)r);
+            sp.byte_lo = std::min(sp.byte_lo, f.payload_offset);
+            sp.byte_hi = std::max(sp.byte_hi, f.payload_offset + size);
+        }
+        for (int i = c0; i < c1; ++i) {
+            const cpt_clip &k = h_clips[i];
+            if (k.flags & (CPT_CLIP_RESUME | CPT_CLIP_DENOISE)) return fail(CPT_ERR_UNSUPPORTED, "clip %d: resume / denoise are not supported by the host-staged calls", i);
+            if (k.n_frames < 0 || k.out_offset < 0 || k.ring_frames != 0) return fail(CPT_ERR_INVALID, "clip %d: bad offsets", i);
+            if (k.frame_offset < h_clip_first[i] || k.frame_offset + k.n_frames > h_clip_first[i + 1] || k.init_offset < h_clip_first[i] ||
+                k.init_offset >= std::max(h_clip_first[i + 1], h_clip_first[i] + 1))
+                return fail(CPT_ERR_INVALID, "clip %d: frames outside the clip's rows of the frame table", i);
+            if (k.out_offset + k.n_frames > total_frames) return fail(CPT_ERR_INVALID, "clip %d: outputs exceed total_frames", i);
+            sp.out_lo = std::min(sp.out_lo, k.out_offset);
+            sp.out_hi = std::max(sp.out_hi, k.out_offset + k.n_frames);
+        }
+        if (sp.row_hi == sp.row_lo) { sp.byte_lo = sp.byte_hi = 0; }
+        if (sp.out_lo == INT64_MAX) sp.out_lo = 0;
+        for (int i = c0; i < c1; ++i) {
+            rebased[i].frame_offset -= sp.row_lo;
+            rebased[i].init_offset -= sp.row_lo;
+            rebased[i].out_offset -= sp.out_lo;
+        }
+        spans[ch] = sp;
+        max_rows = std::max(max_rows, (size_t)(sp.row_hi - sp.row_lo));
+        max_out = std::max(max_out, (size_t)std::max<int64_t>(sp.out_hi - sp.out_lo, 1));
+        max_bytes = std::max(max_bytes, (size_t)(sp.byte_hi - sp.byte_lo));
+    }
+    int rc = ensure_stage(c, std::max<size_t>(max_rows, 1) * npx * sizeof(uint16_t), max_out, false, false);
+    if (rc) return rc;
+    // packed staging: stream bytes (+4: the unpacker's 32-bit window may read past the last payload), frame table rows, the
+    // clips' first rows; the decoder's int32 change images
+    const size_t need_bytes = max_bytes + 4, need_rows = std::max<size_t>(max_rows, 1);
+    if (c->pk_bytes < need_bytes || c->pk_rows < need_rows || c->pk_clips < (size_t)chunk_clips + 1) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->pk_stream[i]); cudaFree(c->pk_table[i]); cudaFree(c->pk_first[i]);
+            cudaFreeHost(c->pk_h_table[i]); cudaFreeHost(c->pk_h_first[i]);
+            c->pk_stream[i] = nullptr; c->pk_table[i] = nullptr; c->pk_first[i] = nullptr; c->pk_h_table[i] = nullptr; c->pk_h_first[i] = nullptr;
+        }
+        cudaFree(c->pk_change);
+        c->pk_change = nullptr;
+        c->pk_bytes = c->pk_rows = c->pk_clips = 0;
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaMalloc(&c->pk_stream[i], need_bytes));
+            CUDA_TRY(cudaMalloc(&c->pk_table[i], need_rows * sizeof(cpt_cptv_frame)));
+            CUDA_TRY(cudaMalloc(&c->pk_first[i], ((size_t)chunk_clips + 1) * sizeof(int32_t)));
+            CUDA_TRY(cudaHostAlloc((void **)&c->pk_h_table[i], need_rows * sizeof(cpt_cptv_frame), cudaHostAllocDefault));
+            CUDA_TRY(cudaHostAlloc((void **)&c->pk_h_first[i], ((size_t)chunk_clips + 1) * sizeof(int32_t), cudaHostAllocDefault));
+        }
+        CUDA_TRY(cudaMalloc(&c->pk_change, need_rows * npx * sizeof(int32_t)));
+        c->pk_bytes = need_bytes; c->pk_rows = need_rows; c->pk_clips = (size_t)chunk_clips + 1;
+    }
+    if (c->d_clips_cap < (size_t)n_clips) {
+        cudaFree(c->d_clips);
+        c->d_clips = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_clips, sizeof(cpt_clip) * n_clips));
+        c->d_clips_cap = n_clips;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_clips, rebased.data(), sizeof(cpt_clip) * n_clips, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int b = ch & 1;
+        const int c0 = ch * chunk_clips, c1 = std::min(n_clips, c0 + chunk_clips);
+        const Span &sp = spans[ch];
+        const int rows = (int)(sp.row_hi - sp.row_lo);
+        // staging buffers b (host tables, packed bytes, decoded frames) are free once the kernels of chunk ch-2 have run
+        if (ch >= 2) {
+            CUDA_TRY(cudaEventSynchronize(c->ev_compute[b]));
+            CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[b], 0));
+        }
+        for (int r = 0; r < rows; ++r) {
+            c->pk_h_table[b][r] = h_table[sp.row_lo + r];
+            c->pk_h_table[b][r].payload_offset -= sp.byte_lo;
+        }
+        for (int i = c0; i <= c1; ++i) c->pk_h_first[b][i - c0] = (int32_t)(h_clip_first[i] - sp.row_lo);
+        if (rows > 0) {
+            CUDA_TRY(cudaMemcpyAsync(c->pk_stream[b], h_stream + sp.byte_lo, (size_t)(sp.byte_hi - sp.byte_lo), cudaMemcpyHostToDevice, c->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(c->pk_table[b], c->pk_h_table[b], (size_t)rows * sizeof(cpt_cptv_frame), cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->pk_first[b], c->pk_h_first[b], (size_t)(c1 - c0 + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+        if (ch >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
+        if (rows > 0) {
+            rc = cpt::cptv_decode_launch(c, c->pk_stream[b], c->pk_table[b], rows, c->pk_first[b], c1 - c0, (uint16_t *)c->stage_frames[b],
+                                         c->pk_change, c->stream);
+            if (rc) return rc;
+        }
+        cpt_outputs out{c->stage_regions[b], c->stage_info[b], nullptr, nullptr, sp.out_hi - sp.out_lo, 0, 0};
+        rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream, sp.out_hi - sp.out_lo);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_compute[b], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->ev_compute[b], 0));
+        const size_t nf = (size_t)std::max<int64_t>(sp.out_hi - sp.out_lo, 0);
+        if (nf) {
+            CUDA_TRY(cudaMemcpyAsync(h_regions + (size_t)sp.out_lo * c->g.max_regions, c->stage_regions[b], nf * c->g.max_regions * sizeof(cpt_region),
+                                     cudaMemcpyDeviceToHost, c->d2h_stream));
+            CUDA_TRY(cudaMemcpyAsync(h_info + sp.out_lo, c->stage_info[b], nf * sizeof(cpt_frame_info), cudaMemcpyDeviceToHost, c->d2h_stream));
+        }
         CUDA_TRY(cudaEventRecord(c->ev_d2h[b], c->d2h_stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));

@@ -83,6 +83,12 @@ struct cpt_ctx {
     size_t u8_bytes = 0;
     void *cptv_scratch = nullptr;  // per-frame change images of cpt_cptv_decode
     size_t cptv_scratch_bytes = 0;
+    // staging of cpt_extract_batch_cptv_host: packed stream bytes, frame table rows and clip row offsets per buffer
+    uint8_t *pk_stream[2] = {nullptr, nullptr};
+    cpt_cptv_frame *pk_table[2] = {nullptr, nullptr}, *pk_h_table[2] = {nullptr, nullptr};
+    int32_t *pk_first[2] = {nullptr, nullptr}, *pk_h_first[2] = {nullptr, nullptr};
+    int32_t *pk_change = nullptr;
+    size_t pk_bytes = 0, pk_rows = 0, pk_clips = 0;
     bool nlm_table_ready = false;  // cpt_nlm_denoise_u8 uploaded its weight table (constant memory of this device)
 };
 

@@ -65,6 +65,18 @@ __global__ void __launch_bounds__(256) cptv_accumulate_kernel(const int32_t *cha
 
 using cpt::fail;
 
+namespace cpt {
+// the two decode launches on `stream`: packed frames of d_stream -> uint16 frames (scratch: n_frames * npx int32)
+int cptv_decode_launch(cpt_ctx *c, const uint8_t *d_stream, const cpt_cptv_frame *d_table, int n_frames, const int32_t *d_clip_first,
+                       int n_clips, uint16_t *d_frames, int32_t *scratch, cudaStream_t stream) {
+    cptv_unpack_kernel<<<n_frames, 256, 0, stream>>>(d_stream, d_table, c->g.W, c->g.H, scratch);
+    dim3 grid((c->g.npx + 255) / 256, n_clips);
+    cptv_accumulate_kernel<<<grid, 256, 0, stream>>>(scratch, d_clip_first, c->g.npx, d_frames);
+    CUDA_TRY(cudaGetLastError());
+    return CPT_OK;
+}
+}  // namespace cpt
+
 extern "C" {
 
 int cpt_cptv_decode(cpt_ctx *c, const uint8_t *d_stream, const cpt_cptv_frame *d_table, int n_frames,
@@ -83,11 +95,7 @@ int cpt_cptv_decode(cpt_ctx *c, const uint8_t *d_stream, const cpt_cptv_frame *d
         CUDA_TRY(cudaMalloc(&c->cptv_scratch, need));
         c->cptv_scratch_bytes = need;
     }
-    cpt::cptv_unpack_kernel<<<n_frames, 256, 0, c->stream>>>(d_stream, d_table, c->g.W, c->g.H, (int32_t *)c->cptv_scratch);
-    dim3 grid((c->g.npx + 255) / 256, n_clips);
-    cpt::cptv_accumulate_kernel<<<grid, 256, 0, c->stream>>>((const int32_t *)c->cptv_scratch, d_clip_first, c->g.npx, d_frames);
-    CUDA_TRY(cudaGetLastError());
-    return CPT_OK;
+    return cpt::cptv_decode_launch(c, d_stream, d_table, n_frames, d_clip_first, n_clips, d_frames, (int32_t *)c->cptv_scratch, c->stream);
 }
 
 }  // extern "C"

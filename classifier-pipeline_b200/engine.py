@@ -8,7 +8,9 @@ from .batch import BatchExtractor
 _lock = threading.Lock()
 _engines = {}
 DEFAULT_DEVICE = 0
-API_MAX_REGIONS = 64
+# region slots per frame of the API engines: every component the uint8 label image can number (CPT_MAX_COMPONENTS).  The
+# reference iterates every stats row (cliptracker.py:263-365); a noisy frame (FFC, lens cap) must not abort a batch.
+API_MAX_REGIONS = 255
 
 
 def set_default_device(device):

@@ -101,6 +101,10 @@ def _usable_frames(regions, ffc_frames, skip_ffc, frame_min_mass, has_no_mass):
     return keep
 
 
+# labels whose tracks keep their false-positive frames (datasetstructures.py:22)
+FP_LABELS = ["other", "unidentified", "rain", "false-positive", "water", "insect"]
+
+
 def get_segments(clip_id, track_id, start_frame, regions, segment_width=25, segment_frame_spacing=9, label=None,
                  segment_min_mass=None, ffc_frames=[], lower_mass=0, repeats=1, min_frames=None,
                  segment_types=[SegmentType.ALL_RANDOM_MASKED], max_segments=None, location=None, station_id=None,
@@ -123,7 +127,7 @@ def get_segments(clip_id, track_id, start_frame, regions, segment_width=25, segm
             raise NotImplementedError("TOP_RANDOM segments raise TypeError in the reference")
         min_mass = None if segment_type == SegmentType.ALL_RANDOM_NOMIN else segment_min_mass
         usable = _usable_frames(regions, ffc_frames, skip_ffc, frame_min_mass, has_no_mass)
-        if fp_frames is not None:
+        if fp_frames is not None and label not in FP_LABELS:  # datasetstructures.py:1028
             usable = [f for f in usable if f not in fp_frames]
         if not usable:
             logging.warning("Nothing to load for %s - %s", clip_id, track_id)

@@ -143,6 +143,7 @@ SYMBOLS = {
     "cpt_detect_objects_u8": (_i, [_vp, _vp, _i, _i, _d, _i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "cpt_nlm_denoise_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "cpt_cptv_decode": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "cpt_extract_batch_cptv_host": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _i, _i64, _vp, _vp, _i]),
     "cpt_motion_open": (_vp, [_vp, _i, _i, _i, _i]),
     "cpt_motion_close": (None, [_vp]),
     "cpt_motion_store": (_i, [_vp, _vp, _i]),
@@ -255,6 +256,14 @@ class Context:
             self.lib.cpt_extract_batch_host(
                 self._h, _ptr(h_frames), _ptr(h_clips), len(h_clips), int(total_frames), _ptr(h_regions), _ptr(h_info),
                 _ptr(h_filtered), _ptr(h_labels), int(chunk_clips),
+            )
+        )
+
+    def extract_batch_cptv_host(self, h_stream, h_table, h_clip_first, h_clips, total_frames, h_regions, h_info, chunk_clips=0):
+        check(
+            self.lib.cpt_extract_batch_cptv_host(
+                self._h, _ptr(h_stream), int(h_stream.size), _ptr(h_table), _ptr(h_clip_first), _ptr(h_clips), len(h_clips),
+                int(total_frames), _ptr(h_regions), _ptr(h_info), int(chunk_clips),
             )
         )
 

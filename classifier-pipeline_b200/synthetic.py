@@ -116,3 +116,56 @@ def make_clips_torch(n_clips, frames, device, first_index=0, width=WIDTH, height
         out[c0:c1].view(torch.int16).copy_(torch.where(v >= 32768, v - 65536, v).to(torch.int16))
     models = [(first_index + i) % 2 for i in range(n_clips)]
     return out, models
+
+
+def pack_clips_torch(d_frames):
+    """CPTV v2 frame payloads of clips resident on the device (the packing ``cptv/reader.py`` undoes): per frame an int32
+    start value, then ``W*H - 1`` two's-complement deltas along the boustrophedon scan of the frame-to-frame change, 8 bits
+    each where they fit and 16 otherwise, MSB first.
+
+    ``d_frames``: ``(n_clips, frames, H, W)`` torch.uint16 CUDA tensor.  Returns ``(stream, table, clip_first)``: the
+    payloads back to back as a pinned uint8 array (plus four slack bytes), one ``native.CPTV_FRAME_DTYPE`` row per frame
+    and the first row of every clip."""
+    import torch
+
+    from . import native
+
+    C, T, H, W = d_frames.shape
+    n = H * W
+    sizes = np.empty((C, T), np.int64)
+    wide = np.zeros((C, T), bool)
+    parts8, parts16, starts = [], [], []
+    for c in range(C):
+        cur = d_frames[c].view(torch.int16).to(torch.int32) & 0xFFFF
+        change = cur - torch.cat([torch.zeros_like(cur[:1]), cur[:-1]])
+        change[:, 1::2] = change[:, 1::2].flip(-1)  # odd rows right to left
+        change = change.reshape(T, n)
+        deltas = change[:, 1:] - change[:, :-1]
+        need16 = (deltas.abs().amax(dim=1) > 127) | (deltas.amin(dim=1) < -128)
+        wide[c] = need16.cpu().numpy()
+        starts.append(change[:, 0].cpu().numpy().astype("<i4"))
+        parts8.append(deltas.to(torch.int8).cpu().numpy())
+        if wide[c].any():
+            d16 = deltas[need16].to(torch.int16)
+            parts16.append(((d16 >> 8) & 0xFF).to(torch.uint8).cpu().numpy()[..., None].repeat(2, -1))
+            parts16[-1][..., 1] = (d16 & 0xFF).to(torch.uint8).cpu().numpy()
+        else:
+            parts16.append(None)
+        sizes[c] = 4 + np.where(wide[c], 2 * (n - 1), n - 1)
+    offsets = np.concatenate([[0], np.cumsum(sizes.reshape(-1))])
+    stream = native.pinned_empty((int(offsets[-1]) + 4,), np.uint8)
+    stream[-4:] = 0
+    table = np.zeros(C * T, native.CPTV_FRAME_DTYPE)
+    table["payload_offset"] = offsets[:-1]
+    table["bit_width"] = np.where(wide.reshape(-1), 16, 8)
+    for c in range(C):
+        k16 = 0
+        for t in range(T):
+            o = int(offsets[c * T + t])
+            stream[o : o + 4] = np.frombuffer(starts[c][t].tobytes(), np.uint8)
+            if wide[c, t]:
+                stream[o + 4 : o + 4 + 2 * (n - 1)] = parts16[c][k16].reshape(-1)
+                k16 += 1
+            else:
+                stream[o + 4 : o + 4 + n - 1] = parts8[c][t].view(np.uint8)
+    return stream, table, np.arange(C + 1, dtype=np.int64) * T

@@ -241,7 +241,9 @@ class ClipTrackExtractor(ClipTracker):
         regions = eng.regions_numpy(out["regions"])
         info = eng.info_numpy(out["info"])
         if total and int(info["n_components"][:total].max()) > eng.max_regions:
-            raise native.NativeError("a frame has more than {} components; raise engine.API_MAX_REGIONS".format(eng.max_regions))
+            # more components than the uint8 label image can number: the first 255 (OpenCV label order) are kept
+            logging.warning("%d frame(s) have more than %d components; the rest are dropped",
+                            int((info["n_components"][:total] > eng.max_regions).sum()), eng.max_regions)
         filtered = out["filtered"].cpu().numpy() if keep_images else None
         labels = out["labels"].cpu().numpy() if keep_images else None
         results = []
@@ -320,8 +322,13 @@ class ClipTrackExtractor(ClipTracker):
         )
         return self._stream
 
-    def process_frame(self, clip, frame):
-        """Track one more frame of a clip (streaming; one kernel launch)."""
+    def process_frame(self, clip, frame, *, update_background=False):
+        """Track one more frame of a clip (streaming; one kernel launch).
+
+        As in the reference (cliptrackextractor.py:198-247) this does NOT touch the background: callers drive
+        ``background_alg`` themselves (``_track_clip`` feeds it the mean of the last 45 frames, the Pi's motion detector its
+        running mean).  ``update_background=True`` (keyword only, not in the reference) fuses ``_track_clip``'s update --
+        ``background_alg.process_frame(mean of the last <=45 frames)`` -- into the same launch."""
         import torch
 
         if getattr(self.config, "denoise", False):
@@ -336,7 +343,9 @@ class ClipTrackExtractor(ClipTracker):
         pix = np.ascontiguousarray(frame.pix, dtype=np.uint16)
         st["ring"][slot].view(torch.int16).copy_(torch.from_numpy(pix.view(np.int16)))
         # the kernel resumes from (and saves to) the background's own state record
-        flags = (self._flags() | native.CLIP_RESUME)
+        flags = (self._flags() | native.CLIP_RESUME) & ~native.CLIP_UPDATE_BACKGROUND
+        if update_background and self.update_background:
+            flags |= native.CLIP_UPDATE_BACKGROUND
         c = linear_clips([1], clip.background_thresh, self.background_alg.weight_slot, flags=flags)
         c["frame_offset"] = 0
         c["init_offset"] = 0
@@ -358,6 +367,6 @@ class ClipTrackExtractor(ClipTracker):
             medians=medians, have_prev=t > 0,
         )
         if int(res["info"]["n_components"][0]) > eng.max_regions:
-            raise native.NativeError("a frame has more than {} components; raise engine.API_MAX_REGIONS".format(eng.max_regions))
+            logging.warning("frame %d has more than %d components; the rest are dropped", t, eng.max_regions)
         st["t"] = t + 1
         return self._consume_frame(clip, frame, res, 0)

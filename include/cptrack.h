@@ -257,6 +257,17 @@ typedef struct {
 int cpt_cptv_decode(cpt_ctx *ctx, const uint8_t *d_stream, const cpt_cptv_frame *d_table, int n_frames,
                     const int32_t *d_clip_first, int n_clips, uint16_t *d_frames);
 
+/* cpt_extract_batch_host for clips that are still PACKED (what ClipTrackExtractor.parse_clip reads through
+ * CptvReader.next_frame, track/cliptrackextractor.py:108-129,160-165): h_stream holds the inflated frame payloads, h_table
+ * one row per frame of every clip (clip i = rows h_clip_first[i] .. h_clip_first[i + 1] - 1, in file order), and the
+ * cpt_clip records address frames in that row space (frame_offset / init_offset = table rows; a leading background frame
+ * is simply a row the clip's frame_offset skips).  The payloads (about one byte per pixel) are staged to the device in
+ * chunks of clips, decoded there and extracted; regions + info come back as in cpt_extract_batch_host.  Every payload is
+ * checked to lie inside the stream before anything is launched. */
+int cpt_extract_batch_cptv_host(cpt_ctx *ctx, const uint8_t *h_stream, uint64_t stream_bytes, const cpt_cptv_frame *h_table,
+                                const int64_t *h_clip_first, const cpt_clip *h_clips, int n_clips, int64_t total_frames,
+                                cpt_region *h_regions, cpt_frame_info *h_info, int chunk_clips);
+
 /* ---- CPTVMotionDetector (piclassifier/cptvmotiondetector.py:14-205), streaming, one launch per frame ----
  * The detector owns a ring of the last ring_frames frames (SlidingWindow of preview_secs * fps + 1 frames), the
  * uint32 running sum (RunningMean over mean_frames = 45) and, for one_diff_only == False, a ring of diff_frames

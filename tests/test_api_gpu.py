@@ -91,62 +91,65 @@ def test_streaming_process_frame_matches_parse_clip():
     for frame in iter(reader.next_frame, None):
         if frame.background_frame:
             continue
-        ext.process_frame(clip, frame)
+        ext.process_frame(clip, frame, update_background=True)  # (_track_clip's background update fused into the launch)
     ext.apply_track_filtering(clip)
     clip.stats.completed()
     assert_tracks_match_golden(clip, meta, d)
     _check_frames_and_state(ext, clip, d, tracked)
 
 
-def test_weighted_background_object_matches_oracle():
-    """WeightedBackground.process_frame on the device == the reference recurrence (oracle) for both weight_add values."""
-    from classifier_pipeline_b200.ml_tools.rectangle import Rectangle
-    from classifier_pipeline_b200.piclassifier.motiondetector import WeightedBackground
+def test_process_frame_leaves_the_background_to_the_caller():
+    """As in the reference, process_frame never updates the background: a caller that drives background_alg itself the way
+    _track_clip does (mean of the last 45 thermal frames after every frame, cliptrackextractor.py:167-176) gets parse_clip's
+    tracks, and without those calls the background stays the initial frame."""
+    from classifier_pipeline_b200.cptv import CptvReader
+    from classifier_pipeline_b200.track.clip import Clip
+    from classifier_pipeline_b200.track.track import Track
+
+    d, meta = helpers.load_golden("possum_raw")
+    path = os.path.join(helpers.GOLDEN, "clips", "possum.cptv")
+    ext, config = _extractor()
+    clip = Clip(config.tracking["thermal"], path)
+    ext.init_clip(clip)
+    first_bg = ext.background_alg.background.copy()
+    Track._track_id = 1
+    reader = CptvReader(path)
+    reader.get_header()
+    n = 0
+    for frame in iter(reader.next_frame, None):
+        if frame.background_frame:
+            continue
+        ext.process_frame(clip, frame)
+        if n == 3:
+            assert np.array_equal(ext.background_alg.background, first_bg)  # untouched so far
+        if n >= 3:
+            last_avg = np.mean([f.thermal for f in clip.frame_buffer.get_last_x(x=45)], axis=0)
+            ext.background_alg.process_frame(last_avg)
+        n += 1
+    assert not np.array_equal(ext.background_alg.background, first_bg)
+
+
+def test_frames_with_many_components_do_not_abort():
+    """A frame with far more components than any sane scene (speckle after a temperature step) is tracked like any other:
+    the API engines keep every component the label image can number, and the region list equals the oracle's."""
+    from classifier_pipeline_b200.synthetic import make_clip
+    from classifier_pipeline_b200.track.clip import Clip
     from oracle import oracle as orc
 
-    rng = np.random.default_rng(5)
-    for weight_add in (0.1, 1):
-        wb = WeightedBackground(1, Rectangle(1, 1, 158, 118), 160, 120, weight_add)
-        ob = orc.Background(160, 120, 1, weight_add)
-        base = rng.integers(2900, 3100, size=(120, 160)).astype(np.float64)
-        for t in range(40):
-            frame = base + rng.integers(-3, 4, size=(120, 160)) + (t % 7 == 0) * rng.integers(-40, 40, size=(120, 160)) + 0.5
-            wb.process_frame(frame)
-            ob.process(np.int32(frame))
-            bg, w, avg = ob.get()
-            assert np.array_equal(wb.background, bg.astype(np.float64)), t
-            assert np.array_equal(wb.background_weight, w), t
-            assert wb.average == avg, t
-
-
-def test_parse_clip_default_config_reproduces_reference_possum_json():
-    """The reference's own regression: tests/clips/possum.txt is extract.py's output for possum.cptv with the DEFAULT
-    config (denoise on).  parse_clip on the device reproduces every track position and both tracking scores."""
-    import json
-
-    from classifier_pipeline_b200.config import Config
-    from classifier_pipeline_b200.ml_tools.tools import CustomJSONEncoder
-    from classifier_pipeline_b200.track.clip import Clip
-    from classifier_pipeline_b200.track.cliptrackextractor import ClipTrackExtractor
-
-    config = Config.get_defaults()
-    assert config.tracking["thermal"].denoise is True
-    ext = ClipTrackExtractor(config.tracking, False, cache_to_disk=False)
-    clip = Clip(config.tracking["thermal"], os.path.join(helpers.GOLDEN, "clips", "possum.cptv"))
-    ext.parse_clip(clip)
-    d, meta = helpers.load_golden("possum_nlm")
-    assert_tracks_match_golden(clip, meta, d)
-    gold = json.load(open(os.path.join(helpers.GOLDEN, "clips", "possum.txt")))
-    got = json.loads(json.dumps(clip.get_metadata(), cls=CustomJSONEncoder))
-    assert len(got["tracks"]) == len(gold["tracks"]) == 2
-    for a, b in zip(got["tracks"], gold["tracks"]):
-        for k in ("id", "start_s", "end_s", "num_frames", "frame_start", "frame_end"):
-            assert a[k] == b[k], k
-        assert a["tracking_score"] == pytest.approx(b["tracking_score"], rel=1e-6)
-        assert len(a["positions"]) == len(b["positions"])
-        for p, q in zip(a["positions"], b["positions"]):
-            for k in q:
-                if k == "pixel_variance":
-                    assert p[k] == pytest.approx(q[k], abs=0.011)
-                else:
-                    assert p[k] == q[k], k
+    pix, model = make_clip(0, frames=30)
+    pix = pix.copy()
+    speck = np.zeros((120, 160), np.uint16)
+    speck[4:116:10, 4:156:10] = 300  # 12 x 16 isolated warm spots
+    speck[5:116:10, 4:156:10] = 300
+    pix[20] += speck
+    ext, config = _extractor()
+    ext.reader_factory = lambda path: MemReader(pix, model)
+    clip = Clip(config.tracking["thermal"], "speckle")
+    ext.parse_clips([clip])
+    o = orc.extract_clip(pix, pix[0], orc.make_params(background_thresh=clip.background_thresh, weight_add=0.1, max_comp=255))
+    assert 64 < o["ncomp"][20] <= 255
+    assert len(clip.frame_buffer.frames) == 30
+    mask = clip.frame_buffer.frames[20].mask
+    assert int(mask.max()) == min(int(o["ncomp"][20]), 255)
+    assert np.array_equal(mask.astype(np.uint8), o["labels"][20])
+    assert len(clip.region_history) == 30
