@@ -86,13 +86,16 @@ class ClockSampler:
 
 
 def measured_traffic(total_frames):
-    """DRAM bytes of one extraction launch, from the committed `ncu --set full` capture (profiles/extract_traffic.json:
-    dram__bytes_read.sum + dram__bytes_write.sum per frame of the captured launch, scaled to this launch's frames)."""
+    """DRAM bytes of one launch of the dominant kernel, CAPTURED ONCE under `ncu --set full` (profiles/extract_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of the captured launch) and SCALED per frame to this launch -- not a
+    measurement of this run (a profiler cannot run inside a timed bench).  Returns (bytes, description)."""
     path = os.path.join(ROOT, "profiles", "extract_traffic.json")
     try:
-        return float(json.load(open(path))["dram_bytes_per_frame"]) * total_frames
+        d = json.load(open(path))
+        return float(d["dram_bytes_per_frame"]) * total_frames, "captured ({} frames, {}) and scaled per frame to this launch".format(
+            d.get("frames_in_captured_launch"), os.path.basename(d.get("source", "ncu")))
     except Exception:
-        return None
+        return None, "no capture committed"
 
 
 def synthetic_tracks(n_tracks, n_clips, frames, rng, span=45, pick=25):
@@ -189,7 +192,7 @@ def bench_motion(n_frames=400):
             "frames_with_motion": int(moved), "realtime_budget_us": 111111}
 
 
-def cpu_baseline(n_threads, clips_per_thread, frames, pix=None):
+def cpu_baseline(n_threads, clips_per_thread, frames, pix=None, want_regions=False):
     """The C port of the reference path (oracle/) on the host cores, regions-only outputs."""
     from classifier_pipeline_b200.synthetic import clip_model, make_clip
     from oracle import oracle as orc
@@ -201,9 +204,127 @@ def cpu_baseline(n_threads, clips_per_thread, frames, pix=None):
     params = [orc.make_params(background_thresh=clip_model(i)[2], weight_add=clip_model(i)[3], max_comp=16) for i in range(n_clips)]
     orc.extract_batch(pix[:1, : min(frames, 20)], params[:1], 1)  # warm the library
     t0 = time.perf_counter()
-    orc.extract_batch(pix, params, n_threads)
+    res = orc.extract_batch(pix, params, n_threads)
     dt = time.perf_counter() - t0
+    if want_regions:
+        return n_clips * frames / dt, dt, n_clips, res
     return n_clips * frames / dt, dt, n_clips
+
+
+def check_parity(hout, port, n_clips, frames, max_regions=16):
+    """The GPU's e2e region lists against the C port's on the clips both processed: component counts and the stats rows
+    (x, y, width, height, area) of every stored region must be identical.  Returns the number of regions compared."""
+    ncomp, comp, _ = port
+    info, regions = hout["info"], hout["regions"]
+    got_n = info["n_components"][: n_clips * frames].reshape(n_clips, frames)
+    if not np.array_equal(got_n, ncomp):
+        bad = np.argwhere(got_n != ncomp)[0]
+        raise SystemExit("PARITY FAILURE: clip {} frame {}: {} components on the GPU, {} in the CPU port".format(
+            bad[0], bad[1], got_n[tuple(bad)], ncomp[tuple(bad)]))
+    r = regions[: n_clips * frames].reshape(n_clips, frames, -1)
+    got = np.stack([r["x"], r["y"], r["width"], r["height"], r["area"]], axis=-1)[:, :, :max_regions]
+    live = np.arange(max_regions)[None, None, :] < np.minimum(ncomp, max_regions)[:, :, None]
+    if not np.array_equal(got[live], comp[:, :, :max_regions, :5][live]):
+        raise SystemExit("PARITY FAILURE: region statistics differ between the GPU and the CPU port")
+    return int(live.sum())
+
+
+def workload_config(C, T):
+    """The workload both arms (`--impl b200` and `--impl reference`) are quoted on."""
+    return {
+        "workload": "BASELINE configs[1]: {} clips x {} frames 160x120 uint16 per GPU, full track extraction (filtered fp32 + labels u8 + regions)".format(C, T),
+        "clips_per_gpu": C, "frames_per_clip": T, "denoise": False,
+        "l2": "inputs ({:.1f} GB) far larger than L2".format(C * T * NPX * 2 / 1e9),
+    }
+
+
+def reference_python_record():
+    """The UNMODIFIED reference's own extractor (Python + numpy + OpenCV) cannot travel to the GPU box (/root/reference is
+    absent there); its throughput was timed in the build container with tools/time_reference.py and is committed."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "reference_python_cpu.json")))
+    except Exception:
+        return None
+
+
+def bench_extras(ex, d_frames, clips, bts, wts, C, T, torch):
+    """Measurement legs beside the headline: TrackingConfig.denoise (the reference's default config) through the device NLM
+    passes, the Python API (parse_clips: decode + launch + D2H + the host matcher) and streaming process_frame latency."""
+    import types
+
+    from classifier_pipeline_b200 import native
+    from classifier_pipeline_b200.batch import linear_clips
+    from classifier_pipeline_b200.config import Config
+    from classifier_pipeline_b200.track.clip import Clip
+    from classifier_pipeline_b200.track.cliptrackextractor import ClipTrackExtractor
+
+    res = {}
+    # ---- denoise on: 32 clips x 100 frames (NLM is compute-bound: 441 search offsets per pixel)
+    n_c, n_t = min(32, C), min(100, T)
+    sub = d_frames[:n_c, :n_t].contiguous()
+    dc = linear_clips([n_t] * n_c, bts[:n_c], wts[:n_c], flags=native.CLIP_UPDATE_BACKGROUND | native.CLIP_DENOISE)
+    o = {}
+    ex.extract_device(sub, dc, keep_filtered=True, keep_labels=True, out=o)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ex.extract_device(sub, dc, keep_filtered=True, keep_labels=True, out=o)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    res["denoise_on"] = {"workload": "{} clips x {} frames, CPT_CLIP_DENOISE (cv2.fastNlMeansDenoising bit-exact on the device)".format(n_c, n_t),
+                         "frames_per_s": n_c * n_t / (ms * 1e-3), "ms": ms}
+    del o, sub
+
+    # ---- the Python API: parse_clips on in-memory clips (device launch, D2H of frames / masks / regions, host matcher)
+    class Mem:
+        def __init__(self, pix, model):
+            self.pix, self.i, self.model = pix, 0, model
+
+        def get_header(self):
+            return types.SimpleNamespace(x_resolution=W, y_resolution=H, model=self.model, brand="flir", timestamp=1_600_000_000_000_000)
+
+        def next_frame(self):
+            if self.i >= len(self.pix):
+                return None
+            f = types.SimpleNamespace(pix=self.pix[self.i], time_on=10_000_000 + self.i * 111, last_ffc_time=0, temp_c=20.0,
+                                      last_ffc_temp_c=20.0, background_frame=False)
+            self.i += 1
+            return f
+
+    n_api, t_api = min(8, C), min(300, T)
+    host = d_frames[:n_api, :t_api].view(torch.int16).cpu().numpy().view(np.uint16)
+    config = Config.get_defaults()
+    config.tracking["thermal"].denoise = False
+    ext = ClipTrackExtractor(config.tracking, False, cache_to_disk=False)
+    store = {"c{}".format(i): (host[i], "lepton3" if i % 2 == 0 else "lepton3.5") for i in range(n_api)}
+    ext.reader_factory = lambda path: Mem(*store[path])
+    for rep in range(2):
+        api_clips = [Clip(config.tracking["thermal"], name) for name in store]
+        t0 = time.perf_counter()
+        ext.parse_clips(api_clips)
+        api_dt = time.perf_counter() - t0
+    res["parse_clips_api"] = {"workload": "{} clips x {} frames through ClipTrackExtractor.parse_clips (launch + D2H of frames, masks, regions + host "
+                              "matcher / Kalman / track filtering in Python)".format(n_api, t_api),
+                              "frames_per_s": n_api * t_api / api_dt, "tracks": int(sum(len(c.tracks) for c in api_clips)), "seconds": api_dt}
+
+    # ---- streaming: process_frame one frame at a time (ring upload, one launch, region read-back, host matcher)
+    clip = Clip(config.tracking["thermal"], "c0")
+    ext2 = ClipTrackExtractor(config.tracking, False, cache_to_disk=False, keep_frames=False, calc_stats=False)
+    ext2.reader_factory = ext.reader_factory
+    ext2.init_clip(clip)
+    lat = []
+    for t in range(min(250, t_api)):
+        f = types.SimpleNamespace(pix=host[0][t], time_on=10_000_000 + t * 111, last_ffc_time=0, background_frame=False)
+        t0 = time.perf_counter()
+        ext2.process_frame(clip, f, update_background=True)
+        if t >= 50:
+            lat.append(time.perf_counter() - t0)
+    lat = np.sort(np.array(lat)) * 1e6
+    res["process_frame_streaming"] = {"workload": "ClipTrackExtractor.process_frame, one frame per call (host frame in, tracks out)",
+                                      "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]),
+                                      "realtime_budget_us": 111111}
+    return res
 
 
 def run_reference(args):
@@ -212,7 +333,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 64))
-    frames = 900
+    frames = args.frames
     per_thread = 2  # ~3 s of work per step on every host thread
     values = []
     sample = ""
@@ -226,8 +347,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean([dt for _, dt in values]) * 1e3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32 (fp32+fp64 scalars)", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 1024 clips x 900 frames 160x120 uint16 extraction; CPU arm runs a bounded sample of it"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.clips, args.frames),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample + " per step (a bounded sample of the workload)",
+                         "reference_python": reference_python_record()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,9 +364,11 @@ def main():
     ap.add_argument("--clips", type=int, default=1024, help="clips per GPU")
     ap.add_argument("--frames", type=int, default=900)
     ap.add_argument("--e2e-clips", type=int, default=0, help="clips per e2e step (0 = auto from host RAM)")
+    ap.add_argument("--e2e-chunk", type=int, default=64, help="clips per staged chunk of the packed e2e call (one CTA per clip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tracks", type=int, default=10000, help="tracks of the preprocessing measurement (0 = skip)")
     ap.add_argument("--no-motion", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the denoise / parse_clips / streaming legs")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -310,15 +434,15 @@ def main():
     # (torch events only see torch's current stream), averaged over a few extra steps outside the timed region
     import ctypes
 
-    kt = np.zeros(4, dtype=np.float64)
-    buf4 = (ctypes.c_float * 4)()
-    native.check(ex.ctx.lib.cpt_debug_kernel_times(ex.ctx._h, 1, None))
+    kt = np.zeros(5, dtype=np.float64)
+    buf5 = (ctypes.c_float * 5)()
+    native.check(ex.ctx.lib.cpt_debug_kernel_times_ex(ex.ctx._h, 1, None, 5))
     n_kt = max(2, min(args.steps, 5))
     for _ in range(n_kt):
         step()
-        native.check(ex.ctx.lib.cpt_debug_kernel_times(ex.ctx._h, 1, buf4))
-        kt += np.array(list(buf4), dtype=np.float64)
-    native.check(ex.ctx.lib.cpt_debug_kernel_times(ex.ctx._h, 0, None))
+        native.check(ex.ctx.lib.cpt_debug_kernel_times_ex(ex.ctx._h, 1, buf5, 5))
+        kt += np.array(list(buf5), dtype=np.float64)
+    native.check(ex.ctx.lib.cpt_debug_kernel_times_ex(ex.ctx._h, 0, None, 5))
     kt /= n_kt
     if dist is not None:
         tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
@@ -344,32 +468,53 @@ def main():
         avail = 16 << 30
     # (every rank pins its own staging copy at the same time: share the host's free memory between the ranks)
     e2e_clips = args.e2e_clips or int(max(8, min(C, (avail // (4 * world)) // (T * NPX * 2), 256)))
+    from classifier_pipeline_b200.synthetic import pack_clips_torch
+
     h_frames = native.pinned_empty((e2e_clips * T, H, W), np.uint16)
     h_frames[:] = d_frames.view(torch.int16)[:e2e_clips].reshape(-1, H, W).cpu().numpy().view(np.uint16)
+    # the same clips PACKED as their CPTV v2 frame payloads (what a reader holds after inflating a .cptv file)
+    p_stream, p_table, p_first = pack_clips_torch(d_frames[:e2e_clips])
     e_clips = linear_clips([T] * e2e_clips, bts[:e2e_clips], wts[:e2e_clips])
+    # ---- the other measurement legs that need the device-resident batch (rank 0 only)
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        extras = bench_extras(ex, d_frames, clips, bts, wts, C, T, torch)
     del d_frames
     out.clear()
     torch.cuda.empty_cache()
-    hout = {}
-    for _ in range(2):
-        ex.extract_host(h_frames, e_clips, chunk_clips=32, out=hout)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        ex.extract_host(h_frames, e_clips, chunk_clips=32, out=hout)
-    barrier()
-    e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        tt = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_dt = float(tt.item())
+
+    def time_host(call):
+        for _ in range(2):
+            call()
+        barrier()
+        t0 = time.perf_counter()
+        n = max(2, min(args.steps, 5))
+        for _ in range(n):
+            call()
+        barrier()
+        dt = (time.perf_counter() - t0) / n
+        if dist is not None:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return dt
+
+    hout, hraw = {}, {}
+    e2e_dt = time_host(lambda: ex.extract_host_packed(p_stream, p_table, p_first, e_clips, chunk_clips=args.e2e_chunk, out=hout))
+    raw_dt = time_host(lambda: ex.extract_host(h_frames, e_clips, chunk_clips=32, out=hraw))
+    d2h = int(e2e_clips * T * (16 * native.REGION_DTYPE.itemsize + native.INFO_DTYPE.itemsize))
     e2e = {
         "value": world * e2e_clips * T / e2e_dt, "unit": UNIT,
-        "h2d_bytes_per_step": int(e2e_clips * T * NPX * 2),
-        "d2h_bytes_per_step": int(e2e_clips * T * (16 * native.REGION_DTYPE.itemsize + native.INFO_DTYPE.itemsize)),
-        "clips_per_step": e2e_clips, "api": "cpt_extract_batch_host (pinned host frames -> host region lists)",
+        "h2d_bytes_per_step": int(p_stream.size + p_table.nbytes), "d2h_bytes_per_step": d2h,
+        "clips_per_step": e2e_clips,
+        "api": "cpt_extract_batch_cptv_host (pinned inflated CPTV frame payloads, {:.2f} B/pixel -> device decode -> host region lists)".format(
+            p_stream.size / (e2e_clips * T * NPX)),
+        "raw_u16": {"value": world * e2e_clips * T / raw_dt, "h2d_bytes_per_step": int(e2e_clips * T * NPX * 2),
+                    "api": "cpt_extract_batch_host (pinned decoded uint16 frames -> host region lists)"},
     }
+    same = np.array_equal(hout["info"]["n_components"], hraw["info"]["n_components"]) and np.array_equal(hout["info"]["thermal_sum"], hraw["info"]["thermal_sum"])
+    if not same:
+        raise SystemExit("PARITY FAILURE: the packed and the raw host-staged calls disagree")
 
     if rank != 0:
         if dist is not None:
@@ -382,38 +527,48 @@ def main():
     sweep_ms = float(kt[0]) if kt[0] > 0 else kernel_ms
     achieved = BYTES_PER_FRAME * total / (sweep_ms * 1e-3) / 1e9
     step_achieved = BYTES_PER_FRAME * total / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(total)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16/int32 (fp32+fp64 scalars)", "data": "synthetic",
-        "config": {
-            "workload": "BASELINE configs[1]: {} clips x {} frames 160x120 uint16 per GPU, full extraction (filtered fp32 + labels u8 + regions)".format(C, T),
-            "clips_per_gpu": C, "frames_per_clip": T, "l2": "inputs ({:.1f} GB) far larger than L2".format(total * NPX * 2 / 1e9),
-            "denoise": False, "regions_found": regions_total,
-        },
+        "config": workload_config(C, T),
+        "run_info": {"regions_found": regions_total, "step": "clip descriptors are re-uploaded every step (pessimistic, a few kB)"},
         "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "extract_sweep_kernel", "kernel_ms": sweep_ms, "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "peak_source": peak_src,
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src,
+            "kernel": "strip_sweep_kernel", "kernel_ms": sweep_ms, "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "peak_source": peak_src,
             "kernel_share_of_step": sweep_ms / kernel_ms,
             "step_ms": kernel_ms, "step_achieved": step_achieved, "step_frac": step_achieved / peak,
-            "kernel_times_ms": {"extract_sweep_kernel": float(kt[0]), "frame_mask_kernel+frame_components_kernel": float(kt[1]),
-                                "denoise_passes": float(kt[2]), "region_variance_kernel": float(kt[3])},
+            "kernel_times_ms": {"strip_sweep_kernel": float(kt[0]), "frame_scalars_kernel": float(kt[1]),
+                                "frame_mask_kernel+frame_components_kernel": float(kt[2]), "denoise_passes": float(kt[3]),
+                                "region_variance_kernel": float(kt[4])},
+            "kernels_per_step": ["strip_sweep_kernel", "strip_sweep_stats_kernel (no clip of its kind: leaves at once)", "frame_scalars_kernel",
+                                 "frame_mask_kernel", "frame_components_kernel", "region_variance_kernel"],
         },
-        "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks.summary(),
+        "e2e": e2e, "gpu_launches": 6 * args.steps, "clocks": clocks.summary(),
     }
-    line["roofline"]["traffic"] = measured_traffic(total)
-    line["roofline"]["kernels_per_step"] = ["extract_sweep_kernel", "frame_mask_kernel", "frame_components_kernel", "region_variance_kernel"]
+    line.update(extras)
     if preprocess is not None:
         line["preprocess"] = preprocess
     if not args.no_motion:
         line["motion_detector"] = bench_motion()
+    if preprocess is not None:
+        # the metric's name: frames tracked AND preprocessed -- one extraction pass plus one preprocessing pass over the batch
+        line["tracked_and_preprocessed"] = {
+            "frames_per_s": total / ((kernel_ms + preprocess["ms"]) * 1e-3), "unit": UNIT,
+            "what": "frames of the batch / (extraction step + preprocessing of {} segments drawn from it)".format(args.tracks)}
     if not args.no_cpu_baseline and world >= 1:
         cores = min(os.cpu_count() or 1, 64)
         n_cpu = min(8 * cores, e2e_clips)  # ~10 s of CPU work: 8 whole clips per host thread
         sample = np.ascontiguousarray(h_frames.reshape(e2e_clips, T, H, W)[:n_cpu])
-        v, dt, n_clips = cpu_baseline(cores, 1, T, pix=sample)
+        v, dt, n_clips, port = cpu_baseline(cores, 1, T, pix=sample, want_regions=True)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "first {} clips x {} frames of this run's batch, {:.1f} s".format(n_clips, sample.shape[1], dt)}
+                                "sample": "first {} clips x {} frames of this run's batch, {:.1f} s".format(n_clips, sample.shape[1], dt),
+                                "reference_python": reference_python_record()}
+        # parity of THIS run: the e2e region lists of the GPU against the CPU port's on the clips both processed
+        line["parity_checked_clips"] = n_clips
+        line["parity_checked_regions"] = check_parity(hout, port, n_clips, T)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

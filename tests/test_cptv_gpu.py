@@ -91,8 +91,10 @@ def test_packed_host_call_matches_raw_host_call():
     assert int(want["info"]["n_components"][:total].sum()) > 50
     for t in range(total):
         n = min(int(want["info"]["n_components"][t]), 16)
-        for f in ("x", "y", "width", "height", "area", "sum_x", "sum_y", "key", "pixel_variance"):
+        for f in ("x", "y", "width", "height", "area", "sum_x", "sum_y", "key"):
             assert np.array_equal(got["regions"][t, :n][f], want["regions"][t, :n][f]), (t, f)
+        # (the regions-only kernel folds the variance sums with atomics: the order, hence the last bits, vary run to run)
+        np.testing.assert_allclose(got["regions"][t, :n]["pixel_variance"], want["regions"][t, :n]["pixel_variance"], rtol=1e-9, atol=1e-9)
 
 
 def test_packed_synthetic_batch_and_malformed_table():
@@ -117,7 +119,9 @@ def test_packed_synthetic_batch_and_malformed_table():
     assert np.array_equal(got["info"]["thermal_sum"], want["info"]["thermal_sum"])
     for t in range(C * T):
         n = min(int(want["info"]["n_components"][t]), 16)
-        assert np.array_equal(got["regions"][t, :n], want["regions"][t, :n]), t
+        for f in ("x", "y", "width", "height", "area", "sum_x", "sum_y", "key"):
+            assert np.array_equal(got["regions"][t, :n][f], want["regions"][t, :n][f]), (t, f)
+        np.testing.assert_allclose(got["regions"][t, :n]["pixel_variance"], want["regions"][t, :n]["pixel_variance"], rtol=1e-9, atol=1e-9)
     # a payload that runs past the end of the stream is refused before anything is launched
     bad = table.copy()
     bad["payload_offset"][7] = stream.size - 100

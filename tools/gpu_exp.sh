@@ -11,6 +11,6 @@ for e in 0 "$@"; do
   python - <<PY
 import json
 d = json.loads(open("gpurun_out/bench_exp$e.json").read().strip().splitlines()[-1])
-print("EXP $e: {:.2f} M frames/s, {:.2f} ms/step, regions {}, kernels {}".format(d["value"] / 1e6, d["ms_per_step"], d["config"]["regions_found"], {k: round(v, 2) for k, v in d["roofline"]["kernel_times_ms"].items()}))
+print("EXP $e: {:.2f} M frames/s, {:.2f} ms/step, regions {}, kernels {}".format(d["value"] / 1e6, d["ms_per_step"], d["run_info"]["regions_found"], {k: round(v, 2) for k, v in d["roofline"]["kernel_times_ms"].items()}))
 PY
 done
