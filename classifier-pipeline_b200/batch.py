@@ -174,50 +174,91 @@ class BatchPreprocessor:
     def build_tables(self, tracks, seed=None):
         """tracks: list of (regions, segments); regions int array (n, >=6) rows [frame, x, y, w, h, blank] with
         ``frame`` an index into the device frame buffers, segments a list of frame arrays (same index space).
-        Returns (limit_regions SAMPLE_DTYPE, samples SAMPLE_DTYPE, segment_samples int32 (n_seg, tiles), seg_track)."""
-        W, H = self.ex.width, self.ex.height
-        lim_parts, samp_parts, seg_rows, seg_track = [], [], [], []
-        n_samples = 0
-        for ti, (regions, segments) in enumerate(tracks):
-            regions = np.asarray(regions)
-            if regions.ndim != 2 or regions.shape[1] < 6:
+        Returns (limit_regions SAMPLE_DTYPE, samples SAMPLE_DTYPE, segment_samples int32 (n_seg, tiles), seg_track).
+
+        Flattens the per-track lists and hands them to ``build_tables_flat`` (one concatenation, one sort, one unique for
+        all tracks together)."""
+        n_tracks = len(tracks)
+        if n_tracks == 0:
+            z = np.zeros(0, native.SAMPLE_DTYPE)
+            return z, z.copy(), np.zeros((0, self.tiles), np.int32), np.zeros(0, np.int32)
+        reg_list = [np.asarray(r) for r, _ in tracks]
+        for r in reg_list:
+            if r.ndim != 2 or r.shape[1] < 6:
                 raise ValueError("regions must be (n, >=6) rows [frame, x, y, w, h, blank]")
-            ok = (regions[:, 5] == 0) & (regions[:, 3] > 0) & (regions[:, 4] > 0) & (regions[:, 0] >= 0)
-            r = regions[ok]
-            if len(r) and ((r[:, 1] < 0).any() or (r[:, 2] < 0).any() or (r[:, 1] + r[:, 3] > W).any() or (r[:, 2] + r[:, 4] > H).any()):
-                raise ValueError("track {}: a region lies outside the {}x{} frame".format(ti, W, H))
-            lim = np.zeros(len(r), native.SAMPLE_DTYPE)
-            lim["frame"], lim["x"], lim["y"], lim["width"], lim["height"], lim["track"] = r[:, 0], r[:, 1], r[:, 2], r[:, 3], r[:, 4], ti
-            lim_parts.append(lim)
-            if not segments:
-                continue
-            seg_frames = [np.asarray(s, dtype=np.int64).reshape(-1) for s in segments]
-            uniq, inverse = np.unique(np.concatenate(seg_frames), return_inverse=True)
-            # the region of each unique frame (first row with that frame number, as unique_regions keeps the first)
-            order = np.argsort(regions[:, 0], kind="stable")
-            pos = np.searchsorted(regions[order, 0], uniq)
-            if (pos >= len(order)).any() or (regions[order[np.minimum(pos, len(order) - 1)], 0] != uniq).any():
-                raise ValueError("track {}: a segment names a frame the track has no region for".format(ti))
-            rows = regions[order[pos]]
-            if (rows[:, 3] <= 0).any() or (rows[:, 4] <= 0).any():
-                raise ValueError("track {}: a segment frame has an empty region".format(ti))
-            if (rows[:, 1] < 0).any() or (rows[:, 2] < 0).any() or (rows[:, 1] + rows[:, 3] > W).any() or (rows[:, 2] + rows[:, 4] > H).any():
-                raise ValueError("track {}: a region lies outside the {}x{} frame".format(ti, W, H))
-            smp = np.zeros(len(uniq), native.SAMPLE_DTYPE)
-            smp["frame"], smp["x"], smp["y"], smp["width"], smp["height"], smp["track"] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], ti
-            samp_parts.append(smp)
-            at = 0
-            for s in seg_frames:
-                idx = inverse[at : at + len(s)] + n_samples
-                at += len(s)
-                if len(s) == 0:
-                    continue
-                seg_rows.append(idx[pad_segment_samples(len(s), self.tiles, seed)])
-                seg_track.append(ti)
-            n_samples += len(uniq)
-        cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
-        seg = np.asarray(seg_rows, dtype=np.int32).reshape(-1, self.tiles)
-        return cat(lim_parts, native.SAMPLE_DTYPE), cat(samp_parts, native.SAMPLE_DTYPE), seg, np.asarray(seg_track, np.int32)
+        reg_n = np.fromiter((len(r) for r in reg_list), np.int64, n_tracks)
+        R = np.concatenate([r[:, :6] for r in reg_list]).astype(np.int64) if reg_n.sum() else np.zeros((0, 6), np.int64)
+        r_track = np.repeat(np.arange(n_tracks, dtype=np.int64), reg_n)
+        seg_arrays, seg_track = [], []
+        for ti, (_, segments) in enumerate(tracks):
+            for sgm in segments or ():
+                a = np.asarray(sgm, dtype=np.int64).reshape(-1)
+                if len(a):
+                    seg_arrays.append(a)
+                    seg_track.append(ti)
+        seg_len = np.fromiter((len(a) for a in seg_arrays), np.int64, len(seg_arrays))
+        seg_frames = np.concatenate(seg_arrays) if seg_arrays else np.zeros(0, np.int64)
+        return self.build_tables_flat(R, r_track, seg_frames, seg_len, np.asarray(seg_track, np.int64), seed=seed)
+
+    def build_tables_flat(self, regions, region_track, seg_frames, seg_len, seg_track, seed=None):
+        """The same tables from flat arrays: ``regions`` (N, 6) rows [frame, x, y, w, h, blank] of all tracks with their
+        track index in ``region_track``; the segments' frames back to back in ``seg_frames`` (``seg_len`` frames each,
+        segment i belongs to track ``seg_track[i]``).  Pure array code: tens of milliseconds for 10 000 tracks."""
+        W, H = self.ex.width, self.ex.height
+        R = np.asarray(regions, dtype=np.int64).reshape(-1, 6)
+        r_track = np.asarray(region_track, dtype=np.int64)
+        seg_frames = np.asarray(seg_frames, dtype=np.int64)
+        seg_len = np.asarray(seg_len, dtype=np.int64)
+        seg_track = np.asarray(seg_track, dtype=np.int64)
+
+        def outside(rows):
+            return (rows[:, 1] < 0) | (rows[:, 2] < 0) | (rows[:, 1] + rows[:, 3] > W) | (rows[:, 2] + rows[:, 4] > H)
+
+        # ---- get_limits: every non-blank region with an area
+        ok = (R[:, 5] == 0) & (R[:, 3] > 0) & (R[:, 4] > 0) & (R[:, 0] >= 0)
+        bad = ok & outside(R)
+        if bad.any():
+            raise ValueError("track {}: a region lies outside the {}x{} frame".format(int(r_track[np.argmax(bad)]), W, H))
+        lim = np.zeros(int(ok.sum()), native.SAMPLE_DTYPE)
+        Rk = R[ok]
+        lim["frame"], lim["x"], lim["y"], lim["width"], lim["height"], lim["track"] = Rk[:, 0], Rk[:, 1], Rk[:, 2], Rk[:, 3], Rk[:, 4], r_track[ok]
+        if len(seg_len) == 0:
+            return lim, np.zeros(0, native.SAMPLE_DTYPE), np.zeros((0, self.tiles), np.int32), np.zeros(0, np.int32)
+        if (seg_len <= 0).any():
+            raise ValueError("empty segment")
+        if (seg_frames < 0).any():
+            raise ValueError("segment frames must be non-negative")
+        # ---- the unique (track, frame) pairs of the segments, in (track, frame) order
+        big = int(max(seg_frames.max(), R[:, 0].max() if len(R) else 0)) + 1
+        key = np.repeat(seg_track, seg_len) * big + seg_frames
+        uniq, inverse = np.unique(key, return_inverse=True)
+        # the region of each unique frame: the first row of the track with that frame number (unique_regions keeps the first)
+        rkey = r_track * big + np.where(R[:, 0] >= 0, R[:, 0], big - 1)
+        order = np.argsort(rkey, kind="stable")
+        pos = np.searchsorted(rkey[order], uniq)
+        hit = pos < len(order)
+        hit[hit] &= rkey[order[pos[hit]]] == uniq[hit]
+        if not hit.all():
+            raise ValueError("track {}: a segment names a frame the track has no region for".format(int(uniq[np.argmin(hit)] // big)))
+        rows = R[order[pos]]
+        u_track = uniq // big
+        empty = (rows[:, 3] <= 0) | (rows[:, 4] <= 0)
+        if empty.any():
+            raise ValueError("track {}: a segment frame has an empty region".format(int(u_track[np.argmax(empty)])))
+        if outside(rows).any():
+            raise ValueError("track {}: a region lies outside the {}x{} frame".format(int(u_track[np.argmax(outside(rows))]), W, H))
+        smp = np.zeros(len(uniq), native.SAMPLE_DTYPE)
+        smp["frame"], smp["x"], smp["y"], smp["width"], smp["height"], smp["track"] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], u_track
+        # ---- the tiles of every segment: its frames in order, padded like preprocess_movement when it is short
+        seg = np.empty((len(seg_len), self.tiles), np.int32)
+        starts = np.concatenate([[0], np.cumsum(seg_len)[:-1]])
+        full = seg_len >= self.tiles
+        if full.any():
+            seg[full] = inverse[starts[full][:, None] + np.arange(self.tiles)[None, :]]
+        for i in np.nonzero(~full)[0]:
+            idx = inverse[starts[i] : starts[i] + seg_len[i]]
+            seg[i] = idx[pad_segment_samples(int(seg_len[i]), self.tiles, seed)]
+        return lim, smp, seg, seg_track.astype(np.int32)
 
     def run_tables(self, d_thermal, d_filtered, limit_regions, samples, segment_samples, n_tracks, crop_rectangle, out=None):
         """Launch on prepared tables (host numpy or CUDA uint8/int32 tensors).  Returns the CUDA float32

@@ -182,6 +182,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
         cudaFreeHost(c->pk_h_table[i]); cudaFreeHost(c->pk_h_first[i]);
     }
     cudaFree(c->pk_change);
+    cudaFree(c->scratch_filtered);
     free_stage(c);
     if (c->events)
         for (int i = 0; i < 2; ++i) {
@@ -517,6 +518,19 @@ int cpt_extract_batch(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *d_cl
     return launch_extract(c, d_frames, d_clips, n_clips, out, d_state, c->stream, out->total_frames);
 }
 
+// Host-staged calls that do not return the filtered images still run the split plan (it keeps the whole GPU busy with
+// (clip, strip) units where the single persistent kernel has one CTA per clip): the images go to a scratch buffer.
+static int ensure_filtered_scratch(cpt_ctx *c, size_t out_frames) {
+    if (c->scratch_filtered_frames >= out_frames) return CPT_OK;
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(c->scratch_filtered);
+    c->scratch_filtered = nullptr;
+    c->scratch_filtered_frames = 0;
+    CUDA_TRY(cudaMalloc(&c->scratch_filtered, out_frames * c->g.npx * sizeof(float)));
+    c->scratch_filtered_frames = out_frames;
+    return CPT_OK;
+}
+
 static int ensure_stage(cpt_ctx *c, size_t frames_bytes, size_t out_frames, bool filtered, bool labels) {
     if (!c->events) {
         for (int i = 0; i < 2; ++i) {
@@ -589,6 +603,7 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
     }
     int rc = ensure_stage(c, max_in * npx * sizeof(uint16_t), max_out, h_filtered != nullptr, h_labels != nullptr);
     if (rc) return rc;
+    if (!h_filtered && (rc = ensure_filtered_scratch(c, max_out))) return rc;
     if (c->d_clips_cap < (size_t)n_clips) {
         cudaFree(c->d_clips);
         c->d_clips = nullptr;
@@ -608,8 +623,8 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
         CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
         if (ch >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
-        cpt_outputs out{c->stage_regions[b], c->stage_info[b], h_filtered ? c->stage_filtered[b] : nullptr,
-                        h_labels ? c->stage_labels[b] : nullptr, sp.out_hi - sp.out_lo, 0};
+        cpt_outputs out{c->stage_regions[b], c->stage_info[b], h_filtered ? c->stage_filtered[b] : c->scratch_filtered,
+                        h_labels ? c->stage_labels[b] : nullptr, sp.out_hi - sp.out_lo, 0, 1};
         rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream,
                             sp.out_hi - sp.out_lo);
         if (rc) return rc;
@@ -688,6 +703,7 @@ int cpt_extract_batch_cptv_host(cpt_ctx *c, const uint8_t *h_stream, uint64_t st
     }
     int rc = ensure_stage(c, std::max<size_t>(max_rows, 1) * npx * sizeof(uint16_t), max_out, false, false);
     if (rc) return rc;
+    if ((rc = ensure_filtered_scratch(c, max_out))) return rc;
     // packed staging: stream bytes (+4: the unpacker's 32-bit window may read past the last payload), frame table rows, the
     // clips' first rows; the decoder's int32 change images
     const size_t need_bytes = max_bytes + 4, need_rows = std::max<size_t>(max_rows, 1);
@@ -747,7 +763,7 @@ int cpt_extract_batch_cptv_host(cpt_ctx *c, const uint8_t *h_stream, uint64_t st
                                          c->pk_change, c->stream);
             if (rc) return rc;
         }
-        cpt_outputs out{c->stage_regions[b], c->stage_info[b], nullptr, nullptr, sp.out_hi - sp.out_lo, 0, 0};
+        cpt_outputs out{c->stage_regions[b], c->stage_info[b], c->scratch_filtered, nullptr, sp.out_hi - sp.out_lo, 0, 1};
         rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream, sp.out_hi - sp.out_lo);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev_compute[b], c->stream));

@@ -89,6 +89,8 @@ struct cpt_ctx {
     int32_t *pk_first[2] = {nullptr, nullptr}, *pk_h_first[2] = {nullptr, nullptr};
     int32_t *pk_change = nullptr;
     size_t pk_bytes = 0, pk_rows = 0, pk_clips = 0;
+    float *scratch_filtered = nullptr;  // filtered images of host-staged calls that do not return them
+    size_t scratch_filtered_frames = 0;
     bool nlm_table_ready = false;  // cpt_nlm_denoise_u8 uploaded its weight table (constant memory of this device)
 };
 
