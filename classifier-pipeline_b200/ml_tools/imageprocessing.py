@@ -151,6 +151,20 @@ def detect_objects(image, otsus=False, threshold=30, kernel=(15, 15)):
     return detect.detect_objects(image, otsus=otsus, threshold=threshold, kernel=kernel)
 
 
+def detect_objects_ir(image, otsus=False, threshold=100, kernel=(15, 15)):
+    """morphologyEx OPEN -> threshold -> connectedComponentsWithStats (imageprocessing.py:185-199)."""
+    from . import detect
+
+    return detect.detect_objects_ir(image, otsus=otsus, threshold=threshold, kernel=kernel)
+
+
+def detect_objects_both(salicencyMap, backsub, threshold=30, kernel=(15, 15), otsus=False):
+    """imageprocessing.py:202-238."""
+    from . import detect
+
+    return detect.detect_objects_both(salicencyMap, backsub, threshold=threshold, kernel=kernel, otsus=otsus)
+
+
 def fast_nl_means_denoising(image):
     """``cv2.fastNlMeansDenoising(np.uint8(image), None)`` as ``ClipTracker._get_filtered_frame`` calls it
     (track/cliptracker.py:116-117): h = 3, 7x7 template, 21x21 search window; uint8 (H, W) or (N, H, W)."""

@@ -71,6 +71,7 @@ class CptMotionResult(ctypes.Structure):
                 ("mean_frames", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+DETECT_CLOSE, DETECT_OPEN_GRAY, DETECT_DILATE, DETECT_OTSU, DETECT_MASK_ONLY = 1, 2, 4, 8, 16
 MOTION_MEAN, MOTION_MEAN_RESTART, MOTION_BACKGROUND, MOTION_DETECT, MOTION_WARMER_ONLY, MOTION_ONE_DIFF = 1, 2, 4, 8, 16, 32
 
 
@@ -141,7 +142,13 @@ SYMBOLS = {
     "cpt_normalize_f32": (_i, [_vp, _vp, _i64, _d, _d, _d, _i, _vp]),
     "cpt_resize_pad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "cpt_detect_objects_u8": (_i, [_vp, _vp, _i, _i, _d, _i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int32)]),
+    "cpt_detect_objects_ex": (_i, [_vp, _vp, _i, _i, _d, _i, ctypes.c_uint32, _vp, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int32),
+                                   ctypes.POINTER(_d)]),
     "cpt_nlm_denoise_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "cpt_ir_motion_open": (_vp, [_vp, _i, _i, _i]),
+    "cpt_ir_motion_close": (None, [_vp]),
+    "cpt_ir_motion_gray": (_i, [_vp, _vp, _i, _vp]),
+    "cpt_ir_motion_detect": (_i, [_vp, _i, _i, _i, _i, _vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "cpt_cptv_decode": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp]),
     "cpt_extract_batch_cptv_host": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _i, _i64, _vp, _vp, _i]),
     "cpt_motion_open": (_vp, [_vp, _i, _i, _i, _i]),
@@ -303,6 +310,16 @@ class Context:
                                              ctypes.byref(n)))
         return n.value
 
+    def detect_objects_ex(self, d_image, width, height, threshold, blur_ksize, steps, max_components, d_labels, d_stats, d_centroids,
+                          d_or_mask=None, d_mask_out=None):
+        """Returns (n_labels, threshold used)."""
+        n = ctypes.c_int32()
+        thr = ctypes.c_double()
+        check(self.lib.cpt_detect_objects_ex(self._h, _ptr(d_image), int(width), int(height), float(threshold), int(blur_ksize), int(steps),
+                                             _ptr(d_or_mask), int(max_components), _ptr(d_labels), _ptr(d_stats), _ptr(d_centroids),
+                                             _ptr(d_mask_out), ctypes.byref(n), ctypes.byref(thr)))
+        return n.value, thr.value
+
     def nlm_denoise_u8(self, d_src, width, height, n_frames, d_dst):
         check(self.lib.cpt_nlm_denoise_u8(self._h, _ptr(d_src), int(width), int(height), int(n_frames), _ptr(d_dst)))
 
@@ -353,3 +370,41 @@ def pinned_empty(shape, dtype):
 
 
 _PINNED_OWNERS = {}
+
+
+class IrMotion:
+    """Device half of IRMotionDetector (cpt_ir_motion_*): a ring of grey frames, grey conversion and the eroded-pixel counts."""
+
+    def __init__(self, ctx, width, height, ring_frames):
+        self.ctx = ctx
+        self.width, self.height, self.ring_frames = width, height, ring_frames
+        self._h = ctx.lib.cpt_ir_motion_open(ctx._h, int(width), int(height), int(ring_frames))
+        if not self._h:
+            raise NativeError("cpt_ir_motion_open failed: {}".format(ctx.lib.cpt_last_error().decode()))
+
+    def gray(self, bgr, slot):
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        if bgr.shape != (self.height, self.width, 3):
+            raise ValueError("IR frames must be ({}, {}, 3) uint8".format(self.height, self.width))
+        out = np.empty((self.height, self.width), np.uint8)
+        check(self.ctx.lib.cpt_ir_motion_gray(self._h, _ptr(bgr), int(slot), _ptr(out)))
+        return out
+
+    def detect(self, slot_new, slot_oldest, threshold, erode_k, mask=None):
+        diff, cnt = ctypes.c_int32(), ctypes.c_int32()
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        check(self.ctx.lib.cpt_ir_motion_detect(self._h, int(slot_new), int(slot_oldest), int(threshold), int(erode_k), _ptr(mask),
+                                                ctypes.byref(diff), ctypes.byref(cnt)))
+        return diff.value, cnt.value
+
+    def close(self):
+        if self._h:
+            self.ctx.lib.cpt_ir_motion_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -203,3 +203,118 @@ class ClipTracker(ABC):
         self.print_if_verbose(reason)
         clip.filtered_tracks.append((reason, track))
         return True
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# background models of the IR tracker / motion detector (track/cliptracker.py:493-668)
+# ---------------------------------------------------------------------------------------------------------------
+import numpy as np  # noqa: E402
+
+
+class Background(ABC):
+    TRIGGER_FRAMES = 2
+
+    def __init__(self):
+        self.rescaled = None
+        self.prev_triggered = False
+        self.triggered = 0
+        self.movement_detected = False
+        self.kernel_trigger = np.ones((15, 15), "uint8")    # erosion when not recording
+        self.kernel_recording = np.ones((10, 10), "uint8")  # erosion when recording
+        self._frames = 0
+
+    @abstractmethod
+    def set_background(self, background, frames=1):
+        ...
+
+    @abstractmethod
+    def update_background(self, thermal, filtered):
+        ...
+
+    @abstractmethod
+    def compute_filtered(self, thermal, threshold):
+        ...
+
+    @property
+    @abstractmethod
+    def background(self):
+        ...
+
+    @property
+    def frames(self):
+        return self._frames
+
+    def get_kernel(self):
+        return self.kernel_recording if self.movement_detected else self.kernel_trigger
+
+
+class CVBackground(Background):
+    """OpenCV's MOG2 background subtractor (cliptracker.py:560-609).  Third-party arithmetic (cv2), on the host: it is used
+    as-is when cv2 is importable and is not restated."""
+
+    def __init__(self, tracking_alg="mog2"):
+        super().__init__()
+        if tracking_alg != "mog2":
+            raise Exception(f"No algorihtm details found for {tracking_alg}")
+        try:
+            import cv2
+        except ImportError as e:  # pragma: no cover
+            raise ImportError("CVBackground wraps cv2.createBackgroundSubtractorMOG2 (third-party); install OpenCV or pass "
+                              "another background model") from e
+        self.use_subsense = False
+        self.algorithm = cv2.createBackgroundSubtractorMOG2(history=1000, detectShadows=False)
+        self._background = None
+
+    def set_background(self, background, frames=1):
+        self.update_background(background, learning_rate=1)
+
+    def update_background(self, thermal, filtered=None, learning_rate=-1):
+        self._background = self.algorithm.apply(thermal, None, learning_rate)
+        self._frames += 1
+
+    @property
+    def background(self):
+        return self.algorithm.getBackgroundImage()
+
+    def compute_filtered(self, thermal, threshold=None):
+        return self._background
+
+
+def get_diff_back_filtered(background, frame, back_thresh):
+    """|frame - background| with everything below back_thresh zeroed, normalised to 0..255 (cliptracker.py:652-668);
+    the normalisation runs on the device (ml_tools.imageprocessing.normalize)."""
+    from ..ml_tools.imageprocessing import normalize
+
+    filtered = np.float32(np.array(frame, copy=True))
+    filtered = abs(filtered - background)
+    filtered[filtered < back_thresh] = 0
+    filtered, _ = normalize(filtered, new_max=255)
+    return filtered
+
+
+class DiffBackground(Background):
+    """Mean of the frames seen so far, not updated where the frame differs from it (cliptracker.py:612-649)."""
+
+    def __init__(self, background_thresh):
+        super().__init__()
+        self._frames = 1
+        self._background = None
+        self.background_thresh = background_thresh
+
+    def set_background(self, background, frames=1):
+        self._frames = frames
+        self._background = np.float32(background) * self.frames
+
+    def update_background(self, thermal, filtered=None):
+        background = self.background
+        filtered = get_diff_back_filtered(background, thermal, self.background_thresh)
+        new_thermal = np.where(filtered > 0, background, thermal)
+        self._background += new_thermal
+        self._frames += 1
+
+    def compute_filtered(self, thermal=None, threshold=None):
+        return get_diff_back_filtered(self.background, thermal, self.background_thresh)
+
+    @property
+    def background(self):
+        return self._background / self.frames

@@ -240,9 +240,27 @@ int cpt_detect_objects_u8(cpt_ctx *ctx, const uint8_t *d_image, int width, int h
                           int close, int max_components, int32_t *d_labels, int32_t *d_stats, double *d_centroids,
                           int32_t *h_count);
 
+/* The same pipeline with every stage the imageprocessing.py variants use, on one uint8 image of any size:
+ *   detect_objects(kernel=(15,15) default, otsus)   imageprocessing.py:240-248  blur_ksize 3 / 5 / 7 / 15 (cv2.GaussianBlur 8-bit
+ *                                                   fixed-point taps), CPT_DETECT_OTSU (cv2.threshold THRESH_OTSU), CPT_DETECT_CLOSE
+ *   detect_objects_ir (IR 640x480 frames)           imageprocessing.py:185-199  CPT_DETECT_OPEN_GRAY (cv2.morphologyEx MORPH_OPEN
+ *                                                   with a tuple kernel = 2x1 element, on the grey image), threshold, components
+ *   detect_objects_both                             imageprocessing.py:202-238  blur, threshold, CPT_DETECT_DILATE, CPT_DETECT_CLOSE,
+ *                                                   d_or_mask (the thresholded saliency map, any non-zero = set) OR-ed in
+ * CPT_DETECT_MASK_ONLY stops after the binary stages and writes the mask (0 / 255) to d_mask_out.  h_threshold_used (may
+ * be NULL) receives the threshold applied (Otsu's when CPT_DETECT_OTSU).  Synchronises the ctx stream. */
+#define CPT_DETECT_CLOSE 1u
+#define CPT_DETECT_OPEN_GRAY 2u
+#define CPT_DETECT_DILATE 4u
+#define CPT_DETECT_OTSU 8u
+#define CPT_DETECT_MASK_ONLY 16u
+int cpt_detect_objects_ex(cpt_ctx *ctx, const uint8_t *d_image, int width, int height, double threshold, int blur_ksize,
+                          uint32_t steps, const uint8_t *d_or_mask, int max_components, int32_t *d_labels, int32_t *d_stats,
+                          double *d_centroids, uint8_t *d_mask_out, int32_t *h_count, double *h_threshold_used);
+
 /* cv2.fastNlMeansDenoising(uint8, None) (track/cliptracker.py:116-117; h = 3, 7x7 template, 21x21 search), OpenCV's
- * integer algorithm bit for bit, on n_frames images [n_frames][H][W].  Stand-alone primitive: the batched extractor
- * does not call it yet (TrackingConfig.denoise must be off there). */
+ * integer algorithm bit for bit, on n_frames images [n_frames][H][W].  The batched extractor runs the same kernel for clips
+ * with CPT_CLIP_DENOISE. */
 int cpt_nlm_denoise_u8(cpt_ctx *ctx, const uint8_t *d_src, int width, int height, int n_frames, uint8_t *d_dst);
 
 /* ---- CPTV v2 frame decode (what cptv_rs_python_bindings.CptvReader.next_frame does per pixel;
@@ -299,6 +317,23 @@ int cpt_motion_mean_init(cpt_motion *m, const int32_t *h_slots, int n);
 int cpt_motion_step(cpt_motion *m, const uint16_t *h_pix, void *d_background_state, int slot_new, int slot_oldest,
                     int slot_nonffc, int diff_slot_new, int diff_slot_old, uint32_t flags, int delta_thresh,
                     double init_average, cpt_motion_result *h_result);
+
+/* ---- IRMotionDetector (piclassifier/irmotiondetector.py:55-153), streaming, 640x480 BGR frames ----
+ * Per frame the reference does cv2.cvtColor(BGR2GRAY), feeds the grey frame to its background model (OpenCV's MOG2: third
+ * party, stays on the host), then absdiff(oldest grey, grey) -> threshold 12 -> erode with a k x k box (15 idle / 10 while
+ * recording) -> count, and the same erode + count on the background model's foreground mask.  The detector owns a ring of
+ * grey frames on the device (SlidingWindow of preview_secs * fps frames).
+ *   cpt_ir_motion_gray    h_bgr [H][W][3] -> grey (OpenCV's fixed point: (B*3735 + G*19235 + R*9798 + 2^14) >> 15) into ring
+ *                         slot slot_new; h_gray_out (may be NULL) receives it for the host's background model
+ *   cpt_ir_motion_detect  *h_diff_pixels = count(erode(|ring[slot_oldest] - ring[slot_new]| > threshold)); with h_mask (the
+ *                         background model's foreground mask, [H][W], non-zero = set; may be NULL) *h_mask_pixels =
+ *                         count(erode(h_mask)).  Pixels outside the image do not constrain the erosion (cv2's default). */
+typedef struct cpt_ir_motion cpt_ir_motion;
+cpt_ir_motion *cpt_ir_motion_open(cpt_ctx *ctx, int width, int height, int ring_frames);
+void cpt_ir_motion_close(cpt_ir_motion *m);
+int cpt_ir_motion_gray(cpt_ir_motion *m, const uint8_t *h_bgr, int slot_new, uint8_t *h_gray_out);
+int cpt_ir_motion_detect(cpt_ir_motion *m, int slot_new, int slot_oldest, int threshold, int erode_k, const uint8_t *h_mask,
+                         int32_t *h_diff_pixels, int32_t *h_mask_pixels);
 
 /* State access for WeightedBackground.background / .background_weight / .average
  * (motiondetector.py:178-248).  h_background int32 [H][W]; h_weight_count uint16 [(H-2e)][(W-2e)]
