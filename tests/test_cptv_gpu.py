@@ -106,7 +106,7 @@ def test_packed_synthetic_batch_and_malformed_table():
     ex = BatchExtractor(device=0, max_regions=16)
     C, T = 5, 60
     d_frames, models = make_clips_torch(C, T, torch.device("cuda", 0))
-    d_frames[3, 10:12, 40:60, 50:80] += 900  # a step large enough to need 16-bit deltas in those frames
+    d_frames.view(torch.int16)[3, 10:12, 40:60, 50:80] += 900  # a step large enough to need 16-bit deltas in those frames
     stream, table, first = pack_clips_torch(d_frames)
     assert set(table["bit_width"]) == {8, 16}
     slots = [ex.ctx.weight_table(m[3], max_frames=1024) for m in MODELS]

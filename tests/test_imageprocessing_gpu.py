@@ -32,13 +32,19 @@ def test_detect_objects_matches_oracle_lepton_and_ir_sizes():
                 assert list(stats[0]) == [xs.min(), ys.min(), xs.max() - xs.min() + 1, ys.max() - ys.min() + 1, bg.sum()]
 
 
-def test_detect_objects_rejects_unbuilt_options():
+def test_detect_objects_options():
+    """The default (15, 15) kernel and Otsu are built (fixtures: tests/test_ir_gpu.py); kernel sizes whose fixed-point taps
+    are not built are refused instead of approximated."""
     from classifier_pipeline_b200.ml_tools import imageprocessing as ip
 
+    n, labels, stats, cents = ip.detect_objects(np.zeros((8, 8)))
+    assert n == 1 and labels.shape == (8, 8) and not labels.any()
+    n, _, _, _ = ip.detect_objects(np.zeros((8, 8)), otsus=True, kernel=(5, 5))
+    assert n == 1
     with pytest.raises(NotImplementedError):
-        ip.detect_objects(np.zeros((8, 8)), otsus=True, kernel=(5, 5))
+        ip.detect_objects(np.zeros((8, 8)), kernel=(9, 9))
     with pytest.raises(NotImplementedError):
-        ip.detect_objects(np.zeros((8, 8)))  # default (15, 15) Gaussian is not built
+        ip.detect_objects(np.zeros((8, 8)), kernel=(5, 7))
 
 
 def test_normalize_matches_numpy_semantics():

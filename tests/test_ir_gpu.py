@@ -90,11 +90,11 @@ def test_ir_erosion_counts_match_cv2():
 
     rng = np.random.default_rng(11)
     dev = native.IrMotion(engine.get_engine().ctx, ir_helpers.W, ir_helpers.H, 2)
-    a = rng.integers(0, 256, (ir_helpers.H, ir_helpers.W, 3), dtype=np.uint8)
+    a = rng.integers(0, 100, (ir_helpers.H, ir_helpers.W, 3), dtype=np.uint8)
     b = a.copy()
-    b[:40, :50] = 255 - b[:40, :50]           # a block touching the corner
-    b[200:260, 300:420] = 255 - b[200:260, 300:420]
-    b[470:, 600:] = 255 - b[470:, 600:]
+    b[:40, :50] += 120           # a block touching the corner
+    b[200:260, 300:420] += 120
+    b[470:, 600:] += 120         # too small to survive a 15 x 15 box away from the border, but the border does not constrain
     ga, gb = dev.gray(a, 0), dev.gray(b, 1)
     mask = (rng.random((ir_helpers.H, ir_helpers.W)) > 0.02).astype(np.uint8) * 255
     for k in (15, 10):
