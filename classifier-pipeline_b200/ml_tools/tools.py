@@ -36,3 +36,16 @@ class CustomJSONEncoder(json.JSONEncoder):
         if isinstance(obj, Enum):
             return str(obj.name)
         return super().default(obj)
+
+
+def load_clip_metadata(filename):
+    """Loads the metadata file of a clip (tools.py:90-104)."""
+    with open(filename, "r") as t:
+        meta = json.load(t)
+    if meta.get("recordingDateTime"):
+        from datetime import datetime
+
+        meta["recordingDateTime"] = datetime.fromisoformat(meta["recordingDateTime"].replace("Z", "+00:00"))
+    if meta.get("tracks") is None and meta.get("Tracks"):
+        meta["tracks"] = meta["Tracks"]
+    return meta

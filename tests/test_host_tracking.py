@@ -102,3 +102,15 @@ def test_possum_matches_reference_repo_golden_json(monkeypatch):
                     assert p[k] == pytest.approx(q[k], abs=0.011)
                 else:
                     assert p[k] == q[k], k
+    # the thumbnail the reference's extract.py chose for each track (classify/thumbnail.py: mass, contour points of the
+    # region's mask, warmth against the frame median): same frame, same contour count, same score
+    from classifier_pipeline_b200.track.trackextractor import get_metadata
+
+    ext._tracking_time = 0.0
+    full = json.loads(json.dumps(get_metadata(None, "possum", None, clip, ext, save=False), cls=CustomJSONEncoder))
+    for a, b in zip(full["tracks"], gold["tracks"]):
+        ta, tb = a["thumbnail"], b["thumbnail"]
+        assert ta["contours"] == tb["contours"] and ta["median_diff"] == tb["median_diff"] and ta["score"] == tb["score"]
+        for k in ("x", "y", "width", "height", "mass", "frame_number", "blank", "in_trap"):
+            assert ta["region"][k] == tb["region"][k], k
+    assert full["algorithm"]["tracker_version"] == gold["algorithm"]["tracker_version"]
