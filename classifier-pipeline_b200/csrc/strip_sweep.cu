@@ -30,15 +30,21 @@ namespace {
 
 using namespace prim;
 
-constexpr int kLead = 7;                             // frames the producer runs ahead of the slowest consumer warp
+#ifndef CPT_LEAD
+#define CPT_LEAD 7
+#endif
+constexpr int kLead = CPT_LEAD;                      // frames the producer runs ahead of the slowest consumer warp
 constexpr int kRingSlots = kMeanFrames + kLead;      // 52 frames of the strip's rows
 constexpr int kSlotBytes = kStripPxMax * 2;          // 3840
 constexpr int kConsWarps = kStripPxMax / 4 / 32;     // 15
 constexpr int kConsThreads = kConsWarps * 32;        // 480
-constexpr int kBarRing = 8;                          // full / done barriers and stat rows are reused every 8 passes
+constexpr int kBarRing = kLead < 8 ? 8 : 16;          // full / done barriers and stat rows are reused every kBarRing passes
 static_assert(kBarRing > kLead, "a barrier is reused only after every warp has passed its previous use");
 static_assert(kStripThreads == kConsThreads + 32, "consumer warps + the producer warp");
-constexpr int kStripTable = 4096;                    // first entries of the clip's keep-test table
+#ifndef CPT_STRIP_TABLE
+#define CPT_STRIP_TABLE 4096
+#endif
+constexpr int kStripTable = CPT_STRIP_TABLE;         // first entries of the clip's keep-test table
 constexpr int kRefLag = kLead + 1;                    // a frame's quad bytes are stored against the strip minimum kRefLag frames earlier
 constexpr int kRefDefault = kQuadRefBias;            // reference of the first kRefLag frames (filtered starts near 0)
 
@@ -295,10 +301,9 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
     auto frame_sync = [&](int t, int &refb) {
         // the frame's rows are in the ring; the reference its quad bytes are stored against was published by the producer
         // before it issued the copy (read after the acquire)
-        mbar_wait(&s.full[t & (kBarRing - 1)], (uint32_t)(t >> 3) & 1u);
+        mbar_wait(&s.full[t & (kBarRing - 1)], (uint32_t)(t / kBarRing) & 1u);
         refb = (t >= kRefLag ? *(volatile const int32_t *)&s.ref_ring[(t - kRefLag) & 15] : kRefDefault) + kBias;
     };
-    static_assert(kBarRing == 8, "parity = (t >> 3) & 1");
     auto after_frame = [&]() {
         th.fptr += npx;
         th.lptr += npx;
