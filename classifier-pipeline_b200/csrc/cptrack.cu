@@ -86,6 +86,10 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
         const int rmax = std::max(cpt::kStripPxMax / width, 1);
         g.n_strips = (height + rmax - 1) / rmax;
     }
+    g.qpr_magic = (uint32_t)(0xffffffffu / (uint32_t)std::max(g.qpr, 1)) + 1u;
+    g.h_magic = (uint32_t)(0xffffffffu / (uint32_t)height) + 1u;
+    g.qw_magic = (uint32_t)(0xffffffffu / (uint32_t)std::max(g.qpr / 4, 1)) + 1u;
+    for (int st = 0; st < 20; ++st) g.strip_y0[st] = (uint8_t)(std::min(st, g.n_strips) * height / g.n_strips);
     g.rows_per_it = cpt::kPThreads / g.qpr;
     g.balanced = 0;
     g.bal_a_oy = g.bal_a_r = g.bal_b_oy = g.bal_b_r = -1;

@@ -65,7 +65,7 @@ constexpr int kWarps = kThreads / 32;
 // warps plus one scalar warp per clip; frame_mask_kernel and frame_components_kernel then turn every frame into its
 // mask and its labels / regions with one CTA per frame
 constexpr int kSThreads = kPThreads + 64;  // sweep warps + scalar warp + producer warp
-constexpr int kFThreads = 256;   // frame_mask_kernel
+constexpr int kFThreads = 128;   // frame_mask_kernel
 constexpr int kGThreads = 256;   // frame_components_kernel
 constexpr int kMaxPx = 19200;
 constexpr int kQIter = (kMaxPx / 4 + kPThreads - 1) / kPThreads;  // 6 quads of 4 pixels per pixel thread
@@ -107,7 +107,12 @@ struct Geometry {
     // strip sweep (strip_sweep.cu): the frame is cut into n_strips bands of whole rows, strip s = rows
     // [s * H / n_strips, (s + 1) * H / n_strips), at most kStripPxMax pixels each
     int n_strips;
+    uint32_t qpr_magic, h_magic;  // q / qpr == umulhi(q, qpr_magic), v / H == umulhi(v, h_magic)  (q * qpr, v * H < 2^32)
+    uint32_t qw_magic;            // i / (qpr / 4) == umulhi(i, qw_magic) unless qpr / 4 == 1 (words of quad bytes per row)
+    uint8_t strip_y0[20];         // first row of strip s (s <= n_strips <= kMaxStrips = 16)
 };
+// strip that holds image row y
+__device__ __forceinline__ int strip_of_row(const Geometry &g, int y) { return (int)__umulhi((uint32_t)((y + 1) * g.n_strips - 1), g.h_magic); }
 
 // sweep slot (iteration, row group) that processes owned row oy; its quads are sweep threads r * qpr .. r * qpr + qpr - 1
 __host__ __device__ inline void owned_row_slot(const Geometry &g, int oy, int &it, int &r) {
@@ -154,7 +159,7 @@ constexpr int kSmemWeights = 1024;
 // ---- strip sweep (split path, strip_sweep.cu) -------------------------------------------------
 constexpr int kStripPxMax = 1920;   // pixels of one strip (12 rows at 160 pixels): 480 quads, one per consumer thread
 constexpr int kMaxStrips = 16;
-constexpr int kStripThreads = kStripPxMax / 4 + 32;  // one consumer thread per quad + the producer warp
+constexpr int kStripThreads = kStripPxMax / 4 + 64;  // one consumer thread per quad + the copy warp + the fold warp
 // What one strip CTA found in one pass (frame t, or the tail pass that only applies the last background update), folded
 // over its warps.  [pass][strip] in global memory; frame_scalars_kernel folds the strips of a frame.
 struct StripRec {
@@ -249,15 +254,23 @@ struct __align__(16) Smem {
     int32_t ncomp;
 };
 
-// shared memory of frame_mask_kernel (one frame per CTA: marks -> work lists -> normalise -> blur + threshold)
+// shared memory of frame_mask_kernel (one frame per CTA, one band of rows at a time: hot quads -> work lists -> normalise
+// -> blur + threshold)
+constexpr int kBandHalo = 4;    // rows of normalised values a blur output can reach above / below a hot quad
+constexpr int kBandRows = 24;   // hot rows one band covers
+constexpr int kBandURows = kBandRows + 2 * kBandHalo;
+constexpr int kBandList = kBandURows * (kMaxW / 8);  // every group of every row of the band: the lists cannot overflow
 struct __align__(16) MaskSmem {
-    uint8_t U[kMaxPx];
-    uint16_t list_u[kListCap], list_b[kListCap];
+    uint8_t U[kBandURows * kMaxW];     // normalised bytes of the band's rows
+    uint16_t list_u[kBandList];        // groups of 8 pixels to normalise: band row * gpr + group
+    uint16_t list_b[kBandList];        // groups to blur: frame group | quad marks << 14
+    unsigned long long hot64[kMaxH];   // per frame row, one bit per quad
+    uint32_t M[1][kMaxWords];          // the frame's mask, bit rows
     int16_t theta[kMaxStrips];
-    unsigned long long hot64[kMaxH];
-    uint32_t M[1][kMaxWords];
-    int32_t bcast_i[16];
+    int32_t count[2];                  // list lengths
 };
+static_assert(kMaxH <= 128, "frame_mask_kernel keeps the set of hot rows in four ballot words");
+static_assert(kMaxH * (kMaxW / 8) <= (1 << 14), "a blur list entry keeps the group in 14 bits");
 
 // shared memory of frame_components_kernel (one frame per CTA: close -> components, statistics, labels)
 struct __align__(16) CompSmem {

@@ -433,8 +433,11 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
 // BORDER_REFLECT_101) in packed 16-bit lanes and threshold `> ith` -> one byte of the bit rows in s.M[buf].
 // Only outputs of the marked quads (q2: one bit per quad of the group) are evaluated: the others cannot exceed the threshold (every input
 // of their window is <= ith) and their windows may reach inputs that were not refreshed.
+// u_row0: image row held by the first row of s.U (frame_mask_kernel keeps one band of rows; 0 everywhere else); or_bits:
+// the byte is OR-ed into the mask (bands overlap) instead of stored.
 template <class SM>
-__device__ __forceinline__ void blur_group(SM &s, const Geometry &g, int grp, uint32_t q2, int buf, int ith) {
+__device__ __forceinline__ void blur_group(SM &s, const Geometry &g, int grp, uint32_t q2, int buf, int ith, int u_row0 = 0,
+                                           bool or_bits = false) {
     const int W = g.W, H = g.H;
     uint8_t *M8 = reinterpret_cast<uint8_t *>(s.M[buf]);
     const uint32_t T = (ith >= 0 && ith < 255) ? (uint32_t)(((ith + 1) << 8) - 128) : 0u;
@@ -451,7 +454,7 @@ __device__ __forceinline__ void blur_group(SM &s, const Geometry &g, int grp, ui
             int yy = y + r - 2;
             yy = (yy < 0) ? -yy : yy;              // H >= 4: one reflection is enough
             yy = (yy >= H) ? 2 * H - 2 - yy : yy;
-            const uint8_t *row = s.U + yy * W + x0;
+            const uint8_t *row = s.U + (yy - u_row0) * W + x0;
             uint2 m = *reinterpret_cast<const uint2 *>(row);
             uint32_t lw = left_edge ? 0u : *reinterpret_cast<const uint32_t *>(row - 4);
             uint32_t rw = right_edge ? 0u : *reinterpret_cast<const uint32_t *>(row + 8);
@@ -475,7 +478,8 @@ __device__ __forceinline__ void blur_group(SM &s, const Geometry &g, int grp, ui
         }
         bits &= ((q2 & 1u) ? 0x0fu : 0u) | ((q2 & 2u) ? 0xf0u : 0u);
     }
-    M8[y * g.row_words * 4 + gx] = (uint8_t)bits;
+    if (or_bits) M8[y * g.row_words * 4 + gx] |= (uint8_t)bits;
+    else M8[y * g.row_words * 4 + gx] = (uint8_t)bits;
 }
 
 // K2 for one group of 8 pixels: U = uint8(255 * (G - min) / (max - min)), G = max(F - avg_change, 0) with F the
@@ -483,7 +487,7 @@ __device__ __forceinline__ void blur_group(SM &s, const Geometry &g, int grp, ui
 // (imageprocessing.py:151-169: multiply, then IEEE divide, truncate).
 template <class SM>
 __device__ __forceinline__ void normalise_values(SM &s, const float4 f0, const float4 f1, int grp, int ac, int gmn, int gmx,
-                                                 uint32_t nmagic, int nshift, uint8_t *u_global = nullptr) {
+                                                 uint32_t nmagic, int nshift, uint8_t *u_global = nullptr, int u_off = 0) {
     const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
     const bool degenerate = (gmx == gmn);
     const float range_f = (float)gmx - (float)gmn;
@@ -504,15 +508,15 @@ __device__ __forceinline__ void normalise_values(SM &s, const float4 f0, const f
     w.x = u[0] | (u[1] << 8) | (u[2] << 16) | (u[3] << 24);
     w.y = u[4] | (u[5] << 8) | (u[6] << 16) | (u[7] << 24);
     if (u_global) *reinterpret_cast<uint2 *>(u_global + grp * 8) = w;
-    else *reinterpret_cast<uint2 *>(s.U + grp * 8) = w;
+    else *reinterpret_cast<uint2 *>(s.U + (grp * 8 - u_off)) = w;
 }
 
 template <class SM>
 __device__ __forceinline__ void normalise_group(SM &s, const float *F, int grp, int ac, int gmn, int gmx,
-                                                uint32_t nmagic, int nshift, uint8_t *u_global = nullptr) {
+                                                uint32_t nmagic, int nshift, uint8_t *u_global = nullptr, int u_off = 0) {
     // written by the sweep warps of this CTA a moment ago: plain (coherent) loads, an L2 hit
     const float4 f0 = *reinterpret_cast<const float4 *>(F + grp * 8), f1 = *reinterpret_cast<const float4 *>(F + grp * 8 + 4);
-    normalise_values(s, f0, f1, grp, ac, gmn, gmx, nmagic, nshift, u_global);
+    normalise_values(s, f0, f1, grp, ac, gmn, gmx, nmagic, nshift, u_global, u_off);
 }
 
 // split path: the scalar warp signals "message f of this clip consumed, byte threshold published" on the shared-memory
@@ -1551,42 +1555,41 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
     }
 }
 
-// One image row of quad bytes (strip_sweep_kernel) against its strip's byte threshold: bit q = quad q may hold a pixel
-// that reaches the threshold.
-__device__ __forceinline__ unsigned long long quad_row_bits(const Geometry &g, const int8_t *qb, const int16_t *theta,
-                                                            uint32_t hot_strips, int y) {
-    const int sidx = ((y + 1) * g.n_strips - 1) / g.H;  // strip s holds rows [s * H / n, (s + 1) * H / n)
-    if (!((hot_strips >> sidx) & 1u)) return 0ull;
-    const int th = theta[sidx];
-    const int8_t *row = qb + y * g.qpr;
+// One row of quad bytes (strip_sweep_kernel) against its strip's byte threshold, any row length: bit q = quad q may hold a
+// pixel that reaches the threshold.
+__device__ __forceinline__ unsigned long long quad_row_bits_bytes(const Geometry &g, const int8_t *row, int th) {
     unsigned long long bits = 0;
-    if ((g.qpr & 3) == 0) {
-        const uint32_t t4 = (uint32_t)(th + 128) * 0x01010101u;
-        for (int w = 0; w < (g.qpr >> 2); ++w) {
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(row) + w);
-            const uint32_t ge = __vcmpgeu4(v ^ 0x80808080u, t4) & 0x01010101u;           // byte i -> bit 8 i
-            bits |= (unsigned long long)((ge * 0x10204080u) >> 28) << (4 * w);           // -> bits 0..3
-        }
-    } else {
-        for (int q = 0; q < g.qpr; ++q) bits |= (unsigned long long)((int)row[q] >= th ? 1u : 0u) << q;
-    }
+    for (int q = 0; q < g.qpr; ++q) bits |= (unsigned long long)((int)row[q] >= th ? 1u : 0u) << q;
     return bits;
 }
 
-// Split path, second launch: one CTA per frame.  Hot-quad words -> per-row marks -> work lists -> normalise (K2) ->
-// blur + threshold (K4) -> the frame's mask as bit rows in global memory.  Frames are independent here, so the latency
-// of these short dependent phases is hidden by the other frames resident on the SM (8 CTAs).
-__global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelArgs a, long long total_frames) {
+// i / d for small i (i * d < 2^32) with magic = 0xffffffff / d + 1 (which wraps to 0 for d == 1)
+__device__ __forceinline__ int div_magic(int i, int d, uint32_t magic) { return d == 1 ? i : (int)__umulhi((uint32_t)i, magic); }
+
+// Split path, second launch: one CTA of four warps per frame, the frame's mask as bit rows in global memory.
+// A pixel can only reach the threshold near a hot quad (blur weights sum to 256: an output fires only within rows +-2 /
+// one quad of a hot quad and reads normalised values within rows +-4 / two quads), and hot quads are rare:
+//   quad bytes of the strips that may hold hot quads (FrameHdr::hot_strips) against their byte thresholds -> hot quads;
+//   then one BAND of up to 32 hot rows at a time (nearly always the only one): the extent of its hot quads (rows, quad
+//   columns) -> normalise (K2, exact integer form of the reference's fp32 multiply-then-divide) the extent grown by
+//   4 rows / 2 quads -> blur + threshold (K4: 5x5 binomial in packed 16-bit lanes) the quads within 2 rows / 1 quad of a
+//   hot quad of the band,
+// with the band's normalised bytes in a 6.4 kB window of shared memory (no full-frame image, no work lists): small CTAs
+// with little shared memory, so that many frames are resident per SM and hide each other's dependent loads.  Bands
+// overlap by their halos; both compute the same bits there and OR them into the mask.
+__global__ void __launch_bounds__(kFThreads, 16) frame_mask_kernel(const KernelArgs a, long long total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MaskSmem &s = *reinterpret_cast<MaskSmem *>(smem_raw);
     const Geometry &g = a.g;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const long long o = blockIdx.x;
     if (o >= total_frames) return;
     const FrameHdr *fh = a.fhdr + o;
     const cpt_frame_info *fi = a.info + o;
+    CPT_TICK_START2(tid == 0);
     // (independent loads first: the header and the info record are in flight together)
     const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(fh));  // nmagic, nshift, flags, hot_strips
+    const uint4 th_lo = __ldg(reinterpret_cast<const uint4 *>(fh->theta)), th_hi = __ldg(reinterpret_cast<const uint4 *>(fh->theta) + 1);
     const float thr = fi->threshold;
     const int ac = fi->avg_change, gmn = fi->norm_min, gmx = fi->norm_max;
     const int dn_marker = fi->reserved[1];
@@ -1603,103 +1606,176 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
     }
     const int ith = (int)floorf(thr);
     const bool no_fg = ith >= 255;  // nothing can exceed the threshold: the mask stays empty
-    bool dense = (hdr.z & kHdrDense) != 0;  // no usable bound: every group is normalised and blurred
+    const bool dense = (hdr.z & kHdrDense) != 0;  // no usable bound for the quad bytes: every quad counts as hot
+    CPT_TICK2(tid == 0, 7);  // header + info
     if (no_fg || (!dense && hdr.w == 0u)) {
         // nothing can reach the threshold (no strip holds a hot quad): the mask is empty, frame_components_kernel leaves at once
         if (tid == 0) a.fhdr[o].flags = hdr.z | kHdrEmpty;
         return;
     }
-    const int owned = g.H - 2 * g.edge;
-    if ((g.words & 3) == 0) {
+    const int8_t *qb = a.qbytes + (size_t)o * (g.H * g.qpr);
+    const int NS = g.n_strips, wpr = g.qpr >> 2;  // words of quad bytes per row (rows of whole words: qpr % 4 == 0)
+    const bool wordq = (g.qpr & 3) == 0;
+    const unsigned long long rowmask = g.qpr >= 64 ? ~0ull : (1ull << g.qpr) - 1ull;
+    const uint32_t wmagic = g.qw_magic;
+    // ---- hot quads of the whole frame: the quad bytes of the hot strips, a word of four per thread and strip (a strip has
+    // at most kStripPxMax / 16 = 120 words), requested before anything waits
+    constexpr int kPre = 4;
+    static_assert(kStripPxMax / 16 <= kFThreads, "one word of a strip's quad bytes per thread");
+    uint32_t pre[kPre];
+    {
+        uint32_t hs = (dense || !wordq) ? 0u : hdr.w;
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            pre[k] = 0x80808080u;  // (-128: never hot)
+            if (hs) {
+                const int sidx = __ffs(hs) - 1;
+                hs &= hs - 1;
+                const int y0 = g.strip_y0[sidx], nw = ((int)g.strip_y0[sidx + 1] - y0) * wpr;
+                if (tid < nw) pre[k] = __ldg(reinterpret_cast<const uint32_t *>(qb + y0 * g.qpr) + tid);
+            }
+        }
+    }
+    const bool vec = (g.words & 3) == 0;
+    if (vec) {
         for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(s.M[0])[i] = make_uint4(0, 0, 0, 0);
     } else {
         for (int i = tid; i < g.words; i += kFThreads) s.M[0][i] = 0;
     }
-    int n_u = 0, n_b = 0;
-    if (!no_fg && !dense) {
-        if (tid < kMaxStrips) s.theta[tid] = fh->theta[tid];
-        if (tid == 0) { s.bcast_i[11] = 0; s.bcast_i[12] = 0; }
-        __syncthreads();
-        // one thread per owned row: its quads' bytes against the strip's byte threshold -> one bit per quad (a border
-        // row's quads count for the owned row next to it, which only widens the marks)
-        const int8_t *qb = a.qbytes + (size_t)o * (g.H * g.qpr);
-        for (int oy = tid; oy < owned; oy += kFThreads) {
-            unsigned long long bits = quad_row_bits(g, qb, s.theta, hdr.w, oy + g.edge);
-            if (g.edge && oy == 0) bits |= quad_row_bits(g, qb, s.theta, hdr.w, 0);
-            if (g.edge && oy == owned - 1) bits |= quad_row_bits(g, qb, s.theta, hdr.w, g.H - 1);
-            s.hot64[oy] = bits;
-        }
-        __syncthreads();
-        // one thread per frame row: OR the hot rows around the row, widen by the neighbouring quads, and turn the marks
-        // into list entries (groups of 8 pixels; a blur entry carries its two quad marks).  Blur weights sum to 256, so
-        // an output can fire only within rows +-2 / neighbouring quads of a hot quad, and reads U within rows +-4 / quads +-2.
-        const unsigned long long rowmask = (1ull << g.qpr) - 1ull;
-        for (int rrow = tid; rrow < g.H; rrow += kFThreads) {
-            unsigned long long near_b = 0, near_u = 0;
-#pragma unroll
-            for (int dy = -4; dy <= 4; ++dy) {
-                const int yy = rrow - g.edge + dy;  // owned-row index
-                if (yy < 0 || yy >= owned) continue;
-                const unsigned long long h = s.hot64[yy];
-                near_u |= h;
-                if (dy >= -2 && dy <= 2) near_b |= h;
-            }
-            const int row_grp = rrow * g.gpr;
-            if (near_u) {
-                const unsigned long long mk = (near_u | (near_u << 1) | (near_u >> 1) | (near_u << 2) | (near_u >> 2)) & rowmask;
-                unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
-                int base = atomicAdd(&s.bcast_i[11], __popcll(grp_bits));
-                while (grp_bits) {
-                    const int bit = __ffsll((long long)grp_bits) - 1;
-                    grp_bits &= grp_bits - 1;
-                    if (base < kListCap) s.list_u[base] = (uint16_t)(row_grp + (bit >> 1));
-                    ++base;
-                }
-            }
-            if (near_b) {
-                const unsigned long long mk = (near_b | (near_b << 1) | (near_b >> 1)) & rowmask;
-                unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
-                int base = atomicAdd(&s.bcast_i[12], __popcll(grp_bits));
-                while (grp_bits) {
-                    const int bit = __ffsll((long long)grp_bits) - 1;
-                    grp_bits &= grp_bits - 1;
-                    const uint32_t quads = (uint32_t)((mk >> bit) & 3ull);
-                    if (base < kListCap) s.list_b[base] = (uint16_t)((row_grp + (bit >> 1)) | (quads << 14));
-                    ++base;
-                }
-            }
-        }
-        __syncthreads();
-        n_u = s.bcast_i[11];
-        n_b = s.bcast_i[12];
-        // lists overflowed: dense work (every quad evaluated; a superset of the marks, so still exact)
-        if (n_u > kListCap || n_b > kListCap) dense = true;
+    if (tid == 0) {
+        reinterpret_cast<uint4 *>(s.theta)[0] = th_lo;
+        reinterpret_cast<uint4 *>(s.theta)[1] = th_hi;
     }
-    if (!no_fg) {
-        if (dense) {
-            for (int grp = tid; grp < g.groups; grp += kFThreads) normalise_group(s, fcur, grp, ac, gmn, gmx, nmagic, nshift);
-        } else {
-            for (int i = tid; i < n_u; i += kFThreads) normalise_group(s, fcur, (int)s.list_u[i], ac, gmn, gmx, nmagic, nshift);
-        }
-        __syncthreads();
-        if (dense) {
-            for (int grp = tid; grp < g.groups; grp += kFThreads) blur_group(s, g, grp, 3u, 0, ith);
-        } else {
-            for (int i = tid; i < n_b; i += kFThreads) {
-                const uint32_t e = s.list_b[i];
-                blur_group(s, g, (int)(e & 0x3fffu), e >> 14, 0, ith);
-            }
-        }
-    }
+    for (int r = tid; r < g.H; r += kFThreads) s.hot64[r] = dense ? rowmask : 0ull;
     __syncthreads();
+    if (!dense) {
+        uint32_t hs = hdr.w;
+        uint32_t *hot32 = reinterpret_cast<uint32_t *>(s.hot64);
+        for (int k = 0; hs; ++k) {  // (uniform over the CTA)
+            const int sidx = __ffs(hs) - 1;
+            hs &= hs - 1;
+            const int y0 = g.strip_y0[sidx], nrows = (int)g.strip_y0[sidx + 1] - y0;
+            const int th = s.theta[sidx];
+            if (!wordq) {
+                for (int r = tid; r < nrows; r += kFThreads) s.hot64[y0 + r] = quad_row_bits_bytes(g, qb + (y0 + r) * g.qpr, th);
+                continue;
+            }
+            uint32_t v = 0x80808080u;
+            if (k < kPre) {
+#pragma unroll
+                for (int j = 0; j < kPre; ++j) v = (j == k) ? pre[j] : v;
+            } else if (tid < nrows * wpr) {
+                v = __ldg(reinterpret_cast<const uint32_t *>(qb + y0 * g.qpr) + tid);
+            }
+            const uint32_t t4 = (uint32_t)(th + 128) * 0x01010101u;
+            const uint32_t ge = __vcmpgeu4(v ^ 0x80808080u, t4) & 0x01010101u;  // byte i -> bit 8 i
+            const uint32_t nib = (ge * 0x10204080u) >> 28;                      // -> bits 0..3
+            if (nib) {
+                const int r = div_magic(tid, wpr, wmagic), c = tid - r * wpr;
+                atomicOr(hot32 + 2 * (y0 + r) + (c >> 3), nib << ((4 * c) & 31));
+            }
+        }
+        __syncthreads();
+    }
+    CPT_TICK2(tid == 0, 15);  // quad bytes -> hot rows
+    // ---- the set of hot rows (every warp for itself: bit r & 31 of rb[r >> 5])
+    uint32_t rb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = 32 * j + lane;
+        rb[j] = __ballot_sync(0xffffffffu, r < g.H && s.hot64[r] != 0ull);
+    }
+    while (rb[0] | rb[1] | rb[2] | rb[3]) {  // (uniform over the CTA)
+        // the band: kBandRows rows from the first hot row on, [lo, hi] = its first and last hot row
+        int w = 0;
+        uint32_t cur = rb[0], nxt = rb[1];
+        if (!cur) { w = 1; cur = rb[1]; nxt = rb[2]; }
+        if (!cur) { w = 2; cur = rb[2]; nxt = rb[3]; }
+        if (!cur) { w = 3; cur = rb[3]; nxt = 0u; }
+        const int b = __ffs(cur) - 1, lo = 32 * w + b;
+        constexpr uint32_t kWin = kBandRows >= 32 ? 0xffffffffu : (1u << kBandRows) - 1u;
+        const uint32_t win = ((cur >> b) | (b ? (nxt << (32 - b)) : 0u)) & kWin;  // bit i: row lo + i is hot
+        const int hi = lo + 31 - __clz(win);
+        const uint32_t m_cur = kWin << b, m_nxt = (b + kBandRows > 32) ? (1u << (b + kBandRows - 32)) - 1u : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j == w) rb[j] &= ~m_cur;
+            if (j == w + 1) rb[j] &= ~m_nxt;
+        }
+        // work lists, one thread per row: warps 0-1 the groups to normalise (rows +-4, quads +-2 around the band's hot
+        // quads), warps 2-3 the groups to blur (rows +-2, one quad; an entry carries its two quad marks)
+        const int ur0 = max(lo - kBandHalo, 0), ur1 = min(hi + kBandHalo, g.H - 1);
+        const int br0 = max(lo - 2, 0), br1 = min(hi + 2, g.H - 1);
+        if (tid == 0) { s.count[0] = 0; s.count[1] = 0; }
+        __syncthreads();  // (also: the previous band is done with U and the lists)
+        if (tid < kFThreads / 2) {
+            const int y = ur0 + tid;
+            if (y <= ur1) {
+                unsigned long long nearq = 0;
+#pragma unroll
+                for (int dy = -kBandHalo; dy <= kBandHalo; ++dy) {
+                    const int rr = y + dy;
+                    if (rr >= lo && rr <= hi) nearq |= s.hot64[rr];
+                }
+                if (nearq) {
+                    const unsigned long long mk = (nearq | (nearq << 1) | (nearq >> 1) | (nearq << 2) | (nearq >> 2)) & rowmask;
+                    unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
+                    int base = atomicAdd(&s.count[0], __popcll(grp_bits));
+                    const int row_grp = tid * g.gpr;  // (band row)
+                    while (grp_bits) {
+                        const int bit = __ffsll((long long)grp_bits) - 1;
+                        grp_bits &= grp_bits - 1;
+                        s.list_u[base++] = (uint16_t)(row_grp + (bit >> 1));
+                    }
+                }
+            }
+        } else {
+            const int y = br0 + tid - kFThreads / 2;
+            if (y <= br1) {
+                unsigned long long nearq = 0;
+#pragma unroll
+                for (int dy = -2; dy <= 2; ++dy) {
+                    const int rr = y + dy;
+                    if (rr >= lo && rr <= hi) nearq |= s.hot64[rr];
+                }
+                if (nearq) {
+                    const unsigned long long mk = (nearq | (nearq << 1) | (nearq >> 1)) & rowmask;
+                    unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
+                    int base = atomicAdd(&s.count[1], __popcll(grp_bits));
+                    const int row_grp = y * g.gpr;  // (frame row)
+                    while (grp_bits) {
+                        const int bit = __ffsll((long long)grp_bits) - 1;
+                        grp_bits &= grp_bits - 1;
+                        s.list_b[base++] = (uint16_t)((row_grp + (bit >> 1)) | ((uint32_t)((mk >> bit) & 3ull) << 14));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        CPT_TICK2(tid == 0, 4);  // marks + lists
+        const int n_u = s.count[0], n_b = s.count[1];
+        CPT_COUNT(tid == 0, 28, n_u);
+        CPT_COUNT(tid == 0, 29, n_b);
+        {
+            const int grp0 = ur0 * g.gpr;
+            for (int i = tid; i < n_u; i += kFThreads)
+                normalise_group(s, fcur, grp0 + (int)s.list_u[i], ac, gmn, gmx, nmagic, nshift, nullptr, ur0 * g.W);
+        }
+        __syncthreads();
+        CPT_TICK2(tid == 0, 5);  // normalise
+        for (int i = tid; i < n_b; i += kFThreads) {
+            const uint32_t e = s.list_b[i];
+            blur_group(s, g, (int)(e & 0x3fffu), e >> 14, 0, ith, ur0, true);
+        }
+        CPT_TICK2(tid == 0, 8);  // blur + threshold
+    }
+    __syncthreads();  // the mask is complete
+    CPT_COUNT(tid == 0, 30, 1);  // frames that reach the mask store
     // an empty mask (frames without an animal) is only flagged: frame_components_kernel leaves at once
     uint32_t *mout = a.maskbits + (size_t)o * kMaxWords;
-    const bool vec = (g.words & 3) == 0;
-    uint4 mine = make_uint4(0, 0, 0, 0);
-    if (vec && tid < g.words / 4) mine = reinterpret_cast<const uint4 *>(s.M[0])[tid];
-    bool any = (mine.x | mine.y | mine.z | mine.w) != 0;
+    bool any = false;
     if (vec) {
-        for (int i = tid + kFThreads; i < g.words / 4; i += kFThreads) {
+        for (int i = tid; i < g.words / 4; i += kFThreads) {
             const uint4 w = reinterpret_cast<const uint4 *>(s.M[0])[i];
             any |= (w.x | w.y | w.z | w.w) != 0;
         }
@@ -1711,11 +1787,11 @@ __global__ void __launch_bounds__(kFThreads, 8) frame_mask_kernel(const KernelAr
         return;
     }
     if (vec) {
-        if (tid < g.words / 4) reinterpret_cast<uint4 *>(mout)[tid] = mine;
-        for (int i = tid + kFThreads; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
+        for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
     } else {
         for (int i = tid; i < g.words; i += kFThreads) mout[i] = s.M[0][i];
     }
+    CPT_TICK2(tid == 0, 9);  // mask store
 }
 
 // K6 for one region record: variance of |norm255(F_t) - norm255(F_t-1)| over the component's bounding box; one warp.
@@ -1754,15 +1830,21 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
     if (o >= total_frames) return;
     const cpt_frame_info *fi = a.info + o;
     const uint32_t *min_ = a.maskbits + (size_t)o * kMaxWords;
+    CPT_TICK_START(tid == 0);
     const uint32_t hflags = a.fhdr[o].flags;  // (plain load: frame_mask_kernel may have set the empty-mask flag)
     const int dn_marker = fi->reserved[1];
+    // (requested together with the header: the words of a frame that turns out empty or invalid are ignored -- the buffer is
+    // allocated for every frame, only its contents are stale then)
+    const bool vec = (g.words & 3) == 0;
+    uint4 w0 = make_uint4(0, 0, 0, 0);
+    if (vec && tid < g.words / 4) w0 = __ldg(reinterpret_cast<const uint4 *>(min_) + tid);
     if (!(hflags & kHdrValid)) return;  // no clip produced this output frame (its mask words were never written)
     if (hflags & kHdrEmpty) return;     // empty mask (flagged by frame_mask_kernel): info.n_components stays 0
     if (dn_marker) return;      // denoise clips: mask_components_kernel
     bool any = false;
-    if ((g.words & 3) == 0) {
+    if (vec) {
         for (int i = tid; i < g.words / 4; i += kGThreads) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(min_) + i);
+            const uint4 w = i == tid ? w0 : __ldg(reinterpret_cast<const uint4 *>(min_) + i);
             reinterpret_cast<uint4 *>(s.M[0])[i] = w;
             any |= ((w.x | w.y | w.z | w.w) != 0);
         }
@@ -1774,6 +1856,8 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
         }
     }
     if (!__syncthreads_or(any)) return;  // empty mask: info.n_components stays 0
+    CPT_TICK(tid == 0, 11);  // header + mask words
+    CPT_COUNT(tid == 0, 31, 1);  // frames with foreground
     const float *fcur = a.filtered + (size_t)o * g.npx;
     const bool have_prev = !(hflags & kHdrFirst);  // not the first frame of its clip
     // (variances in this kernel were measured slower than the separate wide pass, whose warps hide the cold reads of
@@ -1781,6 +1865,7 @@ __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const Ke
     // against the 2.4 ms of region_variance_kernel)
     components_of_frame<CompSmem, kGThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, fi->filtered_min, fi->filtered_max, 0, 0,
                                                  have_prev, true);
+    CPT_TICK(tid == 0, 12);  // components of the frame
 }
 
 // Second half of the frame pipeline for denoise clips (info.reserved[1] != 0): the denoised normalised image of every

@@ -5,16 +5,18 @@
 // per-frame scalars (mean of the frame, extrema of filtered, mean of the background) couple the pixels of a frame, and
 // those are only needed by the later per-frame stages.  So a clip is cut into n_strips bands of whole rows and every
 // (clip, strip) pair is an independent work unit of strip_sweep_kernel:
-//   * one CTA per unit, 15 consumer warps + 1 producer warp; a consumer thread owns ONE quad (4 pixels) for the whole
+//   * one CTA per unit, 15 consumer warps + a copy warp + a fold warp; a consumer thread owns ONE quad (4 pixels) for the whole
 //     clip: background B, weight counter k and sliding sum S of its pixels live in registers from the first frame to the
 //     last -- no per-frame state traffic at all;
 //   * the strip's rows of the last 45 frames (the window of the sliding mean) plus kLead frames of read-ahead sit in a
-//     shared-memory ring filled by the producer warp with one 1-D TMA bulk copy per frame (full mbarriers); the frame
+//     shared-memory ring filled by the copy warp with one 1-D TMA bulk copy per frame (full mbarriers); the frame
 //     leaving the window is read from that ring, so every frame is read from HBM exactly once and never again;
 //   * per frame a consumer writes its filtered quad (fp32), the zeroed label bytes and one byte per quad (max filtered
 //     relative to a strip reference, for the hot-quad test of the per-frame kernels); the warps' partial sums go through
-//     a small shared-memory table to the producer warp, which folds them into the strip's pass record in global memory
-//     before it issues the next bulk copy (done mbarriers).
+//     a small shared-memory table to the fold warp, which folds them into the strip's pass record in global memory
+//     (done mbarriers release the ring slot to the copy warp and the rows to the fold warp; folded mbarriers hand the
+//     table rows and the byte reference back).  Copying and folding were one warp's loop at first: its length, not the
+//     read-ahead, bounded the pipeline (26.7 ms without the fold against 29.6 ms with it).
 // frame_scalars_kernel (one warp per clip) then folds the strips' records into the per-frame scalars of
 // ClipTracker._get_filtered_frame (track/cliptracker.py:93-122): WeightedBackground.average (a running value: scanned over
 // the frames with warp ballots), avg_change, the normalisation range, the mapped threshold, the integer normalise
@@ -33,14 +35,14 @@ using namespace prim;
 #ifndef CPT_LEAD
 #define CPT_LEAD 7
 #endif
-constexpr int kLead = CPT_LEAD;                      // frames the producer runs ahead of the slowest consumer warp
+constexpr int kLead = CPT_LEAD;                      // frames the copy warp runs ahead of the slowest consumer warp
 constexpr int kRingSlots = kMeanFrames + kLead;      // 52 frames of the strip's rows
 constexpr int kSlotBytes = kStripPxMax * 2;          // 3840
 constexpr int kConsWarps = kStripPxMax / 4 / 32;     // 15
 constexpr int kConsThreads = kConsWarps * 32;        // 480
 constexpr int kBarRing = kLead < 8 ? 8 : 16;          // full / done barriers and stat rows are reused every kBarRing passes
 static_assert(kBarRing > kLead, "a barrier is reused only after every warp has passed its previous use");
-static_assert(kStripThreads == kConsThreads + 32, "consumer warps + the producer warp");
+static_assert(kStripThreads == kConsThreads + 64, "consumer warps + the copy warp + the fold warp");
 #ifndef CPT_STRIP_TABLE
 #define CPT_STRIP_TABLE 4096
 #endif
@@ -54,7 +56,7 @@ struct __align__(128) StripSmem {
     uint16_t wbnd[kStripTable];              // ... and their bounds (cptrack_kernels.cuh, WeightTable)
     uint32_t stat[kBarRing][kConsWarps][8];  // per pass and warp: psum, fmin, fmax, nbsum, pmin, pmax, fabs, changed
     int32_t ref_ring[16];                    // byte reference published with pass t, used by pass t + kRefLag
-    unsigned long long full[kBarRing], done[kBarRing];
+    unsigned long long full[kBarRing], done[kBarRing], folded[kBarRing];
     int32_t unit;
 };
 static_assert(sizeof(StripSmem) <= 232448, "shared memory budget (227 KB per CTA on sm_100)");
@@ -224,7 +226,7 @@ __device__ __forceinline__ void pass_advance(PassPos &p) {
     if (p.old_off == (uint32_t)kRingSlots * kSlotBytes) p.old_off = 0;
 }
 
-// the warp's partial results -> its row of the pass table (the producer warp folds the rows), then the warp's arrival
+// the warp's partial results -> its row of the pass table (the fold warp folds the rows), then the warp's arrival
 template <bool kStats>
 __device__ __forceinline__ void pass_report(StripSmem &s, const PassOut &po, int bi, int warp, int lane) {
     const uint32_t psum = __reduce_add_sync(0xffffffffu, po.psum);
@@ -299,8 +301,8 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         return k < kStripTable ? (int)s.wbnd[k] : (int)(__ldg(wt.thr + k) >> 16);
     };
     auto frame_sync = [&](int t, int &refb) {
-        // the frame's rows are in the ring; the reference its quad bytes are stored against was published by the producer
-        // before it issued the copy (read after the acquire)
+        // the frame's rows are in the ring; the reference its quad bytes are stored against was published by the fold warp
+        // before the copy warp issued this frame (read after the acquire)
         mbar_wait(&s.full[t & (kBarRing - 1)], (uint32_t)(t / kBarRing) & 1u);
         refb = (t >= kRefLag ? *(volatile const int32_t *)&s.ref_ring[(t - kRefLag) & 15] : kRefDefault) + kBias;
     };
@@ -325,6 +327,8 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         pc.window_full = t >= kMeanFrames;
         int refb = kRefDefault + kBias;
         if (pc.is_frame) frame_sync(t, refb);
+        // (the tail pass enters no frame: its table rows are free once the fold warp has read those of pass t - kBarRing)
+        else if (t >= kBarRing) mbar_wait(&s.folded[(t - kBarRing) & (kBarRing - 1)], (uint32_t)((t - kBarRing) / kBarRing) & 1u);
         const bool lin = pp.frames_seen < wt.linear_upto;
         quad_state_form(q, th, lin);
         PassOut po;
@@ -398,27 +402,42 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
     }
 }
 
-__device__ void strip_producer(const KernelArgs &a, StripSmem &s, const cpt_clip &clip, int ci, int strip, int y0, int rows,
-                               int lane) {
+// The copy warp: frame t + kLead goes into the ring slot pass t has just released.  Its loop is the critical path of the
+// pipeline (one iteration per pass), so it does nothing else; the records are the fold warp's.
+__device__ void strip_copier(const KernelArgs &a, StripSmem &s, const cpt_clip &clip, int y0, int rows, int lane) {
+    const Geometry &g = a.g;
+    const int n = clip.n_frames;
+    const uint32_t bytes = (uint32_t)(rows * g.W) * 2u;
+    const unsigned long long policy = l2_policy_evict_first();  // every frame is read exactly once
+    const bool linear = clip.ring_frames == 0;
+    const uint16_t *lin_src = a.frames + (size_t)clip.frame_offset * g.npx + (size_t)y0 * g.W;  // frame 0 of a linear clip
+    if (lane != 0) return;
+    auto issue = [&](int fidx) {
+        const uint16_t *src = linear ? lin_src + (size_t)fidx * g.npx
+                                     : a.frames + (size_t)(clip.frame_offset + (clip.first_frame + fidx) % clip.ring_frames) * g.npx + (size_t)y0 * g.W;
+        unsigned long long *bar = &s.full[fidx & (kBarRing - 1)];
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s_hint(s.ring[fidx % kRingSlots], src, bytes, bar, policy);
+    };
+    for (int fidx = 0; fidx < min(kLead, n); ++fidx) issue(fidx);
+    for (int t = 0; t + kLead < n; ++t) {
+        mbar_wait(&s.done[t & (kBarRing - 1)], (uint32_t)(t / kBarRing) & 1u);  // every consumer warp has finished pass t
+        // frame t + kLead lets the consumers into pass t + kLead, whose table rows are those of pass t + kLead - kBarRing and
+        // whose byte reference is that of pass t + kLead - kRefLag = t - 1: the fold warp must be done with both
+        // (the arrive.expect_tx below releases what it published)
+        if (t >= 1) mbar_wait(&s.folded[(t - 1) & (kBarRing - 1)], (uint32_t)((t - 1) / kBarRing) & 1u);
+        issue(t + kLead);
+    }
+}
+
+// The fold warp: the consumer warps' rows of pass t -> the strip's record of pass t in global memory, and the byte
+// reference of pass t + kRefLag.
+__device__ void strip_folder(const KernelArgs &a, StripSmem &s, const cpt_clip &clip, int ci, int strip, int lane) {
     const Geometry &g = a.g;
     const int n = clip.n_frames, NS = g.n_strips;
     const bool update_bg = clip.flags & CPT_CLIP_UPDATE_BACKGROUND;
     const bool skip_first = clip.flags & CPT_CLIP_SKIP_FIRST_UPDATE;
     const bool want_stats = clip.flags & CPT_CLIP_FRAME_STATS;
-    const uint32_t bytes = (uint32_t)(rows * g.W) * 2u;
-    const unsigned long long policy = l2_policy_evict_first();  // every frame is read exactly once
-    const bool linear = clip.ring_frames == 0;
-    const uint16_t *lin_src = a.frames + (size_t)clip.frame_offset * g.npx + (size_t)y0 * g.W;  // frame 0 of a linear clip
-    auto issue = [&](int fidx) {
-        if (lane == 0) {
-            const uint16_t *src = linear ? lin_src + (size_t)fidx * g.npx
-                                         : a.frames + (size_t)(clip.frame_offset + (clip.first_frame + fidx) % clip.ring_frames) * g.npx + (size_t)y0 * g.W;
-            unsigned long long *bar = &s.full[fidx & (kBarRing - 1)];
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s_hint(s.ring[fidx % kRingSlots], src, bytes, bar, policy);
-        }
-    };
-    for (int fidx = 0; fidx < min(kLead, n); ++fidx) issue(fidx);
     uint4 *rec_frame = reinterpret_cast<uint4 *>(a.prec + (size_t)clip.out_offset * NS + strip);  // pass t: + t * NS records
     uint4 *rec_tail = reinterpret_cast<uint4 *>(a.prec + (size_t)(a.total_frames + ci) * NS + strip);
     const bool in = lane < kConsWarps;
@@ -427,9 +446,6 @@ __device__ void strip_producer(const KernelArgs &a, StripSmem &s, const cpt_clip
         const bool update = update_bg && t > 0 && !(skip_first && clip.first_frame + t == 1);
         if (!update && !is_frame) break;
         mbar_wait(&s.done[t & (kBarRing - 1)], (uint32_t)(t / kBarRing) & 1u);  // every consumer warp has finished pass t
-        // first the copy of frame t + kLead into the slot pass t has just released (the critical path of the pipeline) ...
-        if (t + kLead < n) issue(t + kLead);  // (the arrive.expect_tx releases the references published so far)
-        // ... then the fold of the warps' rows into the strip's record of pass t
         const uint32_t *row = s.stat[t & (kBarRing - 1)][in ? lane : 0];
         const uint4 r0 = *reinterpret_cast<const uint4 *>(row);
         const uint32_t psum = __reduce_add_sync(0xffffffffu, in ? (r0.x & 0x7fffffffu) : 0u);
@@ -447,13 +463,14 @@ __device__ void strip_producer(const KernelArgs &a, StripSmem &s, const cpt_clip
             fabs_sum = __reduce_add_sync(0xffffffffu, in ? r1.z : 0u);
         }
         if (lane == 0) {
+            // the reference of pass t + kRefLag: this strip's filtered minimum now, plus the bias (clamped so that it
+            // survives the shift below); published first, the record is nobody's critical path
             const int ref = t >= kRefLag ? s.ref_ring[(t - kRefLag) & 15] : kRefDefault;  // what pass t's bytes were stored against
+            if (is_frame) s.ref_ring[t & 15] = max(min(fmin, 1 << 20), -(1 << 20)) + kQuadRefBias;
+            mbar_arrive(&s.folded[t & (kBarRing - 1)]);  // (release: the rows are read, the reference is written)
             uint4 *dst = is_frame ? rec_frame + (size_t)t * (2 * NS) : rec_tail;
             dst[0] = make_uint4(psum, (uint32_t)fmin, (uint32_t)fmax, (uint32_t)nbsum);
             dst[1] = make_uint4((uint32_t)pmin, (uint32_t)pmax, fabs_sum, ((uint32_t)ref << 1) | (changed & 1u));
-            // the reference of pass t + kRefLag: this strip's filtered minimum now, plus the bias (clamped so that it
-            // survives the shift above)
-            if (is_frame) s.ref_ring[t & 15] = max(min(fmin, 1 << 20), -(1 << 20)) + kQuadRefBias;
         }
         __syncwarp();
     }
@@ -481,10 +498,11 @@ __global__ void __launch_bounds__(kStripThreads, 1) strip_sweep_kernel(const Ker
         const int y0 = strip * g.H / NS, rows = (strip + 1) * g.H / NS - y0;
         if (tid == 0) {
             if (bars_live)
-                for (int i = 0; i < kBarRing; ++i) { mbar_inval(&s.full[i]); mbar_inval(&s.done[i]); }
+                for (int i = 0; i < kBarRing; ++i) { mbar_inval(&s.full[i]); mbar_inval(&s.done[i]); mbar_inval(&s.folded[i]); }
             for (int i = 0; i < kBarRing; ++i) {
-                mbar_init(&s.full[i], 1);           // the producer's arrive.expect_tx
+                mbar_init(&s.full[i], 1);           // the copy warp's arrive.expect_tx
                 mbar_init(&s.done[i], kConsWarps);  // one arrival per consumer warp
+                mbar_init(&s.folded[i], 1);         // the fold warp
             }
             mbar_fence_init();
             bars_live = true;
@@ -506,8 +524,10 @@ __global__ void __launch_bounds__(kStripThreads, 1) strip_sweep_kernel(const Ker
                 if (a.labels) strip_consumer<false, true>(a, s, clip, ci, y0, rows, tid);
                 else strip_consumer<false, false>(a, s, clip, ci, y0, rows, tid);
             }
+        } else if (tid < kConsThreads + 32) {
+            strip_copier(a, s, clip, y0, rows, tid - kConsThreads);
         } else {
-            strip_producer(a, s, clip, ci, strip, y0, rows, tid - kConsThreads);
+            strip_folder(a, s, clip, ci, strip, tid - kConsThreads - 32);
         }
     }
 }

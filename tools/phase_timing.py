@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 PKG = os.path.join(ROOT, "classifier-pipeline_b200")
 
 
-def main(clips=148, frames=300, exp=0):
+def main(clips=148, frames=300, exp=0, split=1):
     import torch
     from classifier_pipeline_b200 import native
 
@@ -28,6 +28,8 @@ def main(clips=148, frames=300, exp=0):
     d_frames, models = make_clips_torch(clips, frames, torch.device("cuda", 0))
     cl = linear_clips([frames] * clips, np.array([MODELS[m][2] for m in models]), np.array([slots[m] for m in models]))
     out = {}
+    if not split:
+        native.check(ex.ctx.lib.cpt_debug_force_single_kernel(ex.ctx._h, 1))
     ex.extract_device(d_frames, cl, out=out)
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 32)()
@@ -35,13 +37,23 @@ def main(clips=148, frames=300, exp=0):
     ex.extract_device(d_frames, cl, out=out)
     torch.cuda.synchronize()
     native.check(ex.ctx.lib.cpt_debug_phase_cycles(ex.ctx._h, buf, 0))
+    total = clips * frames
+    if split:
+        names = {7: "M header + info", 15: "M quad bytes -> hot rows", 4: "M marks + lists", 5: "M normalise", 8: "M blur + threshold",
+                 9: "M mask store", 11: "C header + mask words", 12: "C components",
+                 20: "C  close+reset+bar", 21: "C  run starts+bar", 22: "C  unions+bar", 23: "C  roots+bar", 24: "C  run stats+bar",
+                 25: "C  rank+bar", 26: "C  label writes", 27: "C  tail (records)"}
+        for i, n in names.items():
+            print("{:28s} {:9.0f} cycles/frame".format(n, buf[i] / total))
+        print("lists: normalise {:.1f} groups/frame, blur {:.1f}; frames reaching the mask store {:.4f}, frames with foreground {:.4f}".format(
+            buf[28] / total, buf[29] / total, buf[30] / total, buf[31] / total))
+        return
     names = {14: "S fused sweep", 5: "S  of which: waiting for staged rows", 6: "S wait scalars + ballots", 2: "S message",
              8: "producer: wait free stage", 9: "producer: issue copies",
              7: "M wait sweep", 16: "M scalars thread 0", 3: "M scalars bar", 15: "M quad maxima -> hot rows", 4: "M marks+lists",
              11: "C wait mask", 12: "C components",
              20: "C  close+reset+bar", 21: "C  run starts+bar", 22: "C  unions+bar", 23: "C  roots+bar", 24: "C  run stats+bar",
              25: "C  rank+bar", 26: "C  label writes", 27: "C  variance+bar"}
-    total = clips * frames
     for i, n in names.items():
         print("{:22s} {:9.0f} cycles/frame".format(n, buf[i] / total))
     print("lists: normalise {:.1f} groups/frame, blur {:.1f}; dense frames {:.4f}, no-foreground frames {:.4f}".format(
