@@ -171,6 +171,7 @@ void cpt_ctx_destroy(cpt_ctx *c) {
     cudaFree(c->prec);
     cudaFree(c->fhdr);
     cudaFree(c->maskbits);
+    cudaFree(c->fallback);
     for (int i = 0; i < 6; ++i)
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     cudaFree(c->work_counter);
@@ -447,14 +448,15 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         const size_t qb_frame = (size_t)c->g.H * c->g.qpr;
         if (c->split_frames < (size_t)total_frames || c->split_clips < (size_t)n_clips) {
             CUDA_TRY(cudaStreamSynchronize(stream));
-            cudaFree(c->qbytes); cudaFree(c->prec); cudaFree(c->fhdr); cudaFree(c->maskbits);
-            c->qbytes = nullptr; c->prec = nullptr; c->fhdr = nullptr; c->maskbits = nullptr;
+            cudaFree(c->qbytes); cudaFree(c->prec); cudaFree(c->fhdr); cudaFree(c->maskbits); cudaFree(c->fallback);
+            c->qbytes = nullptr; c->prec = nullptr; c->fhdr = nullptr; c->maskbits = nullptr; c->fallback = nullptr;
             c->split_frames = c->split_clips = 0;
             const size_t nf = std::max(c->split_frames, (size_t)total_frames), nc = std::max(c->split_clips, (size_t)n_clips);
             CUDA_TRY(cudaMalloc(&c->qbytes, nf * qb_frame));
             CUDA_TRY(cudaMalloc(&c->prec, (nf + nc) * c->g.n_strips * sizeof(cpt::StripRec)));
             CUDA_TRY(cudaMalloc(&c->fhdr, nf * sizeof(cpt::FrameHdr)));
             CUDA_TRY(cudaMalloc(&c->maskbits, nf * cpt::kMaxWords * sizeof(uint32_t)));
+            CUDA_TRY(cudaMalloc(&c->fallback, (nf + 1) * sizeof(int)));
             c->split_frames = nf;
             c->split_clips = nc;
         }
@@ -462,6 +464,8 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         a.prec = c->prec;
         a.fhdr = c->fhdr;
         a.maskbits = c->maskbits;
+        a.fallback = c->fallback;
+        CUDA_TRY(cudaMemsetAsync(c->fallback, 0, sizeof(int), stream));
         a.total_frames = total_frames;
         // the valid flag of every output frame starts cleared: frames no clip writes are skipped by the per-frame launches
         CUDA_TRY(cudaMemsetAsync(c->fhdr, 0, (size_t)total_frames * sizeof(cpt::FrameHdr), stream));
@@ -475,7 +479,7 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[2], stream));
         cpt::frame_mask_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::MaskSmem), stream>>>(a, total_frames);
         CUDA_TRY(cudaGetLastError());
-        cpt::frame_components_kernel<<<(unsigned)total_frames, cpt::kGThreads, sizeof(cpt::CompSmem), stream>>>(a, total_frames);
+        cpt::frame_components_kernel<<<(unsigned)std::min<long long>(total_frames, 2LL * c->num_sms), cpt::kGThreads, sizeof(cpt::CompSmem), stream>>>(a, total_frames);
         CUDA_TRY(cudaGetLastError());
     } else {
         cpt::extract_clips_kernel<<<grid, cpt::kThreads, sizeof(cpt::Smem), stream>>>(a);
@@ -497,8 +501,9 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
     }
     if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[4], stream));
     if (a.defer_variance) {
-        const unsigned blocks = (unsigned)((total_frames + 7) / 8);
-        cpt::region_variance_kernel<<<blocks, 256, 0, stream>>>(c->g, total_frames, out->d_filtered, out->d_info, out->d_regions);
+        constexpr int fpb = cpt::kVarThreads / 32;  // frames per block
+        const unsigned blocks = (unsigned)((total_frames + fpb - 1) / fpb);
+        cpt::region_variance_kernel<<<blocks, cpt::kVarThreads, 0, stream>>>(c->g, total_frames, out->d_filtered, out->d_info, out->d_regions);
         CUDA_TRY(cudaGetLastError());
     }
     if (timed) {

@@ -55,6 +55,7 @@ struct cpt_ctx {
     cpt::StripRec *prec = nullptr;
     cpt::FrameHdr *fhdr = nullptr;
     uint32_t *maskbits = nullptr;
+    int *fallback = nullptr;   // [1 + split_frames]: frames left to frame_components_kernel (count first)
     size_t split_frames = 0, split_clips = 0;
     bool force_single = false;  // cpt_debug_force_single_kernel
     bool time_kernels = false;  // cpt_debug_kernel_times

@@ -67,6 +67,14 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kSThreads = kPThreads + 64;  // sweep warps + scalar warp + producer warp
 constexpr int kFThreads = 128;   // frame_mask_kernel
 constexpr int kGThreads = 256;   // frame_components_kernel
+#ifndef CPT_VAR_THREADS
+#define CPT_VAR_THREADS 256
+#endif
+#ifndef CPT_VAR_BATCH
+#define CPT_VAR_BATCH 1
+#endif
+constexpr int kVarThreads = CPT_VAR_THREADS;  // region_variance_kernel: one warp per frame
+constexpr int kVarBatch = CPT_VAR_BATCH;      // pixels per lane whose loads are in flight together
 constexpr int kMaxPx = 19200;
 constexpr int kQIter = (kMaxPx / 4 + kPThreads - 1) / kPThreads;  // 6 quads of 4 pixels per pixel thread
 constexpr int kMaxW = 160;
@@ -201,7 +209,8 @@ struct KernelArgs {
     uint8_t *u8_frames;   // [total_frames][npx] normalised images of denoise clips (ctx scratch), else nullptr
     const uint16_t *zero_frame;  // npx zeros: stands in for the frame leaving the 45-frame window while it fills
     uint32_t *hot;        // [total_frames][kHotStride] (split path), else nullptr
-    uint32_t *maskbits;   // [total_frames][kMaxWords] thresholded masks between the two per-frame kernels (split path)
+    uint32_t *maskbits;   // [total_frames][kMaxWords] thresholded masks of the frames left to frame_components_kernel
+    int *fallback;        // [1 + total_frames]: count, then the frames frame_mask_kernel left to frame_components_kernel
     // strip sweep outputs (split path)
     int8_t *qbytes;       // [total_frames][H][qpr] per quad: max filtered - strip reference, saturated to int8
     StripRec *prec;       // [total_frames + n_clips][n_strips]: pass records (clip ci's tail pass at total_frames + ci)
@@ -260,14 +269,32 @@ constexpr int kBandHalo = 4;    // rows of normalised values a blur output can r
 constexpr int kBandRows = 24;   // hot rows one band covers
 constexpr int kBandURows = kBandRows + 2 * kBandHalo;
 constexpr int kBandList = kBandURows * (kMaxW / 8);  // every group of every row of the band: the lists cannot overflow
+constexpr int kLeanParents = 2048;  // run ids of the in-CTA components stage: rows of the mask's extent * runs per row
+constexpr int kLeanSlots = 32;      // components it numbers; slot kLeanSlots is the overflow sink (more: the fallback kernel)
 struct __align__(16) MaskSmem {
-    uint8_t U[kBandURows * kMaxW];     // normalised bytes of the band's rows
-    uint16_t list_u[kBandList];        // groups of 8 pixels to normalise: band row * gpr + group
-    uint16_t list_b[kBandList];        // groups to blur: frame group | quad marks << 14
-    unsigned long long hot64[kMaxH];   // per frame row, one bit per quad
-    uint32_t M[1][kMaxWords];          // the frame's mask, bit rows
-    int16_t theta[kMaxStrips];
+    union {
+        struct {
+            uint8_t U[kBandURows * kMaxW];     // normalised bytes of the band's rows
+            uint16_t list_u[kBandList];        // groups of 8 pixels to normalise: band row * gpr + group
+            uint16_t list_b[kBandList];        // groups to blur: frame group | quad marks << 14
+        };
+        // ... and once the mask is complete, the components stage: closed mask, run-start bits, run starts in earlier words
+        // of the row (all indexed by word within the mask's row extent)
+        struct {
+            uint32_t C[kMaxWords];
+            uint32_t ST[kMaxWords];
+            uint8_t base[kMaxWords + 8];
+        };
+    };
+    alignas(16) unsigned long long hot64[kMaxH];   // per frame row, one bit per quad
+    alignas(16) uint32_t M[1][kMaxWords];          // the frame's mask, bit rows (moved as 16-byte vectors)
+    uint16_t parent[kLeanParents];     // union-find over runs
+    int32_t c_key[kLeanSlots + 1], c_area[kLeanSlots + 1], c_sx[kLeanSlots + 1], c_sy[kLeanSlots + 1];
+    int32_t c_l[kLeanSlots + 1], c_t[kLeanSlots + 1], c_r[kLeanSlots + 1], c_b[kLeanSlots + 1];
+    uint8_t c_rank[kLeanSlots + 4];
+    alignas(16) int16_t theta[kMaxStrips];         // (written as two 16-byte vectors)
     int32_t count[2];                  // list lengths
+    int32_t ncomp, overflow;
 };
 static_assert(kMaxH <= 128, "frame_mask_kernel keeps the set of hot rows in four ballot words");
 static_assert(kMaxH * (kMaxW / 8) <= (1 << 14), "a blur list entry keeps the group in 14 bits");

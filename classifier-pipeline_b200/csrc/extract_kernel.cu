@@ -1563,6 +1563,195 @@ __device__ __forceinline__ unsigned long long quad_row_bits_bytes(const Geometry
     return bits;
 }
 
+// ---- components of a small mask inside frame_mask_kernel's CTA ---------------------------------------------------------
+// The same algorithm as components_of_frame (close, runs, unions with the row above, statistics, OpenCV label order, label
+// runs, region records), restricted to the rows [r0, r1] the mask stage can have set and sized for the masks real frames
+// have: run ids are (row of the extent) * rpr + index with rpr = min(80, 2048 / rows), at most kLeanSlots components.
+// Returns false -- before anything is written to global memory -- when the frame does not fit (a row with more runs, more
+// components): frame_components_kernel then redoes it from the stored mask.  Called by all kFThreads threads.
+__device__ __forceinline__ int lean_run_id(const MaskSmem &s, int lw, int ry, int rpr, int b) {
+    return ry * rpr + (int)s.base[lw] + __popc(s.ST[lw] & (0xffffffffu >> (31 - b))) - 1;
+}
+
+__device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry &g, int tid, size_t o, int r0, int r1, bool have_prev) {
+    const int rw = g.row_words, W = g.W;
+    const int c0 = r0, c1 = min(r1 + 1, g.H - 1), nrows = c1 - c0 + 1, nw = nrows * rw;
+    const int rpr = min(kRunsPerRow, kLeanParents / nrows);
+    // ---- close: C[y] = M[y-1] | (M[y] & M[y-2]) (C[0] = M[0]); rows outside [c0, c1] are empty
+    bool any = false;
+    for (int lw = tid; lw < nw; lw += kFThreads) {
+        const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), y = c0 + ry, w = lw + c0 * rw;
+        const uint32_t m0 = s.M[0][w];
+        uint32_t c = m0;
+        if (y > 0) c = s.M[0][w - rw] | (m0 & (y >= 2 ? s.M[0][w - 2 * rw] : 0u));
+        s.C[lw] = c;
+        any |= c != 0u;
+    }
+    if (tid == 0) { s.ncomp = 0; s.overflow = 0; }
+    if (!__syncthreads_or(any)) return true;  // no foreground: info.n_components stays 0
+    // ---- run starts and ids
+    for (int lw = tid; lw < nw; lw += kFThreads) {
+        const uint32_t c = s.C[lw];
+        if (c == 0u) continue;  // (ST / base of an empty word are never looked up)
+        const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw;
+        uint32_t carry = 0;
+        int base = 0;
+        for (int q = 0; q < wi; ++q) {
+            const uint32_t cq = s.C[lw - wi + q];
+            base += __popc(cq & ~((cq << 1) | carry));
+            carry = cq >> 31;
+        }
+        const uint32_t stw = c & ~((c << 1) | carry);
+        s.ST[lw] = stw;
+        s.base[lw] = (uint8_t)base;
+        const int n = __popc(stw);
+        if (base + n > rpr) { s.overflow = 1; continue; }
+        for (int k = 0; k < n; ++k) s.parent[ry * rpr + base + k] = (uint16_t)(ry * rpr + base + k);
+    }
+    __syncthreads();
+    if (s.overflow) return false;
+    // ---- unions with the row above (8-connectivity)
+    for (int lw = tid; lw < nw; lw += kFThreads) {
+        const uint32_t c = s.C[lw];
+        const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw;
+        if (c == 0u || ry == 0) continue;  // (the row above the extent is empty)
+        const int up = lw - rw;
+        const uint32_t u = s.C[up];
+        const uint32_t u_l = (wi > 0) ? (s.C[up - 1] >> 31) : 0u, u_r = (wi + 1 < rw) ? (s.C[up + 1] & 1u) : 0u;
+        const uint32_t c_l = (wi > 0) ? (s.C[lw - 1] >> 31) : 0u, c_r = (wi + 1 < rw) ? (s.C[lw + 1] & 1u) : 0u;
+        const uint32_t ul = (u << 1) | u_l, ur = (u >> 1) | (u_r << 31);
+        const uint32_t cl = (c << 1) | c_l, cr = (c >> 1) | (c_r << 31);
+        uint32_t needA = c & u & ~(cl & ul);   // pixel above, unless the left neighbour already links to it
+        uint32_t needB = c & ul & ~u & ~cl;    // upper-left only
+        uint32_t needC = c & ur & ~u & ~cr;    // upper-right only
+        while (needA) {
+            const int b = __ffs(needA) - 1;
+            needA &= needA - 1;
+            uf_union(s.parent, lean_run_id(s, lw, ry, rpr, b), lean_run_id(s, up, ry - 1, rpr, b));
+        }
+        while (needB) {
+            const int b = __ffs(needB) - 1;
+            needB &= needB - 1;
+            // (the upper-left pixel of bit 0 is bit 31 of the previous word)
+            const int id_up = b > 0 ? lean_run_id(s, up, ry - 1, rpr, b - 1) : lean_run_id(s, up - 1, ry - 1, rpr, 31);
+            uf_union(s.parent, lean_run_id(s, lw, ry, rpr, b), id_up);
+        }
+        while (needC) {
+            const int b = __ffs(needC) - 1;
+            needC &= needC - 1;
+            const int id_up = b < 31 ? lean_run_id(s, up, ry - 1, rpr, b + 1) : lean_run_id(s, up + 1, ry - 1, rpr, 0);
+            uf_union(s.parent, lean_run_id(s, lw, ry, rpr, b), id_up);
+        }
+    }
+    __syncthreads();
+    // ---- roots -> component slots
+    for (int lw = tid; lw < nw; lw += kFThreads) {
+        if (s.C[lw] == 0u) continue;
+        const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13);
+        const int n = __popc(s.ST[lw]), id0 = ry * rpr + (int)s.base[lw];
+        for (int k = 0; k < n; ++k) {
+            const int id = id0 + k;
+            if (s.parent[id] == id) {
+                const int slot = min(atomicAdd(&s.ncomp, 1), kLeanSlots);
+                s.c_key[slot] = INT32_MAX; s.c_area[slot] = 0; s.c_sx[slot] = 0; s.c_sy[slot] = 0;
+                s.c_l[slot] = INT32_MAX; s.c_t[slot] = INT32_MAX; s.c_r[slot] = -1; s.c_b[slot] = -1;
+                s.parent[id] = (uint16_t)(kSlotFlag | slot);
+            }
+        }
+    }
+    __syncthreads();
+    const int ncomp = s.ncomp;
+    if (ncomp > kLeanSlots) return false;
+    // ---- per-run statistics into the slot tables; the run's slot is left in its parent entry for the label pass
+    for (int lw = tid; lw < nw; lw += kFThreads) {
+        const uint32_t c = s.C[lw];
+        if (c == 0u) continue;
+        const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw, y = c0 + ry;
+        uint32_t bitsleft = s.ST[lw];
+        int id = ry * rpr + (int)s.base[lw];
+        while (bitsleft) {
+            const int b = __ffs(bitsleft) - 1;
+            bitsleft &= bitsleft - 1;
+            const int slot = uf_slot(s.parent, id);
+            s.parent[id] = (uint16_t)(kSlotFlag | slot);
+            ++id;
+            const int xs = wi * 32 + b;
+            const uint32_t inv = ~(c >> b);
+            int len = (inv == 0) ? 32 : (__ffs(inv) - 1);
+            if (b + len >= 32) {  // run continues into the following words
+                len = 32 - b;
+                for (int q = wi + 1; q < rw; ++q) {
+                    const uint32_t cn = ~s.C[lw - wi + q];
+                    if (cn == 0) { len += 32; continue; }
+                    len += __ffs(cn) - 1;
+                    break;
+                }
+            }
+            atomicMin(&s.c_key[slot], (y >> 1) * g.block_w + (xs >> 1));
+            atomicAdd(&s.c_area[slot], len);
+            atomicAdd(&s.c_sx[slot], len * (2 * xs + len - 1) / 2);
+            atomicAdd(&s.c_sy[slot], len * y);
+            atomicMin(&s.c_l[slot], xs);
+            atomicMax(&s.c_r[slot], xs + len - 1);
+            atomicMin(&s.c_t[slot], y);
+            atomicMax(&s.c_b[slot], y);
+        }
+    }
+    __syncthreads();
+    // ---- OpenCV label order: rank by the key of the component's first 2x2 block
+    const int nout = min(ncomp, g.max_regions);
+    if (tid < ncomp) {
+        const int key = s.c_key[tid];
+        int rank = 0;
+        for (int q = 0; q < ncomp; ++q) rank += (s.c_key[q] < key);
+        s.c_rank[tid] = (uint8_t)rank;
+        if (rank < nout) {
+            cpt_region r;
+            r.x = s.c_l[tid]; r.y = s.c_t[tid];
+            r.width = s.c_r[tid] - r.x + 1; r.height = s.c_b[tid] - r.y + 1;
+            r.area = s.c_area[tid]; r.sum_x = s.c_sx[tid]; r.sum_y = s.c_sy[tid];
+            r.key = key;
+            r.pixel_variance = 0.0;  // region_variance_kernel
+            a.regions[o * g.max_regions + rank] = r;
+        }
+    }
+    if (tid == 0) {
+        a.info[o].n_components = ncomp;
+        if (have_prev) a.info[o].reserved[0] = 1;  // region_variance_kernel fills pixel_variance
+    }
+    if (!a.labels) return true;
+    __syncthreads();
+    // ---- label image: the sweep already stored zeros for this frame; write the runs
+    uint8_t *lab_frame = a.labels + o * g.npx;
+    for (int lw = tid; lw < nw; lw += kFThreads) {
+        const uint32_t c = s.C[lw];
+        if (c == 0u) continue;
+        const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw, y = c0 + ry;
+        uint32_t bitsleft = s.ST[lw];
+        int id = ry * rpr + (int)s.base[lw];
+        while (bitsleft) {
+            const int b = __ffs(bitsleft) - 1;
+            bitsleft &= bitsleft - 1;
+            const uint8_t lab = (uint8_t)(s.c_rank[s.parent[id] & 0xff] + 1);
+            ++id;
+            const uint32_t inv = ~(c >> b);
+            int len = (inv == 0) ? 32 : (__ffs(inv) - 1);
+            if (b + len >= 32) {
+                len = 32 - b;
+                for (int q = wi + 1; q < rw; ++q) {
+                    const uint32_t cn = ~s.C[lw - wi + q];
+                    if (cn == 0) { len += 32; continue; }
+                    len += __ffs(cn) - 1;
+                    break;
+                }
+            }
+            uint8_t *px = lab_frame + y * W + wi * 32 + b;
+            for (int k = 0; k < len; ++k) px[k] = lab;
+        }
+    }
+    return true;
+}
+
 // i / d for small i (i * d < 2^32) with magic = 0xffffffff / d + 1 (which wraps to 0 for d == 1)
 __device__ __forceinline__ int div_magic(int i, int d, uint32_t magic) { return d == 1 ? i : (int)__umulhi((uint32_t)i, magic); }
 
@@ -1577,7 +1766,7 @@ __device__ __forceinline__ int div_magic(int i, int d, uint32_t magic) { return 
 // with the band's normalised bytes in a 6.4 kB window of shared memory (no full-frame image, no work lists): small CTAs
 // with little shared memory, so that many frames are resident per SM and hide each other's dependent loads.  Bands
 // overlap by their halos; both compute the same bits there and OR them into the mask.
-__global__ void __launch_bounds__(kFThreads, 16) frame_mask_kernel(const KernelArgs a, long long total_frames) {
+__global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelArgs a, long long total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MaskSmem &s = *reinterpret_cast<MaskSmem *>(smem_raw);
     const Geometry &g = a.g;
@@ -1608,11 +1797,8 @@ __global__ void __launch_bounds__(kFThreads, 16) frame_mask_kernel(const KernelA
     const bool no_fg = ith >= 255;  // nothing can exceed the threshold: the mask stays empty
     const bool dense = (hdr.z & kHdrDense) != 0;  // no usable bound for the quad bytes: every quad counts as hot
     CPT_TICK2(tid == 0, 7);  // header + info
-    if (no_fg || (!dense && hdr.w == 0u)) {
-        // nothing can reach the threshold (no strip holds a hot quad): the mask is empty, frame_components_kernel leaves at once
-        if (tid == 0) a.fhdr[o].flags = hdr.z | kHdrEmpty;
-        return;
-    }
+    // nothing can reach the threshold (no strip holds a hot quad): the mask is empty, info.n_components stays 0
+    if (no_fg || (!dense && hdr.w == 0u)) return;
     const int8_t *qb = a.qbytes + (size_t)o * (g.H * g.qpr);
     const int NS = g.n_strips, wpr = g.qpr >> 2;  // words of quad bytes per row (rows of whole words: qpr % 4 == 0)
     const bool wordq = (g.qpr & 3) == 0;
@@ -1685,6 +1871,7 @@ __global__ void __launch_bounds__(kFThreads, 16) frame_mask_kernel(const KernelA
         const int r = 32 * j + lane;
         rb[j] = __ballot_sync(0xffffffffu, r < g.H && s.hot64[r] != 0ull);
     }
+    int m_r0 = g.H, m_r1 = -1;  // rows the mask can have set
     while (rb[0] | rb[1] | rb[2] | rb[3]) {  // (uniform over the CTA)
         // the band: kBandRows rows from the first hot row on, [lo, hi] = its first and last hot row
         int w = 0;
@@ -1706,6 +1893,8 @@ __global__ void __launch_bounds__(kFThreads, 16) frame_mask_kernel(const KernelA
         // quads), warps 2-3 the groups to blur (rows +-2, one quad; an entry carries its two quad marks)
         const int ur0 = max(lo - kBandHalo, 0), ur1 = min(hi + kBandHalo, g.H - 1);
         const int br0 = max(lo - 2, 0), br1 = min(hi + 2, g.H - 1);
+        m_r0 = min(m_r0, br0);
+        m_r1 = max(m_r1, br1);
         if (tid == 0) { s.count[0] = 0; s.count[1] = 0; }
         __syncthreads();  // (also: the previous band is done with U and the lists)
         if (tid < kFThreads / 2) {
@@ -1769,29 +1958,23 @@ __global__ void __launch_bounds__(kFThreads, 16) frame_mask_kernel(const KernelA
         }
         CPT_TICK2(tid == 0, 8);  // blur + threshold
     }
-    __syncthreads();  // the mask is complete
-    CPT_COUNT(tid == 0, 30, 1);  // frames that reach the mask store
-    // an empty mask (frames without an animal) is only flagged: frame_components_kernel leaves at once
-    uint32_t *mout = a.maskbits + (size_t)o * kMaxWords;
-    bool any = false;
-    if (vec) {
-        for (int i = tid; i < g.words / 4; i += kFThreads) {
-            const uint4 w = reinterpret_cast<const uint4 *>(s.M[0])[i];
-            any |= (w.x | w.y | w.z | w.w) != 0;
-        }
-    } else {
-        for (int i = tid; i < g.words; i += kFThreads) any |= s.M[0][i] != 0;
-    }
-    if (!__syncthreads_or(any)) {
-        if (tid == 0) a.fhdr[o].flags = hdr.z | kHdrEmpty;
+    if (m_r1 < 0) return;  // the byte thresholds were only bounds: no hot quad after all, the mask is empty
+    __syncthreads();       // the mask is complete; the band's buffers are free
+    CPT_COUNT(tid == 0, 30, 1);  // frames that reach the components stage
+    // ---- close, components, statistics, labels, region records (K4 second half, K5) in place; the variances are left to
+    // region_variance_kernel
+    if (components_lean(a, s, g, tid, (size_t)o, m_r0, m_r1, !(hdr.z & kHdrFirst))) {
+        CPT_TICK2(tid == 0, 9);  // components
         return;
     }
-    if (vec) {
+    // a mask the in-place stage is not sized for: stored for frame_components_kernel
+    uint32_t *mout = a.maskbits + (size_t)o * kMaxWords;
+    if ((g.words & 3) == 0) {
         for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
     } else {
         for (int i = tid; i < g.words; i += kFThreads) mout[i] = s.M[0][i];
     }
-    CPT_TICK2(tid == 0, 9);  // mask store
+    if (tid == 0) a.fallback[1 + atomicAdd(a.fallback, 1)] = (int)o;
 }
 
 // K6 for one region record: variance of |norm255(F_t) - norm255(F_t-1)| over the component's bounding box; one warp.
@@ -1802,12 +1985,29 @@ __device__ __forceinline__ void region_variance_warp(const Geometry &g, cpt_regi
     if (l < 0 || tp < 0 || bw < 1 || bh < 1 || l + bw > g.W || tp + bh > g.H) return;  // not a record of this launch
     double s1 = 0.0, s2 = 0.0;
     const uint32_t rcp = 0xffffffffu / (uint32_t)bw + 1u;  // i / bw == umulhi(i, rcp) for i * bw < 2^32
-    for (int i = lane; i < npix; i += 32) {
-        const int yy = bw == 1 ? i : (int)__umulhi((uint32_t)i, rcp), xx = i - yy * bw, p = (tp + yy) * g.W + l + xx;  // (rcp wraps to 0 for bw == 1)
-        const int fc = (int)__ldg(fcur + p), fp = (int)__ldg(fprev + p);
-        const float d = fabsf(norm255(fc, cur_fmin, cur_fmax, exact) - norm255(fp, prev_fmin, prev_fmax, exact));
-        s1 += (double)d;
-        s2 += (double)d * (double)d;
+    // pixels lane, lane + 32, ... in this order; the loads of eight of them are in flight together (a bounding box is cold:
+    // one DRAM round trip per batch instead of one per pixel)
+    constexpr int kBatch = kVarBatch;
+    for (int i0 = lane; i0 < npix; i0 += 32 * kBatch) {
+        float fcv[kBatch], fpv[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int i = i0 + 32 * k;
+            fcv[k] = 0.0f; fpv[k] = 0.0f;
+            if (i < npix) {
+                const int yy = bw == 1 ? i : (int)__umulhi((uint32_t)i, rcp), xx = i - yy * bw, p = (tp + yy) * g.W + l + xx;  // (rcp wraps to 0 for bw == 1)
+                fcv[k] = __ldg(fcur + p);
+                fpv[k] = __ldg(fprev + p);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (i0 + 32 * k < npix) {
+                const float d = fabsf(norm255((int)fcv[k], cur_fmin, cur_fmax, exact) - norm255((int)fpv[k], prev_fmin, prev_fmax, exact));
+                s1 += (double)d;
+                s2 += (double)d * (double)d;
+            }
+        }
     }
     for (int off = 16; off; off >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, off);
@@ -1819,53 +2019,33 @@ __device__ __forceinline__ void region_variance_warp(const Geometry &g, cpt_regi
     }
 }
 
-// Split path, third launch: one CTA per frame.  The frame's mask -> close -> components, statistics, labels (K4, K5); the
-// variances are left to region_variance_kernel.
+// Split path, third launch: the frames frame_mask_kernel could not finish in place (a.fallback: very busy masks -- more than
+// kLeanSlots components or more runs in a row than its run table holds).  The stored mask -> close -> components, statistics,
+// labels (K4, K5) with the full-size tables; the variances are left to region_variance_kernel.  A small persistent grid
+// over the list, which is nearly always empty.
 __global__ void __launch_bounds__(kGThreads, 6) frame_components_kernel(const KernelArgs a, long long total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CompSmem &s = *reinterpret_cast<CompSmem *>(smem_raw);
     const Geometry &g = a.g;
     const int tid = threadIdx.x;
-    const long long o = blockIdx.x;
-    if (o >= total_frames) return;
-    const cpt_frame_info *fi = a.info + o;
-    const uint32_t *min_ = a.maskbits + (size_t)o * kMaxWords;
-    CPT_TICK_START(tid == 0);
-    const uint32_t hflags = a.fhdr[o].flags;  // (plain load: frame_mask_kernel may have set the empty-mask flag)
-    const int dn_marker = fi->reserved[1];
-    // (requested together with the header: the words of a frame that turns out empty or invalid are ignored -- the buffer is
-    // allocated for every frame, only its contents are stale then)
-    const bool vec = (g.words & 3) == 0;
-    uint4 w0 = make_uint4(0, 0, 0, 0);
-    if (vec && tid < g.words / 4) w0 = __ldg(reinterpret_cast<const uint4 *>(min_) + tid);
-    if (!(hflags & kHdrValid)) return;  // no clip produced this output frame (its mask words were never written)
-    if (hflags & kHdrEmpty) return;     // empty mask (flagged by frame_mask_kernel): info.n_components stays 0
-    if (dn_marker) return;      // denoise clips: mask_components_kernel
-    bool any = false;
-    if (vec) {
-        for (int i = tid; i < g.words / 4; i += kGThreads) {
-            const uint4 w = i == tid ? w0 : __ldg(reinterpret_cast<const uint4 *>(min_) + i);
-            reinterpret_cast<uint4 *>(s.M[0])[i] = w;
-            any |= ((w.x | w.y | w.z | w.w) != 0);
-        }
-    } else {
-        for (int i = tid; i < g.words; i += kGThreads) {
-            const uint32_t w = min_[i];
-            s.M[0][i] = w;
-            any |= (w != 0);
-        }
+    const int n = a.fallback[0];
+    for (int idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const long long o = a.fallback[1 + idx];
+        if (o < 0 || o >= total_frames) continue;
+        __syncthreads();  // the previous frame is done with the tables
+        const cpt_frame_info *fi = a.info + o;
+        const uint32_t *min_ = a.maskbits + (size_t)o * kMaxWords;
+        const uint32_t hflags = a.fhdr[o].flags;
+        for (int i = tid; i < g.words; i += kGThreads) s.M[0][i] = min_[i];
+        __syncthreads();
+        const float *fcur = a.filtered + (size_t)o * g.npx;
+        const bool have_prev = !(hflags & kHdrFirst);  // not the first frame of its clip
+        // (variances in this kernel were measured slower than the separate wide pass, whose warps hide the cold reads of
+        // the filtered images: components_of_frame's own path +4.1 ms, one warp per region record as a tail here +7.9 ms,
+        // against the 2.4 ms of region_variance_kernel)
+        components_of_frame<CompSmem, kGThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, fi->filtered_min, fi->filtered_max, 0, 0,
+                                                     have_prev, true);
     }
-    if (!__syncthreads_or(any)) return;  // empty mask: info.n_components stays 0
-    CPT_TICK(tid == 0, 11);  // header + mask words
-    CPT_COUNT(tid == 0, 31, 1);  // frames with foreground
-    const float *fcur = a.filtered + (size_t)o * g.npx;
-    const bool have_prev = !(hflags & kHdrFirst);  // not the first frame of its clip
-    // (variances in this kernel were measured slower than the separate wide pass, whose warps hide the cold reads of
-    // the filtered images: components_of_frame's own path +4.1 ms, one warp per region record as a tail here +7.9 ms,
-    // against the 2.4 ms of region_variance_kernel)
-    components_of_frame<CompSmem, kGThreads, 1>(a, s, g, tid, 0, (size_t)o, fcur, fcur, fi->filtered_min, fi->filtered_max, 0, 0,
-                                                 have_prev, true);
-    CPT_TICK(tid == 0, 12);  // components of the frame
 }
 
 // Second half of the frame pipeline for denoise clips (info.reserved[1] != 0): the denoised normalised image of every
@@ -1903,7 +2083,7 @@ __global__ void __launch_bounds__(kThreads, 1) mask_components_kernel(const Kern
 // K6 for the frames the extraction kernel deferred (info.reserved[0] == 1): per-region variance of the
 // normalised delta frame |norm255(F_t) - norm255(F_t-1)| over the component's bounding box
 // (track/cliptracker.py:249-261,316-318).  One warp per frame; both filtered images are in the output buffer.
-__global__ void __launch_bounds__(256) region_variance_kernel(Geometry g, long long total_frames, const float *filtered,
+__global__ void __launch_bounds__(kVarThreads, 2048 / kVarThreads > 32 ? 32 : 2048 / kVarThreads) region_variance_kernel(Geometry g, long long total_frames, const float *filtered,
                                                               cpt_frame_info *info, cpt_region *regions) {
     const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
