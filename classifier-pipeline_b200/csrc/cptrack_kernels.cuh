@@ -266,10 +266,20 @@ struct __align__(16) Smem {
 // shared memory of frame_mask_kernel (one frame per CTA, one band of rows at a time: hot quads -> work lists -> normalise
 // -> blur + threshold)
 constexpr int kBandHalo = 4;    // rows of normalised values a blur output can reach above / below a hot quad
-constexpr int kBandRows = 24;   // hot rows one band covers
+#ifndef CPT_BAND_ROWS
+#define CPT_BAND_ROWS 24
+#endif
+#ifndef CPT_LEAN_PARENTS
+#define CPT_LEAN_PARENTS 1024
+#endif
+#ifndef CPT_F_MINBLOCKS
+#define CPT_F_MINBLOCKS 13
+#endif
+constexpr int kBandRows = CPT_BAND_ROWS;   // hot rows one band covers
+constexpr int kFMinBlocks = CPT_F_MINBLOCKS;  // frame_mask_kernel CTAs per SM the register allocation allows
 constexpr int kBandURows = kBandRows + 2 * kBandHalo;
 constexpr int kBandList = kBandURows * (kMaxW / 8);  // every group of every row of the band: the lists cannot overflow
-constexpr int kLeanParents = 2048;  // run ids of the in-CTA components stage: rows of the mask's extent * runs per row
+constexpr int kLeanParents = CPT_LEAN_PARENTS;  // run ids of the in-CTA components stage: rows of the mask's extent * runs per row
 constexpr int kLeanSlots = 32;      // components it numbers; slot kLeanSlots is the overflow sink (more: the fallback kernel)
 struct __align__(16) MaskSmem {
     union {
@@ -284,6 +294,7 @@ struct __align__(16) MaskSmem {
             uint32_t C[kMaxWords];
             uint32_t ST[kMaxWords];
             uint8_t base[kMaxWords + 8];
+            uint16_t wlist[kMaxWords];     // the non-empty words of C
         };
     };
     alignas(16) unsigned long long hot64[kMaxH];   // per frame row, one bit per quad
@@ -293,8 +304,10 @@ struct __align__(16) MaskSmem {
     int32_t c_l[kLeanSlots + 1], c_t[kLeanSlots + 1], c_r[kLeanSlots + 1], c_b[kLeanSlots + 1];
     uint8_t c_rank[kLeanSlots + 4];
     alignas(16) int16_t theta[kMaxStrips];         // (written as two 16-byte vectors)
-    int32_t count[2];                  // list lengths
-    int32_t ncomp, overflow;
+    // per band parity (warp 0 prepares the next band's record while the others may still read this one's):
+    int32_t count[2][2];               // list lengths
+    int32_t band[2][2];                // first / last hot row of the band (last < 0: none left)
+    int32_t ncomp, overflow, nwords;
 };
 static_assert(kMaxH <= 128, "frame_mask_kernel keeps the set of hot rows in four ballot words");
 static_assert(kMaxH * (kMaxW / 8) <= (1 << 14), "a blur list entry keeps the group in 14 bits");

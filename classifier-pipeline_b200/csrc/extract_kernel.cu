@@ -1567,32 +1567,50 @@ __device__ __forceinline__ unsigned long long quad_row_bits_bytes(const Geometry
 // The same algorithm as components_of_frame (close, runs, unions with the row above, statistics, OpenCV label order, label
 // runs, region records), restricted to the rows [r0, r1] the mask stage can have set and sized for the masks real frames
 // have: run ids are (row of the extent) * rpr + index with rpr = min(80, 2048 / rows), at most kLeanSlots components.
-// Returns false -- before anything is written to global memory -- when the frame does not fit (a row with more runs, more
-// components): frame_components_kernel then redoes it from the stored mask.  Called by all kFThreads threads.
+// Returns 0 when the frame is done; when it does not fit (a row with more runs, more components) -- found before anything is
+// written to global memory -- the number of threads that are still there (threads 0 .. n - 1; the others got 0 and left):
+// they store the mask for frame_components_kernel, which redoes the frame.  Called by all kFThreads threads.
 __device__ __forceinline__ int lean_run_id(const MaskSmem &s, int lw, int ry, int rpr, int b) {
     return ry * rpr + (int)s.base[lw] + __popc(s.ST[lw] & (0xffffffffu >> (31 - b))) - 1;
 }
 
-__device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry &g, int tid, size_t o, int r0, int r1, bool have_prev) {
+__device__ int components_lean(const KernelArgs &a, MaskSmem &s, const Geometry &g, int tid, size_t o, int r0, int r1, bool have_prev) {
     const int rw = g.row_words, W = g.W;
     const int c0 = r0, c1 = min(r1 + 1, g.H - 1), nrows = c1 - c0 + 1, nw = nrows * rw;
     const int rpr = min(kRunsPerRow, kLeanParents / nrows);
-    // ---- close: C[y] = M[y-1] | (M[y] & M[y-2]) (C[0] = M[0]); rows outside [c0, c1] are empty
-    bool any = false;
-    for (int lw = tid; lw < nw; lw += kFThreads) {
-        const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), y = c0 + ry, w = lw + c0 * rw;
-        const uint32_t m0 = s.M[0][w];
-        uint32_t c = m0;
-        if (y > 0) c = s.M[0][w - rw] | (m0 & (y >= 2 ? s.M[0][w - 2 * rw] : 0u));
-        s.C[lw] = c;
-        any |= c != 0u;
+    // ---- close: C[y] = M[y-1] | (M[y] & M[y-2]) (C[0] = M[0]); rows outside [c0, c1] are empty.  The non-empty words go
+    // on a list (any order): every later pass walks the list, a few dozen words for the masks real frames have.
+    // (s.ncomp, s.overflow and s.nwords were zeroed by the caller before its last barrier)
+    const int lane = tid & 31;
+    for (int lw0 = 0; lw0 < nw; lw0 += kFThreads) {
+        const int lw = lw0 + tid;
+        uint32_t c = 0u;
+        if (lw < nw) {
+            const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), y = c0 + ry, w = lw + c0 * rw;
+            const uint32_t m0 = s.M[0][w];
+            c = m0;
+            if (y > 0) c = s.M[0][w - rw] | (m0 & (y >= 2 ? s.M[0][w - 2 * rw] : 0u));
+            s.C[lw] = c;
+        }
+        const uint32_t nz = __ballot_sync(0xffffffffu, c != 0u);
+        if (nz) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s.nwords, __popc(nz));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (c != 0u) s.wlist[base + __popc(nz & ((1u << lane) - 1u))] = (uint16_t)lw;
+        }
     }
-    if (tid == 0) { s.ncomp = 0; s.overflow = 0; }
-    if (!__syncthreads_or(any)) return true;  // no foreground: info.n_components stays 0
+    __syncthreads();
+    const int nwl = s.nwords;
+    if (nwl == 0) return 0;  // no foreground: info.n_components stays 0
+    // (letting only as many warps as the list needs continue, with barriers over those, was measured slower: 10.15 ms
+    // against 9.82 ms for the per-frame stage of the bench batch)
+    constexpr int nact = kFThreads;
+    auto sync_act = [&]() { __syncthreads(); };
     // ---- run starts and ids
-    for (int lw = tid; lw < nw; lw += kFThreads) {
+    for (int i = tid; i < nwl; i += nact) {
+        const int lw = s.wlist[i];
         const uint32_t c = s.C[lw];
-        if (c == 0u) continue;  // (ST / base of an empty word are never looked up)
         const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw;
         uint32_t carry = 0;
         int base = 0;
@@ -1608,13 +1626,14 @@ __device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry
         if (base + n > rpr) { s.overflow = 1; continue; }
         for (int k = 0; k < n; ++k) s.parent[ry * rpr + base + k] = (uint16_t)(ry * rpr + base + k);
     }
-    __syncthreads();
-    if (s.overflow) return false;
+    sync_act();
+    if (s.overflow) return nact;
     // ---- unions with the row above (8-connectivity)
-    for (int lw = tid; lw < nw; lw += kFThreads) {
+    for (int i = tid; i < nwl; i += nact) {
+        const int lw = s.wlist[i];
         const uint32_t c = s.C[lw];
         const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw;
-        if (c == 0u || ry == 0) continue;  // (the row above the extent is empty)
+        if (ry == 0) continue;  // (the row above the extent is empty)
         const int up = lw - rw;
         const uint32_t u = s.C[up];
         const uint32_t u_l = (wi > 0) ? (s.C[up - 1] >> 31) : 0u, u_r = (wi + 1 < rw) ? (s.C[up + 1] & 1u) : 0u;
@@ -1643,10 +1662,10 @@ __device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry
             uf_union(s.parent, lean_run_id(s, lw, ry, rpr, b), id_up);
         }
     }
-    __syncthreads();
+    sync_act();
     // ---- roots -> component slots
-    for (int lw = tid; lw < nw; lw += kFThreads) {
-        if (s.C[lw] == 0u) continue;
+    for (int i = tid; i < nwl; i += nact) {
+        const int lw = s.wlist[i];
         const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13);
         const int n = __popc(s.ST[lw]), id0 = ry * rpr + (int)s.base[lw];
         for (int k = 0; k < n; ++k) {
@@ -1659,13 +1678,13 @@ __device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry
             }
         }
     }
-    __syncthreads();
+    sync_act();
     const int ncomp = s.ncomp;
-    if (ncomp > kLeanSlots) return false;
+    if (ncomp > kLeanSlots) return nact;
     // ---- per-run statistics into the slot tables; the run's slot is left in its parent entry for the label pass
-    for (int lw = tid; lw < nw; lw += kFThreads) {
+    for (int i = tid; i < nwl; i += nact) {
+        const int lw = s.wlist[i];
         const uint32_t c = s.C[lw];
-        if (c == 0u) continue;
         const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw, y = c0 + ry;
         uint32_t bitsleft = s.ST[lw];
         int id = ry * rpr + (int)s.base[lw];
@@ -1697,7 +1716,7 @@ __device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry
             atomicMax(&s.c_b[slot], y);
         }
     }
-    __syncthreads();
+    sync_act();
     // ---- OpenCV label order: rank by the key of the component's first 2x2 block
     const int nout = min(ncomp, g.max_regions);
     if (tid < ncomp) {
@@ -1719,13 +1738,13 @@ __device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry
         a.info[o].n_components = ncomp;
         if (have_prev) a.info[o].reserved[0] = 1;  // region_variance_kernel fills pixel_variance
     }
-    if (!a.labels) return true;
-    __syncthreads();
+    if (!a.labels) return 0;
+    sync_act();
     // ---- label image: the sweep already stored zeros for this frame; write the runs
     uint8_t *lab_frame = a.labels + o * g.npx;
-    for (int lw = tid; lw < nw; lw += kFThreads) {
+    for (int i = tid; i < nwl; i += nact) {
+        const int lw = s.wlist[i];
         const uint32_t c = s.C[lw];
-        if (c == 0u) continue;
         const int ry = (int)(((uint32_t)lw * g.rw_magic) >> 13), wi = lw - ry * rw, y = c0 + ry;
         uint32_t bitsleft = s.ST[lw];
         int id = ry * rpr + (int)s.base[lw];
@@ -1749,7 +1768,7 @@ __device__ bool components_lean(const KernelArgs &a, MaskSmem &s, const Geometry
             for (int k = 0; k < len; ++k) px[k] = lab;
         }
     }
-    return true;
+    return 0;
 }
 
 // i / d for small i (i * d < 2^32) with magic = 0xffffffff / d + 1 (which wraps to 0 for d == 1)
@@ -1766,7 +1785,7 @@ __device__ __forceinline__ int div_magic(int i, int d, uint32_t magic) { return 
 // with the band's normalised bytes in a 6.4 kB window of shared memory (no full-frame image, no work lists): small CTAs
 // with little shared memory, so that many frames are resident per SM and hide each other's dependent loads.  Bands
 // overlap by their halos; both compute the same bits there and OR them into the mask.
-__global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelArgs a, long long total_frames) {
+__global__ void __launch_bounds__(kFThreads, kFMinBlocks) frame_mask_kernel(const KernelArgs a, long long total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MaskSmem &s = *reinterpret_cast<MaskSmem *>(smem_raw);
     const Geometry &g = a.g;
@@ -1804,23 +1823,22 @@ __global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelA
     const bool wordq = (g.qpr & 3) == 0;
     const unsigned long long rowmask = g.qpr >= 64 ? ~0ull : (1ull << g.qpr) - 1ull;
     const uint32_t wmagic = g.qw_magic;
-    // ---- hot quads of the whole frame: the quad bytes of the hot strips, a word of four per thread and strip (a strip has
-    // at most kStripPxMax / 16 = 120 words), requested before anything waits
-    constexpr int kPre = 4;
-    static_assert(kStripPxMax / 16 <= kFThreads, "one word of a strip's quad bytes per thread");
-    uint32_t pre[kPre];
-    {
-        uint32_t hs = (dense || !wordq) ? 0u : hdr.w;
+    // ---- hot quads of the whole frame: the quad bytes of the hot strips, one warp per strip (strip s belongs to warp s & 3),
+    // four words of four quads per lane (a strip has at most kStripPxMax / 16 = 120 words); the first strip's words are
+    // requested before anything waits
+    constexpr int kWarpsF = kFThreads / 32;
+    static_assert(kWarpsF == 4, "strip s belongs to warp s & 3");
+    static_assert(kStripPxMax / 16 <= 4 * 32, "four words of a strip's quad bytes per lane");
+    const int warp = tid >> 5;
+    uint32_t pre[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};  // (-128: never hot)
+    const uint32_t my_strips = (dense ? 0u : hdr.w) & (0x11111111u << warp);
+    const int my_first = my_strips ? __ffs(my_strips) - 1 : -1;
+    if (my_first >= 0 && wordq) {
+        const int y0 = g.strip_y0[my_first], nw = ((int)g.strip_y0[my_first + 1] - y0) * wpr;
+        const uint32_t *qw = reinterpret_cast<const uint32_t *>(qb + y0 * g.qpr);
 #pragma unroll
-        for (int k = 0; k < kPre; ++k) {
-            pre[k] = 0x80808080u;  // (-128: never hot)
-            if (hs) {
-                const int sidx = __ffs(hs) - 1;
-                hs &= hs - 1;
-                const int y0 = g.strip_y0[sidx], nw = ((int)g.strip_y0[sidx + 1] - y0) * wpr;
-                if (tid < nw) pre[k] = __ldg(reinterpret_cast<const uint32_t *>(qb + y0 * g.qpr) + tid);
-            }
-        }
+        for (int j = 0; j < 4; ++j)
+            if (4 * lane + j < nw) pre[j] = __ldg(qw + 4 * lane + j);
     }
     const bool vec = (g.words & 3) == 0;
     if (vec) {
@@ -1834,69 +1852,83 @@ __global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelA
     }
     for (int r = tid; r < g.H; r += kFThreads) s.hot64[r] = dense ? rowmask : 0ull;
     __syncthreads();
-    if (!dense) {
-        uint32_t hs = hdr.w;
+    {
+        uint32_t hs = my_strips;
         uint32_t *hot32 = reinterpret_cast<uint32_t *>(s.hot64);
-        for (int k = 0; hs; ++k) {  // (uniform over the CTA)
+        while (hs) {
             const int sidx = __ffs(hs) - 1;
             hs &= hs - 1;
             const int y0 = g.strip_y0[sidx], nrows = (int)g.strip_y0[sidx + 1] - y0;
             const int th = s.theta[sidx];
             if (!wordq) {
-                for (int r = tid; r < nrows; r += kFThreads) s.hot64[y0 + r] = quad_row_bits_bytes(g, qb + (y0 + r) * g.qpr, th);
+                for (int r = lane; r < nrows; r += 32) s.hot64[y0 + r] = quad_row_bits_bytes(g, qb + (y0 + r) * g.qpr, th);
                 continue;
             }
-            uint32_t v = 0x80808080u;
-            if (k < kPre) {
-#pragma unroll
-                for (int j = 0; j < kPre; ++j) v = (j == k) ? pre[j] : v;
-            } else if (tid < nrows * wpr) {
-                v = __ldg(reinterpret_cast<const uint32_t *>(qb + y0 * g.qpr) + tid);
-            }
+            const int nw = nrows * wpr;
             const uint32_t t4 = (uint32_t)(th + 128) * 0x01010101u;
-            const uint32_t ge = __vcmpgeu4(v ^ 0x80808080u, t4) & 0x01010101u;  // byte i -> bit 8 i
-            const uint32_t nib = (ge * 0x10204080u) >> 28;                      // -> bits 0..3
-            if (nib) {
-                const int r = div_magic(tid, wpr, wmagic), c = tid - r * wpr;
-                atomicOr(hot32 + 2 * (y0 + r) + (c >> 3), nib << ((4 * c) & 31));
+            const uint32_t *qw = reinterpret_cast<const uint32_t *>(qb + y0 * g.qpr);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * lane + j;
+                uint32_t v = pre[j];
+                if (sidx != my_first) v = i < nw ? __ldg(qw + i) : 0x80808080u;
+                const uint32_t ge = __vcmpgeu4(v ^ 0x80808080u, t4) & 0x01010101u;  // byte i -> bit 8 i
+                const uint32_t nib = (ge * 0x10204080u) >> 28;                      // -> bits 0..3
+                if (nib) {
+                    const int r = div_magic(i, wpr, wmagic), c = i - r * wpr;
+                    atomicOr(hot32 + 2 * (y0 + r) + (c >> 3), nib << ((4 * c) & 31));
+                }
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
     CPT_TICK2(tid == 0, 15);  // quad bytes -> hot rows
-    // ---- the set of hot rows (every warp for itself: bit r & 31 of rb[r >> 5])
-    uint32_t rb[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int r = 32 * j + lane;
-        rb[j] = __ballot_sync(0xffffffffu, r < g.H && s.hot64[r] != 0ull);
-    }
-    int m_r0 = g.H, m_r1 = -1;  // rows the mask can have set
-    while (rb[0] | rb[1] | rb[2] | rb[3]) {  // (uniform over the CTA)
-        // the band: kBandRows rows from the first hot row on, [lo, hi] = its first and last hot row
-        int w = 0;
-        uint32_t cur = rb[0], nxt = rb[1];
-        if (!cur) { w = 1; cur = rb[1]; nxt = rb[2]; }
-        if (!cur) { w = 2; cur = rb[2]; nxt = rb[3]; }
-        if (!cur) { w = 3; cur = rb[3]; nxt = 0u; }
-        const int b = __ffs(cur) - 1, lo = 32 * w + b;
-        constexpr uint32_t kWin = kBandRows >= 32 ? 0xffffffffu : (1u << kBandRows) - 1u;
-        const uint32_t win = ((cur >> b) | (b ? (nxt << (32 - b)) : 0u)) & kWin;  // bit i: row lo + i is hot
-        const int hi = lo + 31 - __clz(win);
-        const uint32_t m_cur = kWin << b, m_nxt = (b + kBandRows > 32) ? (1u << (b + kBandRows - 32)) - 1u : 0u;
+    // ---- the set of hot rows, kept by warp 0 (bit r & 31 of rb[r >> 5]): it cuts the bands and hands them to the CTA
+    uint32_t rb[4] = {0u, 0u, 0u, 0u};
+    if (warp == 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j == w) rb[j] &= ~m_cur;
-            if (j == w + 1) rb[j] &= ~m_nxt;
+            const int r = 32 * j + lane;
+            rb[j] = __ballot_sync(0xffffffffu, r < g.H && s.hot64[r] != 0ull);
         }
-        // work lists, one thread per row: warps 0-1 the groups to normalise (rows +-4, quads +-2 around the band's hot
-        // quads), warps 2-3 the groups to blur (rows +-2, one quad; an entry carries its two quad marks)
+    }
+    int m_r0 = g.H, m_r1 = -1;  // rows the mask can have set
+    for (int bp = 0;; bp ^= 1) {  // (band parity)
+        if (warp == 0) {
+            // the band: kBandRows rows from the first hot row on, [lo, hi] = its first and last hot row
+            int blo = 0, bhi = -1;
+            if (rb[0] | rb[1] | rb[2] | rb[3]) {
+                int w = 0;
+                uint32_t cur = rb[0], nxt = rb[1];
+                if (!cur) { w = 1; cur = rb[1]; nxt = rb[2]; }
+                if (!cur) { w = 2; cur = rb[2]; nxt = rb[3]; }
+                if (!cur) { w = 3; cur = rb[3]; nxt = 0u; }
+                const int b = __ffs(cur) - 1;
+                blo = 32 * w + b;
+                constexpr uint32_t kWin = kBandRows >= 32 ? 0xffffffffu : (1u << kBandRows) - 1u;
+                const uint32_t win = ((cur >> b) | (b ? (nxt << (32 - b)) : 0u)) & kWin;  // bit i: row lo + i is hot
+                bhi = blo + 31 - __clz(win);
+                const uint32_t m_cur = kWin << b, m_nxt = (b + kBandRows > 32) ? (1u << (b + kBandRows - 32)) - 1u : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j == w) rb[j] &= ~m_cur;
+                    if (j == w + 1) rb[j] &= ~m_nxt;
+                }
+            }
+            if (lane == 0) {
+                s.band[bp][0] = blo; s.band[bp][1] = bhi; s.count[bp][0] = 0; s.count[bp][1] = 0;
+                s.ncomp = 0; s.overflow = 0; s.nwords = 0;  // (for the components stage)
+            }
+        }
+        __syncthreads();  // the band record is there; the previous band is done with U and the lists, the mask has its bits
+        const int lo = s.band[bp][0], hi = s.band[bp][1];
+        if (hi < 0) break;
         const int ur0 = max(lo - kBandHalo, 0), ur1 = min(hi + kBandHalo, g.H - 1);
         const int br0 = max(lo - 2, 0), br1 = min(hi + 2, g.H - 1);
         m_r0 = min(m_r0, br0);
         m_r1 = max(m_r1, br1);
-        if (tid == 0) { s.count[0] = 0; s.count[1] = 0; }
-        __syncthreads();  // (also: the previous band is done with U and the lists)
+        // work lists, one thread per row: warps 0-1 the groups to normalise (rows +-4, quads +-2 around the band's hot
+        // quads), warps 2-3 the groups to blur (rows +-2, one quad; an entry carries its two quad marks)
         if (tid < kFThreads / 2) {
             const int y = ur0 + tid;
             if (y <= ur1) {
@@ -1909,7 +1941,7 @@ __global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelA
                 if (nearq) {
                     const unsigned long long mk = (nearq | (nearq << 1) | (nearq >> 1) | (nearq << 2) | (nearq >> 2)) & rowmask;
                     unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
-                    int base = atomicAdd(&s.count[0], __popcll(grp_bits));
+                    int base = atomicAdd(&s.count[bp][0], __popcll(grp_bits));
                     const int row_grp = tid * g.gpr;  // (band row)
                     while (grp_bits) {
                         const int bit = __ffsll((long long)grp_bits) - 1;
@@ -1930,7 +1962,7 @@ __global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelA
                 if (nearq) {
                     const unsigned long long mk = (nearq | (nearq << 1) | (nearq >> 1)) & rowmask;
                     unsigned long long grp_bits = (mk | (mk >> 1)) & 0x5555555555555555ull;
-                    int base = atomicAdd(&s.count[1], __popcll(grp_bits));
+                    int base = atomicAdd(&s.count[bp][1], __popcll(grp_bits));
                     const int row_grp = y * g.gpr;  // (frame row)
                     while (grp_bits) {
                         const int bit = __ffsll((long long)grp_bits) - 1;
@@ -1942,7 +1974,7 @@ __global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelA
         }
         __syncthreads();
         CPT_TICK2(tid == 0, 4);  // marks + lists
-        const int n_u = s.count[0], n_b = s.count[1];
+        const int n_u = s.count[bp][0], n_b = s.count[bp][1];
         CPT_COUNT(tid == 0, 28, n_u);
         CPT_COUNT(tid == 0, 29, n_b);
         {
@@ -1959,20 +1991,19 @@ __global__ void __launch_bounds__(kFThreads, 12) frame_mask_kernel(const KernelA
         CPT_TICK2(tid == 0, 8);  // blur + threshold
     }
     if (m_r1 < 0) return;  // the byte thresholds were only bounds: no hot quad after all, the mask is empty
-    __syncthreads();       // the mask is complete; the band's buffers are free
+    // (the mask is complete and the band's buffers are free: every thread has passed the barrier that follows the last blur)
     CPT_COUNT(tid == 0, 30, 1);  // frames that reach the components stage
     // ---- close, components, statistics, labels, region records (K4 second half, K5) in place; the variances are left to
     // region_variance_kernel
-    if (components_lean(a, s, g, tid, (size_t)o, m_r0, m_r1, !(hdr.z & kHdrFirst))) {
-        CPT_TICK2(tid == 0, 9);  // components
-        return;
-    }
+    const int left = components_lean(a, s, g, tid, (size_t)o, m_r0, m_r1, !(hdr.z & kHdrFirst));
+    CPT_TICK2(tid == 0, 9);  // components
+    if (left == 0) return;
     // a mask the in-place stage is not sized for: stored for frame_components_kernel
     uint32_t *mout = a.maskbits + (size_t)o * kMaxWords;
     if ((g.words & 3) == 0) {
-        for (int i = tid; i < g.words / 4; i += kFThreads) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
+        for (int i = tid; i < g.words / 4; i += left) reinterpret_cast<uint4 *>(mout)[i] = reinterpret_cast<const uint4 *>(s.M[0])[i];
     } else {
-        for (int i = tid; i < g.words; i += kFThreads) mout[i] = s.M[0][i];
+        for (int i = tid; i < g.words; i += left) mout[i] = s.M[0][i];
     }
     if (tid == 0) a.fallback[1 + atomicAdd(a.fallback, 1)] = (int)o;
 }
