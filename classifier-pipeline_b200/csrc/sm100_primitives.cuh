@@ -37,6 +37,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
 }
 
+// the same on a shared-space address (loops that step through a ring of barriers keep the address, not the pointer)
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity, uint32_t hint_ns = 4000u) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PRIM_WAITA_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra.uni PRIM_WAITA_DONE;\n"
+        "bra.uni PRIM_WAITA_LOOP;\n"
+        "PRIM_WAITA_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

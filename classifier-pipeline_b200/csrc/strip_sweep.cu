@@ -228,7 +228,7 @@ __device__ __forceinline__ void pass_advance(PassPos &p) {
 
 // the warp's partial results -> its row of the pass table (the fold warp folds the rows), then the warp's arrival
 template <bool kStats>
-__device__ __forceinline__ void pass_report(StripSmem &s, const PassOut &po, int bi, int warp, int lane) {
+__device__ __forceinline__ void pass_report(StripSmem &s, const PassOut &po, int bi, int warp, int lane, uint32_t done0) {
     const uint32_t psum = __reduce_add_sync(0xffffffffu, po.psum);
     const int fmin = __reduce_min_sync(0xffffffffu, po.fmin), fmax = __reduce_max_sync(0xffffffffu, po.fmax);
     const int bs = __reduce_add_sync(0xffffffffu, po.bs);
@@ -242,7 +242,7 @@ __device__ __forceinline__ void pass_report(StripSmem &s, const PassOut &po, int
     // (psum < 2^23 for a warp: bit 31 carries `changed`)
     if (lane == 0) row[0] = make_uint4(psum | (chg ? 0x80000000u : 0u), (uint32_t)fmin, (uint32_t)fmax, (uint32_t)bs);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&s.done[bi]);  // (release: the ring reads and the row are done)
+    if (lane == 0) mbar_arrive_addr(done0 + (uint32_t)(bi << 3));  // (release: the ring reads and the row are done)
 }
 
 template <bool kStats, bool kLabels>
@@ -300,11 +300,13 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         if (k > wt.max_count) return 0;
         return k < kStripTable ? (int)s.wbnd[k] : (int)(__ldg(wt.thr + k) >> 16);
     };
+    const uint32_t full0 = smem_u32(&s.full[0]), done0 = smem_u32(&s.done[0]);
     auto frame_sync = [&](int t, int &refb) {
         // the frame's rows are in the ring; the reference its quad bytes are stored against was published by the fold warp
         // before the copy warp issued this frame (read after the acquire)
-        mbar_wait(&s.full[t & (kBarRing - 1)], (uint32_t)(t / kBarRing) & 1u);
-        refb = (t >= kRefLag ? *(volatile const int32_t *)&s.ref_ring[(t - kRefLag) & 15] : kRefDefault) + kBias;
+        mbar_wait_addr(full0 + (uint32_t)((t & (kBarRing - 1)) << 3), (uint32_t)(t / kBarRing) & 1u);
+        // (the first kRefLag entries a pass reads hold the default: strip_sweep_kernel fills the ring before a unit starts)
+        refb = *(volatile const int32_t *)&s.ref_ring[(t + 16 - kRefLag) & 15] + kBias;
     };
     auto after_frame = [&]() {
         th.fptr += npx;
@@ -338,7 +340,7 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
             ++pp.frames_seen;
             pp.bmax = max(pp.bmax, table_bound(pp.frames_seen));
         }
-        pass_report<kStats>(s, po, t & (kBarRing - 1), warp, lane);
+        pass_report<kStats>(s, po, t & (kBarRing - 1), warp, lane, done0);
         if (pc.is_frame) after_frame();
         pass_advance(pp);
     };
@@ -357,7 +359,7 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
             strip_pass<kTab, kStats, true, kLabels>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax);
             ++pp.frames_seen;
             if (kTab != 0) pp.bmax = max(pp.bmax, table_bound(pp.frames_seen));
-            pass_report<kStats>(s, po, pp.t & (kBarRing - 1), warp, lane);
+            pass_report<kStats>(s, po, pp.t & (kBarRing - 1), warp, lane, done0);
             after_frame();
             pass_advance(pp);
         }
@@ -504,6 +506,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) strip_sweep_kernel(const Ker
                 mbar_init(&s.done[i], kConsWarps);  // one arrival per consumer warp
                 mbar_init(&s.folded[i], 1);         // the fold warp
             }
+            for (int i = 0; i < 16; ++i) s.ref_ring[i] = kRefDefault;  // (what the first kRefLag passes read)
             mbar_fence_init();
             bars_live = true;
         }
