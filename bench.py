@@ -551,12 +551,13 @@ def main():
             "kernel_share_of_step": sweep_ms / kernel_ms,
             "step_ms": kernel_ms, "step_achieved": step_achieved, "step_frac": step_achieved / peak,
             "kernel_times_ms": {"strip_sweep_kernel": float(kt[0]), "frame_scalars_kernel": float(kt[1]),
-                                "frame_mask_kernel+frame_components_kernel": float(kt[2]), "denoise_passes": float(kt[3]),
+                                "frame_regions_kernel+frame_components_kernel": float(kt[2]), "denoise_passes": float(kt[3]),
                                 "region_variance_kernel": float(kt[4])},
-            "kernels_per_step": ["strip_sweep_kernel", "strip_sweep_stats_kernel (no clip of its kind: leaves at once)", "frame_scalars_kernel",
-                                 "frame_mask_kernel", "frame_components_kernel", "region_variance_kernel"],
+            "kernels_per_step": ["strip_sweep_kernel", "frame_scalars_kernel", "frame_regions_kernel",
+                                 "frame_components_kernel (the frames frame_regions_kernel left on its list: nearly always none)",
+                                 "region_variance_kernel"],
         },
-        "e2e": e2e, "gpu_launches": 6 * args.steps, "clocks": clocks.summary(),
+        "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks.summary(),
     }
     line.update(extras)
     if preprocess is not None:

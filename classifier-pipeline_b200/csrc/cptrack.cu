@@ -17,7 +17,7 @@ __global__ void mask_components_kernel(const KernelArgs a, long long total_frame
 __global__ void strip_sweep_kernel(const KernelArgs a);
 __global__ void frame_scalars_kernel(const KernelArgs a);
 size_t strip_sweep_smem_bytes();
-__global__ void frame_mask_kernel(const KernelArgs a, long long total_frames);
+__global__ void frame_regions_kernel(const KernelArgs a, long long total_frames);
 __global__ void frame_components_kernel(const KernelArgs a, long long total_frames);
 int cptv_decode_launch(cpt_ctx *c, const uint8_t *d_stream, const cpt_cptv_frame *d_table, int n_frames, const int32_t *d_clip_first,
                        int n_clips, uint16_t *d_frames, int32_t *scratch, cudaStream_t stream);
@@ -127,7 +127,7 @@ cpt_ctx *cpt_ctx_create(int device, int width, int height, int edge_pixels, int 
                              (int)sizeof(cpt::Smem)) != cudaSuccess ||
         cudaFuncSetAttribute(cpt::strip_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)cpt::strip_sweep_smem_bytes()) != cudaSuccess ||
-        cudaFuncSetAttribute(cpt::frame_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(cpt::frame_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(cpt::MaskSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(cpt::frame_components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(cpt::CompSmem)) != cudaSuccess) {
@@ -477,7 +477,7 @@ static int launch_extract(cpt_ctx *c, const uint16_t *d_frames, const cpt_clip *
         cpt::frame_scalars_kernel<<<(n_clips + 3) / 4, 128, 0, stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         if (timed) CUDA_TRY(cudaEventRecord(c->ev_k[2], stream));
-        cpt::frame_mask_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::MaskSmem), stream>>>(a, total_frames);
+        cpt::frame_regions_kernel<<<(unsigned)total_frames, cpt::kFThreads, sizeof(cpt::MaskSmem), stream>>>(a, total_frames);
         CUDA_TRY(cudaGetLastError());
         cpt::frame_components_kernel<<<(unsigned)std::min<long long>(total_frames, 2LL * c->num_sms), cpt::kGThreads, sizeof(cpt::CompSmem), stream>>>(a, total_frames);
         CUDA_TRY(cudaGetLastError());

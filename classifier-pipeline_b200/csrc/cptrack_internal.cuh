@@ -50,7 +50,7 @@ struct cpt_ctx {
     float *scratch = nullptr;
     size_t scratch_ctas = 0;
     // scratch of the split extraction path (grown on demand): quad bytes, strip pass records, per-frame headers and the
-    // thresholded masks between frame_mask_kernel and frame_components_kernel
+    // thresholded masks between frame_regions_kernel and frame_components_kernel
     int8_t *qbytes = nullptr;
     cpt::StripRec *prec = nullptr;
     cpt::FrameHdr *fhdr = nullptr;

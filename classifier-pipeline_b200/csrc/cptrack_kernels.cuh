@@ -15,8 +15,10 @@
 //   label         run-based union-find on the bit rows, OpenCV label order                      (K5)
 //   regions       bbox / area / centroid sums per component, delta-frame variance               (K5, K6)
 // Two launch plans share these device functions:
-//   split path (batch launches that keep the filtered images, no state): extract_sweep_kernel (sweep warps + scalar warp
-//     + producer warp per clip) -> frame_mask_kernel -> frame_components_kernel (one CTA per frame) -> region_variance_kernel
+//   split path (batch launches that keep the filtered images and resume from no state): strip_sweep_kernel (strip_sweep.cu:
+//     the recurrence, one CTA per (clip, strip of rows)) -> frame_scalars_kernel -> frame_regions_kernel (one small CTA per
+//     frame: marks .. regions in place; the rare very busy mask goes on a list for frame_components_kernel) ->
+//     region_variance_kernel
 //   single kernel (streaming, resumed clips, regions-only): extract_clips_kernel, the stages as three warp roles
 //     (sweep / mask / component warps) running concurrently on consecutive frames of the clip
 #pragma once
@@ -61,11 +63,9 @@ constexpr int kCThreads = 256;                  // 8 component warps
 constexpr int kCWarps = kCThreads / 32;
 constexpr int kThreads = kPThreads + kMThreads + kCThreads;
 constexpr int kWarps = kThreads / 32;
-// split path (batch launches that keep the filtered images and carry no state): extract_sweep_kernel runs the sweep
-// warps plus one scalar warp per clip; frame_mask_kernel and frame_components_kernel then turn every frame into its
-// mask and its labels / regions with one CTA per frame
-constexpr int kSThreads = kPThreads + 64;  // sweep warps + scalar warp + producer warp
-constexpr int kFThreads = 128;   // frame_mask_kernel
+// split path: frame_regions_kernel turns every frame into its mask, labels and regions with one four-warp CTA per frame;
+// frame_components_kernel (full-size tables) redoes the frames whose masks are too busy for it
+constexpr int kFThreads = 128;   // frame_regions_kernel
 constexpr int kGThreads = 256;   // frame_components_kernel
 #ifndef CPT_VAR_THREADS
 #define CPT_VAR_THREADS 256
@@ -85,11 +85,6 @@ constexpr int kRunsPerRow = kMaxW / 2;          // 80
 constexpr int kMaxRuns = kMaxH * kRunsPerRow;   // 9600
 constexpr int kCompSlots = 256;                 // slot 255 = overflow sink
 constexpr int kMeanFrames = CPT_MEAN_FRAMES;
-// per output frame of the split path: one ballot word per (sweep warp, sweep iteration) -- bit `lane` of word
-// warp * kQIter + it is the hot bit of owned quad it * kPThreads + warp * 32 + lane -- followed by
-// {byte threshold (0: dense), normalise magic, normalise shift, flags (1: valid, 2: first frame of its clip, 4: empty mask)}
-constexpr int kHotWords = (kQIter * kPWarps + 3) & ~3;  // (the trailer is read and written as one 16-byte vector)
-constexpr int kHotStride = kHotWords + 4;
 constexpr uint16_t kSlotFlag = 0x8000u;
 
 struct Geometry {
@@ -208,9 +203,8 @@ struct KernelArgs {
     int defer_variance;   // leave K6 of frames t > 0 to region_variance_kernel (needs `filtered`)
     uint8_t *u8_frames;   // [total_frames][npx] normalised images of denoise clips (ctx scratch), else nullptr
     const uint16_t *zero_frame;  // npx zeros: stands in for the frame leaving the 45-frame window while it fills
-    uint32_t *hot;        // [total_frames][kHotStride] (split path), else nullptr
     uint32_t *maskbits;   // [total_frames][kMaxWords] thresholded masks of the frames left to frame_components_kernel
-    int *fallback;        // [1 + total_frames]: count, then the frames frame_mask_kernel left to frame_components_kernel
+    int *fallback;        // [1 + total_frames]: count, then the frames frame_regions_kernel left to frame_components_kernel
     // strip sweep outputs (split path)
     int8_t *qbytes;       // [total_frames][H][qpr] per quad: max filtered - strip reference, saturated to int8
     StripRec *prec;       // [total_frames + n_clips][n_strips]: pass records (clip ci's tail pass at total_frames + ci)
@@ -253,9 +247,6 @@ struct __align__(16) Smem {
     unsigned long long hot64[kMaxH];  // per owned row, one bit per quad: some pixel can exceed the threshold
     FrameMsg fm[2];
     int32_t fth_latest;      // last bound the mask warps computed (INT32_MIN: none yet): the next qref
-    unsigned long long done_bar[2];  // split path: mbarrier per message buffer, one phase per message the scalar warp finishes
-    int32_t done_bar_live;
-    int32_t tu_pub[2];       // split path: byte threshold of the frame in message buffer b (0: dense)
     int32_t final_prev[3];   // filtered min / max of the last frame, have_prev (for the state record)
     double init_average, final_average;
     uint16_t list_u[kListCap];  // groups of 8 pixels to normalise this frame (need_u)
@@ -263,7 +254,7 @@ struct __align__(16) Smem {
     int32_t ncomp;
 };
 
-// shared memory of frame_mask_kernel (one frame per CTA, one band of rows at a time: hot quads -> work lists -> normalise
+// shared memory of frame_regions_kernel (one frame per CTA, one band of rows at a time: hot quads -> work lists -> normalise
 // -> blur + threshold)
 constexpr int kBandHalo = 4;    // rows of normalised values a blur output can reach above / below a hot quad
 #ifndef CPT_BAND_ROWS
@@ -276,7 +267,7 @@ constexpr int kBandHalo = 4;    // rows of normalised values a blur output can r
 #define CPT_F_MINBLOCKS 13
 #endif
 constexpr int kBandRows = CPT_BAND_ROWS;   // hot rows one band covers
-constexpr int kFMinBlocks = CPT_F_MINBLOCKS;  // frame_mask_kernel CTAs per SM the register allocation allows
+constexpr int kFMinBlocks = CPT_F_MINBLOCKS;  // frame_regions_kernel CTAs per SM the register allocation allows
 constexpr int kBandURows = kBandRows + 2 * kBandHalo;
 constexpr int kBandList = kBandURows * (kMaxW / 8);  // every group of every row of the band: the lists cannot overflow
 constexpr int kLeanParents = CPT_LEAN_PARENTS;  // run ids of the in-CTA components stage: rows of the mask's extent * runs per row
@@ -309,7 +300,7 @@ struct __align__(16) MaskSmem {
     int32_t band[2][2];                // first / last hot row of the band (last < 0: none left)
     int32_t ncomp, overflow, nwords;
 };
-static_assert(kMaxH <= 128, "frame_mask_kernel keeps the set of hot rows in four ballot words");
+static_assert(kMaxH <= 128, "frame_regions_kernel keeps the set of hot rows in four ballot words");
 static_assert(kMaxH * (kMaxW / 8) <= (1 << 14), "a blur list entry keeps the group in 14 bits");
 
 // shared memory of frame_components_kernel (one frame per CTA: close -> components, statistics, labels)

@@ -8,7 +8,7 @@
 //   with named barriers (full / empty per buffer); everything else the roles touch is disjoint shared memory.
 // extract_sweep_kernel: the same sweep warps on their own, plus a scalar warp (one frame behind: info record, byte
 //   threshold for the hot-quad ballots) and a producer warp (TMA bulk copies of the frame rows into a shared-memory ring);
-//   frame_mask_kernel / frame_components_kernel / region_variance_kernel then do the per-frame stages one CTA (warp) per frame.
+//   frame_regions_kernel / frame_components_kernel / region_variance_kernel then do the per-frame stages one CTA (warp) per frame.
 #include "cptrack_kernels.cuh"
 
 namespace cpt {
@@ -433,7 +433,7 @@ __device__ void component_warps(const KernelArgs &a, Smem &s, const cpt_clip &cl
 // BORDER_REFLECT_101) in packed 16-bit lanes and threshold `> ith` -> one byte of the bit rows in s.M[buf].
 // Only outputs of the marked quads (q2: one bit per quad of the group) are evaluated: the others cannot exceed the threshold (every input
 // of their window is <= ith) and their windows may reach inputs that were not refreshed.
-// u_row0: image row held by the first row of s.U (frame_mask_kernel keeps one band of rows; 0 everywhere else); or_bits:
+// u_row0: image row held by the first row of s.U (frame_regions_kernel keeps one band of rows; 0 everywhere else); or_bits:
 // the byte is OR-ed into the mask (bands overlap) instead of stored.
 template <class SM>
 __device__ __forceinline__ void blur_group(SM &s, const Geometry &g, int grp, uint32_t q2, int buf, int ith, int u_row0 = 0,
@@ -519,110 +519,14 @@ __device__ __forceinline__ void normalise_group(SM &s, const float *F, int grp, 
     normalise_values(s, f0, f1, grp, ac, gmn, gmx, nmagic, nshift, u_global, u_off);
 }
 
-// split path: the scalar warp signals "message f of this clip consumed, byte threshold published" on the shared-memory
-// barrier of the message's buffer (f & 1, one arrival per phase); a sweep warp that is ahead of it waits there in
-// hardware instead of spinning on a flag (a spinning warp takes issue slots from the warps it is waiting for)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// (the suspend-time hint keeps a waiting warp asleep instead of re-issuing try_wait: a spinning warp takes issue slots from
-// the warps it is waiting for)
-constexpr uint32_t kWaitHintNs = 4000;
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra.uni WAIT_DONE;\n"
-        "bra.uni WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// global -> shared bulk copy (TMA, 1-D): bytes a multiple of 16, both addresses 16-byte aligned; completion is
-// counted on the mbarrier
-// L2 policies: a fraction of the frame's lines is kept (evict_last) until the frame is read again, 45 frames later, as
-// P_old; that second read is marked evict_first
+// L2 policy of the bulk prefetch of the next frame: a fraction of its lines is kept (evict_last) until the frame is read
+// again, 45 frames later, as P_old
 __device__ __forceinline__ unsigned long long l2_policy_keep() {
     unsigned long long p;
     // (measured: 0.4 -> 33.9 ms, 1.0 -> 34.3 ms, evict_normal -> 34.5 ms, no hints at all -> 35.1 ms per step)
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.4;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ unsigned long long l2_policy_drop() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, unsigned long long *bar, unsigned long long pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// Split path: the frame rows of one sweep iteration (P and the rows of the frame leaving the window) are staged in shared
-// memory by a producer warp, kStages iterations ahead of the sweep warps (full / empty mbarrier per stage).  The ring
-// lives in the part of Smem only the mask / component warps of the single-kernel path use.
-constexpr int kStages = kPThreads > 800 ? 3 : (kPThreads > 640 ? 4 : (kPThreads < 600 ? 6 : 5));
-constexpr int kStageHalf = kPThreads * 8 + 2 * kMaxW;  // rows_per_it * W <= 4 * kPThreads pixels, plus one remapped row
-constexpr int kStageBytes = 2 * kStageHalf;  // P rows, then P_old rows
-struct SoloStage {
-    uint8_t data[kStages][kStageBytes];
-    unsigned long long full[kStages], empty[kStages];
-};
-static_assert(kStageHalf % 16 == 0, "bulk copies need 16-byte alignment");
-static_assert(sizeof(SoloStage) <= offsetof(Smem, c_rank) - offsetof(Smem, U), "the staging ring overlays U .. c_b");
-static_assert(offsetof(Smem, U) % 128 == 0, "staging ring alignment");
-__device__ __forceinline__ SoloStage &solo_stage(Smem &s) { return *reinterpret_cast<SoloStage *>(s.U); }
-
-// where a frame's iterations sit in the ring: iteration it of this frame is use number k0 + (s0 + it) / kStages of
-// stage (s0 + it) % kStages
-struct StageCtx {
-    int s0, k0, n_it;
-    long long *debug;  // phase-timing builds
-};
-static_assert(kStages - 1 + kQIter - 1 < 3 * kStages, "stage index by at most two subtractions");
-
-// the quad of iteration `it` from the ring (all threads of the warp call this; the warp releases the stage once read)
-template <bool kFrame>
-__device__ __forceinline__ void stage_load(Smem &s, const StageCtx &sc, int it, bool mine, int l4, int lane, uint2 &pw, uint2 &ow) {
-    pw = make_uint2(0, 0);
-    ow = make_uint2(0, 0);
-    if (!kFrame || it >= sc.n_it) return;
-    SoloStage &st = solo_stage(s);
-    const int q = sc.s0 + it;
-    const int wrap = q >= 2 * kStages ? 2 : (q >= kStages ? 1 : 0);
-    const int stage = q - wrap * kStages;
-#ifdef CPT_PHASE_TIMING
-    const long long w0_ = clock64();
-#endif
-    mbar_wait(&st.full[stage], (uint32_t)(sc.k0 + wrap) & 1u);
-#ifdef CPT_PHASE_TIMING
-    if (threadIdx.x == 0 && sc.debug) atomicAdd((unsigned long long *)&sc.debug[(blockIdx.x % 128u) * 32 + 5], (unsigned long long)(clock64() - w0_));
-#endif
-    if (mine) {
-        pw = *reinterpret_cast<const uint2 *>(st.data[stage] + l4 * 2);
-        ow = *reinterpret_cast<const uint2 *>(st.data[stage] + kStageHalf + l4 * 2);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&st.empty[stage]);  // (release: the loads above have completed)
-}
-
 // ------------------------------------------------------------------------------------------------
 // The fused pixel sweep.  For every owned quad (4 pixels) in one pass over the on-chip state:
 //   [update]  WeightedBackground.process_frame for the PREVIOUS frame (K7): A = floor(S / cnt),
@@ -687,7 +591,6 @@ struct SweepThread {
     int p4_last;     // pixel index of the thread's quad in the last iteration (kQIter - 1), see sweep_thread_init
     bool has_last;   // the thread has a quad in the last iteration
     bool skip0;      // the thread's quad of iteration 0 was handed to another thread (balanced 160x120 mapping)
-    int l4_0, l4_last;  // split path: the quad's pixel offset inside the staged rows of an iteration (last iteration: l4_last)
     int lane;
     bool active;     // ptid < rows_per_it * qpr
     bool prefetch;   // first quad of a 128-byte line
@@ -786,11 +689,10 @@ __device__ __forceinline__ int sweep_p4(const SweepThread &th, int it, int strid
 // loop whose maxima go through local memory (first frame, tail pass, exact keep test: once per clip).
 // kLepton: the geometry is 160x120 with a 1-pixel border (20 rows x 40 quads per iteration), so every offset of the
 // straight-line code is an immediate.
-// kSolo: the split path -- the quads come from the staging ring (stage_load) instead of global memory.
-template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled, bool kLepton, bool kSolo>
+template <bool kUpdate, bool kFrame, bool kPacked, int kTable, bool kStats, bool kUnrolled, bool kLepton>
 __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
                                             const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
-                                            uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter], const StageCtx &sc) {
+                                            uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
     const Geometry &g = a.g;
     const int owned_rows = kLepton ? 118 : g.H - 2 * g.edge;
     constexpr int kLeptonRows = kPThreads / 40;  // rows per iteration at 160 pixels
@@ -799,22 +701,6 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
     const int stride = kLepton ? kLeptonRows * 160 : th.stride;
     uint2 nb_top = make_uint2(0, 0), nb_bottom = make_uint2(0, 0);
     if (kUnrolled) {
-        if (kSolo) {
-            // the border rows' pixels: two global loads per frame for two row groups, in flight across the whole sweep
-            uint2 pw_it, ow_it;
-#pragma unroll
-            for (int it = 0; it < kQIter; ++it) {
-                gmaxq[it] = kNoQuad;
-                const bool mine = sweep_mine<kLepton>(th, it, rows_per_it, owned_rows);
-                stage_load<kFrame>(s, sc, it, mine, it == kQIter - 1 ? th.l4_last : th.l4_0, th.lane, pw_it, ow_it);
-                if (!mine) continue;
-                uint2 nb;
-                gmaxq[it] = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw_it, ow_it,
-                                                                                  fcur, lab_frame, acc, nb);
-                if (it == 0) nb_top = nb;
-                if (it == th.last_it) nb_bottom = nb;
-            }
-        } else {
         // software pipeline: the global loads of quad it + 1 are in flight while quad it is processed
         // (two quads ahead, or the next frame's first quad across the message, cost registers the 80-register budget of
         // 21 warps does not have: measured slower)
@@ -834,7 +720,6 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
             if (it == 0) nb_top = nb;
             if (it == th.last_it) nb_bottom = nb;
         }
-        }
     } else {
 #pragma unroll
         for (int j = 0; j < kQIter; ++j) gmaxq[j] = kNoQuad;
@@ -842,9 +727,8 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
         for (int it = 0; it < kQIter; ++it) {
             const bool mine_it = sweep_mine<false>(th, it, rows_per_it, owned_rows);
             uint2 nb, pw, ow;
-            if (kSolo) stage_load<kFrame>(s, sc, it, mine_it, it == kQIter - 1 ? th.l4_last : th.l4_0, th.lane, pw, ow);
             if (!mine_it) continue;
-            if (!kSolo) load_quad<kFrame>(sweep_p4(th, it, stride), P, Pold, pw, ow);
+            load_quad<kFrame>(sweep_p4(th, it, stride), P, Pold, pw, ow);
             const int hi = sweep_quad<kUpdate, kFrame, kPacked, kTable, kStats>(s, wt, th, m, sweep_p4(th, it, stride), pw, ow, fcur,
                                                                                 lab_frame, acc, nb);
             // (selects, not an indexed store: the maxima stay in registers in every instantiation)
@@ -878,22 +762,22 @@ __device__ __forceinline__ void pixel_sweep(const KernelArgs &a, Smem &s, const 
 }
 
 // Runtime mode -> instantiation.
-template <bool kStats, bool kSolo>
+template <bool kStats>
 __device__ __forceinline__ void pixel_sweep_dispatch(const KernelArgs &a, Smem &s, const WeightTable &wt, const SweepThread &th,
                                                      const SweepMode &m, const uint16_t *P, const uint16_t *Pold, float *fcur,
-                                                     uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter], const StageCtx &sc) {
+                                                     uint8_t *lab_frame, SweepAcc &acc, int (&gmaxq)[kQIter]) {
     const bool steady = m.update && m.frame && !m.slow && !m.first_mean && a.g.W == 160 && a.g.H == 120 && a.g.edge == 1;
     constexpr bool kUnroll = true;
     if (steady && m.table == 0)
-        pixel_sweep<true, true, true, 0, kStats, kUnroll, true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
+        pixel_sweep<true, true, true, 0, kStats, kUnroll, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (steady && m.table == 1)
-        pixel_sweep<true, true, true, 1, kStats, kUnroll, true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
+        pixel_sweep<true, true, true, 1, kStats, kUnroll, true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (!m.update)
-        pixel_sweep<false, true, false, 2, kStats, false, false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
+        pixel_sweep<false, true, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else if (m.frame)
-        pixel_sweep<true, true, false, 2, kStats, false, false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
+        pixel_sweep<true, true, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
     else
-        pixel_sweep<true, false, false, 2, kStats, false, false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
+        pixel_sweep<true, false, false, 2, kStats, false, false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
 }
 
 // a frame's sums / extrema, folded by the sweep warps (one shared-memory atomic per value and warp)
@@ -924,60 +808,14 @@ __device__ __forceinline__ uint32_t sweep_reduce_store(FrameMsg &fm, int lane, c
     return bmax;
 }
 
-// split path: the warp's partial results as one row of the message buffer's table (Smem::red_u viewed as
-// [2][kPWarps][8]); the scalar warp folds the rows, so the sweep warps issue no atomics.  Returns the warp's background maximum.
-__device__ __forceinline__ uint32_t sweep_reduce_partials(uint32_t *row, int lane, const SweepAcc &acc, bool want_stats) {
-    const uint32_t psum = __reduce_add_sync(0xffffffffu, acc.psum), bsum = __reduce_add_sync(0xffffffffu, acc.bsum);
-    const uint32_t changed = __reduce_or_sync(0xffffffffu, acc.changed);
-    const int fmin = __reduce_min_sync(0xffffffffu, acc.fmin), fmax = __reduce_max_sync(0xffffffffu, acc.fmax);
-    const uint32_t bmax = __reduce_max_sync(0xffffffffu, max(acc.bmax2 & 0xffffu, acc.bmax2 >> 16));
-    uint32_t v = psum;                       // slot order: FrameMsg::red[0..7]
-    v = lane == 1 ? (uint32_t)fmin : v;
-    v = lane == 2 ? (uint32_t)fmax : v;
-    v = lane == 6 ? bsum : v;
-    v = lane == 7 ? changed : v;
-    if (want_stats) {
-        const int pmin = __reduce_min_sync(0xffffffffu, acc.pmin), pmax = __reduce_max_sync(0xffffffffu, acc.pmax);
-        const uint32_t fabs_sum = __reduce_add_sync(0xffffffffu, acc.fabs_sum);
-        v = lane == 3 ? (uint32_t)pmin : v;
-        v = lane == 4 ? (uint32_t)pmax : v;
-        v = lane == 5 ? fabs_sum : v;
-    }
-    if (lane < 8) row[lane] = v;
-    return bmax;
-}
-static_assert(2 * kPWarps * 8 <= (int)(sizeof(Smem::red_u) / sizeof(uint32_t)), "the partial-result table fits Smem::red_u");
-
 // ================================================================================================
 // sweep warps: the recurrence.  Per frame: fused sweep -> fold the frame's sums into the message of the mask
 // warps -> hot-quad ballots against a PREDICTED bound (the mask warps compute the true one; if the prediction
 // turns out too high they fall back to dense work, so the ballots are always a superset) -> next frame.
 // ================================================================================================
-// split path: the quad maxima this thread stored for frame `of` (message buffer bb) against the byte threshold the scalar
-// warp published -> ballot words for frame_mask_kernel (layout: cptrack_kernels.cuh, kHotWords)
-__device__ __forceinline__ void solo_hot_words(const KernelArgs &a, const Smem &s, size_t of, int bb, int ptid, int lane, int warp) {
-    static_assert(kQIter <= 32, "one lane per sweep iteration");
-    const int tu = s.tu_pub[bb];
-    if (tu == 0) return;  // no usable bound: the frame is processed densely
-    uint32_t mine = 0;
-#pragma unroll
-    for (int it = 0; it < kQIter; ++it) {
-        const unsigned mbits = __ballot_sync(0xffffffffu, (int)s.qmax8[it * kPThreads + ptid] >= tu - 128);
-        if (lane == it) mine = mbits;
-    }
-    if (lane < kQIter) a.hot[of * kHotStride + warp * kQIter + lane] = mine;
-}
-
-// wait until the scalar warp has finished message f of this clip
-__device__ __forceinline__ void solo_wait_done(Smem &s, int f) {
-    mbar_wait(&s.done_bar[f & 1], (uint32_t)(f >> 1) & 1u);
-}
-
-// kSolo: the split path (extract_sweep_kernel) -- the only other role is the scalar warp, which runs one frame behind
-template <bool kSolo>
 __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, int ptid, float *scratch,
                             uint8_t *st_raw) {
-    constexpr int kAll = kSolo ? kSThreads : kThreads;
+    constexpr int kAll = kThreads;
     const Geometry &g = a.g;
     const int lane = ptid & 31, warp = ptid >> 5;
     const int W = g.W, npx = g.npx;
@@ -993,31 +831,12 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
     int frames_seen = 0;
 
     // ---------------------------------------------------------------- init / resume
-    const int n_it = (g.H - 2 * g.edge + g.rows_per_it - 1) / g.rows_per_it;  // sweep iterations that hold rows
-    if (!kSolo)
-        for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
+    for (int i = ptid; i < 2 * kMaxWords; i += kPThreads) (&s.M[0][0])[i] = 0;
     for (int i = ptid; i < kSmemWeights; i += kPThreads) s.wthr[i] = (i <= wt.max_count) ? __ldg(wt.thr + i) : 0xffffu;  // beyond the table: never keep
     if (ptid < 2) frame_msg_reset(s.fm[ptid]);
     if (ptid == 0) {
         s.fth_latest = INT32_MIN;
         s.bcast_i[10] = 0;
-        if (kSolo) {
-            // fresh phase counters for this clip (every thread of the CTA is between clips here)
-            SoloStage &st = solo_stage(s);
-            if (s.done_bar_live) {
-                mbar_inval(&s.done_bar[0]);
-                mbar_inval(&s.done_bar[1]);
-                for (int i = 0; i < kStages; ++i) { mbar_inval(&st.full[i]); mbar_inval(&st.empty[i]); }
-            }
-            mbar_init(&s.done_bar[0], 1);
-            mbar_init(&s.done_bar[1], 1);
-            for (int i = 0; i < kStages; ++i) {
-                mbar_init(&st.full[i], 1);         // the producer's arrive.expect_tx
-                mbar_init(&st.empty[i], kPWarps);  // one arrival per sweep warp
-            }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            s.done_bar_live = 1;
-        }
     }
     if (clip.flags & CPT_CLIP_RESUME) {
         bar_sync(BAR_P, kPThreads);
@@ -1078,26 +897,22 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         th.has_last = th.active && r0 + (kQIter - 1) * g.rows_per_it <= last_row;
         th.p4_last = th.p4_0 + (kQIter - 1) * th.stride;
         th.skip0 = false;
-        th.l4_0 = th.l4_last = r0 * W + qx * 4;
         th.lane = lane;
         if (g.balanced) {
             // 160x120: 118 owned rows + 2 border rows.  The owners of the first and last owned row also produce a border
             // row, so each hands one of its rows to a group whose last iteration is free: no thread has more than 8
             // quads per frame (owned_row_slot() is the inverse map).
             if (r0 == 0) th.has_last = false;
-            if (r0 == g.bal_a_r) { th.has_last = true; th.p4_last = (g.bal_a_oy + g.edge) * W + qx * 4; th.l4_last = qx * 4; }
+            if (r0 == g.bal_a_r) { th.has_last = true; th.p4_last = (g.bal_a_oy + g.edge) * W + qx * 4; }
             if (r0 == g.bal_b_oy) th.skip0 = true;  // (the last owned row's group index equals its first row's index)
-            // (the producer appends that row after the last iteration's own rows)
             if (r0 == g.bal_b_r) {
                 th.has_last = true;
                 th.p4_last = (g.bal_b_oy + g.edge) * W + qx * 4;
-                th.l4_last = (g.H - 2 * g.edge - (kQIter - 1) * g.rows_per_it) * W + qx * 4;
             }
         }
     }
     bar_sync(BAR_INIT, kAll);  // the state and the initial average are in place: the other roles may start
 
-    int last_t = -1;
     uint32_t magic_cnt = 0, magic_val = 0;
     bool slow = true;  // the first update of a launch takes the exact path (no background extrema yet)
     // t == n_frames is the tail pass: only the background update of the last frame
@@ -1142,50 +957,10 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         // ------------------------------------------------------------ fused sweep (K7 of frame t-1, K1/K8 of frame t)
         SweepAcc acc;
         int gmaxq[kQIter];
-        StageCtx sc;
-        sc.n_it = n_it;
-        sc.debug = a.debug;
-        sc.s0 = (t * n_it) % kStages;  // (every t < n_frames is a frame: frame t's iterations are uses t * n_it ...)
-        sc.k0 = (t * n_it) / kStages;
-        if (want_stats) pixel_sweep_dispatch<true, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
-        else pixel_sweep_dispatch<false, kSolo>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq, sc);
+        if (want_stats) pixel_sweep_dispatch<true>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
+        else pixel_sweep_dispatch<false>(a, s, wt, th, m, P, Pold, fcur, lab_frame, acc, gmaxq);
         CPT_TICK(ptid == 0, 14);  // sweep
         // ------------------------------------------------------------ message to the mask warps / the scalar warp
-        last_t = t;
-        if (kSolo) {
-            // the scalar warp has had this whole sweep for frame t-1: its byte threshold turns the maxima stored for that
-            // frame into ballot words, and its message buffer (used again at t+1) is free
-            // (a flag, not a barrier: the sweep warps are not forced into lock step at the end of every frame; they can
-            // drift by less than two frames, which also keeps the FULL barriers' phases apart)
-            if (t >= 1) {
-                solo_wait_done(s, t - 1);
-                solo_hot_words(a, s, (size_t)(clip.out_offset + t - 1), b ^ 1, ptid, lane, warp);
-            }
-            CPT_TICK(ptid == 0, 6);   // wait for the scalar warp + ballots
-            FrameMsg &fm = s.fm[b];
-            const uint32_t warp_bmax = sweep_reduce_partials(s.red_u + (b * kPWarps + warp) * 8, lane, acc, want_stats);
-            const int latest = *(volatile int32_t *)&s.fth_latest;
-            const int qref = (latest == INT32_MIN) ? 0 : latest;
-            if (ptid == 0) {
-                fm.qref = qref;
-                fm.update = m.update;
-                fm.is_frame = is_frame;
-            }
-            {
-                const int k_next = min(frames_seen + 1, wt.max_count);
-                const uint32_t thr_cap = (k_next < wt.linear_upto) ? (uint32_t)k_next + 1u
-                                         : ((k_next < kSmemWeights ? s.wthr[k_next] : __ldg(wt.thr + k_next)) & 0xffffu);
-                slow = warp_bmax + thr_cap > 65535u;
-            }
-            if (is_frame) {
-#pragma unroll
-                for (int it = 0; it < kQIter; ++it) s.qmax8[it * kPThreads + ptid] = quad_byte(gmaxq[it], qref);
-            }
-            if (m.update) ++frames_seen;
-            bar_arrive(BAR_SM_FULL + b, kPThreads + 32);
-            CPT_TICK(ptid == 0, 2);   // message
-            continue;
-        }
         if (t >= 2) bar_sync(BAR_SM_EMPTY + b, kPThreads + kMThreads);  // they are done with the message of frame t-2
         if (t >= 1 && is_frame) bar_sync(BAR_QFREE, kPThreads + kMThreads);  // ... and with the quad maxima of frame t-1
         CPT_TICK(ptid == 0, 6);   // wait for the message buffer
@@ -1217,10 +992,6 @@ __device__ void sweep_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, 
         CPT_TICK(ptid == 0, 2);   // message
     }
 
-    if (kSolo && last_t >= 0) {
-        solo_wait_done(s, last_t);
-        if (last_t < clip.n_frames) solo_hot_words(a, s, (size_t)(clip.out_offset + last_t), last_t & 1, ptid, lane, warp);
-    }
     // ---------------------------------------------------------------- save state
     // (the other roles read the resumed state's filtered frame and header until their last frame is done)
     bar_sync(BAR_DONE, kAll);
@@ -1545,7 +1316,7 @@ __global__ void __launch_bounds__(kThreads, 1) extract_clips_kernel(const Kernel
         float *scratch = a.scratch ? a.scratch + (size_t)blockIdx.x * 8 * npx : nullptr;
         const StateHeader *st_hdr = reinterpret_cast<const StateHeader *>(st_raw);
         if (tid < kPThreads) {
-            sweep_warps<false>(a, s, clip, tid, scratch, st_raw);
+            sweep_warps(a, s, clip, tid, scratch, st_raw);
         } else if (tid < kPThreads + kMThreads) {
             mask_warps(a, s, clip, tid - kPThreads, scratch, st_hdr);
         } else {
@@ -1563,7 +1334,7 @@ __device__ __forceinline__ unsigned long long quad_row_bits_bytes(const Geometry
     return bits;
 }
 
-// ---- components of a small mask inside frame_mask_kernel's CTA ---------------------------------------------------------
+// ---- components of a small mask inside frame_regions_kernel's CTA ---------------------------------------------------------
 // The same algorithm as components_of_frame (close, runs, unions with the row above, statistics, OpenCV label order, label
 // runs, region records), restricted to the rows [r0, r1] the mask stage can have set and sized for the masks real frames
 // have: run ids are (row of the extent) * rpr + index with rpr = min(80, 2048 / rows), at most kLeanSlots components.
@@ -1785,7 +1556,7 @@ __device__ __forceinline__ int div_magic(int i, int d, uint32_t magic) { return 
 // with the band's normalised bytes in a 6.4 kB window of shared memory (no full-frame image, no work lists): small CTAs
 // with little shared memory, so that many frames are resident per SM and hide each other's dependent loads.  Bands
 // overlap by their halos; both compute the same bits there and OR them into the mask.
-__global__ void __launch_bounds__(kFThreads, kFMinBlocks) frame_mask_kernel(const KernelArgs a, long long total_frames) {
+__global__ void __launch_bounds__(kFThreads, kFMinBlocks) frame_regions_kernel(const KernelArgs a, long long total_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MaskSmem &s = *reinterpret_cast<MaskSmem *>(smem_raw);
     const Geometry &g = a.g;
@@ -1819,7 +1590,7 @@ __global__ void __launch_bounds__(kFThreads, kFMinBlocks) frame_mask_kernel(cons
     // nothing can reach the threshold (no strip holds a hot quad): the mask is empty, info.n_components stays 0
     if (no_fg || (!dense && hdr.w == 0u)) return;
     const int8_t *qb = a.qbytes + (size_t)o * (g.H * g.qpr);
-    const int NS = g.n_strips, wpr = g.qpr >> 2;  // words of quad bytes per row (rows of whole words: qpr % 4 == 0)
+    const int wpr = g.qpr >> 2;  // words of quad bytes per row (rows of whole words: qpr % 4 == 0)
     const bool wordq = (g.qpr & 3) == 0;
     const unsigned long long rowmask = g.qpr >= 64 ? ~0ull : (1ull << g.qpr) - 1ull;
     const uint32_t wmagic = g.qw_magic;
@@ -2050,7 +1821,7 @@ __device__ __forceinline__ void region_variance_warp(const Geometry &g, cpt_regi
     }
 }
 
-// Split path, third launch: the frames frame_mask_kernel could not finish in place (a.fallback: very busy masks -- more than
+// Split path, third launch: the frames frame_regions_kernel could not finish in place (a.fallback: very busy masks -- more than
 // kLeanSlots components or more runs in a row than its run table holds).  The stored mask -> close -> components, statistics,
 // labels (K4, K5) with the full-size tables; the variances are left to region_variance_kernel.  A small persistent grid
 // over the list, which is nearly always empty.

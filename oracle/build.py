@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "liboracle.so")
-SOURCES = [os.path.join(HERE, "cptrack_oracle.c"), os.path.join(HERE, "preprocess_oracle.c")]
+SOURCES = [os.path.join(HERE, "cptrack_oracle.c")]  # (the preprocessing and motion oracles are numpy: preprocess_oracle.py, motion_oracle.py)
 
 
 def build(force=False):

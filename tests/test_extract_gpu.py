@@ -103,7 +103,7 @@ def test_kernel_matches_oracle_and_reference(extractor, name, plan):
 
 @pytest.mark.parametrize("name", RAW)
 def test_split_path_matches_oracle_and_reference(extractor, name):
-    """The same clips through the split path (no state record: extract_sweep_kernel + frame_mask_kernel +
+    """The same clips through the split path (no state record: extract_sweep_kernel + frame_regions_kernel +
     frame_components_kernel + region_variance_kernel)."""
     from oracle import oracle as orc
 
