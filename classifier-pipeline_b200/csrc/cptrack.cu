@@ -592,7 +592,6 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
         for (int i = c0; i < c1; ++i) {
             const cpt_clip &k = h_clips[i];
             if (k.flags & CPT_CLIP_RESUME) return fail(CPT_ERR_INVALID, "CPT_CLIP_RESUME is not supported by the host-staged call");
-            if (k.flags & CPT_CLIP_DENOISE) return fail(CPT_ERR_UNSUPPORTED, "CPT_CLIP_DENOISE is not supported by the host-staged call");
             if (k.n_frames < 0 || k.frame_offset < 0 || k.init_offset < 0 || k.out_offset < 0 || k.ring_frames != 0)
                 return fail(CPT_ERR_INVALID, "clip %d: bad offsets", i);
             if (k.out_offset + k.n_frames > total_frames) return fail(CPT_ERR_INVALID, "clip %d: outputs exceed total_frames", i);
@@ -632,8 +631,10 @@ int cpt_extract_batch_host(cpt_ctx *c, const uint16_t *h_frames, const cpt_clip 
         CUDA_TRY(cudaEventRecord(c->ev_h2d[b], c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
         if (ch >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
+        int chunk_denoise = 0;  // (CPT_CLIP_DENOISE clips: the NLM, mask and component passes follow the chunk's launch)
+        for (int i = c0; i < c1; ++i) chunk_denoise |= (h_clips[i].flags & CPT_CLIP_DENOISE) ? 1 : 0;
         cpt_outputs out{c->stage_regions[b], c->stage_info[b], h_filtered ? c->stage_filtered[b] : c->scratch_filtered,
-                        h_labels ? c->stage_labels[b] : nullptr, sp.out_hi - sp.out_lo, 0, 1};
+                        h_labels ? c->stage_labels[b] : nullptr, sp.out_hi - sp.out_lo, chunk_denoise, 1};
         rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream,
                             sp.out_hi - sp.out_lo);
         if (rc) return rc;
@@ -689,7 +690,7 @@ int cpt_extract_batch_cptv_host(cpt_ctx *c, const uint8_t *h_stream, uint64_t st
         }
         for (int i = c0; i < c1; ++i) {
             const cpt_clip &k = h_clips[i];
-            if (k.flags & (CPT_CLIP_RESUME | CPT_CLIP_DENOISE)) return fail(CPT_ERR_UNSUPPORTED, "clip %d: resume / denoise are not supported by the host-staged calls", i);
+            if (k.flags & CPT_CLIP_RESUME) return fail(CPT_ERR_UNSUPPORTED, "clip %d: CPT_CLIP_RESUME is not supported by the host-staged calls", i);
             if (k.n_frames < 0 || k.out_offset < 0 || k.ring_frames != 0) return fail(CPT_ERR_INVALID, "clip %d: bad offsets", i);
             if (k.frame_offset < h_clip_first[i] || k.frame_offset + k.n_frames > h_clip_first[i + 1] || k.init_offset < h_clip_first[i] ||
                 k.init_offset >= std::max(h_clip_first[i + 1], h_clip_first[i] + 1))
@@ -772,7 +773,9 @@ int cpt_extract_batch_cptv_host(cpt_ctx *c, const uint8_t *h_stream, uint64_t st
                                          c->pk_change, c->stream);
             if (rc) return rc;
         }
-        cpt_outputs out{c->stage_regions[b], c->stage_info[b], c->scratch_filtered, nullptr, sp.out_hi - sp.out_lo, 0, 1};
+        int chunk_denoise = 0;
+        for (int i = c0; i < c1; ++i) chunk_denoise |= (h_clips[i].flags & CPT_CLIP_DENOISE) ? 1 : 0;
+        cpt_outputs out{c->stage_regions[b], c->stage_info[b], c->scratch_filtered, nullptr, sp.out_hi - sp.out_lo, chunk_denoise, 1};
         rc = launch_extract(c, (const uint16_t *)c->stage_frames[b], c->d_clips + c0, c1 - c0, &out, nullptr, c->stream, sp.out_hi - sp.out_lo);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(c->ev_compute[b], c->stream));

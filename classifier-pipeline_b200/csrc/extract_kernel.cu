@@ -1121,6 +1121,8 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
         prev_fmax = st_hdr->prev_fmax;
         have_prev = st_hdr->have_prev;
     }
+    // frame-at-a-time denoise: the caller has put the previous frame's outputs at out_offset - 1
+    const bool prev_in_output = have_prev && (clip.flags & CPT_CLIP_PREV_IN_OUTPUT);
     for (int t = 0; t <= clip.n_frames; ++t) {
         CPT_TICK_START2(mtid == 0);
         const bool is_frame = t < clip.n_frames;
@@ -1154,7 +1156,7 @@ __device__ void mask_warps(const KernelArgs &a, Smem &s, const cpt_clip &clip, i
             // close and components run as separate wide passes over all frames (nlm_denoise_kernel, mask_components_kernel)
             uint8_t *u_frame = a.u8_frames + o * npx;
             for (int grp = mtid; grp < g.groups; grp += kMThreads) normalise_group(s, fcur, grp, ac, gmn, gmx, nmagic, nshift, u_frame);
-            if (mtid == 0) a.info[o].reserved[1] = (t > 0) ? 2 : 1;  // 2: the previous filtered image is frame o - 1
+            if (mtid == 0) a.info[o].reserved[1] = (t > 0 || prev_in_output) ? 2 : 1;  // 2: the previous filtered image is frame o - 1
             if (sweep_comes_back) bar_arrive(BAR_SM_EMPTY + b, kPThreads + kMThreads);
             if (t + 1 < clip.n_frames) bar_arrive(BAR_QFREE, kPThreads + kMThreads);
             continue;

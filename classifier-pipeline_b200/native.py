@@ -17,6 +17,7 @@ CLIP_RESUME = 2
 CLIP_DENOISE = 4
 CLIP_FRAME_STATS = 8
 CLIP_SKIP_FIRST_UPDATE = 16
+CLIP_PREV_IN_OUTPUT = 32
 MAX_COMPONENTS = 255
 MEAN_FRAMES = 45
 HAS_NLM = True  # cv2.fastNlMeansDenoising on the device (batched extraction; not the frame-at-a-time streaming path)

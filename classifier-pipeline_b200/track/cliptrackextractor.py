@@ -331,10 +331,7 @@ class ClipTrackExtractor(ClipTracker):
         ``background_alg.process_frame(mean of the last <=45 frames)`` -- into the same launch."""
         import torch
 
-        if getattr(self.config, "denoise", False):
-            raise native.NativeError(
-                "TrackingConfig.denoise=True is built for whole clips (parse_clip / parse_clips); the frame-at-a-time path "
-                "runs the Pi configuration (denoise: false, pi-classifier.yaml:3)")
+        denoise = bool(getattr(self.config, "denoise", False))
         st = self._stream
         if st is None or st["background_alg"] is not self.background_alg:
             st = self._open_stream(clip)
@@ -353,7 +350,19 @@ class ClipTrackExtractor(ClipTracker):
         c["ring_frames"] = RING_FRAMES
         c["out_offset"] = 0
         keep_images = self.keep_frames or self.calculate_filtered
-        out = eng.extract_device(st["ring"], c, keep_filtered=keep_images, keep_labels=keep_images,
+        oi = 0  # output index of this frame
+        if denoise:
+            # TrackingConfig.denoise (cliptracker.py:116-117): the NLM, mask, component and variance passes follow the launch and
+            # read the previous frame's filtered image and info at output index out_offset - 1 -- the frame goes to index 1
+            # and the previous call's outputs are moved to index 0 first
+            oi = 1
+            c["out_offset"] = 1
+            c["flags"] |= native.CLIP_DENOISE | native.CLIP_PREV_IN_OUTPUT
+            prev = st["out"]
+            if t > 0 and prev.get("filtered") is not None and prev["filtered"].shape[0] == 2:
+                prev["filtered"][0].copy_(prev["filtered"][1])
+                prev["info"][0].copy_(prev["info"][1])
+        out = eng.extract_device(st["ring"], c, keep_filtered=keep_images or denoise, keep_labels=keep_images,
                                  d_state=self.background_alg.d_state, out=st["out"])
         medians = None
         if self.calc_stats:
@@ -361,9 +370,9 @@ class ClipTrackExtractor(ClipTracker):
             medians = st["median"].cpu().numpy()
         self.background_alg.invalidate()
         res = dict(
-            regions=eng.regions_numpy(out["regions"])[:1], info=eng.info_numpy(out["info"])[:1],
-            filtered=out["filtered"][:1].cpu().numpy() if keep_images else None,
-            labels=out["labels"][:1].cpu().numpy() if keep_images else None,
+            regions=eng.regions_numpy(out["regions"])[oi:oi + 1], info=eng.info_numpy(out["info"])[oi:oi + 1],
+            filtered=out["filtered"][oi:oi + 1].cpu().numpy() if keep_images else None,
+            labels=out["labels"][oi:oi + 1].cpu().numpy() if keep_images else None,
             medians=medians, have_prev=t > 0,
         )
         if int(res["info"]["n_components"][0]) > eng.max_regions:

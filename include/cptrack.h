@@ -38,6 +38,9 @@ extern "C" {
 #define CPT_CLIP_FRAME_STATS 8u       /* ClipStats.add_frame, clip.py:474-487 (min/max/median/mean, sum|filtered|) */
 #define CPT_CLIP_SKIP_FIRST_UPDATE 16u /* RawDatabase.load_frames, ml_tools/rawdb.py:84-122: the frame that initialised the
                                           background is also the first kept frame and is not followed by a background update */
+#define CPT_CLIP_PREV_IN_OUTPUT 32u   /* with CPT_CLIP_RESUME | CPT_CLIP_DENOISE (frame-at-a-time denoise): the caller has put the
+                                          previous frame's filtered image and cpt_frame_info at output index out_offset - 1, where
+                                          the passes that follow the denoise (mask, components, variance) look for them */
 
 typedef struct cpt_ctx cpt_ctx;
 
@@ -99,7 +102,7 @@ typedef struct {
                                 0 = unknown: they are computed inside the extraction kernel */
     int32_t denoise;         /* 1: some clip carries CPT_CLIP_DENOISE -- the normalised images then go through
                                 cv2.fastNlMeansDenoising and the mask / component passes after the recurrence
-                                (needs total_frames and d_filtered; not with CPT_CLIP_RESUME) */
+                                (needs total_frames and d_filtered; with CPT_CLIP_RESUME see CPT_CLIP_PREV_IN_OUTPUT) */
     int32_t no_resume;       /* 1: no clip of this launch carries CPT_CLIP_RESUME (d_state, if given, is only written).
                                 Lets a launch with a state record take the split plan of DESIGN.md section 3.1; 0 is always safe */
 } cpt_outputs;
@@ -164,7 +167,8 @@ int cpt_extract_batch(cpt_ctx *ctx, const uint16_t *d_frames, const cpt_clip *d_
 
 /* Same call with HOST buffers: stages frames to the device in chunks of clips on two streams
  * (copy / compute overlapped) and copies regions + info (and filtered / labels when
- * requested) back.  h_frames should be pinned (cpt_host_alloc_pinned) for full PCIe speed. */
+ * requested) back.  h_frames should be pinned (cpt_host_alloc_pinned) for full PCIe speed.  CPT_CLIP_DENOISE clips are
+ * allowed (the denoise passes run per chunk); CPT_CLIP_RESUME is not. */
 int cpt_extract_batch_host(cpt_ctx *ctx, const uint16_t *h_frames, const cpt_clip *h_clips, int n_clips,
                            int64_t total_frames, cpt_region *h_regions, cpt_frame_info *h_info,
                            float *h_filtered, uint8_t *h_labels, int chunk_clips);

@@ -75,7 +75,7 @@ def test_clip_flags_match_header():
 
     text = open(os.path.join(ROOT, "include", "cptrack.h")).read()
     flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+CPT_CLIP_([A-Z_]+)\s+(\d+)u", text)}
-    assert set(flags) >= {"UPDATE_BACKGROUND", "RESUME", "DENOISE", "FRAME_STATS", "SKIP_FIRST_UPDATE"}
+    assert set(flags) >= {"UPDATE_BACKGROUND", "RESUME", "DENOISE", "FRAME_STATS", "SKIP_FIRST_UPDATE", "PREV_IN_OUTPUT"}
     for name, value in flags.items():
         assert getattr(native, "CLIP_" + name) == value, name
     assert len(set(flags.values())) == len(flags) and all(v & (v - 1) == 0 for v in flags.values())

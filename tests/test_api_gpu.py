@@ -98,6 +98,35 @@ def test_streaming_process_frame_matches_parse_clip():
     _check_frames_and_state(ext, clip, d, tracked)
 
 
+def test_streaming_process_frame_with_denoise_matches_the_reference():
+    """TrackingConfig.denoise=True (the reference's default) one frame at a time: the NLM, mask, component and variance passes
+    follow every launch, with the previous frame's outputs kept beside the current ones (CPT_CLIP_PREV_IN_OUTPUT); the tracks
+    are those the unmodified reference found with its default configuration."""
+    from classifier_pipeline_b200.config import Config
+    from classifier_pipeline_b200.cptv import CptvReader
+    from classifier_pipeline_b200.track.clip import Clip
+    from classifier_pipeline_b200.track.cliptrackextractor import ClipTrackExtractor
+    from classifier_pipeline_b200.track.track import Track
+
+    d, meta = helpers.load_golden("possum_nlm")
+    path = os.path.join(helpers.GOLDEN, "clips", "possum.cptv")
+    config = Config.get_defaults()
+    assert config.tracking["thermal"].denoise
+    ext = ClipTrackExtractor(config.tracking, False, cache_to_disk=False)
+    clip = Clip(config.tracking["thermal"], path)
+    ext.init_clip(clip)
+    Track._track_id = 1
+    reader = CptvReader(path)
+    reader.get_header()
+    for frame in iter(reader.next_frame, None):
+        if frame.background_frame:
+            continue
+        ext.process_frame(clip, frame, update_background=True)
+    ext.apply_track_filtering(clip)
+    clip.stats.completed()
+    assert_tracks_match_golden(clip, meta, d)
+
+
 def test_process_frame_leaves_the_background_to_the_caller():
     """As in the reference, process_frame never updates the background: a caller that drives background_alg itself the way
     _track_clip does (mean of the last 45 thermal frames after every frame, cliptrackextractor.py:167-176) gets parse_clip's

@@ -260,6 +260,7 @@ def test_resume_equals_one_shot(extractor):
 
 def test_host_staged_call_matches_device_call(extractor):
     import torch
+    from classifier_pipeline_b200 import native
     from classifier_pipeline_b200.batch import linear_clips
     from classifier_pipeline_b200.synthetic import make_clip
 
@@ -267,6 +268,7 @@ def test_host_staged_call_matches_device_call(extractor):
     slot0 = extractor.ctx.weight_table(0.1, max_frames=4096)
     slot1 = extractor.ctx.weight_table(1.0, max_frames=4096)
     clips = linear_clips([40] * 5, np.array([20, 50, 20, 50, 20]), np.array([slot0, slot1, slot0, slot1, slot0]))
+    clips["flags"][3] |= native.CLIP_DENOISE  # (one clip of the default configuration: its chunk runs the denoise passes)
     d_frames = torch.from_numpy(pix.view(np.int16)).cuda().view(torch.uint16)
     dev = extractor.extract_device(d_frames, clips, keep_filtered=True, keep_labels=True, out={})
     torch.cuda.synchronize()
