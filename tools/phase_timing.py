@@ -39,14 +39,13 @@ def main(clips=148, frames=300, exp=0, split=1):
     native.check(ex.ctx.lib.cpt_debug_phase_cycles(ex.ctx._h, buf, 0))
     total = clips * frames
     if split:
-        names = {7: "M header + info", 15: "M quad bytes -> hot rows", 4: "M marks + lists", 5: "M normalise", 8: "M blur + threshold",
-                 9: "M mask store", 11: "C header + mask words", 12: "C components",
-                 20: "C  close+reset+bar", 21: "C  run starts+bar", 22: "C  unions+bar", 23: "C  roots+bar", 24: "C  run stats+bar",
-                 25: "C  rank+bar", 26: "C  label writes", 27: "C  tail (records)"}
+        # frame_regions_kernel, thread 0 of every CTA (cycles include the waits at the CTA's barriers)
+        names = {7: "header + info", 15: "quad bytes -> hot rows", 4: "band record + work lists", 5: "normalise", 8: "blur + threshold",
+                 9: "components (close .. labels)"}
         for i, n in names.items():
             print("{:28s} {:9.0f} cycles/frame".format(n, buf[i] / total))
-        print("lists: normalise {:.1f} groups/frame, blur {:.1f}; frames reaching the mask store {:.4f}, frames with foreground {:.4f}".format(
-            buf[28] / total, buf[29] / total, buf[30] / total, buf[31] / total))
+        print("lists: normalise {:.1f} groups/frame, blur {:.1f}; frames that reach the components stage {:.4f}".format(
+            buf[28] / total, buf[29] / total, buf[30] / total))
         return
     names = {14: "S fused sweep", 5: "S  of which: waiting for staged rows", 6: "S wait scalars + ballots", 2: "S message",
              8: "producer: wait free stage", 9: "producer: issue copies",
