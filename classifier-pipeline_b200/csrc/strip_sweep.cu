@@ -80,9 +80,10 @@ struct StripThread {
     const uint8_t *src, *out;  // the quad inside ring slot 0: the row its state follows / the row it outputs
     int m[4];                  // 1: the pixel counts for the background sum (crop pixel of an owned row)
     int bs0;                   // -(m[0] + .. + m[3]) * kBias
-    float *fptr;               // the thread's quad in this frame's outputs (advanced after every frame)
-    uint8_t *lptr;
+    float *fptr;               // the thread's quad in the clip's first output frame; frame t: + t * npx (t * qstride for the
+    uint8_t *lptr;             // quad bytes) -- one wide multiply-add per store instead of three carried 64-bit pointers
     int8_t *qptr;
+    uint32_t npx, qstride;
 };
 
 // what is uniform over the CTA in one pass of the generic path
@@ -105,9 +106,11 @@ __device__ __forceinline__ uint2 lds8(const uint8_t *p) { return *reinterpret_ca
 // kTab: 0 thr = k + 1 (weight_add == 1; QuadState::lin form), 1 table in shared memory, 2 table in shared + global memory.
 // kSteady: update && frame && window full && cnt == 45 are compile-time facts.
 // bmax: largest bound of the table entries a counter can have reached (bounds only matter for backgrounds below them).
-template <int kTab, bool kStats, bool kSteady, bool kLabels>
+// kFull: every consumer thread owns a quad of the strip (12 rows x 40 quads at 160x120): no activity test, no defaults for
+// the sums of a thread without one.
+template <int kTab, bool kStats, bool kSteady, bool kLabels, bool kFull>
 __device__ __forceinline__ void strip_pass(StripSmem &s, const WeightTable &wt, const PassCtx &pc, const StripThread &th,
-                                           QuadState &q, PassOut &po, uint32_t cur_off, uint32_t old_off, int refb, int bmax) {
+                                           QuadState &q, PassOut &po, uint32_t cur_off, uint32_t old_off, int refb, int bmax, uint32_t t) {
     const bool is_frame = kSteady || pc.is_frame;
     uint2 pw = make_uint2(0, 0), pv = make_uint2(0, 0), ow = make_uint2(0, 0);
     if (is_frame) {
@@ -177,7 +180,7 @@ __device__ __forceinline__ void strip_pass(StripSmem &s, const WeightTable &wt, 
         q.S[2] = (uint32_t)dp2a_us(pw.y, kLoP, dp2a_us(ow.y, kLoN, (int)q.S[2]));
         q.S[3] = (uint32_t)dp2a_us(pw.y, kHiP, dp2a_us(ow.y, kHiN, (int)q.S[3]));
         const int lo = min(min(f[0], f[1]), min(f[2], f[3])), hi = max(max(f[0], f[1]), max(f[2], f[3]));
-        if (th.active) {
+        if (kFull || th.active) {
             po.psum = (uint32_t)dp2a_us(pv.x, kBoth, dp2a_us(pv.y, kBoth, 0));
             po.fmin = lo;
             po.fmax = hi;
@@ -187,12 +190,12 @@ __device__ __forceinline__ void strip_pass(StripSmem &s, const WeightTable &wt, 
                 po.pmax = max(max(p0, p1), max(p2, p3));
                 po.fabs_sum = (uint32_t)(abs(f[0] - kBias) + abs(f[1] - kBias) + abs(f[2] - kBias) + abs(f[3] - kBias));
             }
-            *reinterpret_cast<float4 *>(th.fptr) = make_float4(__int_as_float(f[0]) - kBiasF, __int_as_float(f[1]) - kBiasF,
+            *reinterpret_cast<float4 *>(th.fptr + (size_t)t * th.npx) = make_float4(__int_as_float(f[0]) - kBiasF, __int_as_float(f[1]) - kBiasF,
                                                                __int_as_float(f[2]) - kBiasF, __int_as_float(f[3]) - kBiasF);
-            if (kLabels) *reinterpret_cast<uint32_t *>(th.lptr) = 0u;
+            if (kLabels) *reinterpret_cast<uint32_t *>(th.lptr + (size_t)t * th.npx) = 0u;
             int b;
             asm("cvt.sat.s8.s32 %0, %1;" : "=r"(b) : "r"(hi - refb));
-            *th.qptr = (int8_t)b;
+            th.qptr[(size_t)t * th.qstride] = (int8_t)b;
         }
     }
 }
@@ -245,7 +248,7 @@ __device__ __forceinline__ void pass_report(StripSmem &s, const PassOut &po, int
     if (lane == 0) mbar_arrive_addr(done0 + (uint32_t)(bi << 3));  // (release: the ring reads and the row are done)
 }
 
-template <bool kStats, bool kLabels>
+template <bool kStats, bool kLabels, bool kFull>
 __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip &clip, int ci, int y0, int rows, int tid) {
     const Geometry &g = a.g;
     const int W = g.W, H = g.H, e = g.edge, qpr = g.qpr, npx = g.npx;
@@ -273,7 +276,8 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
     th.fptr = a.filtered + (size_t)clip.out_offset * npx + pix;
     th.lptr = a.labels + (size_t)clip.out_offset * npx + pix;   // (only dereferenced with kLabels)
     th.qptr = a.qbytes + (size_t)clip.out_offset * (H * qpr) + (y * qpr + qx);
-    const int qstride = H * qpr;
+    th.npx = (uint32_t)npx;
+    th.qstride = (uint32_t)(H * qpr);
 
     // ---- WeightedBackground first call (motiondetector.py:199-212): background = the initialising frame, edges replicated
     QuadState q;
@@ -304,14 +308,9 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
     auto frame_sync = [&](int t, int &refb) {
         // the frame's rows are in the ring; the reference its quad bytes are stored against was published by the fold warp
         // before the copy warp issued this frame (read after the acquire)
-        mbar_wait_addr(full0 + (uint32_t)((t & (kBarRing - 1)) << 3), (uint32_t)(t / kBarRing) & 1u);
+        mbar_wait_addr(full0 + (((uint32_t)t & (uint32_t)(kBarRing - 1)) << 3), ((uint32_t)t / (uint32_t)kBarRing) & 1u);
         // (the first kRefLag entries a pass reads hold the default: strip_sweep_kernel fills the ring before a unit starts)
         refb = *(volatile const int32_t *)&s.ref_ring[(t + 16 - kRefLag) & 15] + kBias;
-    };
-    auto after_frame = [&]() {
-        th.fptr += npx;
-        th.lptr += npx;
-        th.qptr += qstride;
     };
 
     // ---- generic pass (the first 45 frames, the tail pass, clips that do not update their background)
@@ -334,14 +333,13 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         const bool lin = pp.frames_seen < wt.linear_upto;
         quad_state_form(q, th, lin);
         PassOut po;
-        if (lin) strip_pass<0, kStats, false, kLabels>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax);
-        else strip_pass<2, kStats, false, kLabels>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax);
+        if (lin) strip_pass<0, kStats, false, kLabels, kFull>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax, (uint32_t)t);
+        else strip_pass<2, kStats, false, kLabels, kFull>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax, (uint32_t)t);
         if (pc.update) {
             ++pp.frames_seen;
             pp.bmax = max(pp.bmax, table_bound(pp.frames_seen));
         }
         pass_report<kStats>(s, po, t & (kBarRing - 1), warp, lane, done0);
-        if (pc.is_frame) after_frame();
         pass_advance(pp);
     };
     // ---- steady passes [pp.t, t_end) with one keep-test form
@@ -352,15 +350,15 @@ __device__ void strip_consumer(const KernelArgs &a, StripSmem &s, const cpt_clip
         PassCtx pc;
         pc.update = true; pc.is_frame = true; pc.window_full = true; pc.first_mean = false;
         pc.magic = kMagic45;
+#pragma unroll 2
         while (pp.t < t_end) {
             int refb;
             frame_sync(pp.t, refb);
             PassOut po;
-            strip_pass<kTab, kStats, true, kLabels>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax);
+            strip_pass<kTab, kStats, true, kLabels, kFull>(s, wt, pc, th, q, po, pp.cur_off, pp.old_off, refb, pp.bmax, (uint32_t)pp.t);
             ++pp.frames_seen;
             if (kTab != 0) pp.bmax = max(pp.bmax, table_bound(pp.frames_seen));
             pass_report<kStats>(s, po, pp.t & (kBarRing - 1), warp, lane, done0);
-            after_frame();
             pass_advance(pp);
         }
     };
@@ -520,12 +518,15 @@ __global__ void __launch_bounds__(kStripThreads, 1) strip_sweep_kernel(const Ker
         }
         __syncthreads();
         if (tid < kConsThreads) {
+            const bool full = rows * g.qpr == kConsThreads;  // every consumer thread owns a quad
             if (clip.flags & CPT_CLIP_FRAME_STATS) {
-                if (a.labels) strip_consumer<true, true>(a, s, clip, ci, y0, rows, tid);
-                else strip_consumer<true, false>(a, s, clip, ci, y0, rows, tid);
+                if (a.labels && full) strip_consumer<true, true, true>(a, s, clip, ci, y0, rows, tid);
+                else if (a.labels) strip_consumer<true, true, false>(a, s, clip, ci, y0, rows, tid);
+                else strip_consumer<true, false, false>(a, s, clip, ci, y0, rows, tid);
             } else {
-                if (a.labels) strip_consumer<false, true>(a, s, clip, ci, y0, rows, tid);
-                else strip_consumer<false, false>(a, s, clip, ci, y0, rows, tid);
+                if (a.labels && full) strip_consumer<false, true, true>(a, s, clip, ci, y0, rows, tid);
+                else if (a.labels) strip_consumer<false, true, false>(a, s, clip, ci, y0, rows, tid);
+                else strip_consumer<false, false, false>(a, s, clip, ci, y0, rows, tid);
             }
         } else if (tid < kConsThreads + 32) {
             strip_copier(a, s, clip, y0, rows, tid - kConsThreads);
