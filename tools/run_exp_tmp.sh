@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_extract_gpu.py tests/test_extract_long_gpu.py tests/test_cptv_gpu.py -m gpu -x -q 2>&1 | tail -2
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 300 python bench.py --no-cpu-baseline --tracks 0 --no-motion --e2e-clips 8 --no-extras > gpurun_out/b.json 2> gpurun_out/b.err
 python - <<PY
 import json
