@@ -2,7 +2,7 @@
 # Per-kernel durations of one full-size bench step (ncu launch list: cold-cache, serialised).  usage: bash tools/gpu_launches.sh <tag>
 tag=${1:-q}
 mkdir -p gpurun_out
-KERNELS='regex:extract_clips|extract_sweep|frame_mask|frame_components|region_variance'
+KERNELS='regex:extract_clips|strip_sweep|frame_scalars|frame_regions|frame_components|region_variance'
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -c 40 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 1 --tracks 0 --no-motion --no-cpu-baseline > gpurun_out/ncu_bench_$tag.log 2>&1
 python - <<PY
