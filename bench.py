@@ -54,7 +54,33 @@ class ClockSampler:
         self.stop = threading.Event()
         self.thread = threading.Thread(target=self.run, daemon=True)
 
+    def run_nvml(self):
+        """NVML from this process: a sample every 25 ms (an nvidia-smi process takes longer to start than a step to run)."""
+        import pynvml as nv
+
+        nv.nvmlInit()
+        index = self.index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:  # the CUDA ordinal counts visible devices only
+            ids = [v.strip() for v in vis.split(",")]
+            if index < len(ids) and ids[index].isdigit():
+                index = int(ids[index])
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = reasons(h)
+            self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            self.stop.wait(0.025)
+
     def run(self):
+        try:
+            return self.run_nvml()
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 out = subprocess.run(
