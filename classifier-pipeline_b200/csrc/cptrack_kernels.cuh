@@ -174,16 +174,19 @@ struct StripRec {
     int32_t ref_changed;  // (reference the strip's quad bytes were stored against) << 1 | (some background pixel changed)
 };
 static_assert(sizeof(StripRec) == 32, "two 16-byte vectors");
-// Per output frame, written by frame_scalars_kernel for the per-frame kernels.
-struct FrameHdr {
+// Per output frame, written by frame_scalars_kernel for frame_regions_kernel: one 64-byte line with everything the kernel
+// needs to know about the frame before it touches pixels.
+struct __align__(16) FrameHdr {
     uint32_t nmagic;   // (255 v) / range == (255 v * nmagic) >> nshift; 0: the fp32 divide
     int32_t nshift;
-    uint32_t flags;    // 1: valid, 2: first frame of its clip, 4: empty mask, 8: dense (no usable bound for the quad bytes)
+    uint32_t flags;    // kHdr*: valid, first frame of its clip, dense (no usable bound for the quad bytes), denoise clip
     uint32_t hot_strips;  // bit s: strip s may hold a hot quad
     int16_t theta[kMaxStrips];  // quad byte b of strip s is hot <=> b >= theta[s]
+    float threshold;   // cpt_frame_info::threshold, avg_change, norm_min, norm_max (K2)
+    int32_t avg_change, norm_min, norm_max;
 };
-static_assert(sizeof(FrameHdr) == 48, "three 16-byte vectors");
-constexpr uint32_t kHdrValid = 1u, kHdrFirst = 2u, kHdrEmpty = 4u, kHdrDense = 8u;
+static_assert(sizeof(FrameHdr) == 64, "four 16-byte vectors");
+constexpr uint32_t kHdrValid = 1u, kHdrFirst = 2u, kHdrDense = 8u, kHdrDenoise = 16u;
 constexpr int kQuadRefBias = 64;    // a strip's quad bytes are stored against (its min filtered value some frames ago) + bias
 constexpr int kListCap = 1024;  // marked groups per frame handled through the work lists (more: dense sweep)
 

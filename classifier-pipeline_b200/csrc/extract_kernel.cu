@@ -1566,14 +1566,14 @@ __global__ void __launch_bounds__(kFThreads, kFMinBlocks) frame_regions_kernel(c
     const long long o = blockIdx.x;
     if (o >= total_frames) return;
     const FrameHdr *fh = a.fhdr + o;
-    const cpt_frame_info *fi = a.info + o;
     CPT_TICK_START2(tid == 0);
-    // (independent loads first: the header and the info record are in flight together)
+    // the frame's header: one 64-byte line, four vector loads in flight together
     const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(fh));  // nmagic, nshift, flags, hot_strips
-    const uint4 th_lo = __ldg(reinterpret_cast<const uint4 *>(fh->theta)), th_hi = __ldg(reinterpret_cast<const uint4 *>(fh->theta) + 1);
-    const float thr = fi->threshold;
-    const int ac = fi->avg_change, gmn = fi->norm_min, gmx = fi->norm_max;
-    const int dn_marker = fi->reserved[1];
+    const uint4 th_lo = __ldg(reinterpret_cast<const uint4 *>(fh) + 1), th_hi = __ldg(reinterpret_cast<const uint4 *>(fh) + 2);
+    const uint4 sc = __ldg(reinterpret_cast<const uint4 *>(fh) + 3);  // threshold, avg_change, norm_min, norm_max
+    const float thr = __uint_as_float(sc.x);
+    const int ac = (int)sc.y, gmn = (int)sc.z, gmx = (int)sc.w;
+    const bool dn_marker = (hdr.z & kHdrDenoise) != 0;
     if (!(hdr.z & kHdrValid)) return;  // no clip produced this output frame
     const uint32_t nmagic = hdr.x;
     const int nshift = (int)hdr.y;

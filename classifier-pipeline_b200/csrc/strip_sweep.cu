@@ -687,7 +687,8 @@ __global__ void __launch_bounds__(128) frame_scalars_kernel(const KernelArgs a) 
             a.info[o] = fi;
             FrameHdr h;
             h.nmagic = fs.nmagic; h.nshift = fs.nshift;
-            h.flags = kHdrValid | (t == 0 ? kHdrFirst : 0u);
+            h.flags = kHdrValid | (t == 0 ? kHdrFirst : 0u) | (denoise ? kHdrDenoise : 0u);
+            h.threshold = fs.thr; h.avg_change = fs.ac; h.norm_min = fs.gmn; h.norm_max = fs.gmx;
             h.hot_strips = 0;
             bool dense = fs.fth == INT32_MIN;
 #pragma unroll
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(128) frame_scalars_kernel(const KernelArgs a) 
             if (dense) { h.flags |= kHdrDense; h.hot_strips = 0xffffffffu; }
             uint4 *hp = reinterpret_cast<uint4 *>(a.fhdr + o);
             const uint4 *hs = reinterpret_cast<const uint4 *>(&h);
-            hp[0] = hs[0]; hp[1] = hs[1]; hp[2] = hs[2];
+            hp[0] = hs[0]; hp[1] = hs[1]; hp[2] = hs[2]; hp[3] = hs[3];
         }
         if (t == n - 1) { last_fmin = fmin; last_fmax = fmax; }
     }
