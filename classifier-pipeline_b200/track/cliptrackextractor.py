@@ -238,8 +238,10 @@ class ClipTrackExtractor(ClipTracker):
             d_med = torch.empty((n_input,), dtype=torch.float32, device=eng.device)
             ctx.frame_medians(d_frames, n_input, d_med)
             medians = d_med.cpu().numpy()
-        regions = eng.regions_numpy(out["regions"])
         info = eng.info_numpy(out["info"])
+        # (only the region slots some frame uses travel: the API engines have 255 per frame)
+        used = min(int(info["n_components"][:total].max()) if total else 0, eng.max_regions)
+        regions = eng.regions_numpy(out["regions"][:, : max(used, 1)].contiguous())
         if total and int(info["n_components"][:total].max()) > eng.max_regions:
             # more components than the uint8 label image can number: the first 255 (OpenCV label order) are kept
             logging.warning("%d frame(s) have more than %d components; the rest are dropped",
