@@ -162,7 +162,7 @@ class BatchPreprocessor:
     clip-at-zero test, then one CTA per (segment, tile) that crops, resizes, normalises and writes the
     tile into the segment image.  Frames stay in HBM (the extraction's thermal input and filtered output)."""
 
-    def __init__(self, extractor, frame_size=32, frames_per_row=5, tiles=None, preprocess_fn=0):
+    def __init__(self, extractor, frame_size=32, frames_per_row=5, tiles=None, preprocess_fn=0, diff_norm=True, thermal_diff_norm=False):
         self.ex = extractor
         self.torch = extractor.torch
         self.device = extractor.device
@@ -170,6 +170,10 @@ class BatchPreprocessor:
         self.frames_per_row = frames_per_row
         self.tiles = tiles if tiles is not None else frames_per_row * 5  # preprocess.py:161: frames_per_row * 5
         self.preprocess_fn = preprocess_fn
+        # HyperParams.diff_norm / thermal_diff_norm (interpreter.py:315-363,405-408): track-wide limits for the filtered / the
+        # thermal channel; with diff_norm off both channels are normalised per tile
+        self.diff_norm = bool(diff_norm)
+        self.thermal_diff_norm = bool(thermal_diff_norm)
 
     def build_tables(self, tracks, seed=None):
         """tracks: list of (regions, segments); regions int array (n, >=6) rows [frame, x, y, w, h, blank] with
@@ -229,7 +233,8 @@ class BatchPreprocessor:
         if (seg_frames < 0).any():
             raise ValueError("segment frames must be non-negative")
         # ---- the unique (track, frame) pairs of the segments, in (track, frame) order
-        big = int(max(seg_frames.max(), R[:, 0].max() if len(R) else 0)) + 1
+        # (rows without a frame -- blank regions, frames the caller could not supply -- get the key big - 1, one past every real frame)
+        big = int(max(seg_frames.max(), R[:, 0].max() if len(R) else 0)) + 2
         key = np.repeat(seg_track, seg_len) * big + seg_frames
         uniq, inverse = np.unique(key, return_inverse=True)
         # the region of each unique frame: the first row of the track with that frame number (unique_regions keeps the first)
@@ -285,10 +290,13 @@ class BatchPreprocessor:
             d_out = torch.empty(shape, dtype=torch.float32, device=self.device)
             if out is not None:
                 out["segments"] = d_out
-        ctx.preprocess_limits(d_filtered, d_lim, n_lim, d_tracks, n_tracks)
+        ctx.preprocess_limits(d_filtered, d_lim, n_lim if self.diff_norm else 0, d_tracks, n_tracks)  # (always resets the rows)
+        if self.thermal_diff_norm:
+            ctx.preprocess_thermal_limits(d_thermal, d_lim, n_lim, d_tracks, n_tracks)
         ctx.preprocess_medians(d_thermal, d_smp, n_smp, d_tracks)
+        fn = int(self.preprocess_fn) | (0 if self.diff_norm else native.PREPROCESS_PER_TILE)
         ctx.preprocess_segments(d_thermal, d_filtered, d_smp, d_tracks, d_seg, n_seg, self.tiles, self.frames_per_row,
-                                self.frame_size, crop_rectangle, self.preprocess_fn, d_out)
+                                self.frame_size, crop_rectangle, fn, d_out)
         return dict(segments=d_out, tracks=d_tracks, samples=d_smp)
 
     def run(self, d_thermal, d_filtered, tracks, crop_rectangle, seed=None, out=None):

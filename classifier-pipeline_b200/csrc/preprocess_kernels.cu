@@ -75,6 +75,7 @@ __device__ __forceinline__ void block_reduce_min_max_min(float &a, float &b, flo
 }
 
 struct MinF { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+struct MaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 
 }  // namespace
 
@@ -86,7 +87,17 @@ __global__ void track_norm_reset_kernel(cpt_track_norm *tracks, int n_tracks) {
         tracks[i].filtered_max = 0.0f;     // interpreter.py:317 max_diff = 0
         tracks[i].clip_at_zero = 1;
         tracks[i].has_limits = 0;
+        tracks[i].thermal_min = FLT_MAX;
+        tracks[i].thermal_max = -FLT_MAX;
+        tracks[i].has_thermal_limits = 0;
+        tracks[i].reserved = 0;
     }
+}
+
+// thermal_diff_norm is on: until a region of the track is seen the limits are (None, None) -- per-tile extrema, no clip
+__global__ void track_thermal_on_kernel(cpt_track_norm *tracks, int n_tracks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tracks) tracks[i].has_thermal_limits = 2;
 }
 
 // one warp per non-blank region of a track (a crop is a few hundred pixels: a warp's worth of work, and many warps in
@@ -142,6 +153,48 @@ __global__ void __launch_bounds__(256) sample_median_kernel(const uint16_t *ther
         sp->median = 0.5f * (float)frame2;
         // np.median(float32(sub_thermal) - median) <= 0  (interpreter.py:393-399); every value is a multiple of 0.5
         if (has_crop && crop2 <= frame2) atomicAnd(&tracks[r.track].clip_at_zero, 0);
+    }
+}
+
+// get_limits with thermal_diff_norm: one CTA per non-blank region of a track -- the extrema of frame.thermal - median over
+// the whole frame (interpreter.py:338-345; float32 arithmetic on integer / half-integer values: exact)
+__global__ void __launch_bounds__(256) track_thermal_limits_kernel(const uint16_t *thermal, int W, int H, const cpt_sample *regions,
+                                                                   cpt_track_norm *tracks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *px = reinterpret_cast<uint16_t *>(smem_raw);
+    uint32_t *bins = reinterpret_cast<uint32_t *>(smem_raw + (((size_t)W * H * sizeof(uint16_t) + 15) & ~(size_t)15));
+    __shared__ int red[80];
+    __shared__ float scratch3[96];
+    const cpt_sample r = regions[blockIdx.x];
+    if (r.width <= 0 || r.height <= 0) return;
+    const int npx = W * H;
+    const uint16_t *src = thermal + (size_t)r.frame * npx;
+    float mn = FLT_MAX, mx = -FLT_MAX, unused = FLT_MAX;
+    for (int i = threadIdx.x; i < npx / 8; i += blockDim.x) {
+        const uint4 q = ldg16(src + i * 8);
+        *reinterpret_cast<uint4 *>(px + i * 8) = q;
+        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float lo = (float)(ws[k] & 0xffffu), hi = (float)(ws[k] >> 16);
+            mn = fminf(mn, fminf(lo, hi));
+            mx = fmaxf(mx, fmaxf(lo, hi));
+        }
+    }
+    for (int i = (npx / 8) * 8 + threadIdx.x; i < npx; i += blockDim.x) {
+        const uint16_t v = src[i];
+        px[i] = v;
+        mn = fminf(mn, (float)v);
+        mx = fmaxf(mx, (float)v);
+    }
+    block_reduce_min_max_min(mn, mx, unused, scratch3);  // (its barriers also publish the staged frame)
+    const int frame2 = rect_median_sum(px, W, 0, 0, W, H, bins, red);  // 2 * median
+    if (threadIdx.x == 0) {
+        const float median = 0.5f * (float)frame2;
+        cpt_track_norm *t = tracks + r.track;
+        atomic_min_float(&t->thermal_min, __fsub_rn(mn, median));
+        atomic_max_float(&t->thermal_max, __fsub_rn(mx, median));
+        t->has_thermal_limits = 1;
     }
 }
 
@@ -235,9 +288,10 @@ __global__ void __launch_bounds__(kTileThreads) segment_tiles_kernel(const Segme
     }
     pad = block_reduce(pad, scratch, MinF(), FLT_MAX);  // (also orders the tap tables before their use)
 
-    // ---- resize + paste, thermal -= median, clip (preprocess.py:92-95)
-    const bool clip0 = tn.clip_at_zero != 0;
-    float tmin = FLT_MAX, tmax = -FLT_MAX, fmin_ = FLT_MAX;
+    // ---- resize + paste, thermal -= median, clip unless thermal limits were asked for (preprocess.py:90-93)
+    const bool clip0 = tn.clip_at_zero != 0 && tn.has_thermal_limits == 0;
+    const bool per_tile = (a.preprocess_fn & CPT_PREPROCESS_PER_TILE) != 0;  // diff_norm off: Frame.normalize, both channels
+    float tmin = FLT_MAX, tmax = -FLT_MAX, fmin_ = FLT_MAX, fmax_ = -FLT_MAX;
     for (int i = tid; i < n; i += blockDim.x) {
         const int y = i / size, x = i - y * size;
         const int dx = x - ox, dy = y - oy;
@@ -257,10 +311,19 @@ __global__ void __launch_bounds__(kTileThreads) segment_tiles_kernel(const Segme
         tmin = fminf(tmin, t);
         tmax = fmaxf(tmax, t);
         fmin_ = fminf(fmin_, f);
+        fmax_ = fmaxf(fmax_, f);
     }
     block_reduce_min_max_min(tmin, tmax, fmin_, scratch3);
     float lo = tn.filtered_min, hi = tn.filtered_max;
     if (!tn.has_limits) lo = fmin_;  // min=None: the tile's own minimum
+    if (per_tile) {
+        fmax_ = block_reduce(fmax_, scratch, MaxF(), -FLT_MAX);
+        lo = fmin_;
+        hi = fmax_;
+    } else if (tn.has_thermal_limits == 1) {
+        tmin = tn.thermal_min;  // (only used together with filtered limits: preprocess.py:96-110)
+        tmax = tn.thermal_max;
+    }
 
     // ---- normalise and write the cell: image[row*size + y][col*size + x][channel]
     const int row = tile / a.per_row, col = tile - row * a.per_row;
@@ -269,7 +332,7 @@ __global__ void __launch_bounds__(kTileThreads) segment_tiles_kernel(const Segme
     for (int i = tid; i < n; i += blockDim.x) {
         const int y = i / size, x = i - y * size;
         float t = normalize255(tile_t[i], tmin, tmax), f = normalize255(tile_f[i], lo, hi);
-        if (a.preprocess_fn == 1) {  // x /= 127.5; x -= 1.0 (preprocess.py:19-22)
+        if (a.preprocess_fn & CPT_PREPROCESS_INC3) {  // x /= 127.5; x -= 1.0 (preprocess.py:19-22)
             t = __fsub_rn(__fdiv_rn(t, 127.5f), 1.0f);
             f = __fsub_rn(__fdiv_rn(f, 127.5f), 1.0f);
         }
@@ -300,6 +363,22 @@ int cpt_preprocess_limits(cpt_ctx *c, const float *d_filtered, const cpt_sample 
     return CPT_OK;
 }
 
+int cpt_preprocess_thermal_limits(cpt_ctx *c, const uint16_t *d_thermal, const cpt_sample *d_regions, int n_regions,
+                                  cpt_track_norm *d_tracks, int n_tracks) {
+    if (!c || !d_tracks) return fail(CPT_ERR_INVALID, "null argument");
+    if (n_regions < 0 || n_tracks < 0) return fail(CPT_ERR_INVALID, "negative count");
+    if (n_tracks == 0) return CPT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cpt::track_thermal_on_kernel<<<(n_tracks + 255) / 256, 256, 0, c->stream>>>(d_tracks, n_tracks);
+    if (n_regions > 0) {
+        if (!d_thermal || !d_regions) return fail(CPT_ERR_INVALID, "null thermal / regions");
+        const size_t smem = (((size_t)c->g.npx * sizeof(uint16_t) + 15) & ~(size_t)15) + cpt::kMedianBins * sizeof(uint32_t);
+        cpt::track_thermal_limits_kernel<<<n_regions, 256, smem, c->stream>>>(d_thermal, c->g.W, c->g.H, d_regions, d_tracks);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CPT_OK;
+}
+
 int cpt_preprocess_medians(cpt_ctx *c, const uint16_t *d_thermal, cpt_sample *d_samples, int n_samples,
                            cpt_track_norm *d_tracks) {
     if (!c) return fail(CPT_ERR_INVALID, "null ctx");
@@ -325,7 +404,7 @@ int cpt_preprocess_segments(cpt_ctx *c, const uint16_t *d_thermal, const float *
         return fail(CPT_ERR_INVALID, "null argument");
     if (tiles_per_segment < 1 || frames_per_row < 1 || frame_size < 1 || frame_size > cpt::kMaxTile)
         return fail(CPT_ERR_INVALID, "bad tiling (frame_size must be in [1,%d])", cpt::kMaxTile);
-    if (preprocess_fn != 0 && preprocess_fn != 1) return fail(CPT_ERR_INVALID, "preprocess_fn must be 0 (none) or 1 (x/127.5-1)");
+    if (preprocess_fn & ~(CPT_PREPROCESS_INC3 | CPT_PREPROCESS_PER_TILE)) return fail(CPT_ERR_INVALID, "preprocess_fn: unknown flag");
     if ((long long)n_segments * tiles_per_segment > 0x7fffffffll) return fail(CPT_ERR_INVALID, "too many tiles for one launch");
     if (n_segments == 0) return CPT_OK;
     CUDA_TRY(cudaSetDevice(c->device));

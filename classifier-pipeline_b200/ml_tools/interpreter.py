@@ -70,8 +70,8 @@ class Interpreter:
         self.labels = []
         if list(self.params.channels) != ["thermal", "filtered"]:
             raise NotImplementedError("the device tiling kernel emits the (thermal, filtered) channel pair")
-        if self.params.thermal_diff_norm or self.params.mvm or not self.params.diff_norm:
-            raise NotImplementedError("only the default normalisation (diff_norm on, thermal_diff_norm off, no mvm) is built")
+        if self.params.mvm:
+            raise NotImplementedError("the movement-feature input (mvm) is outside this path")
 
     def predict(self, frames):
         raise NotImplementedError("model inference is outside the extraction / preprocessing path")
@@ -137,8 +137,14 @@ class Interpreter:
         """(thermal_norm_limits, filtered_norm_limits) (interpreter.py:315-363)."""
         res = self._run(clip, [(track, [])])
         n = BatchPreprocessor.tracks_numpy(res["tracks"])[0]
-        lo = np.float32(n["filtered_min"]) if n["has_limits"] else None
-        return None, (lo, np.float32(n["filtered_max"]) if n["has_limits"] else 0)
+        thermal_limits = filtered_limits = None
+        if self.params.thermal_diff_norm:
+            found = int(n["has_thermal_limits"]) == 1
+            thermal_limits = (np.float32(n["thermal_min"]) if found else None, np.float32(n["thermal_max"]) if found else None)
+        if self.params.diff_norm:
+            lo = np.float32(n["filtered_min"]) if n["has_limits"] else None
+            filtered_limits = (lo, np.float32(n["filtered_max"]) if n["has_limits"] else 0)
+        return thermal_limits, filtered_limits
 
     def _run(self, clip, jobs):
         eng = self._engine_for(clip)
@@ -163,7 +169,8 @@ class Interpreter:
             if self.preprocess_fn not in (inc3_preprocess, _pp.preprocess_fn):
                 raise NotImplementedError("only the x / 127.5 - 1 input scaling is built into the tiling kernel")
             fn = 1
-        bp = BatchPreprocessor(eng, frame_size=self.params.frame_size, frames_per_row=self.params.square_width, preprocess_fn=fn)
+        bp = BatchPreprocessor(eng, frame_size=self.params.frame_size, frames_per_row=self.params.square_width, preprocess_fn=fn,
+                               diff_norm=self.params.diff_norm, thermal_diff_norm=self.params.thermal_diff_norm)
         crop = clip.crop_rectangle
         return bp.run(d_t, d_f, tables, (crop.x, crop.y, crop.width, crop.height), seed=self.seed)
 

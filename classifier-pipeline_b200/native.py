@@ -63,7 +63,8 @@ class CptSample(ctypes.Structure):
 class CptTrackNorm(ctypes.Structure):
     _fields_ = [
         ("filtered_min", ctypes.c_float), ("filtered_max", ctypes.c_float), ("clip_at_zero", ctypes.c_int32),
-        ("has_limits", ctypes.c_int32),
+        ("has_limits", ctypes.c_int32), ("thermal_min", ctypes.c_float), ("thermal_max", ctypes.c_float),
+        ("has_thermal_limits", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -101,10 +102,13 @@ CLIP_DTYPE = np.dtype(
 SAMPLE_DTYPE = np.dtype(
     [("frame", "<i8"), ("x", "<i4"), ("y", "<i4"), ("width", "<i4"), ("height", "<i4"), ("track", "<i4"), ("median", "<f4")]
 )
-TRACK_NORM_DTYPE = np.dtype([("filtered_min", "<f4"), ("filtered_max", "<f4"), ("clip_at_zero", "<i4"), ("has_limits", "<i4")])
+TRACK_NORM_DTYPE = np.dtype([("filtered_min", "<f4"), ("filtered_max", "<f4"), ("clip_at_zero", "<i4"), ("has_limits", "<i4"),
+                             ("thermal_min", "<f4"), ("thermal_max", "<f4"), ("has_thermal_limits", "<i4"), ("reserved", "<i4")])
+PREPROCESS_INC3 = 1       # x / 127.5 - 1
+PREPROCESS_PER_TILE = 2   # HyperParams.diff_norm off: both channels normalised by the tile's own extrema
 CPTV_FRAME_DTYPE = np.dtype([("payload_offset", "<u8"), ("bit_width", "<i4"), ("reserved", "<i4")])
 assert SAMPLE_DTYPE.itemsize == ctypes.sizeof(CptSample) == 32
-assert TRACK_NORM_DTYPE.itemsize == ctypes.sizeof(CptTrackNorm) == 16
+assert TRACK_NORM_DTYPE.itemsize == ctypes.sizeof(CptTrackNorm) == 32
 assert REGION_DTYPE.itemsize == ctypes.sizeof(CptRegion) == 40
 assert INFO_DTYPE.itemsize == ctypes.sizeof(CptFrameInfo) == 64
 assert CLIP_DTYPE.itemsize == ctypes.sizeof(CptClip) == 48
@@ -137,6 +141,7 @@ SYMBOLS = {
     "cpt_background_process": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
     "cpt_frame_medians": (_i, [_vp, _vp, _i64, _vp]),
     "cpt_preprocess_limits": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "cpt_preprocess_thermal_limits": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
     "cpt_preprocess_medians": (_i, [_vp, _vp, _vp, _i, _vp]),
     "cpt_preprocess_segments": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "cpt_minmax_f32": (_i, [_vp, _vp, _i64, _vp]),
@@ -283,6 +288,9 @@ class Context:
 
     def preprocess_limits(self, d_filtered, d_regions, n_regions, d_tracks, n_tracks):
         check(self.lib.cpt_preprocess_limits(self._h, _ptr(d_filtered), _ptr(d_regions), int(n_regions), _ptr(d_tracks), int(n_tracks)))
+
+    def preprocess_thermal_limits(self, d_thermal, d_regions, n_regions, d_tracks, n_tracks):
+        check(self.lib.cpt_preprocess_thermal_limits(self._h, _ptr(d_thermal), _ptr(d_regions), int(n_regions), _ptr(d_tracks), int(n_tracks)))
 
     def preprocess_medians(self, d_thermal, d_samples, n_samples, d_tracks):
         check(self.lib.cpt_preprocess_medians(self._h, _ptr(d_thermal), _ptr(d_samples), int(n_samples), _ptr(d_tracks)))

@@ -199,12 +199,22 @@ typedef struct {
     float filtered_min, filtered_max; /* Interpreter.get_limits with diff_norm (interpreter.py:315-363) */
     int32_t clip_at_zero;             /* clip_thermals_at_zero (interpreter.py:391-399) */
     int32_t has_limits;               /* 0: the track had no usable region, normalise by the tile's own minimum */
+    float thermal_min, thermal_max;   /* get_limits with thermal_diff_norm: extrema of frame.thermal - median over the track's frames */
+    int32_t has_thermal_limits;       /* 0: thermal_diff_norm off; 1: limits above; 2: on, but the track had no usable region
+                                         (per-tile extrema).  With 1 or 2 the thermal channel is not clipped at zero
+                                         (preprocess.py:92-93) */
+    int32_t reserved;
 } cpt_track_norm;
 
 /* get_limits: resets all n_tracks rows (min unset, max 0, clip_at_zero 1), then folds the min / max of
  * region.subimage(frame.filtered) of every entry of d_regions (all non-blank regions of each track). */
 int cpt_preprocess_limits(cpt_ctx *ctx, const float *d_filtered, const cpt_sample *d_regions, int n_regions,
                           cpt_track_norm *d_tracks, int n_tracks);
+/* get_limits with HyperParams.thermal_diff_norm (interpreter.py:338-345,358-359): after cpt_preprocess_limits, folds the
+ * min / max of frame.thermal - np.median(frame.thermal) over the WHOLE frame of every entry of d_regions into the
+ * track rows (one full-frame median per entry). */
+int cpt_preprocess_thermal_limits(cpt_ctx *ctx, const uint16_t *d_thermal, const cpt_sample *d_regions, int n_regions,
+                                  cpt_track_norm *d_tracks, int n_tracks);
 /* Pass 1 of preprocess_segments over the unique track-frames: fills sample.median and clears the track's
  * clip_at_zero when np.median(region.subimage(thermal) - median) <= 0. */
 int cpt_preprocess_medians(cpt_ctx *ctx, const uint16_t *d_thermal, cpt_sample *d_samples, int n_samples,
@@ -214,7 +224,10 @@ int cpt_preprocess_medians(cpt_ctx *ctx, const uint16_t *d_thermal, cpt_sample *
  * and sorted as preprocess_movement does); tile i lands in row i / frames_per_row, column i % frames_per_row of
  * d_out [n_segments][rows*frame_size][frames_per_row*frame_size][2] float32 (channels thermal, filtered).
  * crop_rectangle = {x, y, width, height} of Clip.crop_rectangle (keep_edge anchoring) or NULL;
- * preprocess_fn 0 = none, 1 = x / 127.5 - 1 (interpreter.py:563-566). */
+ * preprocess_fn: CPT_PREPROCESS_INC3 = x / 127.5 - 1 (interpreter.py:563-566); CPT_PREPROCESS_PER_TILE = HyperParams.diff_norm
+ * off: no track-wide limits, both channels are normalised by the tile's own extrema (Frame.normalize, preprocess.py:111). */
+#define CPT_PREPROCESS_INC3 1
+#define CPT_PREPROCESS_PER_TILE 2
 int cpt_preprocess_segments(cpt_ctx *ctx, const uint16_t *d_thermal, const float *d_filtered, const cpt_sample *d_samples,
                             const cpt_track_norm *d_tracks, const int32_t *d_segment_samples, int n_segments,
                             int tiles_per_segment, int frames_per_row, int frame_size, const int32_t *crop_rectangle,

@@ -140,7 +140,22 @@ def track_limits(filtered, regions):
     return lo, hi
 
 
-def preprocess_track(thermal, filtered, regions, crop, segments, dim=(32, 32), frames_per_row=5, seed=None, preprocess_fn=None):
+def thermal_limits(thermal, regions):
+    """get_limits with thermal_diff_norm (interpreter.py:338-345): (min, max) of frame.thermal - np.median(frame.thermal)
+    over the WHOLE frame of every non-blank region of the track (float32 arithmetic, as float_arrays() makes the frames)."""
+    lo = hi = None
+    for frame, x, y, w, h, blank in (r[:6] for r in reversed(regions)):
+        if blank or w <= 0 or h <= 0 or frame < 0 or frame >= len(thermal):
+            continue
+        t = np.float32(thermal[frame])
+        d = t - np.median(t)
+        lo = d.min() if lo is None or d.min() < lo else lo
+        hi = d.max() if hi is None or d.max() > hi else hi
+    return lo, hi
+
+
+def preprocess_track(thermal, filtered, regions, crop, segments, dim=(32, 32), frames_per_row=5, seed=None, preprocess_fn=None,
+                     diff_norm=True, thermal_diff_norm=False):
     """Interpreter.preprocess_segments for one track.  thermal (T,H,W) uint16, filtered (T,H,W) float32
     (frame index == frame number), regions rows [frame, x, y, w, h, blank], segments = list of frame-number
     arrays.  Returns float32 (n_segments, dim*rows, dim*rows, 2)."""
@@ -159,7 +174,10 @@ def preprocess_track(thermal, filtered, regions, crop, segments, dim=(32, 32), f
             sub = np.float32(thermal[f][y : y + h, x : x + w]) - medians[f]
             if np.median(sub) <= 0:
                 clip_at_zero = False
-    lo, hi = track_limits(filtered, regions)
+    # interpreter.py:405-408: limits only when one of the two options asks for them; preprocess.py:92-113: without filtered
+    # limits BOTH channels are normalised per tile (Frame.normalize), and thermal limits only switch the clip off
+    lo, hi = track_limits(filtered, regions) if diff_norm else (None, None)
+    tlim = thermal_limits(thermal, regions) if thermal_diff_norm else None
     tiles = {}
     for f in unique:
         _, x, y, w, h = (int(v) for v in by_frame[f][:5])
@@ -168,10 +186,17 @@ def preprocess_track(thermal, filtered, regions, crop, segments, dim=(32, 32), f
         fl = resize_and_pad(np.float32(filtered[f][y : y + h, x : x + w]), dim, region, crop, keep_edge=True, pad=0)
         t = t - np.float32(medians[f]) if float(medians[f]) == np.float32(medians[f]) else (t - medians[f])
         t = np.float32(t)
-        if clip_at_zero:
+        if tlim is None and clip_at_zero:
             t = np.clip(t, 0, None)
-        fl, _ = normalize(fl, lo, hi, new_max=255)
-        t, _ = normalize(t, new_max=255)
+        if diff_norm:
+            fl, _ = normalize(fl, lo, hi, new_max=255)
+            if tlim is not None:
+                t, _ = normalize(t, tlim[0], tlim[1], new_max=255)
+            else:
+                t, _ = normalize(t, new_max=255)
+        else:
+            fl, _ = normalize(fl, new_max=255)
+            t, _ = normalize(t, new_max=255)
         tiles[f] = (np.float32(t), np.float32(fl))
     out = []
     for seg in segments:

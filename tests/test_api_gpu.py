@@ -127,6 +127,48 @@ def test_streaming_process_frame_with_denoise_matches_the_reference():
     assert_tracks_match_golden(clip, meta, d)
 
 
+@pytest.mark.parametrize("tag", ["default", "tdn", "nodiff"])
+def test_interpreter_preprocess_segments_matches_the_reference(tag):
+    """The reference-facing call chain -- parse_clip, Track.get_segments, Interpreter.preprocess_segments / get_limits
+    (interpreter.py:315-474) -- with the default HyperParams and with thermal_diff_norm / diff_norm=False, against what the
+    unmodified reference produced for the same tracks and frames."""
+    import json
+
+    from classifier_pipeline_b200.ml_tools.interpreter import HyperParams, Interpreter
+    from classifier_pipeline_b200.track.clip import Clip
+    from tests.test_preprocess_oracle import ATOL, OPTION_SETS, RTOL
+
+    path = os.path.join(helpers.GOLDEN, "clips", "possum.cptv")
+    ext, config = _extractor()
+    clip = Clip(config.tracking["thermal"], path)
+    ext.parse_clip(clip)
+    tracks = list(clip.tracks) + [t for _, t in clip.filtered_tracks if len(t) >= 8]
+    opts = {} if tag == "default" else OPTION_SETS[tag]
+    pre = np.load(os.path.join(helpers.GOLDEN, "pre_possum.npz" if tag == "default" else "pre_possum_opts.npz"))
+    meta = json.loads(str(pre["meta"]))
+    interp = Interpreter(HyperParams(opts), seed=1234)
+    assert meta["tracks"]
+    for entry in meta["tracks"]:
+        ti = entry["index"]
+        track = tracks[ti]
+        assert track.get_id() == entry["id"]
+        seg_frames = [pre["t{}_seg{}".format(ti, s)] for s in range(entry["segments"])]
+        segments = track.get_segments(25, segment_frames=seg_frames)
+        used, data, masses = interp.preprocess_segments(clip, track, segments)
+        expected = pre["t{}_out".format(ti) if tag == "default" else "t{}_out_{}".format(ti, tag)]
+        np.testing.assert_allclose(data, expected, rtol=RTOL, atol=ATOL)
+        thermal_limits, filtered_limits = interp.get_limits(clip, track)
+        if tag == "default":
+            assert [float(filtered_limits[0]), float(filtered_limits[1])] == entry["filtered_limits"] and thermal_limits is None
+        else:
+            want_t, want_f = entry[tag + "_thermal_limits"], entry[tag + "_filtered_limits"]
+            assert (thermal_limits is None) == (want_t is None) and (filtered_limits is None) == (want_f is None)
+            if want_t is not None:
+                assert [float(thermal_limits[0]), float(thermal_limits[1])] == want_t
+            if want_f is not None:
+                assert [float(filtered_limits[0]), float(filtered_limits[1])] == want_f
+
+
 def test_process_frame_leaves_the_background_to_the_caller():
     """As in the reference, process_frame never updates the background: a caller that drives background_alg itself the way
     _track_clip does (mean of the last 45 thermal frames after every frame, cliptrackextractor.py:167-176) gets parse_clip's
