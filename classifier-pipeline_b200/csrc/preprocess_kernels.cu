@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kLimitsThreads) track_limits_kernel(const floa
     const int idx = blockIdx.x * (kLimitsThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (idx >= n_regions) return;
     const cpt_sample r = regions[idx];
-    if (r.width <= 0 || r.height <= 0) return;
+    if (r.width <= 0 || r.height <= 0 || r.frame < 0) return;  // (a row without a frame or an area is nobody's region)
     const float *f = filtered + (size_t)r.frame * W * H;
     float mn = FLT_MAX, mx = -FLT_MAX;
     const int n = r.width * r.height;
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256) sample_median_kernel(const uint16_t *ther
     __shared__ int red[80];
     cpt_sample *sp = samples + blockIdx.x;
     const cpt_sample r = *sp;
+    if (r.frame < 0) return;  // (a malformed table must not make the kernel read in front of the frames)
     const int npx = W * H;
     const uint16_t *src = thermal + (size_t)r.frame * npx;
     for (int i = threadIdx.x; i < npx / 8; i += blockDim.x) *reinterpret_cast<uint4 *>(px + i * 8) = ldg16(src + i * 8);
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) track_thermal_limits_kernel(const uint16_
     __shared__ int red[80];
     __shared__ float scratch3[96];
     const cpt_sample r = regions[blockIdx.x];
-    if (r.width <= 0 || r.height <= 0) return;
+    if (r.width <= 0 || r.height <= 0 || r.frame < 0) return;
     const int npx = W * H;
     const uint16_t *src = thermal + (size_t)r.frame * npx;
     float mn = FLT_MAX, mx = -FLT_MAX, unused = FLT_MAX;
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(kTileThreads) segment_tiles_kernel(const Segme
     const int seg = blockIdx.x / a.tiles, tile = blockIdx.x - seg * a.tiles;
     const int sidx = a.segment_samples[blockIdx.x];
     const cpt_sample r = a.samples[sidx];
+    if (r.frame < 0 || r.width <= 0 || r.height <= 0) return;  // (malformed table: the tile is left as it is)
     const cpt_track_norm tn = a.tracks[r.track];
     const int size = a.size, n = size * size, tid = threadIdx.x;
     const int sw = r.width, sh = r.height;
