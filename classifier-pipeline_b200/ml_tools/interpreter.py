@@ -68,8 +68,14 @@ class Interpreter:
         self.seed = seed
         self.device = device
         self.labels = []
-        if list(self.params.channels) != ["thermal", "filtered"]:
-            raise NotImplementedError("the device tiling kernel emits the (thermal, filtered) channel pair")
+        # preprocess_movement stacks one tiled image per entry of params.channels (preprocess.py:169-189): any list over
+        # thermal / filtered (repeats included, e.g. thermal, filtered, filtered) is a selection from the pair the device
+        # kernel emits; the flow and mask channels are outside this path
+        names = [c if isinstance(c, str) else getattr(c, "name", str(c)) for c in self.params.channels]
+        unknown = [c for c in names if c not in ("thermal", "filtered")]
+        if unknown or not names:
+            raise NotImplementedError("channels {}: the device tiling kernel emits thermal and filtered".format(unknown or names))
+        self._channel_index = [0 if c == "thermal" else 1 for c in names]
         if self.params.mvm:
             raise NotImplementedError("the movement-feature input (mvm) is outside this path")
 
@@ -184,7 +190,12 @@ class Interpreter:
         """``preprocess_segments`` for several (track, segments) pairs of one clip in one set of launches."""
         jobs = [(t, list(s)) for t, s in jobs]
         res = self._run(clip, jobs)
-        data = res["segments"].cpu().numpy()
+        d_seg = res["segments"]
+        if self._channel_index != [0, 1]:
+            import torch
+
+            d_seg = d_seg.index_select(-1, torch.tensor(self._channel_index, device=d_seg.device))
+        data = d_seg.cpu().numpy()
         out, at = [], 0
         for track, segments in jobs:
             n = len(segments)

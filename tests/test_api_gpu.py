@@ -167,6 +167,12 @@ def test_interpreter_preprocess_segments_matches_the_reference(tag):
                 assert [float(thermal_limits[0]), float(thermal_limits[1])] == want_t
             if want_f is not None:
                 assert [float(filtered_limits[0]), float(filtered_limits[1])] == want_f
+        if tag == "default":
+            # any channel list over thermal / filtered is a selection of the pair (preprocess.py:169-189)
+            three = Interpreter(HyperParams(channels=["thermal", "filtered", "filtered"]), seed=1234)
+            _, data3, _ = three.preprocess_segments(clip, track, segments)
+            assert data3.shape == expected.shape[:-1] + (3,)
+            assert np.array_equal(data3[..., :2], data) and np.array_equal(data3[..., 2], data[..., 1])
 
 
 def test_process_frame_leaves_the_background_to_the_caller():
