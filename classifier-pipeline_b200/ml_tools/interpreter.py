@@ -172,13 +172,19 @@ class Interpreter:
         if self.preprocess_fn is not None:
             from . import preprocess as _pp
 
-            if self.preprocess_fn not in (inc3_preprocess, _pp.preprocess_fn):
-                raise NotImplementedError("only the x / 127.5 - 1 input scaling is built into the tiling kernel")
-            fn = 1
+            # the x / 127.5 - 1 scaling is built into the tiling kernel; any other callable is applied to each segment's array
+            # on the host afterwards, as preprocess_movement does (preprocess.py:200-201)
+            if self.preprocess_fn in (inc3_preprocess, _pp.preprocess_fn):
+                fn = 1
         bp = BatchPreprocessor(eng, frame_size=self.params.frame_size, frames_per_row=self.params.square_width, preprocess_fn=fn,
                                diff_norm=self.params.diff_norm, thermal_diff_norm=self.params.thermal_diff_norm)
         crop = clip.crop_rectangle
         return bp.run(d_t, d_f, tables, (crop.x, crop.y, crop.width, crop.height), seed=self.seed)
+
+    def _fn_on_device(self):
+        from . import preprocess as _pp
+
+        return self.preprocess_fn in (inc3_preprocess, _pp.preprocess_fn)
 
     # ------------------------------------------------------------------ the path proper
     def preprocess_segments(self, clip, track, segments, predict_from_last=None):
@@ -196,6 +202,8 @@ class Interpreter:
 
             d_seg = d_seg.index_select(-1, torch.tensor(self._channel_index, device=d_seg.device))
         data = d_seg.cpu().numpy()
+        if self.preprocess_fn is not None and not self._fn_on_device():
+            data = np.float32([self.preprocess_fn(seg) for seg in data]) if len(data) else data
         out, at = [], 0
         for track, segments in jobs:
             n = len(segments)

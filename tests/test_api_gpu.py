@@ -173,6 +173,13 @@ def test_interpreter_preprocess_segments_matches_the_reference(tag):
             _, data3, _ = three.preprocess_segments(clip, track, segments)
             assert data3.shape == expected.shape[:-1] + (3,)
             assert np.array_equal(data3[..., :2], data) and np.array_equal(data3[..., 2], data[..., 1])
+            # a preprocess_fn the kernel does not know is applied on the host, the built-in one on the device: same numbers
+            from classifier_pipeline_b200.ml_tools.interpreter import inc3_preprocess
+
+            _, on_device, _ = Interpreter(HyperParams(), preprocess_fn=inc3_preprocess, seed=1234).preprocess_segments(clip, track, segments)
+            _, on_host, _ = Interpreter(HyperParams(), preprocess_fn=lambda x: x / np.float32(127.5) - np.float32(1.0), seed=1234).preprocess_segments(clip, track, segments)
+            np.testing.assert_allclose(on_device, on_host, rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(on_device, expected / np.float32(127.5) - np.float32(1.0), rtol=RTOL, atol=1e-4)
 
 
 def test_process_frame_leaves_the_background_to_the_caller():
