@@ -5,11 +5,11 @@
 //     w = table[dist >> 6],  est += w * ext[p + o],  wsum += w;      out = (est + wsum / 2) / wsum
 // with table[a] = rint(19096 * exp(-(a * 64 / 49) / 9)), zero below 0.001 * 19096 -- only a <= 47 is non-zero.
 // Compute bound by design (441 offsets x 49 template pixels per output pixel).  nlm_quads_kernel, the kernel every
-// ordinary image takes: a thread owns 4 adjacent columns x 8 rows, its 32 estimates and weight sums live in registers for
-// all 441 offsets; per offset it walks down 8 + 6 rows of its columns -- per row three words of the image and of the
+// ordinary image takes: a thread owns 4 adjacent columns x 10 rows, its 40 estimates and weight sums live in registers for
+// all 441 offsets; per offset it walks down 10 + 6 rows of its columns -- per row three words of the image and of the
 // shifted image (funnel shifts bring the shifted bytes into line), |a - b| on four bytes at a time, the squares summed
 // by dp4a into the four 7-wide horizontal sums, a 7-deep register ring for the vertical running sum -- and then looks
-// up the weight of each of its 8 x 4 pixels: about 27 instructions per pixel and offset, no barrier inside the search.
+// up the weight of each of its 10 x 4 pixels: about 27 instructions per pixel and offset, no barrier inside the search.
 // nlm_denoise_kernel (one CTA per 16x16 tile, squared differences box-summed through shared memory, two barriers per
 // offset) is the first version; it remains for images wider than the quad kernel's tile logic is sized for.
 #include <algorithm>
@@ -85,15 +85,21 @@ __global__ void __launch_bounds__(256) nlm_denoise_kernel(const uint8_t *src, in
 // ---- the quad kernel -------------------------------------------------------------------------------------------------
 constexpr int kNqCols = 160;                       // pixels per tile row: 40 threads x 4
 constexpr int kNqQuads = kNqCols / 4;
-constexpr int kNqRowsT = 8;                        // rows per thread
-constexpr int kNqStrips = 4;                       // threads per column quad: 4 strips of 8 rows
-constexpr int kNqRows = kNqRowsT * kNqStrips;      // 32 rows per tile
+#ifndef CPT_NLM_ROWS
+#define CPT_NLM_ROWS 10
+#endif
+#ifndef CPT_NLM_MINBLOCKS
+#define CPT_NLM_MINBLOCKS 3
+#endif
+constexpr int kNqRowsT = CPT_NLM_ROWS;             // rows per thread
+constexpr int kNqStrips = 4;                       // threads per column quad: 4 strips of kNqRowsT rows
+constexpr int kNqRows = kNqRowsT * kNqStrips;      // 40 rows per tile: three tiles cover the 120 rows of a Lepton frame exactly
 constexpr int kNqThreads = kNqQuads * kNqStrips;   // 160
 constexpr int kNqPad = 16;                         // columns left / right of the tile in shared memory (>= 13, a multiple of 4)
 constexpr int kNqExtW = kNqCols + 2 * kNqPad;      // 192 bytes per row
 constexpr int kNqExtH = kNqRows + 2 * kNlmB;       // 58 rows
 
-__global__ void __launch_bounds__(kNqThreads, 3) nlm_quads_kernel(const uint8_t *src, int W, int H, uint8_t *dst, const cpt_frame_info *info) {
+__global__ void __launch_bounds__(kNqThreads, CPT_NLM_MINBLOCKS) nlm_quads_kernel(const uint8_t *src, int W, int H, uint8_t *dst, const cpt_frame_info *info) {
     if (info && info[blockIdx.z].reserved[1] == 0) return;
     __shared__ __align__(16) uint8_t ext[kNqExtH][kNqExtW];
     __shared__ int wtab[kNlmWeights];
