@@ -182,6 +182,60 @@ def test_interpreter_preprocess_segments_matches_the_reference(tag):
             np.testing.assert_allclose(on_device, expected / np.float32(127.5) - np.float32(1.0), rtol=RTOL, atol=1e-4)
 
 
+def test_weighted_background_object_matches_oracle():
+    """WeightedBackground.process_frame on the device == the reference recurrence (oracle) for both weight_add values."""
+    from classifier_pipeline_b200.ml_tools.rectangle import Rectangle
+    from classifier_pipeline_b200.piclassifier.motiondetector import WeightedBackground
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(5)
+    for weight_add in (0.1, 1):
+        wb = WeightedBackground(1, Rectangle(1, 1, 158, 118), 160, 120, weight_add)
+        ob = orc.Background(160, 120, 1, weight_add)
+        base = rng.integers(2900, 3100, size=(120, 160)).astype(np.float64)
+        for t in range(40):
+            frame = base + rng.integers(-3, 4, size=(120, 160)) + (t % 7 == 0) * rng.integers(-40, 40, size=(120, 160)) + 0.5
+            wb.process_frame(frame)
+            ob.process(np.int32(frame))
+            bg, w, avg = ob.get()
+            assert np.array_equal(wb.background, bg.astype(np.float64)), t
+            assert np.array_equal(wb.background_weight, w), t
+            assert wb.average == avg, t
+
+
+def test_parse_clip_default_config_reproduces_reference_possum_json():
+    """The reference's own regression: tests/clips/possum.txt is extract.py's output for possum.cptv with the DEFAULT
+    config (denoise on).  parse_clip on the device reproduces every track position and both tracking scores."""
+    import json
+
+    from classifier_pipeline_b200.config import Config
+    from classifier_pipeline_b200.ml_tools.tools import CustomJSONEncoder
+    from classifier_pipeline_b200.track.clip import Clip
+    from classifier_pipeline_b200.track.cliptrackextractor import ClipTrackExtractor
+
+    config = Config.get_defaults()
+    assert config.tracking["thermal"].denoise is True
+    ext = ClipTrackExtractor(config.tracking, False, cache_to_disk=False)
+    clip = Clip(config.tracking["thermal"], os.path.join(helpers.GOLDEN, "clips", "possum.cptv"))
+    ext.parse_clip(clip)
+    d, meta = helpers.load_golden("possum_nlm")
+    assert_tracks_match_golden(clip, meta, d)
+    gold = json.load(open(os.path.join(helpers.GOLDEN, "clips", "possum.txt")))
+    got = json.loads(json.dumps(clip.get_metadata(), cls=CustomJSONEncoder))
+    assert len(got["tracks"]) == len(gold["tracks"]) == 2
+    for a, b in zip(got["tracks"], gold["tracks"]):
+        for k in ("id", "start_s", "end_s", "num_frames", "frame_start", "frame_end"):
+            assert a[k] == b[k], k
+        assert a["tracking_score"] == pytest.approx(b["tracking_score"], rel=1e-6)
+        assert len(a["positions"]) == len(b["positions"])
+        for p, q in zip(a["positions"], b["positions"]):
+            for k in q:
+                if k == "pixel_variance":
+                    assert p[k] == pytest.approx(q[k], abs=0.011)
+                else:
+                    assert p[k] == q[k], k
+
+
 def test_process_frame_leaves_the_background_to_the_caller():
     """As in the reference, process_frame never updates the background: a caller that drives background_alg itself the way
     _track_clip does (mean of the last 45 thermal frames after every frame, cliptrackextractor.py:167-176) gets parse_clip's
