@@ -87,7 +87,8 @@ class Interpreter:
         """interpreter.py:178-257 for segment models."""
         frames_per_classify = args.get("frames_per_classify", 25)
         if frames_per_classify <= 1:
-            raise NotImplementedError("single-frame models are outside this path")
+            raise NotImplementedError("single-frame models: the reference's own dispatch does not run here (interpreter.py:126-129 calls "
+                                      "preprocess_frames without its samples argument); only segment models are built")
         predict_from_last = args.get("predict_from_last", None)
         segment_frames = args.get("segment_frames", None)
         dont_filter = args.get("dont_filter", False)
