@@ -282,10 +282,13 @@ __global__ void __launch_bounds__(kTileThreads) segment_tiles_kernel(const Segme
     if (tid < fw) tx[tid] = linear_taps(tid, fw, sw, sh == 1 && sw > 1);
     if (tid >= 64 && tid - 64 < fh) ty[tid - 64] = linear_taps(tid - 64, fh, sh, sw == 1 && sh > 1);
 
+    // (index arithmetic without divisions: i / sw by a reciprocal multiply, i / size by a shift for the usual power of two)
+    const uint32_t sw_rcp = 0xffffffffu / (uint32_t)sw + 1u;  // i / sw == umulhi(i, sw_rcp) for i * sw < 2^32 (wraps to 0 for sw == 1)
+    const int size_shift = (size & (size - 1)) == 0 ? __ffs(size) - 1 : -1;
     // ---- pad value of the thermal tile: min of the crop (imageprocessing.py:36-37)
     float pad = FLT_MAX;
     for (int i = tid; i < sw * sh; i += blockDim.x) {
-        const int yy = i / sw, xx = i - yy * sw;
+        const int yy = sw == 1 ? i : (int)__umulhi((uint32_t)i, sw_rcp), xx = i - yy * sw;
         pad = fminf(pad, (float)__ldg(th + yy * a.W + xx));
     }
     pad = block_reduce(pad, scratch, MinF(), FLT_MAX);  // (also orders the tap tables before their use)
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(kTileThreads) segment_tiles_kernel(const Segme
     const bool per_tile = (a.preprocess_fn & CPT_PREPROCESS_PER_TILE) != 0;  // diff_norm off: Frame.normalize, both channels
     float tmin = FLT_MAX, tmax = -FLT_MAX, fmin_ = FLT_MAX, fmax_ = -FLT_MAX;
     for (int i = tid; i < n; i += blockDim.x) {
-        const int y = i / size, x = i - y * size;
+        const int y = size_shift >= 0 ? (i >> size_shift) : i / size, x = i - y * size;
         const int dx = x - ox, dy = y - oy;
         float t = pad, f = 0.0f;
         if (dx >= 0 && dx < fw && dy >= 0 && dy < fh) {
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(kTileThreads) segment_tiles_kernel(const Segme
     const int img_w = a.per_row * size, img_h = ((a.tiles + a.per_row - 1) / a.per_row) * size;
     float2 *img = reinterpret_cast<float2 *>(a.out) + (size_t)seg * img_w * img_h;
     for (int i = tid; i < n; i += blockDim.x) {
-        const int y = i / size, x = i - y * size;
+        const int y = size_shift >= 0 ? (i >> size_shift) : i / size, x = i - y * size;
         float t = normalize255(tile_t[i], tmin, tmax), f = normalize255(tile_f[i], lo, hi);
         if (a.preprocess_fn & CPT_PREPROCESS_INC3) {  // x /= 127.5; x -= 1.0 (preprocess.py:19-22)
             t = __fsub_rn(__fdiv_rn(t, 127.5f), 1.0f);
